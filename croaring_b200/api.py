@@ -1,0 +1,293 @@
+"""Python mirror of the C ABI in include/roaring_b200.h (ctypes; no torch types cross the boundary).
+
+The names follow the reference's C API (roaring_bitmap_and / or / xor / andnot / or_many /
+and_cardinality ..., /root/reference/include/roaring/roaring.h:225-348) so parity tests read
+like the reference's own tests.  Everything here runs on the GPU through
+libroaring_b200.so; there is no CPU fallback — if the library or a CUDA device is missing,
+calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libroaring_b200.so")
+
+AND, OR, XOR, ANDNOT = 0, 1, 2, 3
+OPS = {"and": AND, "or": OR, "xor": XOR, "andnot": ANDNOT}
+
+_P = C.c_void_p
+_lib = None
+
+
+class RB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libroaring_b200.so (build it first with `python -m croaring_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RB200Error(
+            f"{LIB_PATH} is missing: the CUDA extension is not built "
+            "(run `python -m croaring_b200.build`); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH, mode=os.RTLD_LOCAL)
+
+    def sig(name, res, *args):
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = list(args)
+
+    for op in ("and", "or", "xor", "andnot"):
+        sig(f"roaring_bitmap_{op}", _P, _P, _P)
+        sig(f"roaring_bitmap_{op}_cardinality", C.c_uint64, _P, _P)
+    sig("roaring_bitmap_or_many", _P, C.c_size_t, C.POINTER(_P))
+    sig("roaring_bitmap_jaccard_index", C.c_double, _P, _P)
+    sig("roaring_bitmap_intersect", C.c_bool, _P, _P)
+    sig("rb200_bitmap_portable_deserialize_safe", _P, C.c_char_p, C.c_size_t)
+    sig("rb200_bitmap_portable_size_in_bytes", C.c_size_t, _P)
+    sig("rb200_bitmap_portable_serialize", C.c_size_t, _P, C.c_char_p)
+    sig("rb200_bitmap_free", None, _P)
+    sig("rb200_bitmap_get_cardinality", C.c_uint64, _P)
+    sig("rb200_bitmap_validate", C.c_bool, _P, C.POINTER(C.c_char_p))
+    sig("rb200_init", C.c_int, C.c_int)
+    sig("rb200_set_stream", None, _P)
+    sig("rb200_synchronize", None)
+    sig("rb200_last_error", C.c_char_p)
+    sig("rb200_kernel_launches", C.c_uint64)
+    sig("rb200_last_algorithmic_bytes", C.c_uint64)
+    sig("rb200_last_device_ms", C.c_float)
+    sig("rb200_last_compute_ms", C.c_float)
+    sig("rb200_last_download_bytes", C.c_uint64)
+    sig("rb200_set_upload", _P, C.POINTER(_P), C.c_size_t)
+    sig("rb200_set_upload_serialized", _P, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t)
+    sig("rb200_set_free", None, _P)
+    sig("rb200_set_count", C.c_size_t, _P)
+    sig("rb200_set_container_count", C.c_uint64, _P)
+    sig("rb200_set_payload_bytes", C.c_uint64, _P)
+    sig("rb200_batch_op", _P, C.c_int, _P, _P, _P, _P, C.c_size_t)
+    sig("rb200_batch_and_cardinality", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
+    sig("rb200_or_many", _P, _P, _P, C.c_size_t)
+    sig("rb200_or_many_keyrange", _P, _P, _P, C.c_size_t, C.c_uint32, C.c_uint32, _P)
+    sig("rb200_set_cardinalities", C.c_int, _P, _P)
+    sig("rb200_set_download", _P, _P, C.c_size_t)
+    sig("rb200_set_download_all", C.c_int, _P, C.POINTER(_P))
+    sig("rb200_batch_op_host", C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_size_t,
+        C.POINTER(_P))
+    _lib = L
+    return L
+
+
+def last_error():
+    return lib().rb200_last_error().decode()
+
+
+def init(device=0):
+    if lib().rb200_init(int(device)) != 0:
+        raise RB200Error(last_error())
+
+
+def set_stream(cuda_stream_ptr):
+    """Run all library work on this cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+    lib().rb200_set_stream(_P(cuda_stream_ptr) if cuda_stream_ptr else None)
+
+
+def synchronize():
+    lib().rb200_synchronize()
+
+
+def kernel_launches():
+    return int(lib().rb200_kernel_launches())
+
+
+def last_algorithmic_bytes():
+    return int(lib().rb200_last_algorithmic_bytes())
+
+
+def last_device_ms():
+    return float(lib().rb200_last_device_ms())
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+class Bitmap:
+    """A host roaring_bitmap_t* (reference memory layout) owned by this object."""
+
+    def __init__(self, ptr, own=True):
+        if not ptr:
+            raise RB200Error(last_error() or "null bitmap")
+        self.ptr = ptr
+        self.own = own
+
+    # -- construction / destruction
+    @classmethod
+    def deserialize(cls, blob: bytes):
+        p = lib().rb200_bitmap_portable_deserialize_safe(blob, len(blob))
+        if not p:
+            raise RB200Error("malformed portable bitmap")
+        return cls(p)
+
+    def free(self):
+        if self.ptr and self.own:
+            lib().rb200_bitmap_free(self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # -- inspection
+    def serialize(self) -> bytes:
+        n = lib().rb200_bitmap_portable_size_in_bytes(self.ptr)
+        buf = C.create_string_buffer(n)
+        m = lib().rb200_bitmap_portable_serialize(self.ptr, buf)
+        assert m == n, (m, n)
+        return buf.raw
+
+    def cardinality(self) -> int:
+        return int(lib().rb200_bitmap_get_cardinality(self.ptr))
+
+    def validate(self):
+        why = C.c_char_p()
+        ok = lib().rb200_bitmap_validate(self.ptr, C.byref(why))
+        return bool(ok), (why.value.decode() if why.value else "")
+
+    # -- the drop-in entry points (one pair per call: upload -> kernels -> download)
+    def _pair(self, name, other):
+        p = getattr(lib(), f"roaring_bitmap_{name}")(self.ptr, other.ptr)
+        if not p:
+            raise RB200Error(last_error())
+        return Bitmap(p)
+
+    def __and__(self, o): return self._pair("and", o)
+    def __or__(self, o): return self._pair("or", o)
+    def __xor__(self, o): return self._pair("xor", o)
+    def __sub__(self, o): return self._pair("andnot", o)
+
+    def and_cardinality(self, o) -> int:
+        v = int(lib().roaring_bitmap_and_cardinality(self.ptr, o.ptr))
+        if v == 2 ** 64 - 1:
+            raise RB200Error(last_error())
+        return v
+
+    def or_cardinality(self, o): return int(lib().roaring_bitmap_or_cardinality(self.ptr, o.ptr))
+    def xor_cardinality(self, o): return int(lib().roaring_bitmap_xor_cardinality(self.ptr, o.ptr))
+    def andnot_cardinality(self, o): return int(lib().roaring_bitmap_andnot_cardinality(self.ptr, o.ptr))
+    def jaccard_index(self, o): return float(lib().roaring_bitmap_jaccard_index(self.ptr, o.ptr))
+    def intersect(self, o): return bool(lib().roaring_bitmap_intersect(self.ptr, o.ptr))
+
+
+def or_many(bitmaps):
+    """roaring_bitmap_or_many on host bitmaps (drop-in symbol)."""
+    arr = (_P * len(bitmaps))(*[b.ptr for b in bitmaps])
+    p = lib().roaring_bitmap_or_many(len(bitmaps), arr)
+    if not p:
+        raise RB200Error(last_error())
+    return Bitmap(p)
+
+
+def batch_op_host(op, a, b):
+    """out[k] = a[k] op b[k] through the device: one upload, one launch sequence, one download."""
+    n = len(a)
+    assert len(b) == n
+    pa = (_P * n)(*[x.ptr for x in a])
+    pb = (_P * n)(*[x.ptr for x in b])
+    out = (_P * n)()
+    if lib().rb200_batch_op_host(OPS[op] if isinstance(op, str) else op, pa, pb, n, out) != 0:
+        raise RB200Error(last_error())
+    return [Bitmap(out[i]) for i in range(n)]
+
+
+class DeviceSet:
+    """An ordered collection of bitmaps resident in HBM (rb200_set_t*)."""
+
+    def __init__(self, ptr):
+        if not ptr:
+            raise RB200Error(last_error() or "null set")
+        self.ptr = ptr
+
+    @classmethod
+    def upload(cls, bitmaps):
+        arr = (_P * len(bitmaps))(*[b.ptr for b in bitmaps])
+        return cls(lib().rb200_set_upload(arr, len(bitmaps)))
+
+    @classmethod
+    def from_serialized(cls, blobs):
+        n = len(blobs)
+        arr = (C.c_char_p * n)(*blobs)
+        lens = (C.c_size_t * n)(*[len(b) for b in blobs])
+        return cls(lib().rb200_set_upload_serialized(arr, lens, n))
+
+    def free(self):
+        if self.ptr:
+            lib().rb200_set_free(self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(lib().rb200_set_count(self.ptr))
+
+    @property
+    def container_count(self):
+        return int(lib().rb200_set_container_count(self.ptr))
+
+    @property
+    def payload_bytes(self):
+        return int(lib().rb200_set_payload_bytes(self.ptr))
+
+    def batch(self, op, other, ia, ib):
+        """result[k] = self[ia[k]] op other[ib[k]] as a new DeviceSet."""
+        ia, ib = _u32(ia), _u32(ib)
+        assert ia.shape == ib.shape
+        code = OPS[op] if isinstance(op, str) else op
+        p = lib().rb200_batch_op(code, self.ptr, other.ptr, ia.ctypes.data, ib.ctypes.data, ia.size)
+        return DeviceSet(p)
+
+    def and_cardinality(self, other, ia, ib):
+        ia, ib = _u32(ia), _u32(ib)
+        out = np.zeros(ia.size, dtype=np.uint64)
+        rc = lib().rb200_batch_and_cardinality(self.ptr, other.ptr, ia.ctypes.data, ib.ctypes.data,
+                                               ia.size, out.ctypes.data)
+        if rc != 0:
+            raise RB200Error(last_error())
+        return out
+
+    def or_many(self, idx=None, key_lo=0, key_hi=65535, card_per_key=None):
+        if idx is None:
+            ip, n = None, len(self)
+        else:
+            idx = _u32(idx)
+            ip, n = idx.ctypes.data, idx.size
+        cp = card_per_key.ctypes.data if card_per_key is not None else None
+        if card_per_key is not None:
+            assert card_per_key.dtype == np.uint32 and card_per_key.size == 65536
+        p = lib().rb200_or_many_keyrange(self.ptr, ip, n, key_lo, key_hi, cp)
+        return DeviceSet(p)
+
+    def cardinalities(self):
+        out = np.zeros(len(self), dtype=np.uint64)
+        if lib().rb200_set_cardinalities(self.ptr, out.ctypes.data) != 0:
+            raise RB200Error(last_error())
+        return out
+
+    def download(self, i):
+        return Bitmap(lib().rb200_set_download(self.ptr, i))
+
+    def download_all(self):
+        n = len(self)
+        out = (_P * n)()
+        if lib().rb200_set_download_all(self.ptr, out) != 0:
+            raise RB200Error(last_error())
+        return [Bitmap(out[i]) for i in range(n)]

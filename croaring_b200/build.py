@@ -1,0 +1,63 @@
+"""Build recipe for libroaring_b200.so (in-tree, so the built file travels with gpurun snapshots).
+
+    python -m croaring_b200.build [--force] [--verbose]
+
+nvcc cross-compiles for sm_100a without a GPU.  cudart is linked statically so the library is
+self-contained next to torch's own CUDA runtime.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libroaring_b200.so")
+SOURCES = ["rb200_kernels.cu", "rb200_host.cu"]
+HEADERS = ["rb200_common.h", "rb200_device.cuh", os.path.join("..", "..", "include", "roaring_b200.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
+    "--expt-relaxed-constexpr",
+    "-cudart", "static",
+]
+
+
+def _newest(paths):
+    return max(os.path.getmtime(p) for p in paths)
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, h) for h in HEADERS]
+    deps.append(os.path.abspath(__file__))
+    return _newest(deps) > os.path.getmtime(LIB)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    for s in SOURCES:
+        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", os.path.join(CSRC, s), "-o", o]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        objs.append(o)
+    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + \
+          ["-Xlinker", "-Bsymbolic", "-ldl", "-lpthread"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(LIB)

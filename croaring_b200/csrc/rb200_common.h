@@ -1,0 +1,106 @@
+// rb200_common.h — shared between the host engine (rb200_host.cu) and the kernels
+// (rb200_kernels.cu).  Internal: nothing here crosses the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb200 {
+
+// ABI constants restated from the reference (SURVEY.md §8b "ABI constants"):
+//   typecodes           include/roaring/containers/containers.h:48-51
+//   DEFAULT_MAX_SIZE    include/roaring/containers/array.h:38
+//   bitset words        include/roaring/containers/bitset.h:40
+constexpr int T_BITSET = 1;
+constexpr int T_ARRAY = 2;
+constexpr int T_RUN = 3;
+constexpr int T_SHARED = 4;
+constexpr int MAX_ARRAY = 4096;
+constexpr int BITSET_BYTES = 8192;
+constexpr int ACC_WORDS = 2048;  // 65536 bits as 32-bit words
+
+enum Op { OP_AND = 0, OP_OR = 1, OP_XOR = 2, OP_ANDNOT = 3 };
+
+// work-item kinds produced by the planner
+constexpr int K_HOLE = 0;     // nothing to do (slot kept so item order == key order)
+constexpr int K_COMPUTE = 1;  // matched key: run the (typeA,typeB) grid cell
+constexpr int K_COPY_A = 2;   // pass-through of an unmatched container of the left bitmap
+constexpr int K_COPY_B = 3;   // pass-through of an unmatched container of the right bitmap
+
+// Device view of a resident set: SoA container directory + one payload slab.
+// Payload of container c starts at payload + c_off[c] (16-byte aligned, padded to 16 B):
+//   bitset: 1024 x u64;  array: c_len x u16 (sorted);  run: c_len x {u16 start,u16 len-1}.
+// c_card is the true cardinality for every type (runs: sum(len+1), filled at upload).
+struct SetView {
+    const uint32_t *bm_beg;  // [n_bitmaps] first container of bitmap i
+    const uint32_t *bm_cnt;  // [n_bitmaps] number of containers of bitmap i
+    const uint16_t *c_key;
+    const uint8_t *c_type;
+    const uint32_t *c_card;
+    const uint32_t *c_len;
+    const uint64_t *c_off;
+    const uint8_t *payload;
+};
+
+// Mutable directory of a set being produced by a kernel.
+struct SetOut {
+    uint32_t *bm_beg;
+    uint32_t *bm_cnt;
+    uint64_t *bm_card;  // per result bitmap: total cardinality
+    uint16_t *c_key;
+    uint8_t *c_type;
+    uint32_t *c_card;
+    uint32_t *c_len;
+    uint64_t *c_off;
+    uint8_t *payload;
+};
+
+// Work items of one batched pairwise op (SoA, W entries; items of pair p occupy
+// [item_off[p], item_off[p+1]) in key order with holes).
+struct Items {
+    uint8_t *kind;
+    uint16_t *key;
+    uint32_t *ca;        // container index in A (K_COMPUTE, K_COPY_A)
+    uint32_t *cb;        // container index in B (K_COMPUTE, K_COPY_B)
+    uint64_t *slot_off;  // byte offset of the output slot in the result slab
+    uint32_t *slot_cap;  // bytes reserved (upper bound on the result payload, 16-B multiple)
+    uint8_t *otype;      // result container type (0 = dropped)
+    uint32_t *ocard;     // result cardinality
+    uint32_t *olen;      // result length (array values / runs)
+};
+
+// Counters living in device memory, read back once per op.
+struct OpStats {
+    unsigned long long slab_cursor;   // bump allocator over the result slab (bytes)
+    unsigned long long dir_cursor;    // bump allocator over the result directory (containers)
+    unsigned long long algo_bytes;    // SURVEY.md §8(d) algorithmic bytes
+    unsigned long long work_counter;  // dynamic scheduler for the compute kernel
+    unsigned long long work_counter2;
+    unsigned int error;               // 0 = ok; 1 = slot overflow; 2 = slab overflow
+    unsigned int nk;                  // or_many: number of distinct keys
+};
+
+// --- launch wrappers (rb200_kernels.cu); every wrapper bumps g_launches -----------------
+extern unsigned long long g_launches;
+
+void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, const uint32_t *ib,
+                       const uint64_t *item_off, uint32_t npairs, int op, bool card_only,
+                       Items it, OpStats *st, cudaStream_t s);
+void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
+                          uint8_t *slab, uint64_t slab_cap, OpStats *st, cudaStream_t s);
+void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W, OpStats *st,
+                       cudaStream_t s);
+void launch_finalize_pairs(const SetView &A, const SetView &B, Items it, const uint64_t *item_off,
+                           uint32_t npairs, SetOut out, OpStats *st, cudaStream_t s);
+void launch_finalize_cards(Items it, const uint64_t *item_off, uint32_t npairs, uint64_t *out,
+                           cudaStream_t s);
+void launch_set_cardinalities(const SetView &S, uint32_t n_bitmaps, uint64_t *out, cudaStream_t s);
+
+// or_many: mark -> compact keys -> reduce per key
+void launch_many_mark(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo,
+                      uint32_t key_hi, uint32_t *flags /*65536*/, cudaStream_t s);
+void launch_many_compact(const uint32_t *flags, uint16_t *keys_out, OpStats *st, cudaStream_t s);
+void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uint16_t *keys,
+                    SetOut out, uint32_t *card_per_key /*65536 or null*/, OpStats *st,
+                    cudaStream_t s);
+
+}  // namespace rb200

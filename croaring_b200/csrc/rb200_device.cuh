@@ -1,0 +1,550 @@
+// rb200_device.cuh — warp-level building blocks of the container x container grid (sm_100a).
+//
+// One warp owns one 65536-bit accumulator `acc` (2048 x u32 = 8 KiB of shared memory) and
+// evaluates one grid cell on it:
+//   rasterise the left container (bitset copy with 128-bit loads / array scatter /
+//   run range-fill) -> apply the right container with the op -> popcount (+ run count)
+//   -> pick the reference's result type -> re-encode (bitset copy / ordered bit extraction
+//   with a warp scan / run boundary extraction).
+// Cells whose result is always an array (AND / ANDNOT with an array on the filtering side)
+// skip the accumulator round trip and filter the array through bit tests with
+// ballot compaction.
+//
+// Reference semantics restated here (file:line relative to /root/reference):
+//   type rules of the cells      include/roaring/containers/containers.h:726-806 (and),
+//                                :1008-1103 (or), :1449-1524 (xor), :1783-1876 (andnot),
+//                                src/containers/mixed_*.c, src/containers/convert.c:154-200
+#pragma once
+#include "rb200_common.h"
+
+namespace rb200 {
+
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ int popc4(const uint4 &q) {
+    return __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULLMASK, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------- type rules
+__host__ __device__ __forceinline__ int rule_ab(int card) {
+    return card <= MAX_ARRAY ? T_ARRAY : T_BITSET;
+}
+// convert_run_to_efficient_container, src/containers/convert.c:154-200
+__host__ __device__ __forceinline__ int rule_eff(int card, int nruns) {
+    int size_run = 2 + 4 * nruns, size_arr = 2 * card;
+    int min_non_run = size_arr < BITSET_BYTES ? size_arr : BITSET_BYTES;
+    if (size_run <= min_non_run) return T_RUN;
+    return rule_ab(card);
+}
+__host__ __device__ __forceinline__ bool is_full_run(int t, uint32_t len, uint32_t card) {
+    return t == T_RUN && len == 1 && card == 65536;
+}
+
+// Does the type rule of this cell look at the number of runs of the result?
+__host__ __device__ __forceinline__ bool cell_needs_runs(int op, int tA, int tB) {
+    if (tA == T_BITSET || tB == T_BITSET) return false;
+    if (tA == T_RUN && tB == T_RUN) return true;
+    if (op == OP_AND) return false;                // A,R / R,A / A,A -> array
+    if (op == OP_ANDNOT) return tA == T_RUN;       // R,A
+    return tA == T_RUN || tB == T_RUN;             // OR / XOR with a run
+}
+
+// Result container type of a grid cell given the input metadata and the result's
+// cardinality / run count.  Mirrors oracle/roaring_oracle.c cell_* (pinned to the reference).
+__host__ __device__ inline int decide_type(int op, int tA, int tB, uint32_t cA, uint32_t cB,
+                                           uint32_t lA, uint32_t lB, int card, int nruns) {
+    const bool fullA = is_full_run(tA, lA, cA), fullB = is_full_run(tB, lB, cB);
+    const bool hasB = (tA == T_BITSET) || (tB == T_BITSET);
+    const bool bothR = (tA == T_RUN) && (tB == T_RUN);
+    const bool bothA = (tA == T_ARRAY) && (tB == T_ARRAY);
+    switch (op) {
+        case OP_AND:
+            if (tA == T_BITSET && tB == T_BITSET) return rule_ab(card);
+            if (bothR) return rule_eff(card, nruns);
+            if (hasB && (tA == T_RUN || tB == T_RUN)) {  // mixed_intersection.c:117-203
+                if (fullA || fullB) return T_BITSET;
+                uint32_t cR = (tA == T_RUN) ? cA : cB;
+                if (cR <= (uint32_t)MAX_ARRAY) return T_ARRAY;
+                return rule_ab(card);
+            }
+            return T_ARRAY;
+        case OP_OR:
+            if (bothA) return (cA + cB <= (uint32_t)MAX_ARRAY) ? T_ARRAY : rule_ab(card);
+            if (hasB) {
+                if (fullA || fullB) return T_RUN;  // containers.h:1056-1080
+                return T_BITSET;
+            }
+            return rule_eff(card, nruns);
+        case OP_XOR:
+            if (bothA) return (cA + cB <= (uint32_t)MAX_ARRAY) ? T_ARRAY : rule_ab(card);
+            if (hasB) return rule_ab(card);
+            if (bothR) return rule_eff(card, nruns);
+            {  // array_run_container_xor, mixed_xor.c:104-138
+                uint32_t ca = (tA == T_ARRAY) ? cA : cB, cr = (tA == T_ARRAY) ? cB : cA;
+                if (ca < 32) return rule_eff(card, nruns);
+                if (cr <= (uint32_t)MAX_ARRAY)
+                    return (cr + ca <= (uint32_t)MAX_ARRAY) ? T_ARRAY : rule_ab(card);
+                return rule_ab(card);
+            }
+        default:  // OP_ANDNOT
+            if (tA == T_ARRAY) return T_ARRAY;
+            if (bothR) return rule_eff(card, nruns);
+            if (tA == T_BITSET) return rule_ab(card);
+            // tA == RUN
+            if (tB == T_BITSET) return cA <= (uint32_t)MAX_ARRAY ? T_ARRAY : rule_ab(card);
+            // R,A: mixed_andnot.c:277-357
+            if (cA <= 32) return rule_eff(card, nruns);
+            if (cA <= (uint32_t)MAX_ARRAY) return T_ARRAY;
+            return rule_ab(card);
+    }
+}
+
+__host__ __device__ __forceinline__ uint32_t round16(uint32_t x) { return (x + 15u) & ~15u; }
+
+// payload bytes as stored in a slab (runs without the 2-byte n_runs prefix)
+__host__ __device__ __forceinline__ uint32_t stored_bytes(int t, uint32_t len) {
+    return t == T_BITSET ? (uint32_t)BITSET_BYTES : (t == T_ARRAY ? 2u * len : 4u * len);
+}
+// container_size_in_bytes, include/roaring/containers/containers.h:402-416
+__host__ __device__ __forceinline__ uint32_t portable_bytes(int t, uint32_t len) {
+    return t == T_BITSET ? (uint32_t)BITSET_BYTES : (t == T_ARRAY ? 2u * len : 2u + 4u * len);
+}
+
+// Upper bound (bytes, multiple of 16) of the stored result of a COMPUTE cell.
+__host__ __device__ inline uint32_t slot_bound(int op, int tA, int tB, uint32_t cA, uint32_t cB,
+                                               uint32_t lA, uint32_t lB) {
+    const uint32_t FULLB = BITSET_BYTES;
+    uint32_t b = FULLB;
+    const uint32_t nA = (tA == T_ARRAY) ? cA : lA, nB = (tB == T_ARRAY) ? cB : lB;
+    const uint32_t cmin = cA < cB ? cA : cB;
+    if (tA == T_BITSET || tB == T_BITSET) {
+        if (op == OP_AND) {
+            if (tA == T_ARRAY) b = 2 * cA;
+            else if (tB == T_ARRAY) b = 2 * cB;
+            else if (tA == T_RUN) b = cA <= (uint32_t)MAX_ARRAY ? 2 * cA : FULLB;
+            else if (tB == T_RUN) b = cB <= (uint32_t)MAX_ARRAY ? 2 * cB : FULLB;
+        } else if (op == OP_ANDNOT) {
+            if (tA == T_ARRAY) b = 2 * cA;
+            else if (tA == T_RUN) b = cA <= (uint32_t)MAX_ARRAY ? 2 * cA : FULLB;
+        }
+    } else {
+        uint32_t runs_b = 4 * (nA + nB);
+        if (op == OP_AND) {
+            if (tA == T_ARRAY && tB == T_ARRAY) b = 2 * cmin;
+            else if (tA == T_ARRAY) b = 2 * cA;
+            else if (tB == T_ARRAY) b = 2 * cB;
+            else { uint32_t m = 2 * cmin; b = runs_b > m ? runs_b : m; }
+        } else if (op == OP_ANDNOT) {
+            if (tA == T_ARRAY) b = 2 * cA;
+            else { uint32_t m = 2 * cA; b = runs_b > m ? runs_b : m; }
+        } else {
+            uint32_t m = 2 * (cA + cB);
+            if (tA == T_ARRAY && tB == T_ARRAY) b = (cA + cB <= (uint32_t)MAX_ARRAY) ? m : FULLB;
+            else b = runs_b > m ? runs_b : m;
+        }
+        if (b > FULLB) b = FULLB;
+    }
+    return round16(b);
+}
+
+// ---------------------------------------------------------------- accumulator primitives
+__device__ __forceinline__ void acc_zero(uint32_t *acc, int lane) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 16; i++) reinterpret_cast<uint4 *>(acc)[i * 32 + lane] = z;
+}
+
+__device__ __forceinline__ void acc_copy_bitset(uint32_t *acc, const uint8_t *src, int lane) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint4 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = __ldg(s + (h * 8 + i) * 32 + lane);
+#pragma unroll
+        for (int i = 0; i < 8; i++) reinterpret_cast<uint4 *>(acc)[(h * 8 + i) * 32 + lane] = q[i];
+    }
+}
+
+__device__ __forceinline__ void acc_store_bitset(const uint32_t *acc, uint8_t *dst, int lane) {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < 16; i++) d[i * 32 + lane] = reinterpret_cast<const uint4 *>(acc)[i * 32 + lane];
+}
+
+// MODE 0 = set (or), 1 = flip (xor), 2 = clear (andnot)
+template <int MODE>
+__device__ __forceinline__ void acc_atom(uint32_t *p, uint32_t m) {
+    if (MODE == 0) atomicOr(p, m);
+    else if (MODE == 1) atomicXor(p, m);
+    else atomicAnd(p, ~m);
+}
+template <int MODE>
+__device__ __forceinline__ void acc_plain(uint32_t *p) {
+    if (MODE == 0) *p = ~0u;
+    else if (MODE == 1) *p = ~*p;
+    else *p = 0u;
+}
+
+// acc op= {sorted u16 array}.  128-bit loads (8 values per lane); bits that fall in the same
+// 32-bit word are merged in registers before the shared-memory atomic.
+template <int MODE>
+__device__ __forceinline__ void acc_apply_array(uint32_t *acc, const uint8_t *src, uint32_t n,
+                                                int lane) {
+    const uint4 *v4 = reinterpret_cast<const uint4 *>(src);
+    const uint32_t nvec = (n + 7) >> 3;
+    for (uint32_t i = lane; i < nvec; i += 32) {
+        const uint4 q = __ldg(v4 + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t base = i * 8;
+        uint32_t cur_w = 0xffffffffu, cur_m = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (base + k < n) {
+                const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+                const uint32_t wi = v >> 5, bit = 1u << (v & 31);
+                if (wi != cur_w) {
+                    if (cur_m) acc_atom<MODE>(acc + cur_w, cur_m);
+                    cur_w = wi;
+                    cur_m = bit;
+                } else {
+                    cur_m |= bit;
+                }
+            }
+        }
+        if (cur_m) acc_atom<MODE>(acc + cur_w, cur_m);
+    }
+}
+
+// Warp-collective: every lane brings one closed range [lo,hi] (valid==false: none).
+// Boundary words use shared-memory atomics; interior words are owned by exactly one range
+// (ranges of one container never overlap) so they are plain stores; long interiors are
+// filled by the whole warp.  ATOMIC_INTERIOR is for accumulators shared by several warps.
+template <int MODE, bool ATOMIC_INTERIOR>
+__device__ __forceinline__ void acc_apply_ranges(uint32_t *acc, uint32_t lo, uint32_t hi,
+                                                 bool valid, int lane) {
+    const uint32_t ws = lo >> 5, we = hi >> 5;
+    bool longr = false;
+    if (valid) {
+        const uint32_t m_lo = ~0u << (lo & 31), m_hi = ~0u >> (31 - (hi & 31));
+        if (ws == we) {
+            acc_atom<MODE>(acc + ws, m_lo & m_hi);
+        } else {
+            acc_atom<MODE>(acc + ws, m_lo);
+            acc_atom<MODE>(acc + we, m_hi);
+            if (we - ws - 1 <= 8) {
+                for (uint32_t w = ws + 1; w < we; w++) {
+                    if (ATOMIC_INTERIOR) acc_atom<MODE>(acc + w, ~0u);
+                    else acc_plain<MODE>(acc + w);
+                }
+            } else {
+                longr = true;
+            }
+        }
+    }
+    unsigned m = __ballot_sync(FULLMASK, longr);
+    while (m) {
+        const int r = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t s = __shfl_sync(FULLMASK, ws, r), e = __shfl_sync(FULLMASK, we, r);
+        for (uint32_t w = s + 1 + lane; w < e; w += 32) {
+            if (ATOMIC_INTERIOR) acc_atom<MODE>(acc + w, ~0u);
+            else acc_plain<MODE>(acc + w);
+        }
+    }
+}
+
+// acc op= {run container}: one lane per run ("run-length expansion")
+template <int MODE, bool ATOMIC_INTERIOR>
+__device__ __forceinline__ void acc_apply_runs(uint32_t *acc, const uint8_t *src, uint32_t n,
+                                               int lane) {
+    const uint32_t *runs = reinterpret_cast<const uint32_t *>(src);
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        const uint32_t r = valid ? __ldg(runs + i) : 0u;
+        const uint32_t lo = r & 0xffffu, hi = lo + (r >> 16);
+        acc_apply_ranges<MODE, ATOMIC_INTERIOR>(acc, lo, hi, valid, lane);
+    }
+}
+
+// acc &= {run container}: clear the n+1 gaps between / around the runs
+// (bitset_reset_range over the gaps, src/containers/mixed_intersection.c:171-182)
+__device__ __forceinline__ void acc_and_runs(uint32_t *acc, const uint8_t *src, uint32_t n,
+                                             int lane) {
+    const uint32_t *runs = reinterpret_cast<const uint32_t *>(src);
+    for (uint32_t base = 0; base <= n; base += 32) {
+        const uint32_t i = base + lane;
+        bool valid = i <= n;
+        int lo = 0, hi = 65535;
+        if (valid) {
+            if (i > 0) {
+                const uint32_t r = __ldg(runs + i - 1);
+                lo = (int)((r & 0xffffu) + (r >> 16)) + 1;
+            }
+            if (i < n) {
+                const uint32_t r = __ldg(runs + i);
+                hi = (int)(r & 0xffffu) - 1;
+            }
+            valid = lo <= hi;
+        }
+        acc_apply_ranges<2, false>(acc, (uint32_t)lo, (uint32_t)hi, valid, lane);
+    }
+}
+
+// acc &= {sorted array}: clear the gaps between consecutive values
+__device__ __forceinline__ void acc_and_array(uint32_t *acc, const uint8_t *src, uint32_t n,
+                                              int lane) {
+    const uint16_t *arr = reinterpret_cast<const uint16_t *>(src);
+    for (uint32_t base = 0; base <= n; base += 32) {
+        const uint32_t i = base + lane;
+        bool valid = i <= n;
+        int lo = 0, hi = 65535;
+        if (valid) {
+            if (i > 0) lo = (int)arr[i - 1] + 1;
+            if (i < n) hi = (int)arr[i] - 1;
+            valid = lo <= hi;
+        }
+        acc_apply_ranges<2, false>(acc, (uint32_t)lo, (uint32_t)hi, valid, lane);
+    }
+}
+
+// Rasterise any container into the (private) accumulator.
+__device__ __forceinline__ void acc_load(uint32_t *acc, int type, const uint8_t *src,
+                                         uint32_t len, int lane) {
+    if (type == T_BITSET) {
+        acc_copy_bitset(acc, src, lane);
+    } else {
+        acc_zero(acc, lane);
+        __syncwarp();
+        if (type == T_ARRAY) acc_apply_array<0>(acc, src, len, lane);
+        else acc_apply_runs<0, false>(acc, src, len, lane);
+    }
+    __syncwarp();
+}
+
+// acc = acc OP bitset(src), returns nothing (cardinality is taken by acc_count)
+template <int OP>
+__device__ __forceinline__ void acc_op_bitset(uint32_t *acc, const uint8_t *src, int lane) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint4 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = __ldg(s + (h * 8 + i) * 32 + lane);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint4 *p = reinterpret_cast<uint4 *>(acc) + (h * 8 + i) * 32 + lane;
+            uint4 a = *p;
+            if (OP == OP_AND) { a.x &= q[i].x; a.y &= q[i].y; a.z &= q[i].z; a.w &= q[i].w; }
+            else if (OP == OP_OR) { a.x |= q[i].x; a.y |= q[i].y; a.z |= q[i].z; a.w |= q[i].w; }
+            else if (OP == OP_XOR) { a.x ^= q[i].x; a.y ^= q[i].y; a.z ^= q[i].z; a.w ^= q[i].w; }
+            else { a.x &= ~q[i].x; a.y &= ~q[i].y; a.z &= ~q[i].z; a.w &= ~q[i].w; }
+            *p = a;
+        }
+    }
+}
+
+// acc = bitset(a) OP bitset(b) straight from global memory (the B x B cell): 2 x 8 KiB of
+// 128-bit loads per warp, result staged in shared memory, popcount fused.
+template <int OP>
+__device__ __forceinline__ int acc_bitset_op_bitset(uint32_t *acc, const uint8_t *pa,
+                                                    const uint8_t *pb, int lane) {
+    const uint4 *a = reinterpret_cast<const uint4 *>(pa);
+    const uint4 *b = reinterpret_cast<const uint4 *>(pb);
+    int c = 0;
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        uint4 qa[4], qb[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            qa[i] = __ldg(a + (h * 4 + i) * 32 + lane);
+            qb[i] = __ldg(b + (h * 4 + i) * 32 + lane);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint4 r;
+            if (OP == OP_AND) { r.x = qa[i].x & qb[i].x; r.y = qa[i].y & qb[i].y; r.z = qa[i].z & qb[i].z; r.w = qa[i].w & qb[i].w; }
+            else if (OP == OP_OR) { r.x = qa[i].x | qb[i].x; r.y = qa[i].y | qb[i].y; r.z = qa[i].z | qb[i].z; r.w = qa[i].w | qb[i].w; }
+            else if (OP == OP_XOR) { r.x = qa[i].x ^ qb[i].x; r.y = qa[i].y ^ qb[i].y; r.z = qa[i].z ^ qb[i].z; r.w = qa[i].w ^ qb[i].w; }
+            else { r.x = qa[i].x & ~qb[i].x; r.y = qa[i].y & ~qb[i].y; r.z = qa[i].z & ~qb[i].z; r.w = qa[i].w & ~qb[i].w; }
+            reinterpret_cast<uint4 *>(acc)[(h * 4 + i) * 32 + lane] = r;
+            c += popc4(r);
+        }
+    }
+    return __reduce_add_sync(FULLMASK, c);
+}
+
+// popcount(bitset(a) & bitset(b)) without materialising (bitset_container_and_justcard)
+__device__ __forceinline__ int bitset_and_card(const uint8_t *pa, const uint8_t *pb, int lane) {
+    const uint4 *a = reinterpret_cast<const uint4 *>(pa);
+    const uint4 *b = reinterpret_cast<const uint4 *>(pb);
+    int c = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint4 qa[8], qb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            qa[i] = __ldg(a + (h * 8 + i) * 32 + lane);
+            qb[i] = __ldg(b + (h * 8 + i) * 32 + lane);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            c += __popc(qa[i].x & qb[i].x) + __popc(qa[i].y & qb[i].y) +
+                 __popc(qa[i].z & qb[i].z) + __popc(qa[i].w & qb[i].w);
+    }
+    return __reduce_add_sync(FULLMASK, c);
+}
+
+// popcount(acc & bitset(b))
+__device__ __forceinline__ int acc_and_bitset_card(const uint32_t *acc, const uint8_t *pb,
+                                                   int lane) {
+    const uint4 *b = reinterpret_cast<const uint4 *>(pb);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint4 q = __ldg(b + i * 32 + lane);
+        const uint4 a = reinterpret_cast<const uint4 *>(acc)[i * 32 + lane];
+        c += __popc(a.x & q.x) + __popc(a.y & q.y) + __popc(a.z & q.z) + __popc(a.w & q.w);
+    }
+    return __reduce_add_sync(FULLMASK, c);
+}
+
+// cardinality (and number of runs when asked) of the accumulator
+__device__ __forceinline__ void acc_count(const uint32_t *acc, int lane, bool want_runs,
+                                          int &card, int &nruns) {
+    int c = 0, r = 0;
+    if (!want_runs) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) c += popc4(reinterpret_cast<const uint4 *>(acc)[i * 32 + lane]);
+    } else {
+        for (int i = 0; i < 64; i++) {
+            const int w = i * 32 + lane;
+            const uint32_t x = acc[w];
+            const uint32_t prev = w ? (acc[w - 1] >> 31) : 0u;
+            c += __popc(x);
+            r += __popc(x & ~((x << 1) | prev));
+        }
+    }
+    card = __reduce_add_sync(FULLMASK, c);
+    nruns = __reduce_add_sync(FULLMASK, r);
+}
+
+// acc -> sorted u16 list (array_container_from_bitset): per 32-word stripe, per-lane
+// popcount -> warp scan -> every lane emits its bits at its offset.
+__device__ __forceinline__ uint32_t acc_emit_array(const uint32_t *acc, uint16_t *out, int lane) {
+    uint32_t base = 0;
+    for (int it = 0; it < 64; it++) {
+        const uint32_t w = it * 32 + lane;
+        uint32_t x = acc[w];
+        if (!__any_sync(FULLMASK, x != 0)) continue;
+        const uint32_t c = __popc(x);
+        const uint32_t incl = warp_incl_scan(c, lane);
+        const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
+        uint16_t *p = out + base + incl - c;
+        const uint32_t hi = w << 5;
+        while (x) {
+            const int b = __ffs(x) - 1;
+            x &= x - 1;
+            *p++ = (uint16_t)(hi | b);
+        }
+        base += total;
+    }
+    return base;
+}
+
+// acc -> run list {start, length-1}: pass 1 writes run starts, pass 2 run ends, pass 3 turns
+// ends into lengths.  Returns the number of runs.
+__device__ __forceinline__ uint32_t acc_emit_runs(const uint32_t *acc, uint16_t *out, int lane) {
+    uint32_t nr = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        uint32_t base = 0;
+        for (int it = 0; it < 64; it++) {
+            const uint32_t w = it * 32 + lane;
+            const uint32_t x = acc[w];
+            uint32_t e;
+            if (pass == 0) {
+                const uint32_t prev = w ? (acc[w - 1] >> 31) : 0u;
+                e = x & ~((x << 1) | prev);
+            } else {
+                const uint32_t next = (w < ACC_WORDS - 1) ? (acc[w + 1] & 1u) : 0u;
+                e = x & ~((x >> 1) | (next << 31));
+            }
+            if (!__any_sync(FULLMASK, e != 0)) continue;
+            const uint32_t c = __popc(e);
+            const uint32_t incl = warp_incl_scan(c, lane);
+            const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
+            uint32_t k = base + incl - c;
+            const uint32_t hi = w << 5;
+            while (e) {
+                const int b = __ffs(e) - 1;
+                e &= e - 1;
+                out[2 * k + pass] = (uint16_t)(hi | b);
+                k++;
+            }
+            base += total;
+        }
+        nr = base;
+    }
+    __syncwarp();
+    for (uint32_t k = lane; k < nr; k += 32) out[2 * k + 1] = (uint16_t)(out[2 * k + 1] - out[2 * k]);
+    return nr;
+}
+
+// Filter a sorted array through a bit test (array_bitset_container_intersection /
+// _andnot, src/containers/mixed_intersection.c:19-58, mixed_andnot.c:24-38): ballot compaction.
+template <bool NEG, bool WRITE>
+__device__ __forceinline__ uint32_t filter_array(const uint8_t *src, uint32_t n,
+                                                 const uint32_t *bits, uint16_t *out, int lane) {
+    const uint16_t *arr = reinterpret_cast<const uint16_t *>(src);
+    uint32_t cnt = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        bool keep = false;
+        uint16_t v = 0;
+        if (i < n) {
+            v = arr[i];
+            const bool hit = (bits[v >> 5] >> (v & 31)) & 1u;
+            keep = NEG ? !hit : hit;
+        }
+        const unsigned m = __ballot_sync(FULLMASK, keep);
+        if (WRITE && keep) out[cnt + __popc(m & lanemask_lt())] = v;
+        cnt += __popc(m);
+    }
+    return cnt;
+}
+
+// 16-byte vector copy of a stored payload (pass-through containers)
+__device__ __forceinline__ void warp_copy16(uint8_t *dst, const uint8_t *src, uint32_t bytes,
+                                            int lane) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    const uint32_t n = (bytes + 15) >> 4;
+    uint32_t i = lane;
+    for (; i + 96 < n; i += 128) {
+        const uint4 q0 = __ldg(s + i), q1 = __ldg(s + i + 32), q2 = __ldg(s + i + 64),
+                    q3 = __ldg(s + i + 96);
+        d[i] = q0;
+        d[i + 32] = q1;
+        d[i + 64] = q2;
+        d[i + 96] = q3;
+    }
+    for (; i < n; i += 32) d[i] = __ldg(s + i);
+}
+
+}  // namespace rb200

@@ -1,0 +1,1356 @@
+// rb200_host.cu — host side of libroaring_b200.so: context, memory pools, the device mirror
+// of roaring_bitmap_t ("set" upload), the batched-op drivers, host materialisation of
+// results in the reference's memory layout, portable (de)serialisation, and the C ABI of
+// include/roaring_b200.h.  Plain C++ + CUDA runtime; no torch, no reference code.
+//
+// Reference layout / behaviour restated here (file:line relative to /root/reference):
+//   roaring_array_t single-block directory     src/roaring_array.c:42-78
+//   container structs                          include/roaring/containers/{array,bitset,run}.h
+//   ownership of returned bitmaps              src/roaring.c:552-560, src/containers/containers.c:58-77
+//   portable format                            src/roaring_array.c:469-531, :633-813
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#pragma GCC visibility push(default)
+#include "../../include/roaring_b200.h"
+#pragma GCC visibility pop
+#include "rb200_common.h"
+#include "rb200_device.cuh"
+
+using namespace rb200;
+
+// ------------------------------------------------------------------ reference-compatible structs
+namespace {
+
+struct array_container_t { int32_t cardinality; int32_t capacity; uint16_t *array; };   // array.h:46-50
+struct bitset_container_t { int32_t cardinality; uint64_t *words; };                     // bitset.h:45-48
+struct rle16_t { uint16_t value, length; };                                              // run.h:48-51
+struct run_container_t { int32_t n_runs; int32_t capacity; rle16_t *runs; };            // run.h:69-73
+struct shared_container_t { void *container; uint8_t typecode; uint32_t counter; };      // containers.h:71-75
+
+constexpr uint8_t FLAG_COW = 1, FLAG_FROZEN = 2;  // roaring_types.h:46-49
+constexpr uint32_t SERIAL_COOKIE_NO_RUN = 12346, SERIAL_COOKIE = 12347;  // roaring_array.h:35-40
+constexpr int32_t NO_OFFSET_THRESHOLD = 4;
+
+// ------------------------------------------------------------------ host allocation hooks
+// If the reference library is loaded in this process (drop-in deployment) every host object we
+// hand out is allocated with ITS roaring_malloc / roaring_aligned_malloc so roaring_bitmap_free
+// and user memory hooks (src/memory.c:35-60) keep working; otherwise libc, like the defaults.
+typedef void *(*malloc_fn)(size_t);
+typedef void (*free_fn)(void *);
+typedef void *(*amalloc_fn)(size_t, size_t);
+struct HostAlloc {
+    malloc_fn m = nullptr;
+    free_fn f = nullptr;
+    amalloc_fn am = nullptr;
+    free_fn af = nullptr;
+    bool looked = false;
+    void look() {
+        if (looked) return;
+        looked = true;
+        m = (malloc_fn)dlsym(RTLD_DEFAULT, "roaring_malloc");
+        f = (free_fn)dlsym(RTLD_DEFAULT, "roaring_free");
+        am = (amalloc_fn)dlsym(RTLD_DEFAULT, "roaring_aligned_malloc");
+        af = (free_fn)dlsym(RTLD_DEFAULT, "roaring_aligned_free");
+        if (!m || !f || !am || !af) m = nullptr;
+    }
+} g_halloc;
+
+inline void *h_malloc(size_t n) {
+    g_halloc.look();
+    return g_halloc.m ? g_halloc.m(n) : malloc(n);
+}
+inline void h_free(void *p) {
+    g_halloc.look();
+    if (g_halloc.m) g_halloc.f(p); else free(p);
+}
+inline void *h_aligned_malloc(size_t align, size_t n) {
+    g_halloc.look();
+    if (g_halloc.m) return g_halloc.am(align, n);
+    void *p = nullptr;
+    if (posix_memalign(&p, align, n) != 0) return nullptr;
+    return p;
+}
+inline void h_aligned_free(void *p) {
+    g_halloc.look();
+    if (g_halloc.m) g_halloc.af(p); else free(p);
+}
+
+// ------------------------------------------------------------------ context
+struct Ctx {
+    std::recursive_mutex mu;
+    bool inited = false;
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    std::string err;
+    OpStats *d_stats = nullptr;
+    OpStats *h_stats = nullptr;  // pinned
+    uint32_t *d_flags = nullptr;   // 65536 key flags (or_many)
+    uint16_t *d_keys = nullptr;    // 65536 compacted keys
+    uint32_t *d_cardkey = nullptr; // 65536 per-key cardinalities
+    std::multimap<size_t, void *> dpool, hpool;
+    uint64_t last_algo_bytes = 0;
+    float last_ms = 0.f, last_compute_ms = 0.f;
+    uint64_t last_download_bytes = 0;
+} g;
+
+#define CK(call)                                                                    \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            g.err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+            return false;                                                           \
+        }                                                                           \
+    } while (0)
+
+size_t bucket(size_t n) {
+    size_t b = 512;
+    while (b < n) b <<= 1;
+    return b;
+}
+
+bool ctx_init(int device = -1) {
+    if (g.inited) return true;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g.err = "no CUDA device visible: libroaring_b200 has no CPU fallback";
+        return false;
+    }
+    if (device >= 0) CK(cudaSetDevice(device));
+    CK(cudaGetDevice(&g.device));
+    CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
+    CK(cudaEventCreate(&g.ev0));
+    CK(cudaEventCreate(&g.ev1));
+    CK(cudaEventCreate(&g.evk0));
+    CK(cudaEventCreate(&g.evk1));
+    CK(cudaMalloc(&g.d_stats, sizeof(OpStats)));
+    CK(cudaHostAlloc(&g.h_stats, sizeof(OpStats), cudaHostAllocDefault));
+    CK(cudaMalloc(&g.d_flags, 65536 * sizeof(uint32_t)));
+    CK(cudaMalloc(&g.d_keys, 65536 * sizeof(uint16_t)));
+    CK(cudaMalloc(&g.d_cardkey, 65536 * sizeof(uint32_t)));
+    g.inited = true;
+    return true;
+}
+
+void *dev_alloc(size_t n) {
+    if (n == 0) n = 1;
+    const size_t b = bucket(n);
+    auto it = g.dpool.find(b);
+    if (it != g.dpool.end()) {
+        void *p = it->second;
+        g.dpool.erase(it);
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e != cudaSuccess) {
+        // drop the cache and retry once
+        for (auto &kv : g.dpool) cudaFree(kv.second);
+        g.dpool.clear();
+        e = cudaMalloc(&p, b);
+        if (e != cudaSuccess) {
+            g.err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+            return nullptr;
+        }
+    }
+    return p;
+}
+void dev_free(void *p, size_t n) {
+    if (!p) return;
+    if (n == 0) n = 1;
+    g.dpool.insert({bucket(n), p});
+}
+void *pin_alloc(size_t n) {
+    if (n == 0) n = 1;
+    const size_t b = bucket(n);
+    auto it = g.hpool.find(b);
+    if (it != g.hpool.end()) {
+        void *p = it->second;
+        g.hpool.erase(it);
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, b, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        g.err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    return p;
+}
+void pin_free(void *p, size_t n) {
+    if (!p) return;
+    if (n == 0) n = 1;
+    g.hpool.insert({bucket(n), p});
+}
+
+// ------------------------------------------------------------------ set object
+inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Directory arrays carved out of one block (device and, mirrored, pinned host).
+struct DirLayout {
+    size_t o_beg, o_cnt, o_bcard, o_key, o_type, o_card, o_len, o_off, total;
+    void compute(size_t nb, size_t nc) {
+        size_t o = 0;
+        o_beg = o; o += al256(4 * nb);
+        o_cnt = o; o += al256(4 * nb);
+        o_bcard = o; o += al256(8 * nb);
+        o_off = o; o += al256(8 * nc);
+        o_card = o; o += al256(4 * nc);
+        o_len = o; o += al256(4 * nc);
+        o_key = o; o += al256(2 * nc);
+        o_type = o; o += al256(nc);
+        total = o ? o : 256;
+    }
+};
+
+}  // namespace
+
+struct rb200_set {
+    uint32_t n_bitmaps = 0;
+    uint64_t dir_cap = 0;      // directory entries allocated
+    uint64_t n_containers = 0; // directory entries in use
+    uint64_t slab_cap = 0, slab_used = 0;
+    uint64_t portable_bytes = 0;  // sum of container_size_in_bytes
+    DirLayout L;
+    uint8_t *d_dir = nullptr;   // one block
+    uint8_t *d_slab = nullptr;
+    std::vector<uint32_t> h_cnt;    // host mirror: containers per bitmap
+    std::vector<uint64_t> h_bytes;  // host mirror: upper bound of stored payload bytes per bitmap
+    std::vector<uint8_t> h_flags;   // per bitmap: COW flag to propagate
+    // lazily downloaded host mirror (pinned)
+    uint8_t *m_dir = nullptr, *m_slab = nullptr;
+
+    SetView view() const {
+        SetView v;
+        v.bm_beg = (const uint32_t *)(d_dir + L.o_beg);
+        v.bm_cnt = (const uint32_t *)(d_dir + L.o_cnt);
+        v.c_key = (const uint16_t *)(d_dir + L.o_key);
+        v.c_type = (const uint8_t *)(d_dir + L.o_type);
+        v.c_card = (const uint32_t *)(d_dir + L.o_card);
+        v.c_len = (const uint32_t *)(d_dir + L.o_len);
+        v.c_off = (const uint64_t *)(d_dir + L.o_off);
+        v.payload = d_slab;
+        return v;
+    }
+    SetOut out() {
+        SetOut v;
+        v.bm_beg = (uint32_t *)(d_dir + L.o_beg);
+        v.bm_cnt = (uint32_t *)(d_dir + L.o_cnt);
+        v.bm_card = (uint64_t *)(d_dir + L.o_bcard);
+        v.c_key = (uint16_t *)(d_dir + L.o_key);
+        v.c_type = (uint8_t *)(d_dir + L.o_type);
+        v.c_card = (uint32_t *)(d_dir + L.o_card);
+        v.c_len = (uint32_t *)(d_dir + L.o_len);
+        v.c_off = (uint64_t *)(d_dir + L.o_off);
+        v.payload = d_slab;
+        return v;
+    }
+};
+
+namespace {
+
+rb200_set *set_new(uint32_t nb, uint64_t dir_cap, uint64_t slab_cap) {
+    rb200_set *s = new rb200_set();
+    s->n_bitmaps = nb;
+    s->dir_cap = dir_cap;
+    s->slab_cap = slab_cap;
+    s->L.compute(nb, dir_cap);
+    s->d_dir = (uint8_t *)dev_alloc(s->L.total);
+    s->d_slab = (uint8_t *)dev_alloc(slab_cap);
+    if (!s->d_dir || !s->d_slab) {
+        dev_free(s->d_dir, s->L.total);
+        dev_free(s->d_slab, slab_cap);
+        delete s;
+        return nullptr;
+    }
+    s->h_cnt.assign(nb, 0);
+    s->h_bytes.assign(nb, 0);
+    s->h_flags.assign(nb, 0);
+    return s;
+}
+
+void set_drop_mirror(rb200_set *s) {
+    pin_free(s->m_dir, s->L.total);
+    pin_free(s->m_slab, s->slab_used);
+    s->m_dir = s->m_slab = nullptr;
+}
+
+void set_delete(rb200_set *s) {
+    if (!s) return;
+    set_drop_mirror(s);
+    dev_free(s->d_dir, s->L.total);
+    dev_free(s->d_slab, s->slab_cap);
+    delete s;
+}
+
+// ------------------------------------------------------------------ host containers
+inline const void *unwrap_shared(const void *c, uint8_t &type) {  // containers.h:105-114
+    if (type == T_SHARED) {
+        const shared_container_t *sc = (const shared_container_t *)c;
+        type = sc->typecode;
+        return sc->container;
+    }
+    return c;
+}
+
+void container_free_host(void *c, uint8_t type) {  // containers.c:58-77
+    if (!c) return;
+    switch (type) {
+        case T_BITSET: {
+            bitset_container_t *b = (bitset_container_t *)c;
+            h_aligned_free(b->words);
+            h_free(b);
+            break;
+        }
+        case T_ARRAY: {
+            array_container_t *a = (array_container_t *)c;
+            h_free(a->array);
+            h_free(a);
+            break;
+        }
+        case T_RUN: {
+            run_container_t *r = (run_container_t *)c;
+            h_free(r->runs);
+            h_free(r);
+            break;
+        }
+        case T_SHARED: {
+            shared_container_t *sc = (shared_container_t *)c;
+            if (__atomic_sub_fetch(&sc->counter, 1, __ATOMIC_ACQ_REL) == 0) {
+                container_free_host(sc->container, sc->typecode);
+                h_free(sc);
+            }
+            break;
+        }
+    }
+}
+
+// roaring_bitmap_create_with_capacity + ra_init_with_capacity (roaring.c:86, roaring_array.c:80)
+roaring_bitmap_t *bitmap_alloc(int32_t cap) {
+    roaring_bitmap_t *r = (roaring_bitmap_t *)h_malloc(sizeof(roaring_bitmap_t));
+    if (!r) return nullptr;
+    roaring_array_t *ra = &r->high_low_container;
+    ra->size = 0;
+    ra->allocation_size = 0;
+    ra->containers = nullptr;
+    ra->keys = nullptr;
+    ra->typecodes = nullptr;
+    ra->flags = 0;
+    if (cap > 0) {
+        const size_t need = (size_t)cap * (sizeof(void *) + sizeof(uint16_t) + sizeof(uint8_t));
+        void *big = h_malloc(need);
+        if (!big) {
+            h_free(r);
+            return nullptr;
+        }
+        ra->containers = (void **)big;
+        ra->keys = (uint16_t *)(ra->containers + cap);
+        ra->typecodes = (uint8_t *)(ra->keys + cap);
+        ra->allocation_size = cap;
+    }
+    return r;
+}
+
+void bitmap_free_host(roaring_bitmap_t *r) {  // roaring.c:552-560
+    if (!r) return;
+    roaring_array_t *ra = &r->high_low_container;
+    if (!(ra->flags & FLAG_FROZEN)) {
+        for (int32_t i = 0; i < ra->size; i++) container_free_host(ra->containers[i], ra->typecodes[i]);
+        h_free(ra->containers);
+    }
+    h_free(r);
+}
+
+// make a host container from a stored payload (type, card, len)
+void *container_from_payload(uint8_t type, uint32_t card, uint32_t len, const uint8_t *p) {
+    if (type == T_BITSET) {
+        bitset_container_t *b = (bitset_container_t *)h_malloc(sizeof(bitset_container_t));
+        if (!b) return nullptr;
+        b->words = (uint64_t *)h_aligned_malloc(64, BITSET_BYTES);
+        if (!b->words) { h_free(b); return nullptr; }
+        memcpy(b->words, p, BITSET_BYTES);
+        b->cardinality = (int32_t)card;
+        return b;
+    }
+    if (type == T_ARRAY) {
+        array_container_t *a = (array_container_t *)h_malloc(sizeof(array_container_t));
+        if (!a) return nullptr;
+        a->array = (uint16_t *)h_malloc(2 * (size_t)(len ? len : 1));
+        if (!a->array) { h_free(a); return nullptr; }
+        memcpy(a->array, p, 2 * (size_t)len);
+        a->cardinality = (int32_t)len;
+        a->capacity = (int32_t)(len ? len : 1);
+        return a;
+    }
+    run_container_t *r = (run_container_t *)h_malloc(sizeof(run_container_t));
+    if (!r) return nullptr;
+    r->runs = (rle16_t *)h_malloc(4 * (size_t)(len ? len : 1));
+    if (!r->runs) { h_free(r); return nullptr; }
+    memcpy(r->runs, p, 4 * (size_t)len);
+    r->n_runs = (int32_t)len;
+    r->capacity = (int32_t)(len ? len : 1);
+    return r;
+}
+
+inline uint32_t host_container_card(const void *c, uint8_t type) {
+    if (type == T_ARRAY) return (uint32_t)((const array_container_t *)c)->cardinality;
+    if (type == T_RUN) {
+        const run_container_t *r = (const run_container_t *)c;
+        uint32_t s = 0;
+        for (int32_t i = 0; i < r->n_runs; i++) s += (uint32_t)r->runs[i].length + 1;
+        return s;
+    }
+    const bitset_container_t *b = (const bitset_container_t *)c;
+    if (b->cardinality >= 0) return (uint32_t)b->cardinality;
+    uint32_t s = 0;
+    for (int i = 0; i < 1024; i++) s += (uint32_t)__builtin_popcountll(b->words[i]);
+    return s;
+}
+
+}  // namespace
+
+// =================================================================== C ABI: helpers
+extern "C" {
+
+const char *rb200_last_error(void) { return g.err.c_str(); }
+uint64_t rb200_kernel_launches(void) { return g_launches; }
+uint64_t rb200_last_algorithmic_bytes(void) { return g.last_algo_bytes; }
+float rb200_last_device_ms(void) { return g.last_ms; }
+float rb200_last_compute_ms(void) { return g.last_compute_ms; }
+uint64_t rb200_last_download_bytes(void) { return g.last_download_bytes; }
+
+int rb200_init(int device) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return ctx_init(device) ? 0 : -1;
+}
+
+void rb200_set_stream(void *cuda_stream) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return;
+    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+}
+
+void rb200_synchronize(void) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (g.inited) cudaStreamSynchronize(g.stream);
+}
+
+void rb200_bitmap_free(roaring_bitmap_t *r) { bitmap_free_host(r); }
+
+uint64_t rb200_bitmap_get_cardinality(const roaring_bitmap_t *r) {
+    const roaring_array_t *ra = &r->high_low_container;
+    uint64_t s = 0;
+    for (int32_t i = 0; i < ra->size; i++) {
+        uint8_t t = ra->typecodes[i];
+        const void *c = unwrap_shared(ra->containers[i], t);
+        s += host_container_card(c, t);
+    }
+    return s;
+}
+
+bool rb200_bitmap_validate(const roaring_bitmap_t *r, const char **reason) {
+    static const char *why = "";
+    const roaring_array_t *ra = &r->high_low_container;
+#define BAD(msg) do { why = msg; if (reason) *reason = why; return false; } while (0)
+    if (ra->size < 0 || ra->size > 65536) BAD("size out of range");
+    if (ra->allocation_size < ra->size) BAD("allocation smaller than size");
+    for (int32_t i = 0; i < ra->size; i++) {
+        if (i > 0 && ra->keys[i] <= ra->keys[i - 1]) BAD("keys not strictly increasing");
+        uint8_t t = ra->typecodes[i];
+        const void *c = unwrap_shared(ra->containers[i], t);
+        if (!c) BAD("null container");
+        if (t == T_ARRAY) {
+            const array_container_t *a = (const array_container_t *)c;
+            if (a->cardinality < 1 || a->cardinality > MAX_ARRAY) BAD("array cardinality out of range");
+            if (a->capacity < a->cardinality) BAD("array capacity too small");
+            for (int32_t k = 1; k < a->cardinality; k++)
+                if (a->array[k] <= a->array[k - 1]) BAD("array not sorted/unique");
+        } else if (t == T_BITSET) {
+            const bitset_container_t *b = (const bitset_container_t *)c;
+            uint32_t s = 0;
+            for (int k = 0; k < 1024; k++) s += (uint32_t)__builtin_popcountll(b->words[k]);
+            if ((int32_t)s != b->cardinality) BAD("bitset cardinality field wrong");
+            if (s <= (uint32_t)MAX_ARRAY) BAD("bitset with cardinality <= 4096");
+        } else if (t == T_RUN) {
+            const run_container_t *rc = (const run_container_t *)c;
+            if (rc->n_runs < 1) BAD("empty run container");
+            if (rc->capacity < rc->n_runs) BAD("run capacity too small");
+            for (int32_t k = 0; k < rc->n_runs; k++) {
+                uint32_t s = rc->runs[k].value, e = s + rc->runs[k].length;
+                if (e > 65535) BAD("run overflows");
+                if (k > 0) {
+                    uint32_t pe = (uint32_t)rc->runs[k - 1].value + rc->runs[k - 1].length;
+                    if (s <= pe + 1) BAD("runs overlap or are adjacent");
+                }
+            }
+        } else {
+            BAD("unknown typecode");
+        }
+    }
+#undef BAD
+    if (reason) *reason = "";
+    return true;
+}
+
+// ---- portable format ------------------------------------------------------------------
+size_t rb200_bitmap_portable_size_in_bytes(const roaring_bitmap_t *r) {
+    const roaring_array_t *ra = &r->high_low_container;
+    bool hasrun = false;
+    size_t payload = 0;
+    for (int32_t i = 0; i < ra->size; i++) {
+        uint8_t t = ra->typecodes[i];
+        const void *c = unwrap_shared(ra->containers[i], t);
+        if (t == T_RUN) {
+            hasrun = true;
+            payload += 2 + 4 * (size_t)((const run_container_t *)c)->n_runs;
+        } else if (t == T_ARRAY) {
+            payload += 2 * (size_t)((const array_container_t *)c)->cardinality;
+        } else {
+            payload += BITSET_BYTES;
+        }
+    }
+    const size_t n = (size_t)ra->size;
+    size_t hdr;
+    if (hasrun) hdr = 4 + (n + 7) / 8 + (ra->size < NO_OFFSET_THRESHOLD ? 4 * n : 8 * n);
+    else hdr = 8 + 8 * n;
+    return hdr + payload;
+}
+
+size_t rb200_bitmap_portable_serialize(const roaring_bitmap_t *r, char *buf) {
+    const roaring_array_t *ra = &r->high_low_container;
+    const size_t n = (size_t)ra->size;
+    bool hasrun = false;
+    for (int32_t i = 0; i < ra->size; i++) {
+        uint8_t t = ra->typecodes[i];
+        unwrap_shared(ra->containers[i], t);
+        hasrun |= (t == T_RUN);
+    }
+    uint8_t *p = (uint8_t *)buf;
+    uint32_t start;
+    if (hasrun) {
+        const uint32_t cookie = SERIAL_COOKIE | ((uint32_t)(ra->size - 1) << 16);
+        memcpy(p, &cookie, 4);
+        p += 4;
+        const size_t s = (n + 7) / 8;
+        memset(p, 0, s);
+        for (int32_t i = 0; i < ra->size; i++) {
+            uint8_t t = ra->typecodes[i];
+            unwrap_shared(ra->containers[i], t);
+            if (t == T_RUN) p[i / 8] |= (uint8_t)(1 << (i % 8));
+        }
+        p += s;
+        start = (uint32_t)(4 + s + (ra->size < NO_OFFSET_THRESHOLD ? 4 * n : 8 * n));
+    } else {
+        const uint32_t cookie = SERIAL_COOKIE_NO_RUN, sz = (uint32_t)ra->size;
+        memcpy(p, &cookie, 4);
+        memcpy(p + 4, &sz, 4);
+        p += 8;
+        start = (uint32_t)(8 + 8 * n);
+    }
+    for (int32_t i = 0; i < ra->size; i++) {
+        uint8_t t = ra->typecodes[i];
+        const void *c = unwrap_shared(ra->containers[i], t);
+        const uint16_t key = ra->keys[i], cm1 = (uint16_t)(host_container_card(c, t) - 1);
+        memcpy(p, &key, 2);
+        memcpy(p + 2, &cm1, 2);
+        p += 4;
+    }
+    if (!hasrun || ra->size >= NO_OFFSET_THRESHOLD) {
+        uint32_t off = start;
+        for (int32_t i = 0; i < ra->size; i++) {
+            memcpy(p, &off, 4);
+            p += 4;
+            uint8_t t = ra->typecodes[i];
+            const void *c = unwrap_shared(ra->containers[i], t);
+            off += t == T_BITSET ? (uint32_t)BITSET_BYTES
+                   : t == T_ARRAY ? 2u * (uint32_t)((const array_container_t *)c)->cardinality
+                                  : 2u + 4u * (uint32_t)((const run_container_t *)c)->n_runs;
+        }
+    }
+    for (int32_t i = 0; i < ra->size; i++) {
+        uint8_t t = ra->typecodes[i];
+        const void *c = unwrap_shared(ra->containers[i], t);
+        if (t == T_BITSET) {
+            memcpy(p, ((const bitset_container_t *)c)->words, BITSET_BYTES);
+            p += BITSET_BYTES;
+        } else if (t == T_ARRAY) {
+            const array_container_t *a = (const array_container_t *)c;
+            memcpy(p, a->array, 2 * (size_t)a->cardinality);
+            p += 2 * (size_t)a->cardinality;
+        } else {
+            const run_container_t *rc = (const run_container_t *)c;
+            const uint16_t nr = (uint16_t)rc->n_runs;
+            memcpy(p, &nr, 2);
+            memcpy(p + 2, rc->runs, 4 * (size_t)rc->n_runs);
+            p += 2 + 4 * (size_t)rc->n_runs;
+        }
+    }
+    return (size_t)(p - (uint8_t *)buf);
+}
+
+}  // extern "C"
+
+namespace {
+
+// Parsed view of one portable-serialized bitmap (no allocation): per container key, type,
+// cardinality, length and a pointer to the stored payload inside the buffer.
+struct PView {
+    int32_t size = 0;
+    std::vector<uint16_t> key;
+    std::vector<uint8_t> type;
+    std::vector<uint32_t> card, len;
+    std::vector<const uint8_t *> ptr;
+};
+
+bool parse_portable(const uint8_t *buf, size_t len, PView &v) {
+    if (len < 4) return false;
+    uint32_t cookie;
+    memcpy(&cookie, buf, 4);
+    size_t pos = 4;
+    int32_t size;
+    const uint8_t *runflags = nullptr;
+    bool hasrun = false;
+    if ((cookie & 0xFFFF) == SERIAL_COOKIE) {
+        size = (int32_t)(cookie >> 16) + 1;
+        hasrun = true;
+        runflags = buf + pos;
+        pos += (size_t)(size + 7) / 8;
+    } else if (cookie == SERIAL_COOKIE_NO_RUN) {
+        if (len < 8) return false;
+        uint32_t s;
+        memcpy(&s, buf + 4, 4);
+        size = (int32_t)s;
+        pos = 8;
+    } else {
+        return false;
+    }
+    if (size < 0 || size > 65536) return false;
+    if (pos + 4 * (size_t)size > len) return false;
+    const uint8_t *kc = buf + pos;
+    pos += 4 * (size_t)size;
+    if (!hasrun || size >= NO_OFFSET_THRESHOLD) pos += 4 * (size_t)size;
+    v.size = size;
+    v.key.resize(size);
+    v.type.resize(size);
+    v.card.resize(size);
+    v.len.resize(size);
+    v.ptr.resize(size);
+    for (int32_t i = 0; i < size; i++) {
+        uint16_t key, cm1;
+        memcpy(&key, kc + 4 * i, 2);
+        memcpy(&cm1, kc + 4 * i + 2, 2);
+        if (i > 0 && key <= v.key[i - 1]) return false;
+        const uint32_t card = (uint32_t)cm1 + 1;
+        v.key[i] = key;
+        v.card[i] = card;
+        const bool isrun = hasrun && ((runflags[i / 8] >> (i % 8)) & 1);
+        if (isrun) {
+            if (pos + 2 > len) return false;
+            uint16_t nr;
+            memcpy(&nr, buf + pos, 2);
+            pos += 2;
+            if (pos + 4 * (size_t)nr > len) return false;
+            v.type[i] = T_RUN;
+            v.len[i] = nr;
+            v.ptr[i] = buf + pos;
+            pos += 4 * (size_t)nr;
+        } else if (card > (uint32_t)MAX_ARRAY) {
+            if (pos + BITSET_BYTES > len) return false;
+            v.type[i] = T_BITSET;
+            v.len[i] = 1024;
+            v.ptr[i] = buf + pos;
+            pos += BITSET_BYTES;
+        } else {
+            if (pos + 2 * (size_t)card > len) return false;
+            v.type[i] = T_ARRAY;
+            v.len[i] = card;
+            v.ptr[i] = buf + pos;
+            pos += 2 * (size_t)card;
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" roaring_bitmap_t *rb200_bitmap_portable_deserialize_safe(const char *buf, size_t maxbytes) {
+    PView v;
+    if (!parse_portable((const uint8_t *)buf, maxbytes, v)) return nullptr;
+    roaring_bitmap_t *r = bitmap_alloc(v.size);
+    if (!r) return nullptr;
+    roaring_array_t *ra = &r->high_low_container;
+    for (int32_t i = 0; i < v.size; i++) {
+        void *c = container_from_payload(v.type[i], v.card[i], v.len[i], v.ptr[i]);
+        if (!c) {
+            bitmap_free_host(r);
+            return nullptr;
+        }
+        ra->containers[i] = c;
+        ra->keys[i] = v.key[i];
+        ra->typecodes[i] = v.type[i];
+        ra->size = i + 1;
+    }
+    return r;
+}
+
+// =================================================================== upload
+namespace {
+
+// Source of containers for packing: either host bitmaps or parsed portable buffers.
+struct PackSrc {
+    const roaring_bitmap_t *const *bms = nullptr;
+    const std::vector<PView> *views = nullptr;
+    size_t n = 0;
+};
+
+rb200_set *upload_impl(const PackSrc &src) {
+    if (!ctx_init()) return nullptr;
+    const size_t nb = src.n;
+    // pass 1: sizes
+    uint64_t nc = 0, slab = 0;
+    for (size_t b = 0; b < nb; b++) {
+        if (src.bms) {
+            const roaring_array_t *ra = &src.bms[b]->high_low_container;
+            nc += (uint64_t)ra->size;
+            for (int32_t i = 0; i < ra->size; i++) {
+                uint8_t t = ra->typecodes[i];
+                const void *c = unwrap_shared(ra->containers[i], t);
+                uint32_t len = t == T_BITSET ? 1024u
+                               : t == T_ARRAY ? (uint32_t)((const array_container_t *)c)->cardinality
+                                              : (uint32_t)((const run_container_t *)c)->n_runs;
+                slab += round16(stored_bytes(t, len));
+            }
+        } else {
+            const PView &v = (*src.views)[b];
+            nc += (uint64_t)v.size;
+            for (int32_t i = 0; i < v.size; i++) slab += round16(stored_bytes(v.type[i], v.len[i]));
+        }
+    }
+    rb200_set *s = set_new((uint32_t)nb, nc, slab);
+    if (!s) return nullptr;
+    s->n_containers = nc;
+    s->slab_used = slab;
+    // pass 2: directory into one pinned block, payload streamed through two pinned chunks
+    uint8_t *hd = (uint8_t *)pin_alloc(s->L.total);
+    const size_t CH = (size_t)32 << 20;
+    uint8_t *chunk[2] = {(uint8_t *)pin_alloc(CH), (uint8_t *)pin_alloc(CH)};
+    cudaEvent_t cev[2];
+    bool ok = hd && chunk[0] && chunk[1];
+    for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&cev[k], cudaEventDisableTiming);
+    bool cev_used[2] = {false, false};
+    if (ok) {
+        uint32_t *bm_beg = (uint32_t *)(hd + s->L.o_beg), *bm_cnt = (uint32_t *)(hd + s->L.o_cnt);
+        uint64_t *bm_card = (uint64_t *)(hd + s->L.o_bcard);
+        uint16_t *c_key = (uint16_t *)(hd + s->L.o_key);
+        uint8_t *c_type = hd + s->L.o_type;
+        uint32_t *c_card = (uint32_t *)(hd + s->L.o_card), *c_len = (uint32_t *)(hd + s->L.o_len);
+        uint64_t *c_off = (uint64_t *)(hd + s->L.o_off);
+        uint64_t ci = 0, off = 0, chunk_base = 0;
+        int cur = 0;
+        size_t used = 0;
+        auto flush = [&]() -> bool {
+            if (used) {
+                if (cudaMemcpyAsync(s->d_slab + chunk_base, chunk[cur], used, cudaMemcpyHostToDevice,
+                                    g.stream) != cudaSuccess) return false;
+                cudaEventRecord(cev[cur], g.stream);
+                cev_used[cur] = true;
+            }
+            chunk_base += used;
+            used = 0;
+            cur ^= 1;
+            if (cev_used[cur]) cudaEventSynchronize(cev[cur]);
+            return true;
+        };
+        for (size_t b = 0; b < nb && ok; b++) {
+            const roaring_array_t *ra = src.bms ? &src.bms[b]->high_low_container : nullptr;
+            const PView *pv = src.views ? &(*src.views)[b] : nullptr;
+            const int32_t size = ra ? ra->size : pv->size;
+            bm_beg[b] = (uint32_t)ci;
+            bm_cnt[b] = (uint32_t)size;
+            s->h_cnt[b] = (uint32_t)size;
+            s->h_flags[b] = ra ? (ra->flags & FLAG_COW) : 0;
+            uint64_t bcard = 0, bbytes = 0;
+            for (int32_t i = 0; i < size; i++, ci++) {
+                uint8_t t;
+                uint32_t card, len;
+                const uint8_t *p;
+                uint16_t key;
+                if (ra) {
+                    t = ra->typecodes[i];
+                    const void *c = unwrap_shared(ra->containers[i], t);
+                    key = ra->keys[i];
+                    card = host_container_card(c, t);
+                    if (t == T_BITSET) { len = 1024; p = (const uint8_t *)((const bitset_container_t *)c)->words; }
+                    else if (t == T_ARRAY) { len = card; p = (const uint8_t *)((const array_container_t *)c)->array; }
+                    else { len = (uint32_t)((const run_container_t *)c)->n_runs; p = (const uint8_t *)((const run_container_t *)c)->runs; }
+                } else {
+                    t = pv->type[i];
+                    key = pv->key[i];
+                    len = pv->len[i];
+                    p = pv->ptr[i];
+                    if (t == T_RUN) {
+                        card = 0;
+                        for (uint32_t k = 0; k < len; k++) {
+                            uint16_t l;
+                            memcpy(&l, p + 4 * k + 2, 2);
+                            card += (uint32_t)l + 1;
+                        }
+                    } else {
+                        card = pv->card[i];
+                    }
+                }
+                const uint32_t sb = stored_bytes(t, len), sb16 = round16(sb);
+                if (used + sb16 > CH) ok = flush();
+                memcpy(chunk[cur] + used, p, sb);
+                if (sb16 > sb) memset(chunk[cur] + used + sb, 0, sb16 - sb);
+                used += sb16;
+                c_key[ci] = key;
+                c_type[ci] = t;
+                c_card[ci] = card;
+                c_len[ci] = len;
+                c_off[ci] = off;
+                off += sb16;
+                bcard += card;
+                bbytes += sb16;
+                s->portable_bytes += portable_bytes(t, len);
+            }
+            bm_card[b] = bcard;
+            s->h_bytes[b] = bbytes;
+        }
+        if (ok) ok = flush();
+        if (ok && cudaMemcpyAsync(s->d_dir, hd, s->L.total, cudaMemcpyHostToDevice, g.stream) != cudaSuccess)
+            ok = false;
+        if (cudaStreamSynchronize(g.stream) != cudaSuccess) ok = false;
+    }
+    for (int k = 0; k < 2; k++) cudaEventDestroy(cev[k]);
+    pin_free(hd, s->L.total);
+    pin_free(chunk[0], CH);
+    pin_free(chunk[1], CH);
+    if (!ok) {
+        if (g.err.empty()) g.err = "upload failed";
+        set_delete(s);
+        return nullptr;
+    }
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+rb200_set_t *rb200_set_upload(const roaring_bitmap_t *const *bitmaps, size_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    PackSrc src;
+    src.bms = bitmaps;
+    src.n = n;
+    return upload_impl(src);
+}
+
+rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *lens, size_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    std::vector<PView> views(n);
+    for (size_t i = 0; i < n; i++)
+        if (!parse_portable((const uint8_t *)bufs[i], lens[i], views[i])) {
+            g.err = "malformed portable bitmap at index " + std::to_string(i);
+            return nullptr;
+        }
+    PackSrc src;
+    src.views = &views;
+    src.n = n;
+    return upload_impl(src);
+}
+
+void rb200_set_free(rb200_set_t *s) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    set_delete(s);
+}
+size_t rb200_set_count(const rb200_set_t *s) { return s->n_bitmaps; }
+uint64_t rb200_set_container_count(const rb200_set_t *s) { return s->n_containers; }
+uint64_t rb200_set_payload_bytes(const rb200_set_t *s) { return s->portable_bytes; }
+
+}  // extern "C"
+
+// =================================================================== batched pairwise ops
+namespace {
+
+struct ItemsBuf {
+    uint8_t *block = nullptr;
+    size_t bytes = 0;
+    Items it;
+    bool alloc(uint64_t W) {
+        size_t o = 0;
+        const size_t o_off = o; o += al256(8 * W);
+        const size_t o_ca = o; o += al256(4 * W);
+        const size_t o_cb = o; o += al256(4 * W);
+        const size_t o_cap = o; o += al256(4 * W);
+        const size_t o_ocard = o; o += al256(4 * W);
+        const size_t o_olen = o; o += al256(4 * W);
+        const size_t o_key = o; o += al256(2 * W);
+        const size_t o_kind = o; o += al256(W);
+        const size_t o_otype = o; o += al256(W);
+        bytes = o ? o : 256;
+        block = (uint8_t *)dev_alloc(bytes);
+        if (!block) return false;
+        it.slot_off = (uint64_t *)(block + o_off);
+        it.ca = (uint32_t *)(block + o_ca);
+        it.cb = (uint32_t *)(block + o_cb);
+        it.slot_cap = (uint32_t *)(block + o_cap);
+        it.ocard = (uint32_t *)(block + o_ocard);
+        it.olen = (uint32_t *)(block + o_olen);
+        it.key = (uint16_t *)(block + o_key);
+        it.kind = block + o_kind;
+        it.otype = block + o_otype;
+        return true;
+    }
+    void release() { dev_free(block, bytes); block = nullptr; }
+};
+
+// pair lists + item offsets: one pinned staging block, one H2D copy
+struct PairBuf {
+    uint8_t *h = nullptr, *d = nullptr;
+    size_t bytes = 0;
+    uint32_t *d_ia = nullptr, *d_ib = nullptr;
+    uint64_t *d_off = nullptr;
+    uint64_t W = 0, slab_bound = 0;
+    bool build(const rb200_set *A, const rb200_set *B, const uint32_t *ia, const uint32_t *ib,
+               size_t np, bool and_like) {
+        const size_t o_off = 0, o_ia = al256(8 * (np + 1)), o_ib = o_ia + al256(4 * np);
+        bytes = o_ib + al256(4 * np);
+        h = (uint8_t *)pin_alloc(bytes);
+        d = (uint8_t *)dev_alloc(bytes);
+        if (!h || !d) return false;
+        uint64_t *off = (uint64_t *)(h + o_off);
+        uint32_t *hia = (uint32_t *)(h + o_ia), *hib = (uint32_t *)(h + o_ib);
+        uint64_t w = 0, sb = 0;
+        for (size_t p = 0; p < np; p++) {
+            const uint32_t a = ia[p], b = ib[p];
+            if (a >= A->n_bitmaps || b >= B->n_bitmaps) {
+                g.err = "pair index out of range";
+                return false;
+            }
+            hia[p] = a;
+            hib[p] = b;
+            off[p] = w;
+            const uint32_t na = A->h_cnt[a], nb = B->h_cnt[b];
+            w += (uint64_t)na + nb;
+            // upper bound of the result slab: pass-through bytes + 8 KiB per possible match
+            const uint64_t m = na < nb ? na : nb;
+            sb += (and_like ? 0 : A->h_bytes[a] + B->h_bytes[b]) + m * (uint64_t)BITSET_BYTES + 512;
+        }
+        off[np] = w;
+        W = w;
+        slab_bound = sb;
+        d_off = (uint64_t *)(d + o_off);
+        d_ia = (uint32_t *)(d + o_ia);
+        d_ib = (uint32_t *)(d + o_ib);
+        return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, g.stream) == cudaSuccess;
+    }
+    void release() {
+        pin_free(h, bytes);
+        dev_free(d, bytes);
+        h = d = nullptr;
+    }
+};
+
+bool stats_reset() {
+    return cudaMemsetAsync(g.d_stats, 0, sizeof(OpStats), g.stream) == cudaSuccess;
+}
+bool stats_fetch() {
+    if (cudaMemcpyAsync(g.h_stats, g.d_stats, sizeof(OpStats), cudaMemcpyDeviceToHost, g.stream) != cudaSuccess)
+        return false;
+    return true;
+}
+
+rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const uint32_t *ia,
+                         const uint32_t *ib, size_t np) {
+    if (!ctx_init()) return nullptr;
+    if (op < 0 || op > 3) { g.err = "bad op"; return nullptr; }
+    if (np > 0xffffffffull) { g.err = "too many pairs"; return nullptr; }
+    PairBuf pb;
+    ItemsBuf ib_;
+    rb200_set *R = nullptr;
+    uint32_t *h_cnt = nullptr;
+    bool ok = pb.build(A, B, ia, ib, np, op == OP_AND);
+    if (ok) ok = ib_.alloc(pb.W);
+    if (ok) {
+        R = set_new((uint32_t)np, pb.W, pb.slab_bound);
+        ok = R != nullptr;
+    }
+    const size_t cnt_bytes = 4 * np + 8 * np;
+    if (ok) { h_cnt = (uint32_t *)pin_alloc(cnt_bytes); ok = h_cnt != nullptr; }
+    if (ok) {
+        cudaEventRecord(g.ev0, g.stream);
+        ok = stats_reset();
+        const SetView va = A->view(), vb = B->view();
+        launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, ib_.it,
+                          g.d_stats, g.stream);
+        cudaEventRecord(g.evk0, g.stream);
+        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, g.stream);
+        cudaEventRecord(g.evk1, g.stream);
+        launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
+        cudaEventRecord(g.ev1, g.stream);
+        ok = ok && stats_fetch();
+        if (np) {
+            ok = ok && cudaMemcpyAsync(h_cnt, R->d_dir + R->L.o_cnt, 4 * np, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+        }
+        cudaError_t e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess) { g.err = std::string("batch op: ") + cudaGetErrorString(e); ok = false; }
+        if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("batch op launch: ") + cudaGetErrorString(e); ok = false; }
+    }
+    if (ok && g.h_stats->error) {
+        g.err = g.h_stats->error == 2 ? "internal: result slab bound exceeded" : "internal: result slot bound exceeded";
+        ok = false;
+    }
+    if (ok) {
+        cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+        cudaEventElapsedTime(&g.last_compute_ms, g.evk0, g.evk1);
+        g.last_algo_bytes = g.h_stats->algo_bytes;
+        R->n_containers = g.h_stats->dir_cursor;
+        R->slab_used = g.h_stats->slab_cursor;
+        R->portable_bytes = 0;
+        for (size_t p = 0; p < np; p++) {
+            R->h_cnt[p] = h_cnt[p];
+            // stored-bytes upper bound for chained ops: every container <= 8 KiB
+            R->h_bytes[p] = (uint64_t)h_cnt[p] * BITSET_BYTES;
+            R->h_flags[p] = (A->h_flags[ia[p]] | B->h_flags[ib[p]]) & FLAG_COW;
+        }
+    }
+    pin_free(h_cnt, cnt_bytes);
+    pb.release();
+    ib_.release();
+    if (!ok) {
+        set_delete(R);
+        return nullptr;
+    }
+    return R;
+}
+
+}  // namespace
+
+extern "C" {
+
+rb200_set_t *rb200_batch_op(int op, const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
+                            const uint32_t *ib, size_t npairs) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return batch_op_impl(op, A, B, ia, ib, npairs);
+}
+
+int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
+                                const uint32_t *ib, size_t np, uint64_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    if (np == 0) return 0;
+    PairBuf pb;
+    ItemsBuf ib_;
+    uint64_t *d_out = nullptr, *h_out = nullptr;
+    bool ok = pb.build(A, B, ia, ib, np, true);
+    if (ok) ok = ib_.alloc(pb.W);
+    if (ok) { d_out = (uint64_t *)dev_alloc(8 * np); h_out = (uint64_t *)pin_alloc(8 * np); ok = d_out && h_out; }
+    if (ok) {
+        cudaEventRecord(g.ev0, g.stream);
+        ok = stats_reset();
+        const SetView va = A->view(), vb = B->view();
+        launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, OP_AND, true, ib_.it,
+                          g.d_stats, g.stream);
+        cudaEventRecord(g.evk0, g.stream);
+        launch_card_items(va, vb, ib_.it, pb.W, g.d_stats, g.stream);
+        cudaEventRecord(g.evk1, g.stream);
+        launch_finalize_cards(ib_.it, pb.d_off, (uint32_t)np, d_out, g.stream);
+        cudaEventRecord(g.ev1, g.stream);
+        ok = ok && cudaMemcpyAsync(h_out, d_out, 8 * np, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+        cudaError_t e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess) { g.err = std::string("and_cardinality: ") + cudaGetErrorString(e); ok = false; }
+        if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("and_cardinality launch: ") + cudaGetErrorString(e); ok = false; }
+    }
+    if (ok) {
+        memcpy(out, h_out, 8 * np);
+        cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+        cudaEventElapsedTime(&g.last_compute_ms, g.evk0, g.evk1);
+    }
+    dev_free(d_out, 8 * np);
+    pin_free(h_out, 8 * np);
+    pb.release();
+    ib_.release();
+    return ok ? 0 : -1;
+}
+
+rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, size_t n,
+                                    uint32_t key_lo, uint32_t key_hi, uint32_t *card_per_key) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return nullptr;
+    if (key_hi > 65535) key_hi = 65535;
+    if (idx == nullptr) n = S->n_bitmaps;
+    uint64_t tot = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t b = idx ? idx[i] : (uint32_t)i;
+        if (b >= S->n_bitmaps) { g.err = "or_many: index out of range"; return nullptr; }
+        tot += S->h_cnt[b];
+    }
+    uint64_t maxk = key_lo <= key_hi ? (uint64_t)key_hi - key_lo + 1 : 0;
+    if (tot < maxk) maxk = tot;
+    rb200_set *R = set_new(1, maxk, maxk * BITSET_BYTES);
+    if (!R) return nullptr;
+    uint32_t *d_idx = nullptr, *h_idx = nullptr;
+    bool ok = true;
+    if (idx && n) {
+        d_idx = (uint32_t *)dev_alloc(4 * n);
+        h_idx = (uint32_t *)pin_alloc(4 * n);
+        ok = d_idx && h_idx;
+        if (ok) {
+            memcpy(h_idx, idx, 4 * n);
+            ok = cudaMemcpyAsync(d_idx, h_idx, 4 * n, cudaMemcpyHostToDevice, g.stream) == cudaSuccess;
+        }
+    }
+    uint32_t *h_ck = nullptr;
+    if (ok && card_per_key) { h_ck = (uint32_t *)pin_alloc(65536 * 4); ok = h_ck != nullptr; }
+    if (ok) {
+        cudaEventRecord(g.ev0, g.stream);
+        ok = stats_reset();
+        const SetView vs = S->view();
+        launch_many_mark(vs, d_idx, (uint32_t)n, key_lo, key_hi, g.d_flags, g.stream);
+        launch_many_compact(g.d_flags, g.d_keys, g.d_stats, g.stream);
+        if (card_per_key) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
+        cudaEventRecord(g.evk0, g.stream);
+        launch_or_many(vs, d_idx, (uint32_t)n, g.d_keys, R->out(), card_per_key ? g.d_cardkey : nullptr,
+                       g.d_stats, g.stream);
+        cudaEventRecord(g.evk1, g.stream);
+        cudaEventRecord(g.ev1, g.stream);
+        ok = ok && stats_fetch();
+        if (card_per_key)
+            ok = ok && cudaMemcpyAsync(h_ck, g.d_cardkey, 65536 * 4, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+        cudaError_t e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess) { g.err = std::string("or_many: ") + cudaGetErrorString(e); ok = false; }
+        if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("or_many launch: ") + cudaGetErrorString(e); ok = false; }
+    }
+    if (ok) {
+        cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+        cudaEventElapsedTime(&g.last_compute_ms, g.evk0, g.evk1);
+        const uint32_t nk = g.h_stats->nk;
+        R->n_containers = nk;
+        R->slab_used = (uint64_t)nk * BITSET_BYTES;
+        R->h_cnt[0] = nk;
+        R->h_bytes[0] = (uint64_t)nk * BITSET_BYTES;
+        uint8_t fl = 0;
+        // roaring_bitmap_lazy_or propagates COW from the inputs (roaring.c:2523)
+        for (size_t i = 0; i < n; i++) fl |= S->h_flags[idx ? idx[i] : i];
+        R->h_flags[0] = fl & FLAG_COW;
+        if (card_per_key)
+            for (int k = 0; k < 65536; k++) card_per_key[k] += h_ck[k];
+        // algorithmic bytes: all input containers in range + outputs; the
+        // output term is added by the caller-visible stat only when the set is downloaded,
+        // here we account inputs exactly from the host mirrors when the whole key space is used.
+        uint64_t inb = 0;
+        if (key_lo == 0 && key_hi == 65535 && idx == nullptr) inb = S->portable_bytes;
+        g.last_algo_bytes = inb;
+    }
+    dev_free(d_idx, 4 * n);
+    pin_free(h_idx, 4 * n);
+    pin_free(h_ck, 65536 * 4);
+    if (!ok) {
+        set_delete(R);
+        return nullptr;
+    }
+    return R;
+}
+
+rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n) {
+    return rb200_or_many_keyrange(S, idx, n, 0, 65535, nullptr);
+}
+
+int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    const size_t nb = s->n_bitmaps;
+    if (!nb) return 0;
+    uint64_t *h = (uint64_t *)pin_alloc(8 * nb);
+    if (!h) return -1;
+    // bm_card is maintained by upload / finalize / or_many
+    bool ok = cudaMemcpyAsync(h, s->d_dir + s->L.o_bcard, 8 * nb, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(g.stream) == cudaSuccess;
+    if (ok) memcpy(out, h, 8 * nb);
+    else g.err = "set_cardinalities: copy failed";
+    pin_free(h, 8 * nb);
+    return ok ? 0 : -1;
+}
+
+}  // extern "C"
+
+// =================================================================== download
+namespace {
+
+bool ensure_mirror(rb200_set *s) {
+    if (s->m_dir) return true;
+    s->m_dir = (uint8_t *)pin_alloc(s->L.total);
+    s->m_slab = (uint8_t *)pin_alloc(s->slab_used);
+    if (!s->m_dir || !s->m_slab) return false;
+    bool ok = cudaMemcpyAsync(s->m_dir, s->d_dir, s->L.total, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+    if (s->slab_used)
+        ok = ok && cudaMemcpyAsync(s->m_slab, s->d_slab, s->slab_used, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(g.stream) == cudaSuccess;
+    if (!ok) g.err = "download: copy failed";
+    g.last_download_bytes = s->L.total + s->slab_used;
+    return ok;
+}
+
+roaring_bitmap_t *build_bitmap(const rb200_set *s, size_t i) {
+    const uint32_t *bm_beg = (const uint32_t *)(s->m_dir + s->L.o_beg);
+    const uint32_t *bm_cnt = (const uint32_t *)(s->m_dir + s->L.o_cnt);
+    const uint16_t *c_key = (const uint16_t *)(s->m_dir + s->L.o_key);
+    const uint8_t *c_type = s->m_dir + s->L.o_type;
+    const uint32_t *c_card = (const uint32_t *)(s->m_dir + s->L.o_card);
+    const uint32_t *c_len = (const uint32_t *)(s->m_dir + s->L.o_len);
+    const uint64_t *c_off = (const uint64_t *)(s->m_dir + s->L.o_off);
+    const uint32_t beg = bm_beg[i], cnt = bm_cnt[i];
+    roaring_bitmap_t *r = bitmap_alloc((int32_t)cnt);
+    if (!r) return nullptr;
+    roaring_array_t *ra = &r->high_low_container;
+    ra->flags = s->h_flags[i] & FLAG_COW;  // roaring.c:738,890
+    for (uint32_t k = 0; k < cnt; k++) {
+        const uint32_t c = beg + k;
+        void *hc = container_from_payload(c_type[c], c_card[c], c_len[c], s->m_slab + c_off[c]);
+        if (!hc) {
+            bitmap_free_host(r);
+            return nullptr;
+        }
+        ra->containers[k] = hc;
+        ra->keys[k] = c_key[c];
+        ra->typecodes[k] = c_type[c];
+        ra->size = (int32_t)k + 1;
+    }
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+roaring_bitmap_t *rb200_set_download(const rb200_set_t *cs, size_t i) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    rb200_set *s = const_cast<rb200_set *>(cs);
+    if (i >= s->n_bitmaps) { g.err = "download: index out of range"; return nullptr; }
+    if (!ensure_mirror(s)) return nullptr;
+    return build_bitmap(s, i);
+}
+
+int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    rb200_set *s = const_cast<rb200_set *>(cs);
+    if (!ensure_mirror(s)) return -1;
+    for (size_t i = 0; i < s->n_bitmaps; i++) {
+        out[i] = build_bitmap(s, i);
+        if (!out[i]) {
+            for (size_t k = 0; k < i; k++) bitmap_free_host(out[k]);
+            g.err = "download: host allocation failed";
+            return -1;
+        }
+    }
+    set_drop_mirror(s);
+    return 0;
+}
+
+int rb200_batch_op_host(int op, const roaring_bitmap_t *const *a, const roaring_bitmap_t *const *b,
+                        size_t np, roaring_bitmap_t **out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    // upload a[] and b[] as ONE set (2*np bitmaps) so there is a single H2D stream
+    std::vector<const roaring_bitmap_t *> all(2 * np);
+    std::vector<uint32_t> ia(np), ib(np);
+    for (size_t p = 0; p < np; p++) {
+        all[p] = a[p];
+        all[np + p] = b[p];
+        ia[p] = (uint32_t)p;
+        ib[p] = (uint32_t)(np + p);
+    }
+    rb200_set *S = rb200_set_upload(all.data(), all.size());
+    if (!S) return -1;
+    rb200_set *R = batch_op_impl(op, S, S, ia.data(), ib.data(), np);
+    int rc = -1;
+    if (R) {
+        rc = rb200_set_download_all(R, out);
+        set_delete(R);
+    }
+    set_delete(S);
+    return rc;
+}
+
+// =================================================================== drop-in entry points
+static roaring_bitmap_t *dropin_pair(int op, const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    roaring_bitmap_t *out = nullptr;
+    if (rb200_batch_op_host(op, &r1, &r2, 1, &out) != 0) return nullptr;
+    return out;
+}
+
+roaring_bitmap_t *roaring_bitmap_and(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    return dropin_pair(OP_AND, r1, r2);
+}
+roaring_bitmap_t *roaring_bitmap_or(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    return dropin_pair(OP_OR, r1, r2);
+}
+roaring_bitmap_t *roaring_bitmap_xor(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    return dropin_pair(OP_XOR, r1, r2);
+}
+roaring_bitmap_t *roaring_bitmap_andnot(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    return dropin_pair(OP_ANDNOT, r1, r2);
+}
+
+roaring_bitmap_t *roaring_bitmap_or_many(size_t number, const roaring_bitmap_t **rs) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    rb200_set *S = rb200_set_upload(rs, number);
+    if (!S) return nullptr;
+    rb200_set *R = rb200_or_many(S, nullptr, number);
+    roaring_bitmap_t *out = nullptr;
+    if (R) {
+        out = rb200_set_download(R, 0);
+        set_delete(R);
+    }
+    set_delete(S);
+    return out;
+}
+
+uint64_t roaring_bitmap_and_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const roaring_bitmap_t *both[2] = {r1, r2};
+    rb200_set *S = rb200_set_upload(both, 2);
+    if (!S) return UINT64_MAX;
+    const uint32_t ia = 0, ib = 1;
+    uint64_t out = UINT64_MAX;
+    if (rb200_batch_and_cardinality(S, S, &ia, &ib, 1, &out) != 0) out = UINT64_MAX;
+    set_delete(S);
+    return out;
+}
+
+// src/roaring.c:3078-3107: inclusion-exclusion on and_cardinality + the two cardinalities
+uint64_t roaring_bitmap_or_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    const uint64_t c1 = rb200_bitmap_get_cardinality(r1), c2 = rb200_bitmap_get_cardinality(r2);
+    const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
+    return inter == UINT64_MAX ? UINT64_MAX : c1 + c2 - inter;
+}
+uint64_t roaring_bitmap_andnot_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    const uint64_t c1 = rb200_bitmap_get_cardinality(r1);
+    const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
+    return inter == UINT64_MAX ? UINT64_MAX : c1 - inter;
+}
+uint64_t roaring_bitmap_xor_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    const uint64_t c1 = rb200_bitmap_get_cardinality(r1), c2 = rb200_bitmap_get_cardinality(r2);
+    const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
+    return inter == UINT64_MAX ? UINT64_MAX : c1 + c2 - 2 * inter;
+}
+double roaring_bitmap_jaccard_index(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    const uint64_t c1 = rb200_bitmap_get_cardinality(r1), c2 = rb200_bitmap_get_cardinality(r2);
+    const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
+    return (double)inter / (double)(c1 + c2 - inter);
+}
+bool roaring_bitmap_intersect(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
+    return inter != 0 && inter != UINT64_MAX;
+}
+
+}  // extern "C"

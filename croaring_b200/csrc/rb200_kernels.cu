@@ -1,0 +1,825 @@
+// rb200_kernels.cu — sm_100a kernels of the Roaring set-algebra hot path.
+//
+//   k_plan_pairs      warp per bitmap pair: key merge by binary-search ranks (the reference's
+//                     two-pointer loops, src/roaring.c:742-768, 896-951) -> work items.
+//   k_compute_items   warp per work item: one container x container grid cell
+//                     (include/roaring/containers/containers.h:726-1876) or a pass-through copy.
+//   k_card_items      warp per matched item: container_and_cardinality (containers.h:811-859).
+//   k_finalize_pairs  warp per pair: drop empty results (roaring.c:756-760), build the
+//                     key-sorted result directory.
+//   k_or_many         CTA per key: N-way union (roaring.c:775-790, 2509-2682, 2845) with the
+//                     reference's full-container state machine (containers.h:1342-1404).
+#include "rb200_device.cuh"
+
+namespace rb200 {
+
+unsigned long long g_launches = 0;
+
+static inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u16(const uint16_t *a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t upper_bound_u16(const uint16_t *a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------ planner
+__global__ void __launch_bounds__(128)
+k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
+             const uint32_t *__restrict__ ib, const uint64_t *__restrict__ item_off,
+             uint32_t npairs, int op, bool card_only, Items it, OpStats *st) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = warp; p < npairs; p += nwarps) {
+        const uint32_t a = ia[p], b = ib[p];
+        const uint32_t a0 = A.bm_beg[a], na = A.bm_cnt[a];
+        const uint32_t b0 = B.bm_beg[b], nb = B.bm_cnt[b];
+        const uint64_t base_item = item_off[p];
+        const uint32_t tot = na + nb;
+        for (uint32_t t0 = 0; t0 < tot; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            int kind = K_HOLE;
+            uint32_t ca = 0, cb = 0, cap = 0, pos = 0, key = 0;
+            if (t < tot) {
+                if (t < na) {
+                    ca = a0 + t;
+                    key = A.c_key[ca];
+                    const uint32_t lb = lower_bound_u16(B.c_key + b0, nb, key);
+                    const bool matched = lb < nb && B.c_key[b0 + lb] == key;
+                    pos = t + lb;
+                    if (matched) {
+                        cb = b0 + lb;
+                        kind = K_COMPUTE;
+                        if (!card_only)
+                            cap = slot_bound(op, A.c_type[ca], B.c_type[cb], A.c_card[ca],
+                                             B.c_card[cb], A.c_len[ca], B.c_len[cb]);
+                    } else if (op != OP_AND && !card_only) {
+                        kind = K_COPY_A;
+                        cap = round16(stored_bytes(A.c_type[ca], A.c_len[ca]));
+                    }
+                } else {
+                    const uint32_t j = t - na;
+                    cb = b0 + j;
+                    key = B.c_key[cb];
+                    const uint32_t ub = upper_bound_u16(A.c_key + a0, na, key);
+                    const bool matched = ub > 0 && A.c_key[a0 + ub - 1] == key;
+                    pos = j + ub;
+                    if (!matched && (op == OP_OR || op == OP_XOR) && !card_only) {
+                        kind = K_COPY_B;
+                        cap = round16(stored_bytes(B.c_type[cb], B.c_len[cb]));
+                    }
+                }
+            }
+            // warp-aggregated bump allocation of the output slots
+            const uint32_t incl = warp_incl_scan(cap, lane);
+            const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
+            unsigned long long slab_base = 0;
+            if (lane == 31 && total) slab_base = atomicAdd(&st->slab_cursor, (unsigned long long)total);
+            slab_base = __shfl_sync(FULLMASK, slab_base, 31);
+            if (t < tot) {
+                const uint64_t idx = base_item + pos;
+                it.kind[idx] = (uint8_t)kind;
+                it.key[idx] = (uint16_t)key;
+                it.ca[idx] = ca;
+                it.cb[idx] = cb;
+                it.slot_off[idx] = slab_base + incl - cap;
+                it.slot_cap[idx] = cap;
+                it.otype[idx] = 0;
+                it.ocard[idx] = 0;
+                it.olen[idx] = 0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ grid cells
+// Evaluate one matched cell on the warp's accumulator and write the result payload.
+__device__ __forceinline__ void
+cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
+             uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
+             int lane, int &otype, uint32_t &ocard, uint32_t &olen, unsigned int *err) {
+    // ---- result is always an array and one side is an array: filter, no re-encode --------
+    if (op == OP_AND && (tA == T_ARRAY || tB == T_ARRAY)) {
+        // filter the array side through the other side's bits
+        const bool arrA = (tA == T_ARRAY) && !(tB == T_ARRAY && cB < cA);  // filter the smaller
+        const uint8_t *parr = arrA ? pa : pb;
+        const uint32_t narr = arrA ? cA : cB;
+        const int to = arrA ? tB : tA;
+        const uint8_t *po = arrA ? pb : pa;
+        const uint32_t lo = arrA ? lB : lA;
+        uint32_t n;
+        if (2 * narr > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
+        if (to == T_BITSET) {
+            n = filter_array<false, true>(parr, narr, reinterpret_cast<const uint32_t *>(po),
+                                          reinterpret_cast<uint16_t *>(out), lane);
+        } else {
+            acc_load(acc, to, po, lo, lane);
+            n = filter_array<false, true>(parr, narr, acc, reinterpret_cast<uint16_t *>(out), lane);
+            __syncwarp();
+        }
+        otype = n ? T_ARRAY : 0;
+        ocard = olen = n;
+        return;
+    }
+    if (op == OP_ANDNOT && tA == T_ARRAY) {
+        uint32_t n;
+        if (2 * cA > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
+        if (tB == T_BITSET) {
+            n = filter_array<true, true>(pa, cA, reinterpret_cast<const uint32_t *>(pb),
+                                         reinterpret_cast<uint16_t *>(out), lane);
+        } else {
+            acc_load(acc, tB, pb, lB, lane);
+            n = filter_array<true, true>(pa, cA, acc, reinterpret_cast<uint16_t *>(out), lane);
+            __syncwarp();
+        }
+        otype = n ? T_ARRAY : 0;
+        ocard = olen = n;
+        return;
+    }
+
+    // ---- general path: acc = A op B --------------------------------------------------------
+    int card = -1, nruns = 0;
+    if (tA == T_BITSET && tB == T_BITSET) {
+        switch (op) {
+            case OP_AND: card = acc_bitset_op_bitset<OP_AND>(acc, pa, pb, lane); break;
+            case OP_OR: card = acc_bitset_op_bitset<OP_OR>(acc, pa, pb, lane); break;
+            case OP_XOR: card = acc_bitset_op_bitset<OP_XOR>(acc, pa, pb, lane); break;
+            default: card = acc_bitset_op_bitset<OP_ANDNOT>(acc, pa, pb, lane); break;
+        }
+        __syncwarp();
+    } else {
+        acc_load(acc, tA, pa, lA, lane);
+        if (tB == T_BITSET) {
+            switch (op) {
+                case OP_AND: acc_op_bitset<OP_AND>(acc, pb, lane); break;
+                case OP_OR: acc_op_bitset<OP_OR>(acc, pb, lane); break;
+                case OP_XOR: acc_op_bitset<OP_XOR>(acc, pb, lane); break;
+                default: acc_op_bitset<OP_ANDNOT>(acc, pb, lane); break;
+            }
+        } else if (tB == T_ARRAY) {
+            switch (op) {
+                case OP_AND: acc_and_array(acc, pb, cB, lane); break;  // not reached (filter path)
+                case OP_OR: acc_apply_array<0>(acc, pb, cB, lane); break;
+                case OP_XOR: acc_apply_array<1>(acc, pb, cB, lane); break;
+                default: acc_apply_array<2>(acc, pb, cB, lane); break;
+            }
+        } else {
+            switch (op) {
+                case OP_AND: acc_and_runs(acc, pb, lB, lane); break;
+                case OP_OR: acc_apply_runs<0, false>(acc, pb, lB, lane); break;
+                case OP_XOR: acc_apply_runs<1, false>(acc, pb, lB, lane); break;
+                default: acc_apply_runs<2, false>(acc, pb, lB, lane); break;
+            }
+        }
+        __syncwarp();
+    }
+    const bool want_runs = cell_needs_runs(op, tA, tB);
+    if (card < 0 || want_runs) acc_count(acc, lane, want_runs, card, nruns);
+    if (card == 0) { otype = 0; ocard = olen = 0; return; }
+    int t = decide_type(op, tA, tB, cA, cB, lA, lB, card, nruns);
+    if (t == T_RUN && !want_runs) {  // bitset OR full-run -> [0,65535]
+        nruns = 1;
+    }
+    const uint32_t len = (t == T_BITSET) ? 1024u : (t == T_ARRAY ? (uint32_t)card : (uint32_t)nruns);
+    if (stored_bytes(t, len) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
+    if (t == T_BITSET) acc_store_bitset(acc, out, lane);
+    else if (t == T_ARRAY) acc_emit_array(acc, reinterpret_cast<uint16_t *>(out), lane);
+    else acc_emit_runs(acc, reinterpret_cast<uint16_t *>(out), lane);
+    __syncwarp();
+    otype = t;
+    ocard = (uint32_t)card;
+    olen = len;
+}
+
+__global__ void __launch_bounds__(128)
+k_compute_items(SetView A, SetView B, Items it, uint64_t W, int op, uint8_t *slab,
+                uint64_t slab_cap, OpStats *st) {
+    __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
+    const int lane = threadIdx.x & 31;
+    uint32_t *acc = s_acc[threadIdx.x >> 5];
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(&st->work_counter, 1ull);
+    item = __shfl_sync(FULLMASK, item, 0);
+    while (item < W) {
+        unsigned long long next = 0;
+        if (lane == 0) next = atomicAdd(&st->work_counter, 1ull);  // prefetch the next ticket
+        const int kind = it.kind[item];
+        if (kind != K_HOLE) {
+            const uint64_t off = it.slot_off[item];
+            const uint32_t cap = it.slot_cap[item];
+            int otype = 0;
+            uint32_t ocard = 0, olen = 0;
+            if (off + cap > slab_cap) {
+                if (lane == 0) atomicExch(&st->error, 2u);
+            } else if (kind == K_COMPUTE) {
+                const uint32_t ca = it.ca[item], cb = it.cb[item];
+                cell_compute(acc, op, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
+                             B.payload + B.c_off[cb], A.c_card[ca], B.c_card[cb], A.c_len[ca],
+                             B.c_len[cb], slab + off, cap, lane, otype, ocard, olen, &st->error);
+            } else {
+                const SetView &S = (kind == K_COPY_A) ? A : B;
+                const uint32_t c = (kind == K_COPY_A) ? it.ca[item] : it.cb[item];
+                otype = S.c_type[c];
+                ocard = S.c_card[c];
+                olen = S.c_len[c];
+                warp_copy16(slab + off, S.payload + S.c_off[c], stored_bytes(otype, olen), lane);
+            }
+            if (lane == 0) {
+                it.otype[item] = (uint8_t)otype;
+                it.ocard[item] = ocard;
+                it.olen[item] = olen;
+            }
+        }
+        item = __shfl_sync(FULLMASK, next, 0);
+    }
+}
+
+// container_and_cardinality for one matched cell (containers.h:811-859)
+__device__ __forceinline__ uint32_t cell_and_card(uint32_t *acc, int tA, int tB, const uint8_t *pa,
+                                                  const uint8_t *pb, uint32_t cA, uint32_t cB,
+                                                  uint32_t lA, uint32_t lB, int lane) {
+    if (tA == T_BITSET && tB == T_BITSET) return (uint32_t)bitset_and_card(pa, pb, lane);
+    if (tA == T_ARRAY || tB == T_ARRAY) {
+        const bool arrA = (tA == T_ARRAY) && !(tB == T_ARRAY && cB < cA);
+        const uint8_t *parr = arrA ? pa : pb;
+        const uint32_t narr = arrA ? cA : cB;
+        const int to = arrA ? tB : tA;
+        const uint8_t *po = arrA ? pb : pa;
+        const uint32_t lo = arrA ? lB : lA;
+        if (to == T_BITSET)
+            return filter_array<false, false>(parr, narr, reinterpret_cast<const uint32_t *>(po),
+                                              nullptr, lane);
+        acc_load(acc, to, po, lo, lane);
+        const uint32_t n = filter_array<false, false>(parr, narr, acc, nullptr, lane);
+        __syncwarp();
+        return n;
+    }
+    // run x bitset / bitset x run / run x run
+    int card, nr;
+    if (tA == T_RUN && tB == T_RUN) {
+        acc_load(acc, tA, pa, lA, lane);
+        acc_and_runs(acc, pb, lB, lane);
+        __syncwarp();
+        acc_count(acc, lane, false, card, nr);
+    } else {
+        const bool runA = tA == T_RUN;
+        acc_load(acc, T_RUN, runA ? pa : pb, runA ? lA : lB, lane);
+        card = acc_and_bitset_card(acc, runA ? pb : pa, lane);
+    }
+    __syncwarp();
+    return (uint32_t)card;
+}
+
+__global__ void __launch_bounds__(128)
+k_card_items(SetView A, SetView B, Items it, uint64_t W, OpStats *st) {
+    __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
+    const int lane = threadIdx.x & 31;
+    uint32_t *acc = s_acc[threadIdx.x >> 5];
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(&st->work_counter, 1ull);
+    item = __shfl_sync(FULLMASK, item, 0);
+    while (item < W) {
+        unsigned long long next = 0;
+        if (lane == 0) next = atomicAdd(&st->work_counter, 1ull);
+        if (it.kind[item] == K_COMPUTE) {
+            const uint32_t ca = it.ca[item], cb = it.cb[item];
+            const uint32_t c =
+                cell_and_card(acc, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
+                              B.payload + B.c_off[cb], A.c_card[ca], B.c_card[cb], A.c_len[ca],
+                              B.c_len[cb], lane);
+            if (lane == 0) it.ocard[item] = c;
+        }
+        item = __shfl_sync(FULLMASK, next, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------ finalize
+__global__ void __launch_bounds__(128)
+k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ item_off,
+                 uint32_t npairs, SetOut out, OpStats *st) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = warp; p < npairs; p += nwarps) {
+        const uint64_t i0 = item_off[p], i1 = item_off[p + 1];
+        // pass 1: count surviving containers, cardinality and algorithmic bytes
+        uint32_t cnt = 0;
+        unsigned long long card = 0, bytes = 0;
+        for (uint64_t i = i0 + lane; i < i1; i += 32) {
+            const int kind = it.kind[i];
+            if (kind == K_HOLE) continue;
+            const int ot = it.otype[i];
+            const uint32_t osz = ot ? portable_bytes(ot, it.olen[i]) : 0u;
+            if (kind == K_COMPUTE) {
+                const uint32_t ca = it.ca[i], cb = it.cb[i];
+                bytes += portable_bytes(A.c_type[ca], A.c_len[ca]) +
+                         portable_bytes(B.c_type[cb], B.c_len[cb]) + osz;
+            } else {
+                bytes += 2ull * osz;
+            }
+            if (ot) {
+                cnt++;
+                card += it.ocard[i];
+            }
+        }
+        cnt = __reduce_add_sync(FULLMASK, cnt);
+        for (int d = 16; d > 0; d >>= 1) {
+            card += __shfl_xor_sync(FULLMASK, card, d);
+            bytes += __shfl_xor_sync(FULLMASK, bytes, d);
+        }
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&st->dir_cursor, (unsigned long long)cnt);
+            atomicAdd(&st->algo_bytes, bytes);
+            out.bm_beg[p] = (uint32_t)base;
+            out.bm_cnt[p] = cnt;
+            out.bm_card[p] = card;
+        }
+        base = __shfl_sync(FULLMASK, base, 0);
+        // pass 2: ordered compaction into the directory
+        uint32_t done = 0;
+        for (uint64_t i = i0; i < i1; i += 32) {
+            const uint64_t idx = i + lane;
+            const bool live = idx < i1 && it.kind[idx] != K_HOLE && it.otype[idx] != 0;
+            const unsigned m = __ballot_sync(FULLMASK, live);
+            if (live) {
+                const uint64_t o = base + done + __popc(m & lanemask_lt());
+                out.c_key[o] = it.key[idx];
+                out.c_type[o] = it.otype[idx];
+                out.c_card[o] = it.ocard[idx];
+                out.c_len[o] = it.olen[idx];
+                out.c_off[o] = it.slot_off[idx];
+            }
+            done += __popc(m);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_finalize_cards(Items it, const uint64_t *__restrict__ item_off, uint32_t npairs,
+                 uint64_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = warp; p < npairs; p += nwarps) {
+        const uint64_t i0 = item_off[p], i1 = item_off[p + 1];
+        unsigned long long card = 0;
+        for (uint64_t i = i0 + lane; i < i1; i += 32)
+            if (it.kind[i] == K_COMPUTE) card += it.ocard[i];
+        for (int d = 16; d > 0; d >>= 1) card += __shfl_xor_sync(FULLMASK, card, d);
+        if (lane == 0) out[p] = card;
+    }
+}
+
+__global__ void k_set_cardinalities(SetView S, uint32_t n, uint64_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < n; b += nwarps) {
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        unsigned long long card = 0;
+        for (uint32_t i = lane; i < nc; i += 32) card += S.c_card[c0 + i];
+        for (int d = 16; d > 0; d >>= 1) card += __shfl_xor_sync(FULLMASK, card, d);
+        if (lane == 0) out[b] = card;
+    }
+}
+
+// ------------------------------------------------------------------------------ or_many
+__global__ void k_many_mark(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
+                            uint32_t key_lo, uint32_t key_hi, uint32_t *__restrict__ flags) {
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t b = idx ? idx[i] : i;
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        for (uint32_t c = threadIdx.x; c < nc; c += blockDim.x) {
+            const uint32_t k = S.c_key[c0 + c];
+            if (k >= key_lo && k <= key_hi) flags[k] = 1u;
+        }
+    }
+}
+
+// single CTA, 1024 threads: ordered list of the keys whose flag is set
+__global__ void __launch_bounds__(1024)
+k_many_compact(const uint32_t *__restrict__ flags, uint16_t *__restrict__ keys, OpStats *st) {
+    __shared__ uint32_t s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t cnt = 0;
+    for (int k = 0; k < 64; k++) cnt += flags[tid * 64 + k] ? 1u : 0u;
+    const uint32_t incl = warp_incl_scan(cnt, lane);
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t v = s_warp[lane];
+        const uint32_t s = warp_incl_scan(v, lane);
+        s_warp[lane] = s - v;
+        if (lane == 31) st->nk = s;
+    }
+    __syncthreads();
+    uint32_t o = s_warp[wid] + incl - cnt;
+    for (int k = 0; k < 64; k++)
+        if (flags[tid * 64 + k]) keys[o++] = (uint16_t)(tid * 64 + k);
+}
+
+constexpr int OM_THREADS = 256;
+constexpr int OM_CHUNK = 1024;  // participants gathered per round
+
+// CTA per key.  The union of all containers carrying this key is accumulated in a shared
+// 65536-bit accumulator (arrays / runs, shared-memory atomics) plus a register slice per
+// thread (bitset containers: every thread owns two 128-bit words of the 8 KiB block, so a
+// bitset participant is two coalesced 128-bit loads per thread and no shared-memory traffic).
+// Types follow roaring_bitmap_or_many: a key present in one input is cloned and "repaired"
+// (runs re-checked by convert_run_to_efficient_container); a key present in several inputs
+// becomes a bitset accumulator, repaired to array when card <= 4096, or the full run
+// [0,65535] when the reference's lazy fold would have produced it (state machine below).
+__global__ void __launch_bounds__(OM_THREADS)
+k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
+          const uint16_t *__restrict__ keys, SetOut out, uint32_t *__restrict__ card_per_key,
+          OpStats *st) {
+    __shared__ __align__(16) uint32_t s_acc[ACC_WORDS];
+    __shared__ uint32_t s_plist[OM_CHUNK];   // container index of each participant (input order)
+    __shared__ uint32_t s_ppos[OM_CHUNK];    // position in idx[] of each participant
+    __shared__ uint32_t s_warp[OM_THREADS / 32];
+    __shared__ uint32_t s_np, s_ki, s_flag;
+    __shared__ int s_red[OM_THREADS / 32][2];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nk = st->nk;
+
+    for (;;) {
+        if (tid == 0) s_ki = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
+        __syncthreads();
+        const uint32_t ki = s_ki;
+        __syncthreads();
+        if (ki >= nk) break;
+        const uint32_t key = keys[ki];
+
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < ACC_WORDS / 4; i += OM_THREADS)
+            reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
+
+        // state of the reference's fold (thread 0 only)
+        uint32_t m_total = 0;        // participants so far
+        uint32_t first_c = 0, first_pos = 0, second_pos = 0;
+        bool any_inplace_bitset = false;  // a bitset participant at an in-place step
+        bool run_full = false;            // accumulator became the full run (rule i)
+        bool decided_skip = false;        // accumulator known full -> later inputs skipped
+        bool first_is_full_bitset = false;
+
+        for (uint32_t c0 = 0; c0 < n; c0 += OM_CHUNK) {
+            // ---- gather the participants of this chunk, in input order -----------------
+            uint32_t found[OM_CHUNK / OM_THREADS];
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int k = 0; k < OM_CHUNK / OM_THREADS; k++) {
+                const uint32_t i = c0 + tid * (OM_CHUNK / OM_THREADS) + k;
+                found[k] = 0xffffffffu;
+                if (i < n) {
+                    const uint32_t b = idx ? idx[i] : i;
+                    const uint32_t b0 = S.bm_beg[b], nb = S.bm_cnt[b];
+                    const uint32_t lb = lower_bound_u16(S.c_key + b0, nb, key);
+                    if (lb < nb && S.c_key[b0 + lb] == key) {
+                        found[k] = b0 + lb;
+                        cnt++;
+                    }
+                }
+            }
+            const uint32_t incl = warp_incl_scan(cnt, lane);
+            if (lane == 31) s_warp[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                const uint32_t v = lane < OM_THREADS / 32 ? s_warp[lane] : 0u;
+                const uint32_t s = warp_incl_scan(v, lane);
+                if (lane < OM_THREADS / 32) s_warp[lane] = s - v;
+                if (lane == 31) s_np = s;
+            }
+            __syncthreads();
+            uint32_t o = s_warp[wid] + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < OM_CHUNK / OM_THREADS; k++)
+                if (found[k] != 0xffffffffu) {
+                    s_plist[o] = found[k];
+                    s_ppos[o] = c0 + tid * (OM_CHUNK / OM_THREADS) + k;
+                    o++;
+                }
+            __syncthreads();
+            const uint32_t np = s_np;
+
+            // ---- thread 0: metadata part of the reference's lazy fold --------------------
+            // (roaring.c:2535-2545 first combine, :2621-2640 in-place steps,
+            //  containers.h:1342-1404 container_lazy_ior, :1113-1215 container_lazy_or)
+            if (tid == 0) {
+                for (uint32_t j = 0; j < np; j++) {
+                    const uint32_t c = s_plist[j];
+                    const int t = S.c_type[c];
+                    const bool full_run = is_full_run(t, S.c_len[c], S.c_card[c]);
+                    if (m_total == 0) {
+                        first_c = c;
+                        first_pos = s_ppos[j];
+                        if (full_run) { run_full = true; decided_skip = true; }
+                        if (t == T_BITSET && S.c_card[c] == 65536) {
+                            first_is_full_bitset = true;
+                            decided_skip = true;
+                        }
+                    } else {
+                        if (m_total == 1) second_pos = s_ppos[j];
+                        const bool non_inplace = (m_total == 1) && first_pos == 0 && second_pos == 1;
+                        if (non_inplace) {
+                            // first combine: no "is full" skip.
+                            const int t1 = S.c_type[first_c];
+                            decided_skip = false;
+                            first_is_full_bitset = false;
+                            if (t1 != T_BITSET && t != T_BITSET) {
+                                // c1 -> bitset, lazy_ior(B, c2): only a full-run c2 gives a run
+                                run_full = full_run;
+                            } else {
+                                // container_lazy_or: a full run on either side is copied
+                                run_full = full_run || is_full_run(t1, S.c_len[first_c], S.c_card[first_c]);
+                            }
+                            decided_skip = run_full;
+                        } else if (!decided_skip) {
+                            if (full_run) { run_full = true; decided_skip = true; }
+                            else if (t == T_BITSET) any_inplace_bitset = true;
+                        }
+                    }
+                    m_total++;
+                }
+            }
+
+            // ---- accumulate the payloads (order-free: OR is associative) -------------------
+            // bitset participants: registers, 4 at a time for memory-level parallelism
+            {
+                uint32_t j = 0;
+                while (j < np) {
+                    const uint4 *src[4];
+                    int nb4 = 0;
+                    while (j < np && nb4 < 4) {
+                        const uint32_t c = s_plist[j++];
+                        if (S.c_type[c] == T_BITSET)
+                            src[nb4++] = reinterpret_cast<const uint4 *>(S.payload + S.c_off[c]);
+                    }
+                    uint4 qa[4], qb[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (k < nb4) {
+                            qa[k] = __ldg(src[k] + tid);
+                            qb[k] = __ldg(src[k] + tid + OM_THREADS);
+                        }
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (k < nb4) {
+                            r0.x |= qa[k].x; r0.y |= qa[k].y; r0.z |= qa[k].z; r0.w |= qa[k].w;
+                            r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
+                        }
+                }
+            }
+            // array / run participants: one warp per participant, shared-memory atomics
+            for (uint32_t j = wid; j < np; j += OM_THREADS / 32) {
+                const uint32_t c = s_plist[j];
+                const int t = S.c_type[c];
+                if (t == T_ARRAY) acc_apply_array<0>(s_acc, S.payload + S.c_off[c], S.c_len[c], lane);
+                else if (t == T_RUN) acc_apply_runs<0, true>(s_acc, S.payload + S.c_off[c], S.c_len[c], lane);
+            }
+            __syncthreads();
+        }
+
+        // ---- merge the register slice into the shared accumulator, count -------------------
+        {
+            uint4 *a4 = reinterpret_cast<uint4 *>(s_acc);
+            uint4 a = a4[tid], b = a4[tid + OM_THREADS];
+            a.x |= r0.x; a.y |= r0.y; a.z |= r0.z; a.w |= r0.w;
+            b.x |= r1.x; b.y |= r1.y; b.z |= r1.z; b.w |= r1.w;
+            a4[tid] = a;
+            a4[tid + OM_THREADS] = b;
+        }
+        __syncthreads();
+        int c = 0, r = 0;
+        for (int w = tid; w < ACC_WORDS; w += OM_THREADS) {
+            const uint32_t x = s_acc[w];
+            const uint32_t prev = w ? (s_acc[w - 1] >> 31) : 0u;
+            c += __popc(x);
+            r += __popc(x & ~((x << 1) | prev));
+        }
+        c = __reduce_add_sync(FULLMASK, c);
+        r = __reduce_add_sync(FULLMASK, r);
+        if (lane == 0) { s_red[wid][0] = c; s_red[wid][1] = r; }
+        __syncthreads();
+        int card = 0, nruns = 0;
+        for (int w = 0; w < OM_THREADS / 32; w++) { card += s_red[w][0]; nruns += s_red[w][1]; }
+
+        // ---- decide the result type (thread 0 knows the fold state; broadcast) ---------------
+        if (tid == 0) {
+            int t;
+            if (m_total == 1) {
+                // single participant: clone + container_repair_after_lazy (containers.h:344-371)
+                const int t1 = S.c_type[first_c];
+                if (t1 == T_RUN) t = rule_eff(card, nruns);
+                else if (t1 == T_ARRAY) t = T_ARRAY;
+                else t = rule_ab(card);
+            } else if (run_full) {
+                t = T_RUN;
+            } else if (card == 65536 && any_inplace_bitset && !first_is_full_bitset) {
+                t = 0x80;  // saturated: need the ordered replay to know if a B,B step saw it
+            } else {
+                t = rule_ab(card);
+            }
+            s_flag = (uint32_t)t;
+        }
+        __syncthreads();
+        int otype = (int)s_flag;
+        __syncthreads();
+
+        if (otype == 0x80) {
+            // Ordered replay (rare: saturated key with bitset participants).  Find whether an
+            // in-place bitset step observes cardinality 65536 (containers.h:1345-1352) before
+            // anything else makes the accumulator a run.  Prefix unions are recomputed in input
+            // order; fullness is tested after every in-place bitset participant.
+            for (int i = tid; i < ACC_WORDS; i += OM_THREADS) s_acc[i] = 0;
+            __syncthreads();
+            bool became_run = false;
+            uint32_t m = 0, fpos = 0;
+            for (uint32_t i = 0; i < n && !became_run; i++) {
+                const uint32_t b = idx ? idx[i] : i;
+                const uint32_t b0 = S.bm_beg[b], nb = S.bm_cnt[b];
+                const uint32_t lb = lower_bound_u16(S.c_key + b0, nb, key);
+                if (!(lb < nb && S.c_key[b0 + lb] == key)) continue;  // uniform across the CTA
+                const uint32_t cc = b0 + lb;
+                const int t = S.c_type[cc];
+                if (m == 0) fpos = i;
+                const bool non_inplace = (m == 1) && fpos == 0 && i == 1;
+                if (t == T_BITSET) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(S.payload + S.c_off[cc]);
+                    uint4 *a4 = reinterpret_cast<uint4 *>(s_acc);
+                    for (int k = tid; k < ACC_WORDS / 4; k += OM_THREADS) {
+                        uint4 a = a4[k];
+                        const uint4 q = __ldg(src + k);
+                        a.x |= q.x; a.y |= q.y; a.z |= q.z; a.w |= q.w;
+                        a4[k] = a;
+                    }
+                } else if (wid == 0) {
+                    if (t == T_ARRAY) acc_apply_array<0>(s_acc, S.payload + S.c_off[cc], S.c_len[cc], lane);
+                    else acc_apply_runs<0, true>(s_acc, S.payload + S.c_off[cc], S.c_len[cc], lane);
+                }
+                __syncthreads();
+                if (t == T_BITSET && m >= 1 && !non_inplace) {
+                    bool full = true;
+                    for (int k = tid; k < ACC_WORDS; k += OM_THREADS) full = full && (s_acc[k] == 0xffffffffu);
+                    if (__syncthreads_and(full)) became_run = true;
+                }
+                m++;
+            }
+            __syncthreads();
+            for (int i = tid; i < ACC_WORDS; i += OM_THREADS) s_acc[i] = 0xffffffffu;
+            __syncthreads();
+            otype = became_run ? T_RUN : T_BITSET;
+        }
+
+        // ---- emit ----------------------------------------------------------------------------
+        const uint64_t off = (uint64_t)ki * BITSET_BYTES;
+        uint8_t *dst = out.payload + off;
+        uint32_t olen;
+        if (otype == T_BITSET) {
+            olen = 1024;
+            for (int i = tid; i < ACC_WORDS / 4; i += OM_THREADS)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(s_acc)[i];
+        } else if (otype == T_ARRAY) {
+            olen = (uint32_t)card;
+            if (wid == 0) acc_emit_array(s_acc, reinterpret_cast<uint16_t *>(dst), lane);
+        } else {
+            olen = (uint32_t)nruns;
+            if (wid == 0) acc_emit_runs(s_acc, reinterpret_cast<uint16_t *>(dst), lane);
+        }
+        if (tid == 0) {
+            out.c_key[ki] = (uint16_t)key;
+            out.c_type[ki] = (uint8_t)otype;
+            out.c_card[ki] = (uint32_t)card;
+            out.c_len[ki] = olen;
+            out.c_off[ki] = off;
+            if (card_per_key) card_per_key[key] = (uint32_t)card;
+        }
+        __syncthreads();
+    }
+    // bitmap-level directory (one result bitmap) — written by the CTA that sees ticket nk
+    if (blockIdx.x == 0 && tid == 0) {
+        out.bm_beg[0] = 0;
+        out.bm_cnt[0] = nk;
+    }
+}
+
+// total cardinality of the one-bitmap result of or_many
+__global__ void k_sum_cards(const uint32_t *__restrict__ c_card, const OpStats *st,
+                            uint64_t *__restrict__ out) {
+    __shared__ unsigned long long s[32];
+    const uint32_t n = st->nk;
+    unsigned long long v = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) v += c_card[i];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s[i];
+        out[0] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------ launchers
+static inline uint32_t blocks_for_warps(uint64_t warps, int warps_per_block, int max_blocks) {
+    uint64_t b = (warps + warps_per_block - 1) / warps_per_block;
+    if (b < 1) b = 1;
+    if (b > (uint64_t)max_blocks) b = max_blocks;
+    return (uint32_t)b;
+}
+
+void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, const uint32_t *ib,
+                       const uint64_t *item_off, uint32_t npairs, int op, bool card_only,
+                       Items it, OpStats *st, cudaStream_t s) {
+    if (!npairs) return;
+    const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * 16);
+    k_plan_pairs<<<g, 128, 0, s>>>(A, B, ia, ib, item_off, npairs, op, card_only, it, st);
+    g_launches++;
+}
+
+void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
+                          uint8_t *slab, uint64_t slab_cap, OpStats *st, cudaStream_t s) {
+    if (!W) return;
+    const uint32_t g = blocks_for_warps(W, 4, sm_count() * 7);
+    k_compute_items<<<g, 128, 0, s>>>(A, B, it, W, op, slab, slab_cap, st);
+    g_launches++;
+}
+
+void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W, OpStats *st,
+                       cudaStream_t s) {
+    if (!W) return;
+    const uint32_t g = blocks_for_warps(W, 4, sm_count() * 7);
+    k_card_items<<<g, 128, 0, s>>>(A, B, it, W, st);
+    g_launches++;
+}
+
+void launch_finalize_pairs(const SetView &A, const SetView &B, Items it, const uint64_t *item_off,
+                           uint32_t npairs, SetOut out, OpStats *st, cudaStream_t s) {
+    if (!npairs) return;
+    const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * 16);
+    k_finalize_pairs<<<g, 128, 0, s>>>(A, B, it, item_off, npairs, out, st);
+    g_launches++;
+}
+
+void launch_finalize_cards(Items it, const uint64_t *item_off, uint32_t npairs, uint64_t *out,
+                           cudaStream_t s) {
+    if (!npairs) return;
+    const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * 16);
+    k_finalize_cards<<<g, 128, 0, s>>>(it, item_off, npairs, out);
+    g_launches++;
+}
+
+void launch_set_cardinalities(const SetView &S, uint32_t n, uint64_t *out, cudaStream_t s) {
+    if (!n) return;
+    const uint32_t g = blocks_for_warps(n, 4, sm_count() * 16);
+    k_set_cardinalities<<<g, 128, 0, s>>>(S, n, out);
+    g_launches++;
+}
+
+void launch_many_mark(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo,
+                      uint32_t key_hi, uint32_t *flags, cudaStream_t s) {
+    cudaMemsetAsync(flags, 0, 65536 * sizeof(uint32_t), s);
+    if (!n) return;
+    const uint32_t g = n < (uint32_t)sm_count() * 8 ? n : (uint32_t)sm_count() * 8;
+    k_many_mark<<<g, 128, 0, s>>>(S, idx, n, key_lo, key_hi, flags);
+    g_launches++;
+}
+
+void launch_many_compact(const uint32_t *flags, uint16_t *keys_out, OpStats *st, cudaStream_t s) {
+    k_many_compact<<<1, 1024, 0, s>>>(flags, keys_out, st);
+    g_launches++;
+}
+
+void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uint16_t *keys,
+                    SetOut out, uint32_t *card_per_key, OpStats *st, cudaStream_t s) {
+    k_or_many<<<sm_count() * 4, OM_THREADS, 0, s>>>(S, idx, n, keys, out, card_per_key, st);
+    g_launches++;
+    k_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
+    g_launches++;
+}
+
+}  // namespace rb200

@@ -1,0 +1,164 @@
+/*
+ * roaring_b200.h — C ABI of the B200-native Roaring set-algebra engine (libroaring_b200.so).
+ *
+ * Plain C: only pointers, sizes and PODs cross this boundary; no torch / C++ / CUDA types.
+ *
+ * Part 1 (DROP-IN) exports, under the reference's own names, exactly the entry points of the
+ * hot path of CRoaring 5.1.0 — the functions a caller / FFI binding of the reference binds
+ * for set algebra.  Each declaration cites the reference declaration it replaces
+ * (paths relative to the reference tree).  They take and return host `roaring_bitmap_t`
+ * objects in the reference's memory layout, so every other reference function
+ * (roaring_bitmap_free, _contains, _portable_serialize, iterators ...) keeps working on what
+ * they return.  The work itself is done by sm_100a CUDA kernels; there is NO CPU fallback:
+ * on a CUDA failure they return NULL / UINT64_MAX and rb200_last_error() says why.
+ *
+ * Part 2 (rb200_*) is the batched, device-resident form the GPU needs to be worth using:
+ * upload a set of bitmaps once, run thousands of pairwise ops / an N-way union per launch,
+ * keep results on the device, download only what the caller asks for.
+ */
+#ifndef ROARING_B200_H
+#define ROARING_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------
+ * Layout-compatible types.  If the reference's headers are already included we use theirs.
+ * include/roaring/roaring_types.h:61-68 (roaring_array_t), include/roaring/roaring.h:39-41
+ * (roaring_bitmap_t), containers/array.h:46-50, containers/bitset.h:45-48,
+ * containers/run.h:48-51,69-73, containers/containers.h:48-51 (typecodes).
+ * ------------------------------------------------------------------------------------- */
+#ifndef ROARING_TYPES_H
+typedef struct roaring_array_s {
+    int32_t size;
+    int32_t allocation_size;
+    void **containers; /* base of ONE block [containers | keys | typecodes], roaring_array.c:55-66 */
+    uint16_t *keys;
+    uint8_t *typecodes;
+    uint8_t flags; /* ROARING_FLAG_COW = 1, ROARING_FLAG_FROZEN = 2 (roaring_types.h:46-49) */
+} roaring_array_t;
+#endif
+#ifndef ROARING_H
+typedef struct roaring_bitmap_s {
+    roaring_array_t high_low_container;
+} roaring_bitmap_t;
+#endif
+
+/* ---------------------------------------------------------------------------------------
+ * Part 1 — drop-in hot-path entry points (reference names, reference semantics).
+ * ------------------------------------------------------------------------------------- */
+
+/* include/roaring/roaring.h:225  (src/roaring.c:731) */
+roaring_bitmap_t *roaring_bitmap_and(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+/* include/roaring/roaring.h:288  (src/roaring.c:877) */
+roaring_bitmap_t *roaring_bitmap_or(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+/* include/roaring/roaring.h:320  (src/roaring.c:1121) */
+roaring_bitmap_t *roaring_bitmap_xor(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+/* include/roaring/roaring.h:342  (src/roaring.c:1275) */
+roaring_bitmap_t *roaring_bitmap_andnot(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+/* include/roaring/roaring.h:304  (src/roaring.c:775) */
+roaring_bitmap_t *roaring_bitmap_or_many(size_t number, const roaring_bitmap_t **rs);
+/* include/roaring/roaring.h:231  (src/roaring.c:3048) */
+uint64_t roaring_bitmap_and_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+/* include/roaring/roaring.h:258-271 (src/roaring.c:3086-3107): inclusion-exclusion on the above */
+uint64_t roaring_bitmap_or_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+uint64_t roaring_bitmap_andnot_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+uint64_t roaring_bitmap_xor_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+/* include/roaring/roaring.h:252  (src/roaring.c:3078) */
+double roaring_bitmap_jaccard_index(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+/* include/roaring/roaring.h:237  (src/roaring.c:2998) */
+bool roaring_bitmap_intersect(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+
+/* ---------------------------------------------------------------------------------------
+ * Stand-alone helpers (our own implementations of the steps either side of the path, so the
+ * library is usable without linking the reference; when the reference IS loaded in the
+ * process its roaring_malloc/roaring_free hooks are used for every host allocation).
+ * ------------------------------------------------------------------------------------- */
+
+/* portable format: src/roaring_array.c:469-531 (write), :633-813 (read) */
+roaring_bitmap_t *rb200_bitmap_portable_deserialize_safe(const char *buf, size_t maxbytes);
+size_t rb200_bitmap_portable_size_in_bytes(const roaring_bitmap_t *r);
+size_t rb200_bitmap_portable_serialize(const roaring_bitmap_t *r, char *buf);
+/* src/roaring.c:552-560 */
+void rb200_bitmap_free(roaring_bitmap_t *r);
+/* src/roaring.c:1436 */
+uint64_t rb200_bitmap_get_cardinality(const roaring_bitmap_t *r);
+/* structural invariants of src/roaring.c:454-523; returns true when valid */
+bool rb200_bitmap_validate(const roaring_bitmap_t *r, const char **reason);
+
+/* ---------------------------------------------------------------------------------------
+ * Part 2 — batched, device-resident API.
+ * ------------------------------------------------------------------------------------- */
+typedef struct rb200_set rb200_set_t; /* an ordered collection of bitmaps resident in HBM */
+
+enum { RB200_AND = 0, RB200_OR = 1, RB200_XOR = 2, RB200_ANDNOT = 3 };
+
+/* Context.  rb200_init is optional (first call initialises on the current device).
+ * `cuda_stream` is a cudaStream_t passed as void*; NULL selects the library's own stream. */
+int rb200_init(int device);
+void rb200_set_stream(void *cuda_stream);
+void rb200_synchronize(void);
+const char *rb200_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t rb200_kernel_launches(void);
+
+/* Upload (H2D): pack n host bitmaps into one device-resident set (one contiguous copy). */
+rb200_set_t *rb200_set_upload(const roaring_bitmap_t *const *bitmaps, size_t n);
+/* Same from portable-serialized bytes ("identical serialized inputs"). */
+rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *lens, size_t n);
+void rb200_set_free(rb200_set_t *s);
+size_t rb200_set_count(const rb200_set_t *s);              /* number of bitmaps */
+uint64_t rb200_set_container_count(const rb200_set_t *s);   /* total containers */
+uint64_t rb200_set_payload_bytes(const rb200_set_t *s);     /* container_size_in_bytes summed */
+
+/* Pairwise batch: result bitmap k = A[ia[k]] op B[ib[k]], k < npairs (ia/ib host arrays).
+ * Returns a new device-resident set of npairs bitmaps (NULL on error).  A may equal B. */
+rb200_set_t *rb200_batch_op(int op, const rb200_set_t *A, const rb200_set_t *B,
+                            const uint32_t *ia, const uint32_t *ib, size_t npairs);
+
+/* out[k] = |A[ia[k]] AND B[ib[k]]|  (roaring_bitmap_and_cardinality per pair); 0 on success. */
+int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
+                                const uint32_t *ib, size_t npairs, uint64_t *out);
+
+/* roaring_bitmap_or_many over S[idx[0..n)] (idx == NULL: all bitmaps in order).
+ * Returns a device-resident set holding ONE bitmap. */
+rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n);
+
+/* Key-sharded form used for multi-GPU aggregation: only containers whose high-16 key lies in
+ * [key_lo, key_hi] take part; per-key result cardinalities are ADDED into card_per_key[65536]
+ * when non-NULL (host array; the caller all-reduces it across ranks). */
+rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, size_t n,
+                                    uint32_t key_lo, uint32_t key_hi, uint32_t *card_per_key);
+
+/* Per-bitmap cardinalities of a set (host array of rb200_set_count entries); 0 on success. */
+int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out);
+
+/* Download (D2H) bitmap i / all bitmaps as host roaring_bitmap_t in the reference layout,
+ * owned by the caller (free with roaring_bitmap_free or rb200_bitmap_free). */
+roaring_bitmap_t *rb200_set_download(const rb200_set_t *s, size_t i);
+int rb200_set_download_all(const rb200_set_t *s, roaring_bitmap_t **out);
+
+/* Host-to-host batch through the device (what the drop-in symbols do for one pair):
+ * upload a[], b[] -> batch op -> download.  out[k] owned by the caller. 0 on success. */
+int rb200_batch_op_host(int op, const roaring_bitmap_t *const *a, const roaring_bitmap_t *const *b,
+                        size_t npairs, roaring_bitmap_t **out);
+
+/* Algorithmic bytes of the last batch / many op as defined in SURVEY.md §8(d)
+ * (container_size_in_bytes of matched inputs + outputs + 2x pass-through). */
+uint64_t rb200_last_algorithmic_bytes(void);
+/* Device time (ms) of the last batch / many op, measured with CUDA events on its stream. */
+float rb200_last_device_ms(void);
+/* Device time (ms) of the grid-cell kernel (k_compute_items / k_card_items / k_or_many) alone. */
+float rb200_last_compute_ms(void);
+/* Bytes copied device->host by the last rb200_set_download* call (directory + payload slab). */
+uint64_t rb200_last_download_bytes(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROARING_B200_H */

@@ -1,0 +1,85 @@
+"""CPU tests (-m "not gpu"): pin the plain-C oracle (oracle/roaring_oracle.c) against
+(a) the committed golden values generated from the reference and (b) the unmodified reference
+itself (oracle/_ref/libroaring_ref.so), byte-for-byte on the portable serialization."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import croaring_b200.datasets as dsm
+from helpers import DATASETS, OPS, no_run_twins, sha_concat, synth_blobs
+
+
+@pytest.mark.parametrize("ds", DATASETS)
+def test_oracle_vs_golden_realdata(O, golden, ds):
+    blobs = dsm.load_realdata(ds)
+    assert len(blobs) == golden[ds]["n"] == 200
+    assert sum(map(len, blobs)) == golden[ds]["portable_bytes"]
+    g = golden[ds]["run_optimized"]
+    for op in OPS:
+        outs = [O.op_bytes(op, blobs[i], blobs[i + 1]) for i in range(199)]
+        assert sum(O.cardinality(b) for b in outs) == g[op]["sum_card"], (ds, op)
+        assert sha_concat(outs) == g[op]["sha256"], (ds, op)
+    assert sum(O.and_cardinality(blobs[i], blobs[i + 1]) for i in range(199)) == g["and_cardinality"]
+    for name in ("or_many", "xor_many"):
+        out = O.many_bytes(name, blobs)
+        assert O.cardinality(out) == g[name]["card"]
+        assert hashlib.sha256(out).hexdigest() == g[name]["sha256"], (ds, name)
+
+
+@pytest.mark.parametrize("ds", ["census1881", "wikileaks-noquotes", "weather_sept_85"])
+def test_oracle_vs_golden_no_runs(O, R, golden, ds):
+    blobs = no_run_twins(R, dsm.load_realdata(ds))
+    g = golden[ds]["no_runs"]
+    for op in OPS:
+        outs = [O.op_bytes(op, blobs[i], blobs[i + 1]) for i in range(199)]
+        assert sha_concat(outs) == g[op]["sha256"], (ds, op)
+    assert hashlib.sha256(O.many_bytes("or_many", blobs)).hexdigest() == g["or_many"]["sha256"]
+    assert hashlib.sha256(O.many_bytes("xor_many", blobs)).hexdigest() == g["xor_many"]["sha256"]
+
+
+def test_survey_golden_sum_cards(golden):
+    """The checksums measured in SURVEY.md §6 / BASELINE.md §2."""
+    exp = {"census1881": (23, 2007691, 2007668, 1003836, 988653, 973455),
+           "weather_sept_85": (642019, 24729002, 24086983, 11960876, 1015367, 526545),
+           "wikileaks-noquotes": (3327, 541893, 538566, 271605, 242540, 212267)}
+    for ds, (a, o, x, n, om, xm) in exp.items():
+        g = golden[ds]["run_optimized"]
+        assert (g["and"]["sum_card"], g["or"]["sum_card"], g["xor"]["sum_card"],
+                g["andnot"]["sum_card"], g["or_many"]["card"], g["xor_many"]["card"]) == (a, o, x, n, om, xm)
+
+
+@pytest.mark.parametrize("seed", [1234, 99])
+def test_oracle_vs_reference_synthetic(O, R, seed):
+    blobs = synth_blobs(R, seed, 100)
+    rng = np.random.default_rng(seed)
+    for _ in range(400):
+        i, j = rng.integers(0, len(blobs), 2)
+        for op in OPS:
+            assert O.op_bytes(op, blobs[i], blobs[j]) == R.op_bytes(op, blobs[i], blobs[j]), (op, i, j)
+        ra, rb_ = R.deserialize(blobs[i]), R.deserialize(blobs[j])
+        assert O.and_cardinality(blobs[i], blobs[j]) == int(R.L.roaring_bitmap_and_cardinality(ra, rb_))
+        R.free(ra), R.free(rb_)
+    for _ in range(200):
+        idx = rng.integers(0, len(blobs), int(rng.integers(0, 9)))
+        sub = [blobs[k] for k in idx]
+        for name in ("or_many", "xor_many"):
+            assert O.many_bytes(name, sub) == R.many_bytes(name, sub), (name, idx.tolist())
+
+
+def test_reference_known_answers(R, O):
+    """Known answers of the reference's own tests: tests/toplevel_unit.c:1730-1806
+    (array x array -> 2*34 ; bitset x bitset -> 26666)."""
+    a = np.arange(0, 100, dtype=np.uint32) * 2
+    b = np.arange(0, 100, dtype=np.uint32) * 3
+    r1, r2 = R.from_values(a, False), R.from_values(b, False)
+    exp = len(np.intersect1d(a, b))
+    assert O.and_cardinality(R.serialize(r1), R.serialize(r2)) == exp == 34
+    x1 = R.from_values(np.arange(0, 20000, dtype=np.uint32) * 2, False)   # toplevel_unit.c:1781
+    x2 = R.from_values(np.arange(0, 20000, dtype=np.uint32) * 3, False)
+    inter = len(np.intersect1d(np.arange(20000) * 2, np.arange(20000) * 3))
+    out = O.op_bytes("and", R.serialize(x1), R.serialize(x2))
+    assert O.cardinality(out) == inter == 6667
+    assert out == R.op_bytes("and", R.serialize(x1), R.serialize(x2))
+    for r in (r1, r2, x1, x2):
+        R.free(r)
