@@ -260,10 +260,9 @@ def main():
                 ia, ib = pairs[ds]
                 for op in OPS:
                     r = S.batch(op, S, ia, ib)
-                    outs = r.download_all()                        # D2H + host materialisation
+                    outs = r.download_all_raw()                    # D2H + host materialisation
                     d2h += int(rb.api.lib().rb200_last_download_bytes())
-                    for o in outs:
-                        o.free()
+                    rb.DeviceSet.free_raw(outs)                    # roaring_bitmap_free x npairs
                     r.free()
                 S.free()
 

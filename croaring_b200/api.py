@@ -75,6 +75,7 @@ def lib():
     sig("rb200_set_cardinalities", C.c_int, _P, _P)
     sig("rb200_set_download", _P, _P, C.c_size_t)
     sig("rb200_set_download_all", C.c_int, _P, C.POINTER(_P))
+    sig("rb200_bitmaps_free", None, C.POINTER(_P), C.c_size_t)
     sig("rb200_batch_op_host", C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_size_t,
         C.POINTER(_P))
     _lib = L
@@ -284,6 +285,19 @@ class DeviceSet:
 
     def download(self, i):
         return Bitmap(lib().rb200_set_download(self.ptr, i))
+
+    def download_all_raw(self):
+        """All bitmaps as a ctypes array of roaring_bitmap_t* (no Python wrappers); release with
+        free_raw().  This is the bulk form bench.py's e2e leg times."""
+        n = len(self)
+        out = (_P * n)()
+        if lib().rb200_set_download_all(self.ptr, out) != 0:
+            raise RB200Error(last_error())
+        return out
+
+    @staticmethod
+    def free_raw(arr):
+        lib().rb200_bitmaps_free(arr, len(arr))
 
     def download_all(self):
         n = len(self)

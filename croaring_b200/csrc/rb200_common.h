@@ -95,6 +95,12 @@ void launch_finalize_cards(Items it, const uint64_t *item_off, uint32_t npairs, 
                            cudaStream_t s);
 void launch_set_cardinalities(const SetView &S, uint32_t n_bitmaps, uint64_t *out, cudaStream_t s);
 
+// packing for download: measure+scan (off/beg have n+1 entries), then copy
+void launch_pack(const SetView &S, uint32_t n, uint64_t *bytes, uint32_t *cnts, uint64_t *off,
+                 uint64_t *beg, cudaStream_t s);
+void launch_pack_copy(const SetView &S, uint32_t n, const uint64_t *off, const uint64_t *beg,
+                      SetOut out, cudaStream_t s);
+
 // or_many: mark -> compact keys -> reduce per key
 void launch_many_mark(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo,
                       uint32_t key_hi, uint32_t *flags /*65536*/, cudaStream_t s);

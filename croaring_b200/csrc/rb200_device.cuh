@@ -211,15 +211,15 @@ __device__ __forceinline__ void acc_apply_array(uint32_t *acc, const uint8_t *sr
     for (uint32_t i = lane; i < nvec; i += 32) {
         const uint4 q = __ldg(v4 + i);
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        const uint32_t base = i * 8;
-        uint32_t cur_w = 0xffffffffu, cur_m = 0;
+        const uint32_t left = n - i * 8;           // values valid in this vector (>= 1)
+        uint32_t cur_w = (w[0] & 0xffffu) >> 5, cur_m = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            if (base + k < n) {
-                const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
-                const uint32_t wi = v >> 5, bit = 1u << (v & 31);
+            const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+            const uint32_t wi = v >> 5, bit = 1u << (v & 31);
+            if (k == 0 || k < (int)left) {         // k == 0 is always valid
                 if (wi != cur_w) {
-                    if (cur_m) acc_atom<MODE>(acc + cur_w, cur_m);
+                    acc_atom<MODE>(acc + cur_w, cur_m);
                     cur_w = wi;
                     cur_m = bit;
                 } else {
@@ -227,7 +227,7 @@ __device__ __forceinline__ void acc_apply_array(uint32_t *acc, const uint8_t *sr
                 }
             }
         }
-        if (cur_m) acc_atom<MODE>(acc + cur_w, cur_m);
+        acc_atom<MODE>(acc + cur_w, cur_m);
     }
 }
 
@@ -445,23 +445,32 @@ __device__ __forceinline__ void acc_count(const uint32_t *acc, int lane, bool wa
     nruns = __reduce_add_sync(FULLMASK, r);
 }
 
-// acc -> sorted u16 list (array_container_from_bitset): per 32-word stripe, per-lane
-// popcount -> warp scan -> every lane emits its bits at its offset.
+// acc -> sorted u16 list (array_container_from_bitset).  16 stripes of 128 words: every lane
+// owns one 128-bit group per stripe (conflict-free LDS.128, value order == lane order),
+// per-lane popcount -> warp scan -> every lane emits its bits at its offset, so a stripe's
+// output is one contiguous, mostly sector-coalesced range.
 __device__ __forceinline__ uint32_t acc_emit_array(const uint32_t *acc, uint16_t *out, int lane) {
     uint32_t base = 0;
-    for (int it = 0; it < 64; it++) {
-        const uint32_t w = it * 32 + lane;
-        uint32_t x = acc[w];
-        if (!__any_sync(FULLMASK, x != 0)) continue;
-        const uint32_t c = __popc(x);
+#pragma unroll 1
+    for (int it = 0; it < 16; it++) {
+        const uint4 q = reinterpret_cast<const uint4 *>(acc)[it * 32 + lane];
+        const uint32_t c = popc4(q);
+        if (!__any_sync(FULLMASK, c != 0)) continue;
         const uint32_t incl = warp_incl_scan(c, lane);
         const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
         uint16_t *p = out + base + incl - c;
-        const uint32_t hi = w << 5;
-        while (x) {
-            const int b = __ffs(x) - 1;
-            x &= x - 1;
+        const uint32_t hi = (uint32_t)(it * 32 + lane) << 7;
+        unsigned long long lo64 = ((unsigned long long)q.y << 32) | q.x;
+        unsigned long long hi64 = ((unsigned long long)q.w << 32) | q.z;
+        while (lo64) {
+            const int b = __ffsll((long long)lo64) - 1;
+            lo64 &= lo64 - 1;
             *p++ = (uint16_t)(hi | b);
+        }
+        while (hi64) {
+            const int b = __ffsll((long long)hi64) - 1;
+            hi64 &= hi64 - 1;
+            *p++ = (uint16_t)(hi | 64 | b);
         }
         base += total;
     }

@@ -13,6 +13,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1241,20 +1243,153 @@ roaring_bitmap_t *rb200_set_download(const rb200_set_t *cs, size_t i) {
     return build_bitmap(s, i);
 }
 
+// Download every bitmap of a set as host roaring_bitmap_t (reference layout).
+// Pipeline: (1) device-side pack — directory in bitmap order, payload contiguous in bitmap
+// order, no slot slack; (2) D2H of the payload in ~32 MB chunks of whole bitmaps into pinned
+// memory, one event per chunk; (3) host threads build the bitmaps of a chunk (per-container
+// roaring_malloc + memcpy, the ownership contract of src/containers/containers.c:58-77) as soon
+// as its event fires, while later chunks are still crossing PCIe.
 int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
-    rb200_set *s = const_cast<rb200_set *>(cs);
-    if (!ensure_mirror(s)) return -1;
-    for (size_t i = 0; i < s->n_bitmaps; i++) {
-        out[i] = build_bitmap(s, i);
-        if (!out[i]) {
-            for (size_t k = 0; k < i; k++) bitmap_free_host(out[k]);
-            g.err = "download: host allocation failed";
-            return -1;
+    if (!ctx_init()) return -1;
+    const rb200_set *s = cs;
+    const size_t nb = s->n_bitmaps;
+    if (nb == 0) return 0;
+    // ---- (1) pack
+    uint64_t *d_bytes = (uint64_t *)dev_alloc(8 * nb), *d_off = (uint64_t *)dev_alloc(8 * (nb + 1)),
+             *d_beg = (uint64_t *)dev_alloc(8 * (nb + 1));
+    uint32_t *d_cnt = (uint32_t *)dev_alloc(4 * nb);
+    uint64_t *h_ob = (uint64_t *)pin_alloc(16 * (nb + 1));
+    rb200_set *P = nullptr;
+    uint8_t *hp = nullptr;
+    size_t hp_bytes = 0;
+    std::vector<cudaEvent_t> evs;
+    bool ok = d_bytes && d_off && d_beg && d_cnt && h_ob;
+    if (ok) {
+        launch_pack(s->view(), (uint32_t)nb, d_bytes, d_cnt, d_off, d_beg, g.stream);
+        ok = cudaMemcpyAsync(h_ob, d_off, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaMemcpyAsync(h_ob + nb + 1, d_beg, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaStreamSynchronize(g.stream) == cudaSuccess;
+    }
+    const uint64_t *h_off = h_ob, *h_beg = h_ob ? h_ob + nb + 1 : nullptr;
+    if (ok) {
+        P = set_new((uint32_t)nb, h_beg[nb], h_off[nb]);
+        ok = P != nullptr;
+    }
+    if (ok) {
+        P->n_containers = h_beg[nb];
+        P->slab_used = h_off[nb];
+        P->h_flags = s->h_flags;
+        launch_pack_copy(s->view(), (uint32_t)nb, d_off, d_beg, P->out(), g.stream);
+        // ---- (2) directory, then payload chunks
+        P->m_dir = (uint8_t *)pin_alloc(P->L.total);
+        hp_bytes = P->slab_used;
+        hp = (uint8_t *)pin_alloc(hp_bytes);
+        ok = P->m_dir && hp;
+    }
+    std::vector<size_t> chunk_end;  // bitmap index (exclusive) closing each chunk
+    if (ok) {
+        P->m_slab = hp;
+        ok = cudaMemcpyAsync(P->m_dir, P->d_dir, P->L.total, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+        const uint64_t CH = (uint64_t)32 << 20;
+        size_t p0 = 0;
+        while (ok && p0 < nb) {
+            size_t p1 = p0 + 1;
+            while (p1 < nb && h_off[p1 + 1] - h_off[p0] <= CH) p1++;
+            const uint64_t b0 = h_off[p0], b1 = h_off[p1];
+            if (b1 > b0)
+                ok = cudaMemcpyAsync(hp + b0, P->d_slab + b0, b1 - b0, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+            cudaEvent_t ev;
+            ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+            if (ok) {
+                cudaEventRecord(ev, g.stream);
+                evs.push_back(ev);
+                chunk_end.push_back(p1);
+            }
+            p0 = p1;
         }
     }
-    set_drop_mirror(s);
-    return 0;
+    // ---- (3) host threads
+    if (ok) {
+        std::atomic<size_t> next(0);
+        std::atomic<int> failed(0);
+        const size_t BLK = 16;
+        unsigned T = std::thread::hardware_concurrency();
+        if (T > 48) T = 48;
+        if (T < 1) T = 1;
+        if ((size_t)T * BLK > nb) T = (unsigned)((nb + BLK - 1) / BLK);
+        const int dev = g.device;
+        auto work = [&]() {
+            cudaSetDevice(dev);
+            size_t cur = 0, done_upto = 0;  // chunks [0, done_upto) are known complete
+            for (;;) {
+                const size_t i0 = next.fetch_add(BLK);
+                if (i0 >= nb) break;
+                const size_t i1 = std::min(nb, i0 + BLK);
+                while (cur + 1 < chunk_end.size() && chunk_end[cur] < i1) cur++;
+                // the chunk holding bitmap i1-1 (and every earlier one: same stream) must be done
+                if (cur >= done_upto) {
+                    if (cudaEventSynchronize(evs[cur]) != cudaSuccess) { failed = 1; break; }
+                    done_upto = cur + 1;
+                }
+                for (size_t i = i0; i < i1; i++) {
+                    out[i] = build_bitmap(P, i);
+                    if (!out[i]) failed = 1;
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        if (cudaStreamSynchronize(g.stream) != cudaSuccess) failed = 1;
+        if (failed) {
+            for (size_t i = 0; i < nb; i++) { bitmap_free_host(out[i]); out[i] = nullptr; }
+            g.err = "download: host allocation or copy failed";
+            ok = false;
+        }
+        g.last_download_bytes = P->L.total + P->slab_used;
+    } else {
+        cudaStreamSynchronize(g.stream);
+        if (g.err.empty()) g.err = "download: packing failed";
+    }
+    for (auto ev : evs) cudaEventDestroy(ev);
+    if (P) {
+        pin_free(P->m_dir, P->L.total);
+        P->m_dir = nullptr;
+        P->m_slab = nullptr;
+        set_delete(P);
+    }
+    pin_free(hp, hp_bytes);
+    pin_free(h_ob, 16 * (nb + 1));
+    dev_free(d_bytes, 8 * nb);
+    dev_free(d_off, 8 * (nb + 1));
+    dev_free(d_beg, 8 * (nb + 1));
+    dev_free(d_cnt, 4 * nb);
+    return ok ? 0 : -1;
+}
+
+// Free many host bitmaps (results of rb200_set_download_all) with several threads.
+void rb200_bitmaps_free(roaring_bitmap_t **bms, size_t n) {
+    unsigned T = std::thread::hardware_concurrency();
+    if (T > 32) T = 32;
+    if (n < 256 || T <= 1) {
+        for (size_t i = 0; i < n; i++) bitmap_free_host(bms[i]);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const size_t i0 = next.fetch_add(64);
+            if (i0 >= n) break;
+            const size_t i1 = std::min(n, i0 + 64);
+            for (size_t i = i0; i < i1; i++) bitmap_free_host(bms[i]);
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
 }
 
 int rb200_batch_op_host(int op, const roaring_bitmap_t *const *a, const roaring_bitmap_t *const *b,

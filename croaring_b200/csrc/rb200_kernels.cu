@@ -220,14 +220,19 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, int op, uint8_t *sla
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
     const int lane = threadIdx.x & 31;
     uint32_t *acc = s_acc[threadIdx.x >> 5];
-    unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(&st->work_counter, 1ull);
-    item = __shfl_sync(FULLMASK, item, 0);
-    while (item < W) {
+    // dynamic scheduling: a ticket is TICKET consecutive items; the next ticket is requested
+    // before the current one is processed so its latency hides behind the work.
+    constexpr unsigned long long TICKET = 4;
+    unsigned long long tk = 0;
+    if (lane == 0) tk = atomicAdd(&st->work_counter, TICKET);
+    tk = __shfl_sync(FULLMASK, tk, 0);
+    while (tk < W) {
         unsigned long long next = 0;
-        if (lane == 0) next = atomicAdd(&st->work_counter, 1ull);  // prefetch the next ticket
-        const int kind = it.kind[item];
-        if (kind != K_HOLE) {
+        if (lane == 0) next = atomicAdd(&st->work_counter, TICKET);
+        const unsigned long long tend = tk + TICKET < W ? tk + TICKET : W;
+        for (unsigned long long item = tk; item < tend; item++) {
+            const int kind = it.kind[item];
+            if (kind == K_HOLE) continue;
             const uint64_t off = it.slot_off[item];
             const uint32_t cap = it.slot_cap[item];
             int otype = 0;
@@ -253,7 +258,7 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, int op, uint8_t *sla
                 it.olen[item] = olen;
             }
         }
-        item = __shfl_sync(FULLMASK, next, 0);
+        tk = __shfl_sync(FULLMASK, next, 0);
     }
 }
 
@@ -298,13 +303,16 @@ k_card_items(SetView A, SetView B, Items it, uint64_t W, OpStats *st) {
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
     const int lane = threadIdx.x & 31;
     uint32_t *acc = s_acc[threadIdx.x >> 5];
-    unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(&st->work_counter, 1ull);
-    item = __shfl_sync(FULLMASK, item, 0);
-    while (item < W) {
+    constexpr unsigned long long TICKET = 8;
+    unsigned long long tk = 0;
+    if (lane == 0) tk = atomicAdd(&st->work_counter, TICKET);
+    tk = __shfl_sync(FULLMASK, tk, 0);
+    while (tk < W) {
         unsigned long long next = 0;
-        if (lane == 0) next = atomicAdd(&st->work_counter, 1ull);
-        if (it.kind[item] == K_COMPUTE) {
+        if (lane == 0) next = atomicAdd(&st->work_counter, TICKET);
+        const unsigned long long tend = tk + TICKET < W ? tk + TICKET : W;
+        for (unsigned long long item = tk; item < tend; item++) {
+            if (it.kind[item] != K_COMPUTE) continue;
             const uint32_t ca = it.ca[item], cb = it.cb[item];
             const uint32_t c =
                 cell_and_card(acc, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
@@ -312,7 +320,7 @@ k_card_items(SetView A, SetView B, Items it, uint64_t W, OpStats *st) {
                               B.c_len[cb], lane);
             if (lane == 0) it.ocard[item] = c;
         }
-        item = __shfl_sync(FULLMASK, next, 0);
+        tk = __shfl_sync(FULLMASK, next, 0);
     }
 }
 
@@ -744,6 +752,117 @@ __global__ void k_sum_cards(const uint32_t *__restrict__ c_card, const OpStats *
     }
 }
 
+// ------------------------------------------------------------------------------ packing
+// Compact a set for download: directory in bitmap order, payload contiguous in bitmap order
+// without slot slack, so that any range of bitmaps is one directory range + one payload range
+// (chunked D2H overlapped with host materialisation).
+__global__ void __launch_bounds__(128)
+k_pack_measure(SetView S, uint32_t n, uint64_t *__restrict__ bytes, uint32_t *__restrict__ cnts) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < n; b += nwarps) {
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        unsigned long long v = 0;
+        for (uint32_t i = lane; i < nc; i += 32)
+            v += round16(stored_bytes(S.c_type[c0 + i], S.c_len[c0 + i]));
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+        if (lane == 0) {
+            bytes[b] = v;
+            cnts[b] = nc;
+        }
+    }
+}
+
+// single CTA: exclusive scans of per-bitmap container counts and payload bytes
+// (n+1 outputs each: the last entry is the total)
+__global__ void __launch_bounds__(1024)
+k_pack_scan(const uint64_t *__restrict__ bytes, const uint32_t *__restrict__ cnts, uint32_t n,
+            uint64_t *__restrict__ off_out, uint64_t *__restrict__ beg_out) {
+    __shared__ unsigned long long s_b[32], s_c[32];
+    __shared__ unsigned long long carry_b, carry_c;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_b = carry_c = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        unsigned long long vb = i < n ? bytes[i] : 0ull, vc = i < n ? cnts[i] : 0ull;
+        unsigned long long ib = vb, ic = vc;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long tb = __shfl_up_sync(FULLMASK, ib, d), tc = __shfl_up_sync(FULLMASK, ic, d);
+            if (lane >= d) { ib += tb; ic += tc; }
+        }
+        if (lane == 31) { s_b[wid] = ib; s_c[wid] = ic; }
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long wb = s_b[lane], wc = s_c[lane], xb = wb, xc = wc;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long tb = __shfl_up_sync(FULLMASK, xb, d), tc = __shfl_up_sync(FULLMASK, xc, d);
+                if (lane >= d) { xb += tb; xc += tc; }
+            }
+            s_b[lane] = xb - wb;
+            s_c[lane] = xc - wc;
+        }
+        __syncthreads();
+        const unsigned long long eb = carry_b + s_b[wid] + ib - vb, ec = carry_c + s_c[wid] + ic - vc;
+        if (i < n) { off_out[i] = eb; beg_out[i] = ec; }
+        __syncthreads();
+        if (tid == 1023) { carry_b = eb + vb; carry_c = ec + vc; }
+        __syncthreads();
+    }
+    if (tid == 0) { off_out[n] = carry_b; beg_out[n] = carry_c; }
+}
+
+__global__ void __launch_bounds__(128)
+k_pack_copy(SetView S, uint32_t n, const uint64_t *__restrict__ off_in,
+            const uint64_t *__restrict__ beg_in, SetOut out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < n; b += nwarps) {
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        const uint64_t nb = beg_in[b];
+        uint64_t run = off_in[b];
+        unsigned long long card = 0;
+        for (uint32_t i0 = 0; i0 < nc; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t sz = 0, t = 0, len = 0, cd = 0;
+            uint64_t soff = 0;
+            if (i < nc) {
+                t = S.c_type[c0 + i];
+                len = S.c_len[c0 + i];
+                cd = S.c_card[c0 + i];
+                soff = S.c_off[c0 + i];
+                sz = round16(stored_bytes(t, len));
+            }
+            const uint32_t incl = warp_incl_scan(sz, lane);
+            const uint64_t doff = run + incl - sz;
+            if (i < nc) {
+                out.c_key[nb + i] = S.c_key[c0 + i];
+                out.c_type[nb + i] = (uint8_t)t;
+                out.c_card[nb + i] = cd;
+                out.c_len[nb + i] = len;
+                out.c_off[nb + i] = doff;
+                card += cd;
+            }
+            // the warp copies the (up to 32) payloads one after the other
+            const uint32_t m = nc - i0 < 32 ? nc - i0 : 32;
+            for (uint32_t k = 0; k < m; k++) {
+                const uint64_t so = __shfl_sync(FULLMASK, soff, k), d_o = __shfl_sync(FULLMASK, doff, k);
+                const uint32_t bytes = __shfl_sync(FULLMASK, sz, k);
+                warp_copy16(out.payload + d_o, S.payload + so, bytes, lane);
+            }
+            run += __shfl_sync(FULLMASK, incl, 31);
+        }
+        for (int d = 16; d > 0; d >>= 1) card += __shfl_xor_sync(FULLMASK, card, d);
+        if (lane == 0) {
+            out.bm_beg[b] = (uint32_t)nb;
+            out.bm_cnt[b] = nc;
+            out.bm_card[b] = card;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ launchers
 static inline uint32_t blocks_for_warps(uint64_t warps, int warps_per_block, int max_blocks) {
     uint64_t b = (warps + warps_per_block - 1) / warps_per_block;
@@ -764,7 +883,7 @@ void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, c
 void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
                           uint8_t *slab, uint64_t slab_cap, OpStats *st, cudaStream_t s) {
     if (!W) return;
-    const uint32_t g = blocks_for_warps(W, 4, sm_count() * 7);
+    const uint32_t g = blocks_for_warps((W + 3) / 4, 4, sm_count() * 6);
     k_compute_items<<<g, 128, 0, s>>>(A, B, it, W, op, slab, slab_cap, st);
     g_launches++;
 }
@@ -772,7 +891,7 @@ void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t
 void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W, OpStats *st,
                        cudaStream_t s) {
     if (!W) return;
-    const uint32_t g = blocks_for_warps(W, 4, sm_count() * 7);
+    const uint32_t g = blocks_for_warps((W + 7) / 8, 4, sm_count() * 5);
     k_card_items<<<g, 128, 0, s>>>(A, B, it, W, st);
     g_launches++;
 }
@@ -822,4 +941,21 @@ void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uin
     g_launches++;
 }
 
+}  // namespace rb200
+
+namespace rb200 {
+void launch_pack(const SetView &S, uint32_t n, uint64_t *bytes, uint32_t *cnts, uint64_t *off,
+                 uint64_t *beg, cudaStream_t s) {
+    const uint32_t g = blocks_for_warps(n ? n : 1, 4, sm_count() * 16);
+    k_pack_measure<<<g, 128, 0, s>>>(S, n, bytes, cnts);
+    k_pack_scan<<<1, 1024, 0, s>>>(bytes, cnts, n, off, beg);
+    g_launches += 2;
+}
+void launch_pack_copy(const SetView &S, uint32_t n, const uint64_t *off, const uint64_t *beg,
+                      SetOut out, cudaStream_t s) {
+    if (!n) return;
+    const uint32_t g = blocks_for_warps(n, 4, sm_count() * 16);
+    k_pack_copy<<<g, 128, 0, s>>>(S, n, off, beg, out);
+    g_launches++;
+}
 }  // namespace rb200

@@ -142,6 +142,8 @@ int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out);
  * owned by the caller (free with roaring_bitmap_free or rb200_bitmap_free). */
 roaring_bitmap_t *rb200_set_download(const rb200_set_t *s, size_t i);
 int rb200_set_download_all(const rb200_set_t *s, roaring_bitmap_t **out);
+/* Free n host bitmaps (e.g. the results of rb200_set_download_all) using several threads. */
+void rb200_bitmaps_free(roaring_bitmap_t **bitmaps, size_t n);
 
 /* Host-to-host batch through the device (what the drop-in symbols do for one pair):
  * upload a[], b[] -> batch op -> download.  out[k] owned by the caller. 0 on success. */
