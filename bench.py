@@ -260,9 +260,12 @@ def main():
                 ia, ib = pairs[ds]
                 for op in OPS:
                     r = S.batch(op, S, ia, ib)
-                    outs = r.download_all_raw()                    # D2H + host materialisation
+                    # streaming D2H + host materialisation; every result bitmap is built in the
+                    # reference layout, handed to the caller, then freed (as the reference's
+                    # benchmark loop does with each result, microbenchmarks/bench.cpp:85-96)
+                    for arr, n in r.download_stream(4096):
+                        rb.DeviceSet.free_raw(arr, n)
                     d2h += int(rb.api.lib().rb200_last_download_bytes())
-                    rb.DeviceSet.free_raw(outs)                    # roaring_bitmap_free x npairs
                     r.free()
                 S.free()
 
@@ -280,7 +283,8 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": args.e2e_steps, "host_threads": host_threads(),
                "api": "rb200_set_upload(host roaring_bitmap_t[]) -> rb200_batch_op -> "
-                      "rb200_set_download_all (host roaring_bitmap_t[] in reference layout)"}
+                      "rb200_download_begin/next/end (every result as host roaring_bitmap_t in the "
+                      "reference layout, chunks of <=4096 bitmaps / 64 MB) -> rb200_bitmaps_free"}
 
     if rank != 0:
         if world > 1:

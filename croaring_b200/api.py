@@ -76,6 +76,10 @@ def lib():
     sig("rb200_set_download", _P, _P, C.c_size_t)
     sig("rb200_set_download_all", C.c_int, _P, C.POINTER(_P))
     sig("rb200_bitmaps_free", None, C.POINTER(_P), C.c_size_t)
+    sig("rb200_download_begin", _P, _P, C.c_size_t)
+    sig("rb200_download_chunk_capacity", C.c_size_t, _P)
+    sig("rb200_download_next", C.c_size_t, _P, C.POINTER(_P))
+    sig("rb200_download_end", None, _P)
     sig("rb200_batch_op_host", C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_size_t,
         C.POINTER(_P))
     _lib = L
@@ -296,8 +300,27 @@ class DeviceSet:
         return out
 
     @staticmethod
-    def free_raw(arr):
-        lib().rb200_bitmaps_free(arr, len(arr))
+    def free_raw(arr, n=None):
+        lib().rb200_bitmaps_free(arr, len(arr) if n is None else n)
+
+    def download_stream(self, chunk_bitmaps=1024):
+        """Generator over (ctypes array of roaring_bitmap_t*, count): streaming download.  The
+        caller owns each chunk's bitmaps (free with DeviceSet.free_raw(arr, n))."""
+        st = lib().rb200_download_begin(self.ptr, chunk_bitmaps)
+        if not st:
+            raise RB200Error(last_error())
+        try:
+            cap = max(1, int(lib().rb200_download_chunk_capacity(st)))
+            while True:
+                out = (_P * cap)()
+                n = lib().rb200_download_next(st, out)
+                if n == 0:
+                    break
+                if n == 2 ** 64 - 1:
+                    raise RB200Error(last_error())
+                yield out, int(n)
+        finally:
+            lib().rb200_download_end(st)
 
     def download_all(self):
         n = len(self)

@@ -14,6 +14,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <stdio.h>
 #include <thread>
 #include <map>
 #include <mutex>
@@ -1203,7 +1207,8 @@ bool ensure_mirror(rb200_set *s) {
     return ok;
 }
 
-roaring_bitmap_t *build_bitmap(const rb200_set *s, size_t i) {
+roaring_bitmap_t *build_bitmap(const rb200_set *s, size_t i, const uint8_t *slab = nullptr, uint64_t bias = 0) {
+    if (!slab) slab = s->m_slab;
     const uint32_t *bm_beg = (const uint32_t *)(s->m_dir + s->L.o_beg);
     const uint32_t *bm_cnt = (const uint32_t *)(s->m_dir + s->L.o_cnt);
     const uint16_t *c_key = (const uint16_t *)(s->m_dir + s->L.o_key);
@@ -1218,7 +1223,7 @@ roaring_bitmap_t *build_bitmap(const rb200_set *s, size_t i) {
     ra->flags = s->h_flags[i] & FLAG_COW;  // roaring.c:738,890
     for (uint32_t k = 0; k < cnt; k++) {
         const uint32_t c = beg + k;
-        void *hc = container_from_payload(c_type[c], c_card[c], c_len[c], s->m_slab + c_off[c]);
+        void *hc = container_from_payload(c_type[c], c_card[c], c_len[c], slab + (c_off[c] - bias));
         if (!hc) {
             bitmap_free_host(r);
             return nullptr;
@@ -1234,6 +1239,235 @@ roaring_bitmap_t *build_bitmap(const rb200_set *s, size_t i) {
 }  // namespace
 
 extern "C" {
+
+}  // extern "C" (reopened below)
+
+namespace {
+
+// Persistent host worker pool (materialisation / bulk free).  run(fn, T) executes fn() on T
+// threads (the caller is one of them); fn pulls its own work from a shared atomic counter.
+class Pool {
+   public:
+    void run(const std::function<void()> &fn, unsigned T) {
+        if (T <= 1) { fn(); return; }
+        std::unique_lock<std::mutex> lk(mu_);
+        while (workers_.size() < T - 1) workers_.emplace_back([this]() { loop(); });
+        fn_ = &fn;
+        want_ = T - 1;
+        started_ = 0;
+        running_ = 0;
+        gen_++;
+        lk.unlock();
+        cv_.notify_all();
+        fn();
+        lk.lock();
+        done_cv_.wait(lk, [this]() { return started_ == want_ && running_ == 0; });
+        fn_ = nullptr;
+    }
+
+   private:
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&]() { return gen_ != seen && fn_ != nullptr && started_ < want_; });
+            seen = gen_;
+            started_++;
+            running_++;
+            const std::function<void()> *f = fn_;
+            lk.unlock();
+            (*f)();
+            lk.lock();
+            running_--;
+            if (started_ == want_ && running_ == 0) done_cv_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> workers_;
+    const std::function<void()> *fn_ = nullptr;
+    unsigned want_ = 0, started_ = 0, running_ = 0;
+    uint64_t gen_ = 0;
+};
+Pool &pool() {
+    static Pool *p = new Pool();  // intentionally leaked: workers are detached for process life
+    return *p;
+}
+unsigned host_workers() {
+    static unsigned T = 0;
+    if (!T) {
+        const char *e = getenv("RB200_HOST_THREADS");
+        T = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
+        if (T > 64) T = 64;
+        if (T < 1) T = 1;
+    }
+    return T;
+}
+
+}  // namespace
+
+// Streaming download: results leave the device chunk by chunk while the caller consumes (and
+// frees) the previous chunk, so host memory stays bounded and D2H overlaps materialisation.
+struct rb200_download_stream {
+    rb200_set *P = nullptr;        // packed copy (device)
+    size_t nb = 0;
+    uint64_t *h_ob = nullptr;      // [off(nb+1) | beg(nb+1)] pinned
+    std::vector<size_t> chunk_end; // bitmap index closing each chunk
+    uint8_t *hbuf[2] = {nullptr, nullptr};
+    size_t hbuf_bytes = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    size_t next_copy = 0, next_build = 0;
+    uint64_t total_bytes = 0;
+};
+
+namespace {
+
+bool stream_enqueue(rb200_download_stream *st) {
+    if (st->next_copy >= st->chunk_end.size()) return true;
+    const size_t k = st->next_copy;
+    const size_t p0 = k ? st->chunk_end[k - 1] : 0, p1 = st->chunk_end[k];
+    const uint64_t b0 = st->h_ob[p0], b1 = st->h_ob[p1];
+    if (b1 > b0 && cudaMemcpyAsync(st->hbuf[k & 1], st->P->d_slab + b0, b1 - b0, cudaMemcpyDeviceToHost,
+                                   g.stream) != cudaSuccess)
+        return false;
+    cudaEventRecord(st->ev[k & 1], g.stream);
+    st->next_copy++;
+    return true;
+}
+
+void stream_free(rb200_download_stream *st) {
+    if (!st) return;
+    cudaStreamSynchronize(g.stream);
+    for (int k = 0; k < 2; k++) {
+        if (st->ev[k]) cudaEventDestroy(st->ev[k]);
+        pin_free(st->hbuf[k], st->hbuf_bytes);
+    }
+    if (st->P) {
+        pin_free(st->P->m_dir, st->P->L.total);
+        st->P->m_dir = st->P->m_slab = nullptr;
+        set_delete(st->P);
+    }
+    pin_free(st->h_ob, 16 * (st->nb + 1));
+    delete st;
+}
+
+}  // namespace
+
+extern "C" {
+
+rb200_download_stream_t *rb200_download_begin(const rb200_set_t *s, size_t chunk_bitmaps) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return nullptr;
+    const size_t nb = s->n_bitmaps;
+    rb200_download_stream *st = new rb200_download_stream();
+    st->nb = nb;
+    if (nb == 0) return st;
+    if (chunk_bitmaps == 0) chunk_bitmaps = 1024;
+    uint64_t *d_bytes = (uint64_t *)dev_alloc(8 * nb), *d_off = (uint64_t *)dev_alloc(8 * (nb + 1)),
+             *d_beg = (uint64_t *)dev_alloc(8 * (nb + 1));
+    uint32_t *d_cnt = (uint32_t *)dev_alloc(4 * nb);
+    st->h_ob = (uint64_t *)pin_alloc(16 * (nb + 1));
+    bool ok = d_bytes && d_off && d_beg && d_cnt && st->h_ob;
+    if (ok) {
+        launch_pack(s->view(), (uint32_t)nb, d_bytes, d_cnt, d_off, d_beg, g.stream);
+        ok = cudaMemcpyAsync(st->h_ob, d_off, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaMemcpyAsync(st->h_ob + nb + 1, d_beg, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaStreamSynchronize(g.stream) == cudaSuccess;
+    }
+    const uint64_t *h_off = st->h_ob, *h_beg = st->h_ob ? st->h_ob + nb + 1 : nullptr;
+    if (ok) {
+        st->P = set_new((uint32_t)nb, h_beg[nb], h_off[nb]);
+        ok = st->P != nullptr;
+    }
+    if (ok) {
+        rb200_set *P = st->P;
+        P->n_containers = h_beg[nb];
+        P->slab_used = h_off[nb];
+        P->h_flags = s->h_flags;
+        launch_pack_copy(s->view(), (uint32_t)nb, d_off, d_beg, P->out(), g.stream);
+        P->m_dir = (uint8_t *)pin_alloc(P->L.total);
+        ok = P->m_dir != nullptr &&
+             cudaMemcpyAsync(P->m_dir, P->d_dir, P->L.total, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+        // chunks: at most chunk_bitmaps bitmaps and ~64 MB of payload each
+        const uint64_t CAP = (uint64_t)64 << 20;
+        uint64_t maxb = 0;
+        size_t p0 = 0;
+        while (p0 < nb) {
+            size_t p1 = p0 + 1;
+            while (p1 < nb && p1 - p0 < chunk_bitmaps && h_off[p1 + 1] - h_off[p0] <= CAP) p1++;
+            st->chunk_end.push_back(p1);
+            maxb = std::max(maxb, h_off[p1] - h_off[p0]);
+            p0 = p1;
+        }
+        st->hbuf_bytes = maxb;
+        for (int k = 0; k < 2 && ok; k++) {
+            st->hbuf[k] = (uint8_t *)pin_alloc(maxb);
+            ok = st->hbuf[k] != nullptr && cudaEventCreateWithFlags(&st->ev[k], cudaEventDisableTiming) == cudaSuccess;
+        }
+        st->total_bytes = P->L.total + P->slab_used;
+        g.last_download_bytes = st->total_bytes;
+        ok = ok && stream_enqueue(st) && stream_enqueue(st);
+    }
+    dev_free(d_bytes, 8 * nb);
+    dev_free(d_off, 8 * (nb + 1));
+    dev_free(d_beg, 8 * (nb + 1));
+    dev_free(d_cnt, 4 * nb);
+    if (!ok) {
+        if (g.err.empty()) g.err = "download_begin failed";
+        stream_free(st);
+        return nullptr;
+    }
+    return st;
+}
+
+size_t rb200_download_chunk_capacity(const rb200_download_stream_t *st) {
+    size_t m = 0, p0 = 0;
+    for (size_t e : st->chunk_end) { m = std::max(m, e - p0); p0 = e; }
+    return m;
+}
+
+// Materialise the next chunk into out[] (capacity >= rb200_download_chunk_capacity); returns the
+// number of bitmaps produced, 0 at the end of the stream, (size_t)-1 on error.
+size_t rb200_download_next(rb200_download_stream_t *st, roaring_bitmap_t **out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (st->next_build >= st->chunk_end.size()) return 0;
+    const size_t k = st->next_build;
+    const size_t p0 = k ? st->chunk_end[k - 1] : 0, p1 = st->chunk_end[k];
+    if (cudaEventSynchronize(st->ev[k & 1]) != cudaSuccess) { g.err = "download_next: copy failed"; return (size_t)-1; }
+    const uint8_t *buf = st->hbuf[k & 1];
+    const uint64_t bias = st->h_ob[p0];
+    const size_t n = p1 - p0;
+    std::atomic<size_t> next(0);
+    std::atomic<int> failed(0);
+    const rb200_set *P = st->P;
+    std::function<void()> work = [&]() {
+        for (;;) {
+            const size_t i0 = next.fetch_add(8);
+            if (i0 >= n) break;
+            const size_t i1 = std::min(n, i0 + 8);
+            for (size_t i = i0; i < i1; i++) {
+                out[i] = build_bitmap(P, p0 + i, buf, bias);
+                if (!out[i]) failed = 1;
+            }
+        }
+    };
+    unsigned T = host_workers();
+    if ((size_t)T * 8 > n) T = (unsigned)((n + 7) / 8);
+    pool().run(work, T);
+    st->next_build++;
+    if (!stream_enqueue(st)) failed = 1;  // refill the buffer we just drained
+    if (failed) {
+        for (size_t i = 0; i < n; i++) { bitmap_free_host(out[i]); out[i] = nullptr; }
+        g.err = "download_next: host allocation or copy failed";
+        return (size_t)-1;
+    }
+    return n;
+}
+
+void rb200_download_end(rb200_download_stream_t *st) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    stream_free(st);
+}
 
 roaring_bitmap_t *rb200_set_download(const rb200_set_t *cs, size_t i) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -1255,6 +1489,10 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
     const rb200_set *s = cs;
     const size_t nb = s->n_bitmaps;
     if (nb == 0) return 0;
+    const bool trace = getenv("RB200_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    double t_packed = 0, t_copies = 0, t_built = 0;
     // ---- (1) pack
     uint64_t *d_bytes = (uint64_t *)dev_alloc(8 * nb), *d_off = (uint64_t *)dev_alloc(8 * (nb + 1)),
              *d_beg = (uint64_t *)dev_alloc(8 * (nb + 1));
@@ -1272,6 +1510,7 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
              cudaStreamSynchronize(g.stream) == cudaSuccess;
     }
     const uint64_t *h_off = h_ob, *h_beg = h_ob ? h_ob + nb + 1 : nullptr;
+    t_packed = now();
     if (ok) {
         P = set_new((uint32_t)nb, h_beg[nb], h_off[nb]);
         ok = P != nullptr;
@@ -1309,6 +1548,7 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
             p0 = p1;
         }
     }
+    t_copies = now();
     // ---- (3) host threads
     if (ok) {
         std::atomic<size_t> next(0);
@@ -1342,6 +1582,7 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
         for (unsigned t = 1; t < T; t++) th.emplace_back(work);
         work();
         for (auto &t : th) t.join();
+        t_built = now();
         if (cudaStreamSynchronize(g.stream) != cudaSuccess) failed = 1;
         if (failed) {
             for (size_t i = 0; i < nb; i++) { bitmap_free_host(out[i]); out[i] = nullptr; }
@@ -1353,6 +1594,11 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
         cudaStreamSynchronize(g.stream);
         if (g.err.empty()) g.err = "download: packing failed";
     }
+    if (trace)
+        fprintf(stderr, "[rb200] download_all nb=%zu bytes=%.1f MB: measure+scan %.2f ms, alloc+enqueue %.2f ms, "
+                        "copy+build %.2f ms, total %.2f ms (chunks %zu)\n",
+                nb, P ? (P->L.total + P->slab_used) / 1e6 : 0.0, t_packed - t_start, t_copies - t_packed,
+                t_built - t_copies, now() - t_start, evs.size());
     for (auto ev : evs) cudaEventDestroy(ev);
     if (P) {
         pin_free(P->m_dir, P->L.total);
@@ -1371,25 +1617,22 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
 
 // Free many host bitmaps (results of rb200_set_download_all) with several threads.
 void rb200_bitmaps_free(roaring_bitmap_t **bms, size_t n) {
-    unsigned T = std::thread::hardware_concurrency();
-    if (T > 32) T = 32;
-    if (n < 256 || T <= 1) {
+    unsigned T = host_workers();
+    if (n < 64 || T <= 1) {
         for (size_t i = 0; i < n; i++) bitmap_free_host(bms[i]);
         return;
     }
     std::atomic<size_t> next(0);
-    auto work = [&]() {
+    std::function<void()> work = [&]() {
         for (;;) {
-            const size_t i0 = next.fetch_add(64);
+            const size_t i0 = next.fetch_add(8);
             if (i0 >= n) break;
-            const size_t i1 = std::min(n, i0 + 64);
+            const size_t i1 = std::min(n, i0 + 8);
             for (size_t i = i0; i < i1; i++) bitmap_free_host(bms[i]);
         }
     };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < T; t++) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
+    if ((size_t)T * 8 > n) T = (unsigned)((n + 7) / 8);
+    pool().run(work, T);
 }
 
 int rb200_batch_op_host(int op, const roaring_bitmap_t *const *a, const roaring_bitmap_t *const *b,

@@ -142,6 +142,18 @@ int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out);
  * owned by the caller (free with roaring_bitmap_free or rb200_bitmap_free). */
 roaring_bitmap_t *rb200_set_download(const rb200_set_t *s, size_t i);
 int rb200_set_download_all(const rb200_set_t *s, roaring_bitmap_t **out);
+/* Streaming download: the set is packed on the device once, then leaves it chunk by chunk
+ * (<= chunk_bitmaps bitmaps / ~64 MB each, double-buffered pinned staging) while the caller
+ * consumes and frees the previous chunk — bounded host memory, D2H overlapped with host work.
+ *   st = rb200_download_begin(set, 1024);
+ *   while ((n = rb200_download_next(st, out)) != 0 && n != (size_t)-1) { use(out, n); rb200_bitmaps_free(out, n); }
+ *   rb200_download_end(st);                                                               */
+typedef struct rb200_download_stream rb200_download_stream_t;
+rb200_download_stream_t *rb200_download_begin(const rb200_set_t *s, size_t chunk_bitmaps);
+size_t rb200_download_chunk_capacity(const rb200_download_stream_t *st);
+size_t rb200_download_next(rb200_download_stream_t *st, roaring_bitmap_t **out);
+void rb200_download_end(rb200_download_stream_t *st);
+
 /* Free n host bitmaps (e.g. the results of rb200_set_download_all) using several threads. */
 void rb200_bitmaps_free(roaring_bitmap_t **bitmaps, size_t n);
 

@@ -288,3 +288,28 @@ def test_large_properties_bitset_heavy(rb):
     assert [x.serialize() for x in again.download_all()] == [x.serialize() for x in r_or.download_all()]
     again = r_and.batch("and", S, k, ib)
     assert [x.serialize() for x in again.download_all()] == [x.serialize() for x in r_and.download_all()]
+
+
+def test_streaming_download_matches(rb, R):
+    """rb200_download_begin/next/end yields the same bitmaps, in order, as download_all."""
+    blobs = rb.load_realdata("weather_sept_85")[:60]
+    S = rb.DeviceSet.from_serialized(blobs)
+    i, j = np.triu_indices(len(blobs), 1)
+    res = S.batch("xor", S, i.astype(np.uint32), j.astype(np.uint32))
+    ref_all = [o.serialize() for o in res.download_all()]
+    got = []
+    for arr, n in res.download_stream(97):
+        assert 0 < n <= 97
+        for k in range(n):
+            b = rb.Bitmap(arr[k])
+            ok, why = R.validate(b.ptr)
+            assert ok, why
+            got.append(b.serialize())
+            b.own = False
+        rb.DeviceSet.free_raw(arr, n)
+    assert got == ref_all
+    for k in (0, 500, len(got) - 1):
+        assert got[k] == R.op_bytes("xor", blobs[i[k]], blobs[j[k]])
+    # empty set streams nothing
+    e = S.batch("and", S, np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+    assert list(e.download_stream()) == []
