@@ -86,3 +86,93 @@ def values_to_blob(vals):
             bits[low] = 1
             conts.append(("b", np.packbits(bits, bitorder="little").view(np.uint64)))
     return serialize_containers(keys.tolist(), conts)
+
+
+# ------------------------------------------------------------------------------------------
+# Zipfian many-way-union inputs (BASELINE.json configs[2] and [4]).
+#
+# SURVEY.md defines bitmap b as "draw v = floor(U^u) - 1, u ~ U(0,1], until n distinct values":
+# P(v) ∝ 1/(v+1) (Zipf s=1).  Drawing ~n*ln(U) samples per bitmap is far too slow for a bench
+# that must finish in minutes, so we generate the Poissonised form of the same process: value v
+# is present independently with probability 1 - exp(-c/(v+1)), c chosen so that the expected
+# cardinality is n.  Per 2^16-value container the inclusion density is (nearly) constant, so a
+# container is filled either by thresholding random bits (density >= 1/16, quantised to 1/16)
+# or by geometric gap sampling (sparse).  Low keys saturate (full containers -> exercises the
+# or_many full-container state machine), high keys are sparse arrays.
+def _zipf_key_density(n_keys, n_values):
+    mid = (np.arange(n_keys, dtype=np.float64) * 65536.0 + 32768.0)
+    lo, hi = 1e-3, 1e12
+    for _ in range(200):
+        c = np.sqrt(lo * hi)
+        tot = (1.0 - np.exp(-c / mid)).sum() * 65536.0
+        if tot > n_values:
+            hi = c
+        else:
+            lo = c
+    return 1.0 - np.exp(-np.sqrt(lo * hi) / mid)
+
+
+def _random_words(rng, n_words, sixteenths):
+    """n_words u64 with each bit set with probability sixteenths/16 (1..16)."""
+    if sixteenths >= 16:
+        return np.full(n_words, np.uint64(0xFFFFFFFFFFFFFFFF))
+    r = rng.integers(0, 2 ** 63, size=(4, n_words), dtype=np.int64).view(np.uint64)
+    r = r ^ (rng.integers(0, 2, size=(4, n_words), dtype=np.int64).view(np.uint64) << np.uint64(63))
+    acc = np.zeros(n_words, dtype=np.uint64)          # probability 0
+    for k in range(4):                                 # binary expansion, LSB first
+        acc = (acc | r[k]) if (sixteenths >> k) & 1 else (acc & r[k])
+    return acc
+
+
+def zipf_bitmap_blob(rng, n_values, density, run_optimize_full=True):
+    """One portable bitmap with ~n_values Zipf-distributed values over universe n_values/density
+    (clamped to 2^32).  Saturated containers are emitted as the full run [0,65535]."""
+    universe = min(2 ** 32, int(np.ceil(n_values / density)))
+    n_keys = (universe + 65535) // 65536
+    dens = _zipf_key_density(n_keys, n_values)
+    keys, conts = [], []
+    dense = np.flatnonzero(dens >= 1.0 / 16)
+    for k in dense:
+        q = int(min(16, max(1, round(dens[k] * 16))))
+        if q >= 16 and run_optimize_full:
+            conts.append(("r", np.array([[0, 65535]], dtype=np.uint16)))
+        else:
+            w = _random_words(rng, 1024, q)
+            card = int(np.unpackbits(w.view(np.uint8)).sum())
+            if card <= 4096:
+                bits = np.unpackbits(w.view(np.uint8), bitorder="little")
+                conts.append(("a", np.flatnonzero(bits).astype(np.uint16)))
+            else:
+                conts.append(("b", w))
+        keys.append(int(k))
+    # sparse tail: geometric gaps over the concatenated remaining universe, piecewise by key
+    sparse = np.flatnonzero(dens < 1.0 / 16)
+    if len(sparse):
+        # one gap stream per block of keys with similar density keeps this vectorised
+        for blk in np.array_split(sparse, max(1, len(sparse) // 64)):
+            if len(blk) == 0:
+                continue
+            d = float(dens[blk].mean())
+            span = len(blk) * 65536
+            m = int(span * d * 1.3 + 64)
+            pos = np.cumsum(rng.geometric(d, size=m)) - 1
+            pos = pos[pos < span]
+            kk = pos >> 16
+            low = (pos & 0xFFFF).astype(np.uint16)
+            ks, starts = np.unique(kk, return_index=True)
+            ends = np.append(starts[1:], len(pos))
+            for kidx, s, e in zip(ks, starts, ends):
+                if e - s > 4096:                      # cannot happen for d < 1/16 (mean 4096) but be safe
+                    bits = np.zeros(65536, dtype=np.uint8)
+                    bits[low[s:e]] = 1
+                    conts.append(("b", np.packbits(bits, bitorder="little").view(np.uint64)))
+                else:
+                    conts.append(("a", low[s:e]))
+                keys.append(int(blk[int(kidx)]))
+    order = np.argsort(keys, kind="stable")
+    return serialize_containers([keys[i] for i in order], [conts[i] for i in order])
+
+
+def zipf_blobs(n_bitmaps, n_values, density, seed=0):
+    return [zipf_bitmap_blob(np.random.default_rng(seed * 100003 + b), n_values, density)
+            for b in range(n_bitmaps)]
