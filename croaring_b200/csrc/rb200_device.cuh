@@ -538,6 +538,72 @@ __device__ __forceinline__ uint32_t filter_array(const uint8_t *src, uint32_t n,
     return cnt;
 }
 
+// Union / symmetric difference of two sorted u16 arrays WITHOUT the bitset round trip
+// (array_container_union / xor, src/array_util.c:1104,1198 — here a warp merge path).
+// Both inputs are staged in the low 4 KiB of the warp's accumulator, the output in the high
+// 4 KiB, so it needs round8(n) + round8(m) <= 2048.  Every lane owns one contiguous slice of
+// the merged sequence (diagonal binary search), runs the sequential merge twice (count, then
+// write at its scanned offset) and the warp copies the staged result out with 128-bit stores.
+// Duplicates (a value present in both inputs) are adjacent in the merged order: OR keeps the
+// first, XOR drops both.
+template <bool IS_XOR>
+__device__ __forceinline__ uint32_t merge_arrays(uint32_t *acc, const uint8_t *pa, uint32_t n,
+                                                 const uint8_t *pb, uint32_t m, uint8_t *out,
+                                                 int lane) {
+    uint16_t *sa = reinterpret_cast<uint16_t *>(acc);
+    uint16_t *sb = sa + ((n + 7) & ~7u);
+    uint16_t *so = reinterpret_cast<uint16_t *>(acc) + 2048;
+    for (uint32_t i = lane; i < (n + 7) / 8; i += 32)
+        reinterpret_cast<uint4 *>(sa)[i] = __ldg(reinterpret_cast<const uint4 *>(pa) + i);
+    for (uint32_t i = lane; i < (m + 7) / 8; i += 32)
+        reinterpret_cast<uint4 *>(sb)[i] = __ldg(reinterpret_cast<const uint4 *>(pb) + i);
+    __syncwarp();
+    const uint32_t T = n + m, per = (T + 31) >> 5;
+    const uint32_t d0 = min((uint32_t)lane * per, T), d1 = min(d0 + per, T);
+    // merge-path split: i0 = how many of the first d0 merged elements come from a (ties: a first)
+    uint32_t lo = d0 > m ? d0 - m : 0u, hi = min(d0, n);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sa[mid] <= sb[d0 - 1 - mid]) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t i0 = lo, j0 = d0 - lo;
+    const uint32_t NONE = 0x10000u;
+    uint32_t prev0 = NONE + 1;  // element at merged position d0-1 (none for d0 == 0)
+    if (d0 > 0) {
+        const uint32_t pa_ = i0 > 0 ? sa[i0 - 1] : 0u, pb_ = j0 > 0 ? sb[j0 - 1] : 0u;
+        prev0 = (i0 > 0 && j0 > 0) ? max(pa_, pb_) : (i0 > 0 ? pa_ : pb_);
+    }
+    uint32_t off = 0, count = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        uint32_t i = i0, j = j0, prev = prev0, c = 0;
+        uint32_t ai = i < n ? sa[i] : NONE, bj = j < m ? sb[j] : NONE;
+        for (uint32_t p = d0; p < d1; p++) {
+            const bool take_a = ai <= bj;
+            const uint32_t x = take_a ? ai : bj;
+            if (take_a) { i++; ai = i < n ? sa[i] : NONE; }
+            else { j++; bj = j < m ? sb[j] : NONE; }
+            const bool emit = IS_XOR ? (x != prev && x != min(ai, bj)) : (x != prev);
+            if (emit) {
+                if (pass == 1) so[off + c] = (uint16_t)x;
+                c++;
+            }
+            prev = x;
+        }
+        if (pass == 0) {
+            const uint32_t incl = warp_incl_scan(c, lane);
+            off = incl - c;
+            count = __shfl_sync(FULLMASK, incl, 31);
+        }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < (count + 7) / 8; i += 32)
+        reinterpret_cast<uint4 *>(out)[i] = reinterpret_cast<const uint4 *>(so)[i];
+    __syncwarp();
+    return count;
+}
+
 // 16-byte vector copy of a stored payload (pass-through containers)
 __device__ __forceinline__ void warp_copy16(uint8_t *dst, const uint8_t *src, uint32_t bytes,
                                             int lane) {

@@ -230,6 +230,7 @@ struct rb200_set {
     uint8_t *d_dir = nullptr;   // one block
     uint8_t *d_slab = nullptr;
     std::vector<uint32_t> h_cnt;    // host mirror: containers per bitmap
+    std::vector<uint64_t> h_card;   // host mirror: cardinality per bitmap (empty = not cached)
     std::vector<uint64_t> h_bytes;  // host mirror: upper bound of stored payload bytes per bitmap
     std::vector<uint8_t> h_flags;   // per bitmap: COW flag to propagate
     // lazily downloaded host mirror (pinned)
@@ -991,7 +992,8 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         R = set_new((uint32_t)np, pb.W, pb.slab_bound);
         ok = R != nullptr;
     }
-    const size_t cnt_bytes = 4 * np + 8 * np;
+    // bm_cnt and bm_card are adjacent in the directory block: one D2H brings both
+    const size_t cnt_bytes = R ? (R->L.o_bcard - R->L.o_cnt) + 8 * np : 0;
     if (ok) { h_cnt = (uint32_t *)pin_alloc(cnt_bytes); ok = h_cnt != nullptr; }
     if (ok) {
         cudaEventRecord(g.ev0, g.stream);
@@ -1006,7 +1008,7 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         cudaEventRecord(g.ev1, g.stream);
         ok = ok && stats_fetch();
         if (np) {
-            ok = ok && cudaMemcpyAsync(h_cnt, R->d_dir + R->L.o_cnt, 4 * np, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(h_cnt, R->d_dir + R->L.o_cnt, cnt_bytes, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
         }
         cudaError_t e = cudaStreamSynchronize(g.stream);
         if (e != cudaSuccess) { g.err = std::string("batch op: ") + cudaGetErrorString(e); ok = false; }
@@ -1023,6 +1025,8 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         R->n_containers = g.h_stats->dir_cursor;
         R->slab_used = g.h_stats->slab_cursor;
         R->portable_bytes = 0;
+        const uint64_t *h_card = (const uint64_t *)((const uint8_t *)h_cnt + (R->L.o_bcard - R->L.o_cnt));
+        R->h_card.assign(h_card, h_card + np);
         for (size_t p = 0; p < np; p++) {
             R->h_cnt[p] = h_cnt[p];
             // stored-bytes upper bound for chained ops: every container <= 8 KiB
@@ -1177,6 +1181,10 @@ int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out) {
     if (!ctx_init()) return -1;
     const size_t nb = s->n_bitmaps;
     if (!nb) return 0;
+    if (s->h_card.size() == nb) {  // cached by the op that produced this set
+        memcpy(out, s->h_card.data(), 8 * nb);
+        return 0;
+    }
     uint64_t *h = (uint64_t *)pin_alloc(8 * nb);
     if (!h) return -1;
     // bm_card is maintained by upload / finalize / or_many

@@ -160,6 +160,17 @@ cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uin
         return;
     }
 
+    // ---- array x array union / xor whose result is known to stay an array: warp merge path ---
+    if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY &&
+        ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= 2048u) {
+        if (round16(2 * (cA + cB)) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
+        const uint32_t n = (op == OP_OR) ? merge_arrays<false>(acc, pa, cA, pb, cB, out, lane)
+                                         : merge_arrays<true>(acc, pa, cA, pb, cB, out, lane);
+        otype = n ? T_ARRAY : 0;  // cA + cB <= 4096 -> array (mixed_union.c:162-176, mixed_xor.c:196-205)
+        ocard = olen = n;
+        return;
+    }
+
     // ---- general path: acc = A op B --------------------------------------------------------
     int card = -1, nruns = 0;
     if (tA == T_BITSET && tB == T_BITSET) {
