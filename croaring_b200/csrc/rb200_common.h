@@ -106,7 +106,8 @@ void launch_many_mark(const SetView &S, const uint32_t *idx, uint32_t n, uint32_
                       uint32_t key_hi, uint32_t *flags /*65536*/, cudaStream_t s);
 void launch_many_compact(const uint32_t *flags, uint16_t *keys_out, OpStats *st, cudaStream_t s);
 void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uint16_t *keys,
-                    SetOut out, uint32_t *card_per_key /*65536 or null*/, OpStats *st,
-                    cudaStream_t s);
+                    uint32_t want_slices, uint32_t *scratch_acc, uint32_t *scratch_tickets,
+                    uint32_t scratch_keys, SetOut out, uint32_t *card_per_key /*65536 or null*/,
+                    OpStats *st, int sms, cudaStream_t s);
 
 }  // namespace rb200

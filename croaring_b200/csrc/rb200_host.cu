@@ -44,6 +44,7 @@ struct shared_container_t { void *container; uint8_t typecode; uint32_t counter;
 constexpr uint8_t FLAG_COW = 1, FLAG_FROZEN = 2;  // roaring_types.h:46-49
 constexpr uint32_t SERIAL_COOKIE_NO_RUN = 12346, SERIAL_COOKIE = 12347;  // roaring_array.h:35-40
 constexpr int32_t NO_OFFSET_THRESHOLD = 4;
+constexpr uint32_t MANY_SCRATCH_KEYS = 4096;  // keys that may be split over several CTAs in or_many
 
 // ------------------------------------------------------------------ host allocation hooks
 // If the reference library is loaded in this process (drop-in deployment) every host object we
@@ -102,6 +103,8 @@ struct Ctx {
     uint32_t *d_flags = nullptr;   // 65536 key flags (or_many)
     uint16_t *d_keys = nullptr;    // 65536 compacted keys
     uint32_t *d_cardkey = nullptr; // 65536 per-key cardinalities
+    uint32_t *d_many_acc = nullptr, *d_many_tickets = nullptr;  // split-key scratch (kept zeroed)
+    int sms = 148;
     std::multimap<size_t, void *> dpool, hpool;
     uint64_t last_algo_bytes = 0;
     float last_ms = 0.f, last_compute_ms = 0.f;
@@ -143,6 +146,11 @@ bool ctx_init(int device = -1) {
     CK(cudaMalloc(&g.d_flags, 65536 * sizeof(uint32_t)));
     CK(cudaMalloc(&g.d_keys, 65536 * sizeof(uint16_t)));
     CK(cudaMalloc(&g.d_cardkey, 65536 * sizeof(uint32_t)));
+    CK(cudaMalloc(&g.d_many_acc, (size_t)MANY_SCRATCH_KEYS * BITSET_BYTES));
+    CK(cudaMalloc(&g.d_many_tickets, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
+    CK(cudaMemset(g.d_many_acc, 0, (size_t)MANY_SCRATCH_KEYS * BITSET_BYTES));
+    CK(cudaMemset(g.d_many_tickets, 0, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
+    CK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, g.device));
     g.inited = true;
     return true;
 }
@@ -1130,8 +1138,17 @@ rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, s
         launch_many_compact(g.d_flags, g.d_keys, g.d_stats, g.stream);
         if (card_per_key) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
         cudaEventRecord(g.evk0, g.stream);
-        launch_or_many(vs, d_idx, (uint32_t)n, g.d_keys, R->out(), card_per_key ? g.d_cardkey : nullptr,
-                       g.d_stats, g.stream);
+        // few keys x many bitmaps: split every key over several CTAs (partial unions merged in a
+        // global scratch accumulator); the estimate of the key count is the largest directory
+        uint32_t nk_est = 1;
+        for (size_t i = 0; i < n; i++) nk_est = std::max(nk_est, S->h_cnt[idx ? idx[i] : i]);
+        uint32_t slices = (uint32_t)((4ull * g.sms + nk_est - 1) / nk_est);
+        slices = std::min<uint32_t>(slices, 16u);
+        slices = std::min<uint32_t>(slices, (uint32_t)(n / 32));
+        if (slices < 1) slices = 1;
+        launch_or_many(vs, d_idx, (uint32_t)n, g.d_keys, slices, g.d_many_acc, g.d_many_tickets,
+                       MANY_SCRATCH_KEYS, R->out(), card_per_key ? g.d_cardkey : nullptr, g.d_stats,
+                       g.sms, g.stream);
         cudaEventRecord(g.evk1, g.stream);
         cudaEventRecord(g.ev1, g.stream);
         ok = ok && stats_fetch();

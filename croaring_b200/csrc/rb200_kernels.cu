@@ -461,308 +461,6 @@ k_many_compact(const uint32_t *__restrict__ flags, uint16_t *__restrict__ keys, 
         if (flags[tid * 64 + k]) keys[o++] = (uint16_t)(tid * 64 + k);
 }
 
-constexpr int OM_THREADS = 256;
-constexpr int OM_CHUNK = 1024;  // participants gathered per round
-
-// CTA per key.  The union of all containers carrying this key is accumulated in a shared
-// 65536-bit accumulator (arrays / runs, shared-memory atomics) plus a register slice per
-// thread (bitset containers: every thread owns two 128-bit words of the 8 KiB block, so a
-// bitset participant is two coalesced 128-bit loads per thread and no shared-memory traffic).
-// Types follow roaring_bitmap_or_many: a key present in one input is cloned and "repaired"
-// (runs re-checked by convert_run_to_efficient_container); a key present in several inputs
-// becomes a bitset accumulator, repaired to array when card <= 4096, or the full run
-// [0,65535] when the reference's lazy fold would have produced it (state machine below).
-__global__ void __launch_bounds__(OM_THREADS)
-k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
-          const uint16_t *__restrict__ keys, SetOut out, uint32_t *__restrict__ card_per_key,
-          OpStats *st) {
-    __shared__ __align__(16) uint32_t s_acc[ACC_WORDS];
-    __shared__ uint32_t s_plist[OM_CHUNK];   // container index of each participant (input order)
-    __shared__ uint32_t s_ppos[OM_CHUNK];    // position in idx[] of each participant
-    __shared__ uint32_t s_warp[OM_THREADS / 32];
-    __shared__ uint32_t s_np, s_ki, s_flag;
-    __shared__ int s_red[OM_THREADS / 32][2];
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t nk = st->nk;
-
-    for (;;) {
-        if (tid == 0) s_ki = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
-        __syncthreads();
-        const uint32_t ki = s_ki;
-        __syncthreads();
-        if (ki >= nk) break;
-        const uint32_t key = keys[ki];
-
-        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < ACC_WORDS / 4; i += OM_THREADS)
-            reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
-
-        // state of the reference's fold (thread 0 only)
-        uint32_t m_total = 0;        // participants so far
-        uint32_t first_c = 0, first_pos = 0, second_pos = 0;
-        bool any_inplace_bitset = false;  // a bitset participant at an in-place step
-        bool run_full = false;            // accumulator became the full run (rule i)
-        bool decided_skip = false;        // accumulator known full -> later inputs skipped
-        bool first_is_full_bitset = false;
-
-        for (uint32_t c0 = 0; c0 < n; c0 += OM_CHUNK) {
-            // ---- gather the participants of this chunk, in input order -----------------
-            uint32_t found[OM_CHUNK / OM_THREADS];
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int k = 0; k < OM_CHUNK / OM_THREADS; k++) {
-                const uint32_t i = c0 + tid * (OM_CHUNK / OM_THREADS) + k;
-                found[k] = 0xffffffffu;
-                if (i < n) {
-                    const uint32_t b = idx ? idx[i] : i;
-                    const uint32_t b0 = S.bm_beg[b], nb = S.bm_cnt[b];
-                    const uint32_t lb = lower_bound_u16(S.c_key + b0, nb, key);
-                    if (lb < nb && S.c_key[b0 + lb] == key) {
-                        found[k] = b0 + lb;
-                        cnt++;
-                    }
-                }
-            }
-            const uint32_t incl = warp_incl_scan(cnt, lane);
-            if (lane == 31) s_warp[wid] = incl;
-            __syncthreads();
-            if (wid == 0) {
-                const uint32_t v = lane < OM_THREADS / 32 ? s_warp[lane] : 0u;
-                const uint32_t s = warp_incl_scan(v, lane);
-                if (lane < OM_THREADS / 32) s_warp[lane] = s - v;
-                if (lane == 31) s_np = s;
-            }
-            __syncthreads();
-            uint32_t o = s_warp[wid] + incl - cnt;
-#pragma unroll
-            for (int k = 0; k < OM_CHUNK / OM_THREADS; k++)
-                if (found[k] != 0xffffffffu) {
-                    s_plist[o] = found[k];
-                    s_ppos[o] = c0 + tid * (OM_CHUNK / OM_THREADS) + k;
-                    o++;
-                }
-            __syncthreads();
-            const uint32_t np = s_np;
-
-            // ---- thread 0: metadata part of the reference's lazy fold --------------------
-            // (roaring.c:2535-2545 first combine, :2621-2640 in-place steps,
-            //  containers.h:1342-1404 container_lazy_ior, :1113-1215 container_lazy_or)
-            if (tid == 0) {
-                for (uint32_t j = 0; j < np; j++) {
-                    const uint32_t c = s_plist[j];
-                    const int t = S.c_type[c];
-                    const bool full_run = is_full_run(t, S.c_len[c], S.c_card[c]);
-                    if (m_total == 0) {
-                        first_c = c;
-                        first_pos = s_ppos[j];
-                        if (full_run) { run_full = true; decided_skip = true; }
-                        if (t == T_BITSET && S.c_card[c] == 65536) {
-                            first_is_full_bitset = true;
-                            decided_skip = true;
-                        }
-                    } else {
-                        if (m_total == 1) second_pos = s_ppos[j];
-                        const bool non_inplace = (m_total == 1) && first_pos == 0 && second_pos == 1;
-                        if (non_inplace) {
-                            // first combine: no "is full" skip.
-                            const int t1 = S.c_type[first_c];
-                            decided_skip = false;
-                            first_is_full_bitset = false;
-                            if (t1 != T_BITSET && t != T_BITSET) {
-                                // c1 -> bitset, lazy_ior(B, c2): only a full-run c2 gives a run
-                                run_full = full_run;
-                            } else {
-                                // container_lazy_or: a full run on either side is copied
-                                run_full = full_run || is_full_run(t1, S.c_len[first_c], S.c_card[first_c]);
-                            }
-                            decided_skip = run_full;
-                        } else if (!decided_skip) {
-                            if (full_run) { run_full = true; decided_skip = true; }
-                            else if (t == T_BITSET) any_inplace_bitset = true;
-                        }
-                    }
-                    m_total++;
-                }
-            }
-
-            // ---- accumulate the payloads (order-free: OR is associative) -------------------
-            // bitset participants: registers, 4 at a time for memory-level parallelism
-            {
-                uint32_t j = 0;
-                while (j < np) {
-                    const uint4 *src[4];
-                    int nb4 = 0;
-                    while (j < np && nb4 < 4) {
-                        const uint32_t c = s_plist[j++];
-                        if (S.c_type[c] == T_BITSET)
-                            src[nb4++] = reinterpret_cast<const uint4 *>(S.payload + S.c_off[c]);
-                    }
-                    uint4 qa[4], qb[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (k < nb4) {
-                            qa[k] = __ldg(src[k] + tid);
-                            qb[k] = __ldg(src[k] + tid + OM_THREADS);
-                        }
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (k < nb4) {
-                            r0.x |= qa[k].x; r0.y |= qa[k].y; r0.z |= qa[k].z; r0.w |= qa[k].w;
-                            r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
-                        }
-                }
-            }
-            // array / run participants: one warp per participant, shared-memory atomics
-            for (uint32_t j = wid; j < np; j += OM_THREADS / 32) {
-                const uint32_t c = s_plist[j];
-                const int t = S.c_type[c];
-                if (t == T_ARRAY) acc_apply_array<0>(s_acc, S.payload + S.c_off[c], S.c_len[c], lane);
-                else if (t == T_RUN) acc_apply_runs<0, true>(s_acc, S.payload + S.c_off[c], S.c_len[c], lane);
-            }
-            __syncthreads();
-        }
-
-        // ---- merge the register slice into the shared accumulator, count -------------------
-        {
-            uint4 *a4 = reinterpret_cast<uint4 *>(s_acc);
-            uint4 a = a4[tid], b = a4[tid + OM_THREADS];
-            a.x |= r0.x; a.y |= r0.y; a.z |= r0.z; a.w |= r0.w;
-            b.x |= r1.x; b.y |= r1.y; b.z |= r1.z; b.w |= r1.w;
-            a4[tid] = a;
-            a4[tid + OM_THREADS] = b;
-        }
-        __syncthreads();
-        int c = 0, r = 0;
-        for (int w = tid; w < ACC_WORDS; w += OM_THREADS) {
-            const uint32_t x = s_acc[w];
-            const uint32_t prev = w ? (s_acc[w - 1] >> 31) : 0u;
-            c += __popc(x);
-            r += __popc(x & ~((x << 1) | prev));
-        }
-        c = __reduce_add_sync(FULLMASK, c);
-        r = __reduce_add_sync(FULLMASK, r);
-        if (lane == 0) { s_red[wid][0] = c; s_red[wid][1] = r; }
-        __syncthreads();
-        int card = 0, nruns = 0;
-        for (int w = 0; w < OM_THREADS / 32; w++) { card += s_red[w][0]; nruns += s_red[w][1]; }
-
-        // ---- decide the result type (thread 0 knows the fold state; broadcast) ---------------
-        if (tid == 0) {
-            int t;
-            if (m_total == 1) {
-                // single participant: clone + container_repair_after_lazy (containers.h:344-371)
-                const int t1 = S.c_type[first_c];
-                if (t1 == T_RUN) t = rule_eff(card, nruns);
-                else if (t1 == T_ARRAY) t = T_ARRAY;
-                else t = rule_ab(card);
-            } else if (run_full) {
-                t = T_RUN;
-            } else if (card == 65536 && any_inplace_bitset && !first_is_full_bitset) {
-                t = 0x80;  // saturated: need the ordered replay to know if a B,B step saw it
-            } else {
-                t = rule_ab(card);
-            }
-            s_flag = (uint32_t)t;
-        }
-        __syncthreads();
-        int otype = (int)s_flag;
-        __syncthreads();
-
-        if (otype == 0x80) {
-            // Ordered replay (rare: saturated key with bitset participants).  Find whether an
-            // in-place bitset step observes cardinality 65536 (containers.h:1345-1352) before
-            // anything else makes the accumulator a run.  Prefix unions are recomputed in input
-            // order; fullness is tested after every in-place bitset participant.
-            for (int i = tid; i < ACC_WORDS; i += OM_THREADS) s_acc[i] = 0;
-            __syncthreads();
-            bool became_run = false;
-            uint32_t m = 0, fpos = 0;
-            for (uint32_t i = 0; i < n && !became_run; i++) {
-                const uint32_t b = idx ? idx[i] : i;
-                const uint32_t b0 = S.bm_beg[b], nb = S.bm_cnt[b];
-                const uint32_t lb = lower_bound_u16(S.c_key + b0, nb, key);
-                if (!(lb < nb && S.c_key[b0 + lb] == key)) continue;  // uniform across the CTA
-                const uint32_t cc = b0 + lb;
-                const int t = S.c_type[cc];
-                if (m == 0) fpos = i;
-                const bool non_inplace = (m == 1) && fpos == 0 && i == 1;
-                if (t == T_BITSET) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(S.payload + S.c_off[cc]);
-                    uint4 *a4 = reinterpret_cast<uint4 *>(s_acc);
-                    for (int k = tid; k < ACC_WORDS / 4; k += OM_THREADS) {
-                        uint4 a = a4[k];
-                        const uint4 q = __ldg(src + k);
-                        a.x |= q.x; a.y |= q.y; a.z |= q.z; a.w |= q.w;
-                        a4[k] = a;
-                    }
-                } else if (wid == 0) {
-                    if (t == T_ARRAY) acc_apply_array<0>(s_acc, S.payload + S.c_off[cc], S.c_len[cc], lane);
-                    else acc_apply_runs<0, true>(s_acc, S.payload + S.c_off[cc], S.c_len[cc], lane);
-                }
-                __syncthreads();
-                if (t == T_BITSET && m >= 1 && !non_inplace) {
-                    bool full = true;
-                    for (int k = tid; k < ACC_WORDS; k += OM_THREADS) full = full && (s_acc[k] == 0xffffffffu);
-                    if (__syncthreads_and(full)) became_run = true;
-                }
-                m++;
-            }
-            __syncthreads();
-            for (int i = tid; i < ACC_WORDS; i += OM_THREADS) s_acc[i] = 0xffffffffu;
-            __syncthreads();
-            otype = became_run ? T_RUN : T_BITSET;
-        }
-
-        // ---- emit ----------------------------------------------------------------------------
-        const uint64_t off = (uint64_t)ki * BITSET_BYTES;
-        uint8_t *dst = out.payload + off;
-        uint32_t olen;
-        if (otype == T_BITSET) {
-            olen = 1024;
-            for (int i = tid; i < ACC_WORDS / 4; i += OM_THREADS)
-                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(s_acc)[i];
-        } else if (otype == T_ARRAY) {
-            olen = (uint32_t)card;
-            if (wid == 0) acc_emit_array(s_acc, reinterpret_cast<uint16_t *>(dst), lane);
-        } else {
-            olen = (uint32_t)nruns;
-            if (wid == 0) acc_emit_runs(s_acc, reinterpret_cast<uint16_t *>(dst), lane);
-        }
-        if (tid == 0) {
-            out.c_key[ki] = (uint16_t)key;
-            out.c_type[ki] = (uint8_t)otype;
-            out.c_card[ki] = (uint32_t)card;
-            out.c_len[ki] = olen;
-            out.c_off[ki] = off;
-            if (card_per_key) card_per_key[key] = (uint32_t)card;
-        }
-        __syncthreads();
-    }
-    // bitmap-level directory (one result bitmap) — written by the CTA that sees ticket nk
-    if (blockIdx.x == 0 && tid == 0) {
-        out.bm_beg[0] = 0;
-        out.bm_cnt[0] = nk;
-    }
-}
-
-// total cardinality of the one-bitmap result of or_many
-__global__ void k_sum_cards(const uint32_t *__restrict__ c_card, const OpStats *st,
-                            uint64_t *__restrict__ out) {
-    __shared__ unsigned long long s[32];
-    const uint32_t n = st->nk;
-    unsigned long long v = 0;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) v += c_card[i];
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s[i];
-        out[0] = t;
-    }
-}
-
 // ------------------------------------------------------------------------------ packing
 // Compact a set for download: directory in bitmap order, payload contiguous in bitmap order
 // without slot slack, so that any range of bitmaps is one directory range + one payload range
@@ -941,14 +639,6 @@ void launch_many_mark(const SetView &S, const uint32_t *idx, uint32_t n, uint32_
 
 void launch_many_compact(const uint32_t *flags, uint16_t *keys_out, OpStats *st, cudaStream_t s) {
     k_many_compact<<<1, 1024, 0, s>>>(flags, keys_out, st);
-    g_launches++;
-}
-
-void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uint16_t *keys,
-                    SetOut out, uint32_t *card_per_key, OpStats *st, cudaStream_t s) {
-    k_or_many<<<sm_count() * 4, OM_THREADS, 0, s>>>(S, idx, n, keys, out, card_per_key, st);
-    g_launches++;
-    k_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
     g_launches++;
 }
 

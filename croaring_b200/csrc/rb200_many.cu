@@ -1,0 +1,449 @@
+// rb200_many.cu — N-way union (roaring_bitmap_or_many, src/roaring.c:775-790) on sm_100a.
+//
+// The reference folds the inputs left to right with lazy cells (roaring_bitmap_lazy_or
+// :2509-2598, roaring_bitmap_lazy_or_inplace :2600-2682, container_lazy_or / container_lazy_ior
+// include/roaring/containers/containers.h:1113-1215, 1333-1442) and repairs once
+// (roaring_bitmap_repair_after_lazy :2845).  OR is associative, so on the GPU each KEY is
+// reduced independently:
+//
+//   work unit = (key, slice of the input list).  A CTA gathers the containers carrying the key
+//   (binary search in every bitmap's sorted key array, ordered compaction into shared memory),
+//   ORs bitset containers into a per-thread register slice (two 128-bit words per thread, loads
+//   batched four containers deep), flattens all array values / runs of the slice into one work
+//   list spread over the 256 threads (shared-memory atomics on a 65536-bit accumulator), and
+//   — when the key was split over several CTAs for parallelism — merges into a global scratch
+//   accumulator; the last CTA of a key finalises: popcount, result type, re-encode.
+//
+// Result types follow the reference's fold exactly: the metadata of the participants is
+// replayed through the fold's state machine (full runs / full bitsets short-circuit the fold,
+// a bitset x bitset in-place step converts a saturated accumulator to the full run,
+// containers.h:1342-1352); the rare saturated-with-bitsets case is decided by an ordered
+// replay of the prefix unions.
+#include "rb200_device.cuh"
+
+namespace rb200 {
+
+__device__ __forceinline__ uint32_t lower_bound_key(const uint16_t *a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+constexpr int OM_THREADS = 256;
+constexpr int OM_CHUNK = 512;  // bitmaps gathered per round: two per thread
+constexpr uint32_t PF_FULL_RUN = 16, PF_FULL_BITSET = 32;
+
+// The reference's fold, metadata only (lives in thread 0's registers).
+struct FoldState {
+    uint32_t m_total = 0, first_pos = 0, second_pos = 0, first_tf = 0;
+    bool any_inplace_bitset = false, run_full = false, decided_skip = false,
+         first_is_full_bitset = false;
+};
+
+// (roaring.c:2535-2545 first combine; :2621-2640 in-place steps; containers.h:1342-1404)
+__device__ __forceinline__ void fold_step(FoldState &f, uint32_t tf, uint32_t pos) {
+    const int t = tf & 15;
+    const bool full_run = tf & PF_FULL_RUN, full_bitset = tf & PF_FULL_BITSET;
+    if (f.m_total == 0) {
+        f.first_tf = tf;
+        f.first_pos = pos;
+        if (full_run) { f.run_full = true; f.decided_skip = true; }
+        if (full_bitset) { f.first_is_full_bitset = true; f.decided_skip = true; }
+    } else {
+        if (f.m_total == 1) f.second_pos = pos;
+        const bool non_inplace = f.m_total == 1 && f.first_pos == 0 && f.second_pos == 1;
+        if (non_inplace) {
+            // first combine of x[0], x[1]: no "is full" skip (roaring.c:2535-2550)
+            const int t1 = f.first_tf & 15;
+            f.first_is_full_bitset = false;
+            if (t1 != T_BITSET && t != T_BITSET) f.run_full = full_run;  // c1 -> bitset, lazy_ior(B, c2)
+            else f.run_full = full_run || (f.first_tf & PF_FULL_RUN);    // container_lazy_or copies a full run
+            f.decided_skip = f.run_full;
+        } else if (!f.decided_skip) {
+            if (full_run) { f.run_full = true; f.decided_skip = true; }
+            else if (t == T_BITSET) f.any_inplace_bitset = true;
+        }
+    }
+    f.m_total++;
+}
+
+struct ManySmem {
+    uint32_t acc[ACC_WORDS];
+    unsigned long long poff[OM_CHUNK];
+    uint32_t plen[OM_CHUNK];
+    uint32_t ppos[OM_CHUNK];
+    uint32_t pustart[OM_CHUNK + 1];  // exclusive prefix of flattened work units (array vectors / runs)
+    uint8_t ptf[OM_CHUNK];           // type | PF_* flags
+    uint32_t warp_a[OM_THREADS / 32], warp_b[OM_THREADS / 32];
+    int red[OM_THREADS / 32][2];
+    uint32_t np, ki, flag, anyfull;
+};
+
+// Gather the participants of `key` among bitmaps [c0, c0+OM_CHUNK) ∩ [0,n) in input order.
+__device__ __forceinline__ uint32_t many_gather(ManySmem &sm, const SetView &S,
+                                                const uint32_t *__restrict__ idx, uint32_t n,
+                                                uint32_t key, uint32_t c0, uint32_t c1) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t cont[2], tf[2], len[2], units[2];
+    unsigned long long off[2];
+    uint32_t cnt = 0, ucnt = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t i = c0 + tid * 2 + k;
+        cont[k] = 0xffffffffu;
+        units[k] = 0;
+        if (i < c1) {
+            const uint32_t b = idx ? idx[i] : i;
+            const uint32_t b0 = S.bm_beg[b], nb = S.bm_cnt[b];
+            const uint32_t lb = lower_bound_key(S.c_key + b0, nb, key);
+            if (lb < nb && S.c_key[b0 + lb] == key) {
+                const uint32_t c = b0 + lb;
+                const uint32_t t = S.c_type[c], l = S.c_len[c], cd = S.c_card[c];
+                cont[k] = c;
+                off[k] = S.c_off[c];
+                len[k] = l;
+                uint32_t f = t;
+                if (t == T_RUN && l == 1 && cd == 65536) f |= PF_FULL_RUN;
+                if (t == T_BITSET && cd == 65536) f |= PF_FULL_BITSET;
+                tf[k] = f;
+                if (t == T_ARRAY) units[k] = (l + 7) >> 3;
+                else if (t == T_RUN && !(f & PF_FULL_RUN)) units[k] = l;
+                cnt++;
+                ucnt += units[k];
+            }
+        }
+    }
+    const uint32_t incl = warp_incl_scan(cnt, lane), uincl = warp_incl_scan(ucnt, lane);
+    if (lane == 31) { sm.warp_a[wid] = incl; sm.warp_b[wid] = uincl; }
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t va = lane < OM_THREADS / 32 ? sm.warp_a[lane] : 0u;
+        const uint32_t vb = lane < OM_THREADS / 32 ? sm.warp_b[lane] : 0u;
+        const uint32_t sa = warp_incl_scan(va, lane), sb = warp_incl_scan(vb, lane);
+        if (lane < OM_THREADS / 32) { sm.warp_a[lane] = sa - va; sm.warp_b[lane] = sb - vb; }
+        if (lane == 31) { sm.np = sa; sm.pustart[sa] = sb; }
+    }
+    __syncthreads();
+    uint32_t o = sm.warp_a[wid] + incl - cnt, u = sm.warp_b[wid] + uincl - ucnt;
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+        if (cont[k] != 0xffffffffu) {
+            sm.poff[o] = off[k];
+            sm.plen[o] = len[k];
+            sm.ppos[o] = c0 + tid * 2 + k;
+            sm.ptf[o] = (uint8_t)tf[k];
+            sm.pustart[o] = u;
+            u += units[k];
+            o++;
+        }
+    __syncthreads();
+    return sm.np;
+}
+
+// OR the payloads of the gathered participants into (r0,r1) registers + shared accumulator.
+__device__ __forceinline__ void many_accumulate(ManySmem &sm, const SetView &S, uint32_t np,
+                                                uint4 &r0, uint4 &r1) {
+    const int tid = threadIdx.x;
+    // bitset containers: registers, four containers in flight per thread
+    uint32_t j = 0;
+    while (j < np) {
+        const uint4 *src[4];
+        int nb4 = 0;
+        while (j < np && nb4 < 4) {
+            if ((sm.ptf[j] & 15) == T_BITSET)
+                src[nb4++] = reinterpret_cast<const uint4 *>(S.payload + sm.poff[j]);
+            j++;
+        }
+        uint4 qa[4], qb[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < nb4) {
+                qa[k] = __ldg(src[k] + tid);
+                qb[k] = __ldg(src[k] + tid + OM_THREADS);
+            }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < nb4) {
+                r0.x |= qa[k].x; r0.y |= qa[k].y; r0.z |= qa[k].z; r0.w |= qa[k].w;
+                r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
+            }
+    }
+    // arrays and runs: one flat list of work units over all participants
+    const uint32_t V = sm.pustart[np];
+    for (uint32_t u = tid; u < V; u += OM_THREADS) {
+        uint32_t lo = 0, hi = np;  // last participant with pustart <= u
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sm.pustart[mid] <= u) lo = mid;
+            else hi = mid;
+        }
+        const uint32_t local = u - sm.pustart[lo];
+        const uint8_t *p = S.payload + sm.poff[lo];
+        if ((sm.ptf[lo] & 15) == T_ARRAY) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + local);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t left = sm.plen[lo] - local * 8;
+            uint32_t cur_w = (w[0] & 0xffffu) >> 5, cur_m = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+                const uint32_t wi = v >> 5, bit = 1u << (v & 31);
+                if (k == 0 || k < (int)left) {
+                    if (wi != cur_w) {
+                        atomicOr(sm.acc + cur_w, cur_m);
+                        cur_w = wi;
+                        cur_m = bit;
+                    } else {
+                        cur_m |= bit;
+                    }
+                }
+            }
+            atomicOr(sm.acc + cur_w, cur_m);
+        } else {  // one run per thread
+            const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p) + local);
+            const uint32_t s = r & 0xffffu, e = s + (r >> 16);
+            const uint32_t ws = s >> 5, we = e >> 5;
+            const uint32_t m_lo = ~0u << (s & 31), m_hi = ~0u >> (31 - (e & 31));
+            if (ws == we) {
+                atomicOr(sm.acc + ws, m_lo & m_hi);
+            } else {
+                atomicOr(sm.acc + ws, m_lo);
+                for (uint32_t w = ws + 1; w < we; w++) atomicOr(sm.acc + w, ~0u);
+                atomicOr(sm.acc + we, m_hi);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(OM_THREADS)
+k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
+          const uint16_t *__restrict__ keys, uint32_t want_slices, uint32_t *scratch_acc,
+          uint32_t *scratch_tickets, uint32_t scratch_keys, SetOut out,
+          uint32_t *__restrict__ card_per_key, OpStats *st) {
+    __shared__ __align__(16) ManySmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nk = st->nk;
+    // split a key over several CTAs only when there are few keys and the scratch can hold them
+    const uint32_t ns = (want_slices > 1 && nk <= scratch_keys) ? want_slices : 1u;
+    const uint32_t per_slice = (n + ns - 1) / ns;
+    const unsigned long long total_units = (unsigned long long)nk * ns;
+
+    for (;;) {
+        if (tid == 0) sm.ki = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
+        __syncthreads();
+        const uint32_t unit = sm.ki;
+        __syncthreads();
+        if (unit >= total_units) break;
+        const uint32_t ki = unit / ns, sl = unit % ns;
+        const uint32_t key = keys[ki];
+        const uint32_t i_lo = min(sl * per_slice, n), i_hi = min(i_lo + per_slice, n);
+
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < ACC_WORDS / 4; i += OM_THREADS)
+            reinterpret_cast<uint4 *>(sm.acc)[i] = make_uint4(0, 0, 0, 0);
+        if (tid == 0) sm.anyfull = 0;
+        FoldState f;
+        __syncthreads();
+
+        for (uint32_t c0 = i_lo; c0 < i_hi; c0 += OM_CHUNK) {
+            const uint32_t np = many_gather(sm, S, idx, n, key, c0, min(c0 + OM_CHUNK, i_hi));
+            if (tid == 0) {
+                uint32_t af = 0;
+                for (uint32_t j = 0; j < np; j++) {
+                    fold_step(f, sm.ptf[j], sm.ppos[j]);
+                    af |= sm.ptf[j] & (PF_FULL_RUN | PF_FULL_BITSET);
+                }
+                if (af) sm.anyfull = 1;
+            }
+            many_accumulate(sm, S, np, r0, r1);
+            __syncthreads();
+        }
+        // merge the register slice into the shared accumulator
+        {
+            uint4 *a4 = reinterpret_cast<uint4 *>(sm.acc);
+            uint4 a = a4[tid], b = a4[tid + OM_THREADS];
+            a.x |= r0.x; a.y |= r0.y; a.z |= r0.z; a.w |= r0.w;
+            b.x |= r1.x; b.y |= r1.y; b.z |= r1.z; b.w |= r1.w;
+            if (sm.anyfull) a = b = make_uint4(~0u, ~0u, ~0u, ~0u);  // a full container took part
+            a4[tid] = a;
+            a4[tid + OM_THREADS] = b;
+        }
+        __syncthreads();
+
+        if (ns > 1) {
+            // ---- split key: publish the partial union, the last slice finalises --------------
+            uint32_t *g = scratch_acc + (size_t)ki * ACC_WORDS;
+            for (int w = tid; w < ACC_WORDS; w += OM_THREADS) {
+                const uint32_t v = sm.acc[w];
+                if (v) atomicOr(g + w, v);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) sm.flag = (atomicAdd(scratch_tickets + ki, 1u) == ns - 1) ? 1u : 0u;
+            __syncthreads();
+            const bool last = sm.flag != 0;
+            __syncthreads();
+            if (!last) continue;
+            __threadfence();
+            for (int w = tid; w < ACC_WORDS; w += OM_THREADS) {
+                sm.acc[w] = __ldcg(g + w);
+                g[w] = 0;  // leave the scratch clean for the next call
+            }
+            if (tid == 0) scratch_tickets[ki] = 0;
+            // the fold needs every participant's metadata, in input order
+            f = FoldState();
+            for (uint32_t c0 = 0; c0 < n; c0 += OM_CHUNK) {
+                const uint32_t np = many_gather(sm, S, idx, n, key, c0, min(c0 + OM_CHUNK, n));
+                if (tid == 0)
+                    for (uint32_t j = 0; j < np; j++) fold_step(f, sm.ptf[j], sm.ppos[j]);
+                __syncthreads();
+            }
+        }
+
+        // ---- count -------------------------------------------------------------------------
+        int c = 0, r = 0;
+        for (int w = tid; w < ACC_WORDS; w += OM_THREADS) {
+            const uint32_t x = sm.acc[w];
+            const uint32_t prev = w ? (sm.acc[w - 1] >> 31) : 0u;
+            c += __popc(x);
+            r += __popc(x & ~((x << 1) | prev));
+        }
+        c = __reduce_add_sync(FULLMASK, c);
+        r = __reduce_add_sync(FULLMASK, r);
+        if (lane == 0) { sm.red[wid][0] = c; sm.red[wid][1] = r; }
+        __syncthreads();
+        int card = 0, nruns = 0;
+        for (int w = 0; w < OM_THREADS / 32; w++) { card += sm.red[w][0]; nruns += sm.red[w][1]; }
+
+        // ---- result type (thread 0 holds the fold state) ---------------------------------------
+        if (tid == 0) {
+            int t;
+            if (f.m_total == 1) {
+                // one input carries the key: clone, then container_repair_after_lazy
+                // (containers.h:344-371); n == 1 is a plain copy (roaring.c:780-782)
+                const int t1 = f.first_tf & 15;
+                if (n == 1) t = t1;
+                else if (t1 == T_RUN) t = rule_eff(card, nruns);
+                else if (t1 == T_ARRAY) t = T_ARRAY;
+                else t = rule_ab(card);
+            } else if (f.run_full) {
+                t = T_RUN;
+            } else if (card == 65536 && f.any_inplace_bitset && !f.first_is_full_bitset) {
+                t = 0x80;  // saturated with bitset steps: ordered replay decides
+            } else {
+                t = rule_ab(card);
+            }
+            sm.flag = (uint32_t)t;
+        }
+        __syncthreads();
+        int otype = (int)sm.flag;
+        __syncthreads();
+
+        if (otype == 0x80) {
+            // Ordered replay: does an in-place bitset x bitset step observe cardinality 65536
+            // (containers.h:1345-1352)?  Prefix unions are rebuilt in input order and tested
+            // after every in-place bitset participant.
+            for (int i = tid; i < ACC_WORDS; i += OM_THREADS) sm.acc[i] = 0;
+            __syncthreads();
+            bool became_run = false;
+            uint32_t m = 0, fpos = 0;
+            for (uint32_t i = 0; i < n && !became_run; i++) {
+                const uint32_t b = idx ? idx[i] : i;
+                const uint32_t b0 = S.bm_beg[b], nb = S.bm_cnt[b];
+                const uint32_t lb = lower_bound_key(S.c_key + b0, nb, key);
+                if (!(lb < nb && S.c_key[b0 + lb] == key)) continue;  // uniform across the CTA
+                const uint32_t cc = b0 + lb;
+                const int t = S.c_type[cc];
+                if (m == 0) fpos = i;
+                const bool non_inplace = (m == 1) && fpos == 0 && i == 1;
+                if (t == T_BITSET) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(S.payload + S.c_off[cc]);
+                    uint4 *a4 = reinterpret_cast<uint4 *>(sm.acc);
+                    for (int k = tid; k < ACC_WORDS / 4; k += OM_THREADS) {
+                        uint4 a = a4[k];
+                        const uint4 q = __ldg(src + k);
+                        a.x |= q.x; a.y |= q.y; a.z |= q.z; a.w |= q.w;
+                        a4[k] = a;
+                    }
+                } else if (wid == 0) {
+                    if (t == T_ARRAY) acc_apply_array<0>(sm.acc, S.payload + S.c_off[cc], S.c_len[cc], lane);
+                    else acc_apply_runs<0, true>(sm.acc, S.payload + S.c_off[cc], S.c_len[cc], lane);
+                }
+                __syncthreads();
+                if (t == T_BITSET && m >= 1 && !non_inplace) {
+                    bool full = true;
+                    for (int k = tid; k < ACC_WORDS; k += OM_THREADS) full = full && (sm.acc[k] == 0xffffffffu);
+                    if (__syncthreads_and(full)) became_run = true;
+                }
+                m++;
+            }
+            __syncthreads();
+            for (int i = tid; i < ACC_WORDS; i += OM_THREADS) sm.acc[i] = 0xffffffffu;
+            __syncthreads();
+            otype = became_run ? T_RUN : T_BITSET;
+        }
+
+        // ---- emit ----------------------------------------------------------------------------
+        const uint64_t off = (uint64_t)ki * BITSET_BYTES;
+        uint8_t *dst = out.payload + off;
+        uint32_t olen;
+        if (otype == T_BITSET) {
+            olen = 1024;
+            for (int i = tid; i < ACC_WORDS / 4; i += OM_THREADS)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(sm.acc)[i];
+        } else if (otype == T_ARRAY) {
+            olen = (uint32_t)card;
+            if (wid == 0) acc_emit_array(sm.acc, reinterpret_cast<uint16_t *>(dst), lane);
+        } else {
+            olen = (uint32_t)nruns;
+            if (wid == 0) acc_emit_runs(sm.acc, reinterpret_cast<uint16_t *>(dst), lane);
+        }
+        if (tid == 0) {
+            out.c_key[ki] = (uint16_t)key;
+            out.c_type[ki] = (uint8_t)otype;
+            out.c_card[ki] = (uint32_t)card;
+            out.c_len[ki] = olen;
+            out.c_off[ki] = off;
+            if (card_per_key) card_per_key[key] = (uint32_t)card;
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        out.bm_beg[0] = 0;
+        out.bm_cnt[0] = nk;
+    }
+}
+
+// total cardinality of the one-bitmap result of or_many
+__global__ void k_sum_cards(const uint32_t *__restrict__ c_card, const OpStats *st,
+                            uint64_t *__restrict__ out) {
+    __shared__ unsigned long long s[32];
+    const uint32_t n = st->nk;
+    unsigned long long v = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) v += c_card[i];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s[i];
+        out[0] = t;
+    }
+}
+
+void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uint16_t *keys,
+                    uint32_t want_slices, uint32_t *scratch_acc, uint32_t *scratch_tickets,
+                    uint32_t scratch_keys, SetOut out, uint32_t *card_per_key, OpStats *st,
+                    int sms, cudaStream_t s) {
+    k_or_many<<<sms * 4, OM_THREADS, 0, s>>>(S, idx, n, keys, want_slices, scratch_acc,
+                                             scratch_tickets, scratch_keys, out, card_per_key, st);
+    g_launches++;
+    k_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
+    g_launches++;
+}
+
+}  // namespace rb200
