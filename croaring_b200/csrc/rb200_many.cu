@@ -39,7 +39,7 @@ constexpr uint32_t PF_FULL_RUN = 16, PF_FULL_BITSET = 32;
 
 // The reference's fold, metadata only (lives in thread 0's registers).
 struct FoldState {
-    uint32_t m_total = 0, first_pos = 0, second_pos = 0, first_tf = 0;
+    uint32_t m_total = 0, first_pos = 0, second_pos = 0, first_tf = 0, last_ib_pos = 0;
     bool any_inplace_bitset = false, run_full = false, decided_skip = false,
          first_is_full_bitset = false;
 };
@@ -65,7 +65,7 @@ __device__ __forceinline__ void fold_step(FoldState &f, uint32_t tf, uint32_t po
             f.decided_skip = f.run_full;
         } else if (!f.decided_skip) {
             if (full_run) { f.run_full = true; f.decided_skip = true; }
-            else if (t == T_BITSET) f.any_inplace_bitset = true;
+            else if (t == T_BITSET) { f.any_inplace_bitset = true; f.last_ib_pos = pos; }
         }
     }
     f.m_total++;
@@ -80,7 +80,7 @@ struct ManySmem {
     uint8_t ptf[OM_CHUNK];           // type | PF_* flags
     uint32_t warp_a[OM_THREADS / 32], warp_b[OM_THREADS / 32];
     int red[OM_THREADS / 32][2];
-    uint32_t np, ki, flag, anyfull;
+    uint32_t np, ki, flag, anyfull, aux;
 };
 
 // Gather the participants of `key` among bitmaps [c0, c0+OM_CHUNK) ∩ [0,n) in input order.
@@ -338,50 +338,32 @@ k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
                 t = rule_ab(card);
             }
             sm.flag = (uint32_t)t;
+            sm.aux = f.last_ib_pos;
         }
         __syncthreads();
         int otype = (int)sm.flag;
         __syncthreads();
 
         if (otype == 0x80) {
-            // Ordered replay: does an in-place bitset x bitset step observe cardinality 65536
-            // (containers.h:1345-1352)?  Prefix unions are rebuilt in input order and tested
-            // after every in-place bitset participant.
+            // Saturated accumulator with in-place bitset steps: the reference turns it into the
+            // full run iff some in-place bitset x bitset step observes cardinality 65536
+            // (containers.h:1345-1352).  Prefix unions only grow, so that happens iff the union
+            // of the inputs up to and including the LAST in-place bitset participant is already
+            // full: one more (order-free) accumulation over that prefix decides.
+            const uint32_t L = sm.aux;
             for (int i = tid; i < ACC_WORDS; i += OM_THREADS) sm.acc[i] = 0;
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
             __syncthreads();
-            bool became_run = false;
-            uint32_t m = 0, fpos = 0;
-            for (uint32_t i = 0; i < n && !became_run; i++) {
-                const uint32_t b = idx ? idx[i] : i;
-                const uint32_t b0 = S.bm_beg[b], nb = S.bm_cnt[b];
-                const uint32_t lb = lower_bound_key(S.c_key + b0, nb, key);
-                if (!(lb < nb && S.c_key[b0 + lb] == key)) continue;  // uniform across the CTA
-                const uint32_t cc = b0 + lb;
-                const int t = S.c_type[cc];
-                if (m == 0) fpos = i;
-                const bool non_inplace = (m == 1) && fpos == 0 && i == 1;
-                if (t == T_BITSET) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(S.payload + S.c_off[cc]);
-                    uint4 *a4 = reinterpret_cast<uint4 *>(sm.acc);
-                    for (int k = tid; k < ACC_WORDS / 4; k += OM_THREADS) {
-                        uint4 a = a4[k];
-                        const uint4 q = __ldg(src + k);
-                        a.x |= q.x; a.y |= q.y; a.z |= q.z; a.w |= q.w;
-                        a4[k] = a;
-                    }
-                } else if (wid == 0) {
-                    if (t == T_ARRAY) acc_apply_array<0>(sm.acc, S.payload + S.c_off[cc], S.c_len[cc], lane);
-                    else acc_apply_runs<0, true>(sm.acc, S.payload + S.c_off[cc], S.c_len[cc], lane);
-                }
+            for (uint32_t c0 = 0; c0 <= L; c0 += OM_CHUNK) {
+                const uint32_t np = many_gather(sm, S, idx, n, key, c0, min(c0 + OM_CHUNK, L + 1));
+                many_accumulate(sm, S, np, q0, q1);
                 __syncthreads();
-                if (t == T_BITSET && m >= 1 && !non_inplace) {
-                    bool full = true;
-                    for (int k = tid; k < ACC_WORDS; k += OM_THREADS) full = full && (sm.acc[k] == 0xffffffffu);
-                    if (__syncthreads_and(full)) became_run = true;
-                }
-                m++;
             }
-            __syncthreads();
+            const uint4 *a4 = reinterpret_cast<const uint4 *>(sm.acc);
+            const uint4 a = a4[tid], b = a4[tid + OM_THREADS];
+            const bool full = ((a.x | q0.x) & (a.y | q0.y) & (a.z | q0.z) & (a.w | q0.w) &
+                               (b.x | q1.x) & (b.y | q1.y) & (b.z | q1.z) & (b.w | q1.w)) == 0xffffffffu;
+            const bool became_run = __syncthreads_and(full);
             for (int i = tid; i < ACC_WORDS; i += OM_THREADS) sm.acc[i] = 0xffffffffu;
             __syncthreads();
             otype = became_run ? T_RUN : T_BITSET;
