@@ -19,6 +19,8 @@
 // a bitset x bitset in-place step converts a saturated accumulator to the full run,
 // containers.h:1342-1352); the rare saturated-with-bitsets case is decided by an ordered
 // replay of the prefix unions.
+#include <stdlib.h>
+
 #include "rb200_device.cuh"
 
 namespace rb200 {
@@ -80,7 +82,7 @@ struct ManySmem {
     uint8_t ptf[OM_CHUNK];           // type | PF_* flags
     uint32_t warp_a[OM_THREADS / 32], warp_b[OM_THREADS / 32];
     int red[OM_THREADS / 32][2];
-    uint32_t np, ki, flag, anyfull, aux;
+    uint32_t np, ki, flag, anyfull, aux, rfull;
 };
 
 // Gather the participants of `key` among bitmaps [c0, c0+OM_CHUNK) ∩ [0,n) in input order.
@@ -91,32 +93,62 @@ __device__ __forceinline__ uint32_t many_gather(ManySmem &sm, const SetView &S,
     uint32_t cont[2], tf[2], len[2], units[2];
     unsigned long long off[2];
     uint32_t cnt = 0, ucnt = 0;
+    // two lower_bound searches per thread, advanced in lockstep so their loads overlap
+    uint32_t b0[2], nb[2], lo[2], hi[2];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const uint32_t i = c0 + tid * 2 + k;
         cont[k] = 0xffffffffu;
         units[k] = 0;
+        b0[k] = nb[k] = 0;
         if (i < c1) {
             const uint32_t b = idx ? idx[i] : i;
-            const uint32_t b0 = S.bm_beg[b], nb = S.bm_cnt[b];
-            const uint32_t lb = lower_bound_key(S.c_key + b0, nb, key);
-            if (lb < nb && S.c_key[b0 + lb] == key) {
-                const uint32_t c = b0 + lb;
-                const uint32_t t = S.c_type[c], l = S.c_len[c], cd = S.c_card[c];
-                cont[k] = c;
-                off[k] = S.c_off[c];
-                len[k] = l;
-                uint32_t f = t;
-                if (t == T_RUN && l == 1 && cd == 65536) f |= PF_FULL_RUN;
-                if (t == T_BITSET && cd == 65536) f |= PF_FULL_BITSET;
-                tf[k] = f;
-                if (t == T_ARRAY) units[k] = (l + 7) >> 3;
-                else if (t == T_RUN && !(f & PF_FULL_RUN)) units[k] = l;
-                cnt++;
-                ucnt += units[k];
-            }
+            b0[k] = S.bm_beg[b];
+            nb[k] = S.bm_cnt[b];
         }
+        lo[k] = 0;
+        hi[k] = nb[k];
     }
+    while (lo[0] < hi[0] || lo[1] < hi[1]) {
+        uint32_t mid[2], kv[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            mid[k] = (lo[k] + hi[k]) >> 1;
+            kv[k] = lo[k] < hi[k] ? (uint32_t)S.c_key[b0[k] + mid[k]] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            if (lo[k] < hi[k]) {
+                if (kv[k] < key) lo[k] = mid[k] + 1;
+                else hi[k] = mid[k];
+            }
+    }
+    uint32_t ct[2], cl[2], cc[2];
+    bool hit[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        hit[k] = lo[k] < nb[k] && S.c_key[b0[k] + lo[k]] == key;
+        const uint32_t c = b0[k] + lo[k];
+        ct[k] = hit[k] ? (uint32_t)S.c_type[c] : 0u;
+        cl[k] = hit[k] ? S.c_len[c] : 0u;
+        cc[k] = hit[k] ? S.c_card[c] : 0u;
+        off[k] = hit[k] ? S.c_off[c] : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+        if (hit[k]) {
+            const uint32_t t = ct[k], l = cl[k], cd = cc[k];
+            cont[k] = b0[k] + lo[k];
+            len[k] = l;
+            uint32_t f = t;
+            if (t == T_RUN && l == 1 && cd == 65536) f |= PF_FULL_RUN;
+            if (t == T_BITSET && cd == 65536) f |= PF_FULL_BITSET;
+            tf[k] = f;
+            if (t == T_ARRAY) units[k] = (l + 7) >> 3;
+            else if (t == T_RUN && !(f & PF_FULL_RUN)) units[k] = l;
+            cnt++;
+            ucnt += units[k];
+        }
     const uint32_t incl = warp_incl_scan(cnt, lane), uincl = warp_incl_scan(ucnt, lane);
     if (lane == 31) { sm.warp_a[wid] = incl; sm.warp_b[wid] = uincl; }
     __syncthreads();
@@ -172,55 +204,79 @@ __device__ __forceinline__ void many_accumulate(ManySmem &sm, const SetView &S, 
                 r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
             }
     }
-    // arrays and runs: one flat list of work units over all participants
+    // arrays and runs: one flat list of work units over all participants; a thread takes four
+    // consecutive units (one participant search, then a linear advance) and issues their loads
+    // together so several are in flight per thread
     const uint32_t V = sm.pustart[np];
-    for (uint32_t u = tid; u < V; u += OM_THREADS) {
-        uint32_t lo = 0, hi = np;  // last participant with pustart <= u
+    for (uint32_t u0 = tid * 4; u0 < V; u0 += OM_THREADS * 4) {
+        uint32_t lo = 0, hi = np;  // last participant with pustart <= u0
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (sm.pustart[mid] <= u) lo = mid;
+            if (sm.pustart[mid] <= u0) lo = mid;
             else hi = mid;
         }
-        const uint32_t local = u - sm.pustart[lo];
-        const uint8_t *p = S.payload + sm.poff[lo];
-        if ((sm.ptf[lo] & 15) == T_ARRAY) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + local);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-            const uint32_t left = sm.plen[lo] - local * 8;
-            uint32_t cur_w = (w[0] & 0xffffu) >> 5, cur_m = 0;
+        uint4 q[4];
+        uint32_t left[4];
+        int kind[4];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
-                const uint32_t wi = v >> 5, bit = 1u << (v & 31);
-                if (k == 0 || k < (int)left) {
-                    if (wi != cur_w) {
-                        atomicOr(sm.acc + cur_w, cur_m);
-                        cur_w = wi;
-                        cur_m = bit;
-                    } else {
-                        cur_m |= bit;
-                    }
+        for (int k = 0; k < 4; k++) {
+            const uint32_t u = u0 + k;
+            kind[k] = 0;
+            left[k] = 0;
+            q[k] = make_uint4(0, 0, 0, 0);
+            if (u < V) {
+                while (lo + 1 < np && sm.pustart[lo + 1] <= u) lo++;
+                const uint32_t local = u - sm.pustart[lo];
+                const uint8_t *p = S.payload + sm.poff[lo];
+                if ((sm.ptf[lo] & 15) == T_ARRAY) {
+                    q[k] = __ldg(reinterpret_cast<const uint4 *>(p) + local);
+                    left[k] = sm.plen[lo] - local * 8;
+                    kind[k] = 1;
+                } else {
+                    q[k].x = __ldg(reinterpret_cast<const uint32_t *>(p) + local);
+                    kind[k] = 2;
                 }
             }
-            atomicOr(sm.acc + cur_w, cur_m);
-        } else {  // one run per thread
-            const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p) + local);
-            const uint32_t s = r & 0xffffu, e = s + (r >> 16);
-            const uint32_t ws = s >> 5, we = e >> 5;
-            const uint32_t m_lo = ~0u << (s & 31), m_hi = ~0u >> (31 - (e & 31));
-            if (ws == we) {
-                atomicOr(sm.acc + ws, m_lo & m_hi);
-            } else {
-                atomicOr(sm.acc + ws, m_lo);
-                for (uint32_t w = ws + 1; w < we; w++) atomicOr(sm.acc + w, ~0u);
-                atomicOr(sm.acc + we, m_hi);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (kind[k] == 1) {
+                const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+                uint32_t cur_w = (w[0] & 0xffffu) >> 5, cur_m = 0;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const uint32_t v = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+                    const uint32_t wi = v >> 5, bit = 1u << (v & 31);
+                    if (e == 0 || e < (int)left[k]) {
+                        if (wi != cur_w) {
+                            atomicOr(sm.acc + cur_w, cur_m);
+                            cur_w = wi;
+                            cur_m = bit;
+                        } else {
+                            cur_m |= bit;
+                        }
+                    }
+                }
+                atomicOr(sm.acc + cur_w, cur_m);
+            } else if (kind[k] == 2) {  // one run
+                const uint32_t r = q[k].x;
+                const uint32_t s0 = r & 0xffffu, e0 = s0 + (r >> 16);
+                const uint32_t ws = s0 >> 5, we = e0 >> 5;
+                const uint32_t m_lo = ~0u << (s0 & 31), m_hi = ~0u >> (31 - (e0 & 31));
+                if (ws == we) {
+                    atomicOr(sm.acc + ws, m_lo & m_hi);
+                } else {
+                    atomicOr(sm.acc + ws, m_lo);
+                    for (uint32_t w2 = ws + 1; w2 < we; w2++) atomicOr(sm.acc + w2, ~0u);
+                    atomicOr(sm.acc + we, m_hi);
+                }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(OM_THREADS)
-k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
+__device__ __forceinline__ void
+or_many_body(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
           const uint16_t *__restrict__ keys, uint32_t want_slices, uint32_t *scratch_acc,
           uint32_t *scratch_tickets, uint32_t scratch_keys, SetOut out,
           uint32_t *__restrict__ card_per_key, OpStats *st) {
@@ -354,8 +410,14 @@ k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
             for (int i = tid; i < ACC_WORDS; i += OM_THREADS) sm.acc[i] = 0;
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
             __syncthreads();
+            if (tid == 0) sm.rfull = 0;
             for (uint32_t c0 = 0; c0 <= L; c0 += OM_CHUNK) {
                 const uint32_t np = many_gather(sm, S, idx, n, key, c0, min(c0 + OM_CHUNK, L + 1));
+                if (tid == 0) {  // a full container in the prefix (its payload is not rasterised)
+                    uint32_t af = 0;
+                    for (uint32_t j = 0; j < np; j++) af |= sm.ptf[j] & (PF_FULL_RUN | PF_FULL_BITSET);
+                    if (af) sm.rfull = 1;
+                }
                 many_accumulate(sm, S, np, q0, q1);
                 __syncthreads();
             }
@@ -363,7 +425,7 @@ k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
             const uint4 a = a4[tid], b = a4[tid + OM_THREADS];
             const bool full = ((a.x | q0.x) & (a.y | q0.y) & (a.z | q0.z) & (a.w | q0.w) &
                                (b.x | q1.x) & (b.y | q1.y) & (b.z | q1.z) & (b.w | q1.w)) == 0xffffffffu;
-            const bool became_run = __syncthreads_and(full);
+            const bool became_run = __syncthreads_and(full) || sm.rfull != 0;
             for (int i = tid; i < ACC_WORDS; i += OM_THREADS) sm.acc[i] = 0xffffffffu;
             __syncthreads();
             otype = became_run ? T_RUN : T_BITSET;
@@ -400,6 +462,21 @@ k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
     }
 }
 
+// Two register budgets of the same body: 2 CTAs/SM (no spills) and 3 CTAs/SM (more warps in
+// flight to cover the gather / payload latency, a few spills).  RB200_OM_CTAS=2|3 selects.
+__global__ void __launch_bounds__(OM_THREADS, 2)
+k_or_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n, const uint16_t *__restrict__ keys,
+          uint32_t want_slices, uint32_t *scratch_acc, uint32_t *scratch_tickets, uint32_t scratch_keys,
+          SetOut out, uint32_t *__restrict__ card_per_key, OpStats *st) {
+    or_many_body(S, idx, n, keys, want_slices, scratch_acc, scratch_tickets, scratch_keys, out, card_per_key, st);
+}
+__global__ void __launch_bounds__(OM_THREADS, 3)
+k_or_many_occ3(SetView S, const uint32_t *__restrict__ idx, uint32_t n, const uint16_t *__restrict__ keys,
+               uint32_t want_slices, uint32_t *scratch_acc, uint32_t *scratch_tickets, uint32_t scratch_keys,
+               SetOut out, uint32_t *__restrict__ card_per_key, OpStats *st) {
+    or_many_body(S, idx, n, keys, want_slices, scratch_acc, scratch_tickets, scratch_keys, out, card_per_key, st);
+}
+
 // total cardinality of the one-bitmap result of or_many
 __global__ void k_sum_cards(const uint32_t *__restrict__ c_card, const OpStats *st,
                             uint64_t *__restrict__ out) {
@@ -421,8 +498,17 @@ void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uin
                     uint32_t want_slices, uint32_t *scratch_acc, uint32_t *scratch_tickets,
                     uint32_t scratch_keys, SetOut out, uint32_t *card_per_key, OpStats *st,
                     int sms, cudaStream_t s) {
-    k_or_many<<<sms * 4, OM_THREADS, 0, s>>>(S, idx, n, keys, want_slices, scratch_acc,
-                                             scratch_tickets, scratch_keys, out, card_per_key, st);
+    static int ctas = 0;
+    if (!ctas) {
+        const char *e = getenv("RB200_OM_CTAS");
+        ctas = (e && atoi(e) == 3) ? 3 : 2;
+    }
+    if (ctas == 3)
+        k_or_many_occ3<<<sms * 3, OM_THREADS, 0, s>>>(S, idx, n, keys, want_slices, scratch_acc,
+                                                      scratch_tickets, scratch_keys, out, card_per_key, st);
+    else
+        k_or_many<<<sms * 2, OM_THREADS, 0, s>>>(S, idx, n, keys, want_slices, scratch_acc,
+                                                 scratch_tickets, scratch_keys, out, card_per_key, st);
     g_launches++;
     k_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
     g_launches++;
