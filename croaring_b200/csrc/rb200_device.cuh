@@ -460,17 +460,16 @@ __device__ __forceinline__ uint32_t acc_emit_array(const uint32_t *acc, uint16_t
         const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
         uint16_t *p = out + base + incl - c;
         const uint32_t hi = (uint32_t)(it * 32 + lane) << 7;
-        unsigned long long lo64 = ((unsigned long long)q.y << 32) | q.x;
-        unsigned long long hi64 = ((unsigned long long)q.w << 32) | q.z;
-        while (lo64) {
-            const int b = __ffsll((long long)lo64) - 1;
-            lo64 &= lo64 - 1;
-            *p++ = (uint16_t)(hi | b);
-        }
-        while (hi64) {
-            const int b = __ffsll((long long)hi64) - 1;
-            hi64 &= hi64 - 1;
-            *p++ = (uint16_t)(hi | 64 | b);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t x = w[j];
+            const uint32_t h = hi | (j << 5);
+            while (x) {
+                const int b = __ffs(x) - 1;
+                x &= x - 1;
+                *p++ = (uint16_t)(h | b);
+            }
         }
         base += total;
     }
@@ -602,6 +601,146 @@ __device__ __forceinline__ uint32_t merge_arrays(uint32_t *acc, const uint8_t *p
         reinterpret_cast<uint4 *>(out)[i] = reinterpret_cast<const uint4 *>(so)[i];
     __syncwarp();
     return count;
+}
+
+// ---------------------------------------------------------------- interval (run) algebra
+// Cells with a run container on either side and few intervals (run x run, array x run with
+// nA' + nB' <= 512, n' = runs or array values) skip the 65536-bit accumulator: both containers
+// become sorted lists of interval boundaries {start, end+1} in shared memory, a warp merge path
+// walks the merged boundaries with the coverage state (inA, inB) given by the parity of how many
+// boundaries of each list were passed, and emits a boundary of the result wherever op(inA, inB)
+// flips (run_container_union / _intersection / _xor / _andnot, src/containers/run.c:231-633,
+// as one parallel sweep).  Returns false when the reference's type rule wants a bitset
+// (card > 4096), in which case the caller takes the general path.
+__device__ __forceinline__ bool op_state(int op, bool a, bool b) {
+    return op == OP_AND ? (a && b) : op == OP_OR ? (a || b) : op == OP_XOR ? (a != b) : (a && !b);
+}
+
+// boundaries of one container into pts[] (2 per interval); returns the number of intervals
+__device__ __forceinline__ uint32_t load_boundaries(uint32_t *pts, int type, const uint8_t *src,
+                                                    uint32_t len, int lane) {
+    if (type == T_RUN) {
+        const uint32_t *runs = reinterpret_cast<const uint32_t *>(src);
+        for (uint32_t i = lane; i < len; i += 32) {
+            const uint32_t r = __ldg(runs + i), s = r & 0xffffu;
+            pts[2 * i] = s;
+            pts[2 * i + 1] = s + (r >> 16) + 1;
+        }
+        return len;
+    }
+    // array: coalesce consecutive values into intervals
+    const uint16_t *arr = reinterpret_cast<const uint16_t *>(src);
+    uint32_t nint = 0;
+    for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t v = 0;
+        bool st = false, en = false;
+        if (i < len) {
+            v = arr[i];
+            st = (i == 0) || ((uint32_t)arr[i - 1] + 1 != v);
+            en = (i + 1 == len) || ((uint32_t)arr[i + 1] != v + 1);
+        }
+        const unsigned ms = __ballot_sync(FULLMASK, st), me = __ballot_sync(FULLMASK, en);
+        // the k-th start pairs with the k-th end; an interval open at the end of this stripe is
+        // closed by a later stripe, so count ends seen before this stripe separately
+        if (st) pts[2 * (nint + __popc(ms & lanemask_lt()))] = v;
+        if (en) {
+            // ends so far == starts so far - (1 if an interval is open at stripe start)
+            const uint32_t ke = (nint + __popc(ms & (lanemask_lt() | (1u << lane)))) - 1;
+            pts[2 * ke + 1] = v + 1;
+        }
+        nint += __popc(ms);
+    }
+    return nint;
+}
+
+__device__ __forceinline__ bool
+interval_cell(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
+              uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
+              int lane, int &otype, uint32_t &ocard, uint32_t &olen) {
+    uint32_t *pA = acc;
+    const uint32_t nA = load_boundaries(pA, tA, pa, lA, lane);
+    uint32_t *pB = acc + 2 * nA;
+    const uint32_t nB = load_boundaries(pB, tB, pb, lB, lane);
+    uint32_t *ev = acc + 1024;
+    __syncwarp();
+    const uint32_t n = 2 * nA, m = 2 * nB, T = n + m, per = (T + 31) >> 5;
+    const uint32_t d0 = min((uint32_t)lane * per, T), d1 = min(d0 + per, T);
+    uint32_t lo = d0 > m ? d0 - m : 0u, hi = min(d0, n);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pA[mid] <= pB[d0 - 1 - mid]) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t i0 = lo, j0 = d0 - lo;
+    const uint32_t NONE = 0x20000u;
+    uint32_t prev0 = NONE + 1;
+    if (d0 > 0) {
+        const uint32_t x = i0 > 0 ? pA[i0 - 1] : 0u, y = j0 > 0 ? pB[j0 - 1] : 0u;
+        prev0 = (i0 > 0 && j0 > 0) ? max(x, y) : (i0 > 0 ? x : y);
+    }
+    uint32_t off = 0, nev = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        uint32_t i = i0, j = j0, prev = prev0, c = 0;
+        uint32_t ai = i < n ? pA[i] : NONE, bj = j < m ? pB[j] : NONE;
+        for (uint32_t p = d0; p < d1; p++) {
+            const bool take_a = ai <= bj;
+            const uint32_t x = take_a ? ai : bj;
+            if (take_a) { i++; ai = i < n ? pA[i] : NONE; }
+            else { j++; bj = j < m ? pB[j] : NONE; }
+            if (x != min(ai, bj)) {  // last boundary with this value: evaluate the flip
+                const bool inA = i & 1, inB = j & 1;
+                const bool tie = (x == prev);  // the other list had a boundary at the same value
+                const bool wasA = (take_a || tie) ? !inA : inA, wasB = (!take_a || tie) ? !inB : inB;
+                if (op_state(op, inA, inB) != op_state(op, wasA, wasB)) {
+                    if (pass == 1) ev[off + c] = x;
+                    c++;
+                }
+            }
+            prev = x;
+        }
+        if (pass == 0) {
+            const uint32_t incl = warp_incl_scan(c, lane);
+            off = incl - c;
+            nev = __shfl_sync(FULLMASK, incl, 31);
+        }
+    }
+    __syncwarp();
+    const uint32_t nruns = nev >> 1;
+    uint32_t card = 0;
+    for (uint32_t k = lane; k < nruns; k += 32) card += ev[2 * k + 1] - ev[2 * k];
+    card = __reduce_add_sync(FULLMASK, card);
+    if (card == 0) { otype = 0; ocard = olen = 0; __syncwarp(); return true; }
+    const int t = decide_type(op, tA, tB, cA, cB, lA, lB, (int)card, (int)nruns);
+    if (t == T_BITSET) { __syncwarp(); return false; }
+    if (t == T_RUN) {
+        if (4 * nruns > cap) { __syncwarp(); return false; }
+        uint32_t *o = reinterpret_cast<uint32_t *>(out);
+        for (uint32_t k = lane; k < nruns; k += 32) {
+            const uint32_t s = ev[2 * k], e = ev[2 * k + 1];
+            o[k] = s | ((e - s - 1) << 16);
+        }
+        otype = T_RUN;
+        ocard = card;
+        olen = nruns;
+    } else {  // array: expand the runs at their scanned offsets
+        if (2 * card > cap) { __syncwarp(); return false; }
+        uint16_t *o = reinterpret_cast<uint16_t *>(out);
+        uint32_t base = 0;
+        for (uint32_t k0 = 0; k0 < nruns; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const uint32_t s = k < nruns ? ev[2 * k] : 0u, len = k < nruns ? ev[2 * k + 1] - s : 0u;
+            const uint32_t incl = warp_incl_scan(len, lane);
+            uint16_t *p = o + base + incl - len;
+            for (uint32_t q = 0; q < len; q++) p[q] = (uint16_t)(s + q);
+            base += __shfl_sync(FULLMASK, incl, 31);
+        }
+        otype = T_ARRAY;
+        ocard = olen = card;
+    }
+    __syncwarp();
+    return true;
 }
 
 // 16-byte vector copy of a stored payload (pass-through containers)

@@ -1476,7 +1476,13 @@ size_t rb200_download_next(rb200_download_stream_t *st, roaring_bitmap_t **out) 
             }
         }
     };
+    // threads scaled to the work of this chunk: waking 64 workers for a few hundred tiny
+    // bitmaps costs more than it saves
+    const uint64_t chunk_bytes = st->h_ob[p1] - st->h_ob[p0];
+    const uint64_t chunk_conts = st->h_ob[st->nb + 1 + p1] - st->h_ob[st->nb + 1 + p0];
+    uint64_t want = (chunk_bytes + 256 * chunk_conts + 512 * n) / (192 << 10) + 1;
     unsigned T = host_workers();
+    if (want < T) T = (unsigned)want;
     if ((size_t)T * 8 > n) T = (unsigned)((n + 7) / 8);
     pool().run(work, T);
     st->next_build++;

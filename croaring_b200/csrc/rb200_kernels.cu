@@ -121,6 +121,13 @@ __device__ __forceinline__ void
 cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
              uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
              int lane, int &otype, uint32_t &ocard, uint32_t &olen, unsigned int *err) {
+    // ---- run x run / array x run with few intervals: boundary sweep, no accumulator ---------
+    if ((tA == T_RUN || tB == T_RUN) && tA != T_BITSET && tB != T_BITSET &&
+        (tA == T_RUN ? lA : cA) + (tB == T_RUN ? lB : cB) <= 512u) {
+        if (interval_cell(acc, op, tA, tB, pa, pb, cA, cB, lA, lB, out, cap, lane, otype, ocard, olen))
+            return;
+    }
+
     // ---- result is always an array and one side is an array: filter, no re-encode --------
     if (op == OP_AND && (tA == T_ARRAY || tB == T_ARRAY)) {
         // filter the array side through the other side's bits
