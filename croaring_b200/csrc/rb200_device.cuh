@@ -545,6 +545,17 @@ __device__ __forceinline__ uint32_t filter_array(const uint8_t *src, uint32_t n,
 // write at its scanned offset) and the warp copies the staged result out with 128-bit stores.
 // Duplicates (a value present in both inputs) are adjacent in the merged order: OR keeps the
 // first, XOR drops both.
+// global -> shared staging of a u16 range (128-bit when the source is 16-byte aligned)
+__device__ __forceinline__ void stage_u16(uint16_t *dst, const uint8_t *src, uint32_t n, int lane) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (uint32_t i = lane; i < (n + 7) / 8; i += 32)
+            reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+    } else {
+        const uint16_t *s16 = reinterpret_cast<const uint16_t *>(src);
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = s16[i];
+    }
+}
+
 template <bool IS_XOR>
 __device__ __forceinline__ uint32_t merge_arrays(uint32_t *acc, const uint8_t *pa, uint32_t n,
                                                  const uint8_t *pb, uint32_t m, uint8_t *out,
@@ -552,10 +563,8 @@ __device__ __forceinline__ uint32_t merge_arrays(uint32_t *acc, const uint8_t *p
     uint16_t *sa = reinterpret_cast<uint16_t *>(acc);
     uint16_t *sb = sa + ((n + 7) & ~7u);
     uint16_t *so = reinterpret_cast<uint16_t *>(acc) + 2048;
-    for (uint32_t i = lane; i < (n + 7) / 8; i += 32)
-        reinterpret_cast<uint4 *>(sa)[i] = __ldg(reinterpret_cast<const uint4 *>(pa) + i);
-    for (uint32_t i = lane; i < (m + 7) / 8; i += 32)
-        reinterpret_cast<uint4 *>(sb)[i] = __ldg(reinterpret_cast<const uint4 *>(pb) + i);
+    stage_u16(sa, pa, n, lane);
+    stage_u16(sb, pb, m, lane);
     __syncwarp();
     const uint32_t T = n + m, per = (T + 31) >> 5;
     const uint32_t d0 = min((uint32_t)lane * per, T), d1 = min(d0 + per, T);
@@ -597,10 +606,39 @@ __device__ __forceinline__ uint32_t merge_arrays(uint32_t *acc, const uint8_t *p
         }
     }
     __syncwarp();
-    for (uint32_t i = lane; i < (count + 7) / 8; i += 32)
-        reinterpret_cast<uint4 *>(out)[i] = reinterpret_cast<const uint4 *>(so)[i];
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        for (uint32_t i = lane; i < (count + 7) / 8; i += 32)
+            reinterpret_cast<uint4 *>(out)[i] = reinterpret_cast<const uint4 *>(so)[i];
+    } else {
+        uint16_t *o16 = reinterpret_cast<uint16_t *>(out);
+        for (uint32_t i = lane; i < count; i += 32) o16[i] = so[i];
+    }
     __syncwarp();
     return count;
+}
+
+// Same for cA + cB up to 4064 values: the merged sequence is cut in two at its middle diagonal
+// (never between the two copies of a value present in both inputs) and each half goes through
+// the staged merge; the second half's output is appended to the first.
+template <bool IS_XOR>
+__device__ __forceinline__ uint32_t merge_arrays_split(uint32_t *acc, const uint8_t *pa, uint32_t n,
+                                                       const uint8_t *pb, uint32_t m, uint8_t *out,
+                                                       int lane) {
+    if (((n + 7) & ~7u) + ((m + 7) & ~7u) <= 2048u) return merge_arrays<IS_XOR>(acc, pa, n, pb, m, out, lane);
+    const uint16_t *a = reinterpret_cast<const uint16_t *>(pa), *b = reinterpret_cast<const uint16_t *>(pb);
+    const uint32_t d = (n + m) >> 1;
+    uint32_t lo = d > m ? d - m : 0u, hi = min(d, n);
+    while (lo < hi) {  // uniform across the warp
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= b[d - 1 - mid]) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t i = lo;
+    uint32_t j = d - lo;
+    if (i > 0 && j < m && a[i - 1] == b[j]) j++;  // keep both copies of a shared value together
+    const uint32_t n1 = merge_arrays<IS_XOR>(acc, pa, i, pb, j, out, lane);
+    const uint32_t n2 = merge_arrays<IS_XOR>(acc, pa + 2 * i, n - i, pb + 2 * j, m - j, out + 2 * n1, lane);
+    return n1 + n2;
 }
 
 // ---------------------------------------------------------------- interval (run) algebra

@@ -139,7 +139,7 @@ cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uin
         const uint32_t lo = arrA ? lB : lA;
         uint32_t n;
         if (2 * narr > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-        if (to == T_BITSET) {
+        if (to == T_BITSET && narr < 192) {  // few probes: test the bits where they are
             n = filter_array<false, true>(parr, narr, reinterpret_cast<const uint32_t *>(po),
                                           reinterpret_cast<uint16_t *>(out), lane);
         } else {
@@ -154,7 +154,7 @@ cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uin
     if (op == OP_ANDNOT && tA == T_ARRAY) {
         uint32_t n;
         if (2 * cA > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-        if (tB == T_BITSET) {
+        if (tB == T_BITSET && cA < 192) {
             n = filter_array<true, true>(pa, cA, reinterpret_cast<const uint32_t *>(pb),
                                          reinterpret_cast<uint16_t *>(out), lane);
         } else {
@@ -168,11 +168,10 @@ cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uin
     }
 
     // ---- array x array union / xor whose result is known to stay an array: warp merge path ---
-    if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY &&
-        ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= 2048u) {
+    if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY && cA + cB <= 4064u) {
         if (round16(2 * (cA + cB)) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-        const uint32_t n = (op == OP_OR) ? merge_arrays<false>(acc, pa, cA, pb, cB, out, lane)
-                                         : merge_arrays<true>(acc, pa, cA, pb, cB, out, lane);
+        const uint32_t n = (op == OP_OR) ? merge_arrays_split<false>(acc, pa, cA, pb, cB, out, lane)
+                                         : merge_arrays_split<true>(acc, pa, cA, pb, cB, out, lane);
         otype = n ? T_ARRAY : 0;  // cA + cB <= 4096 -> array (mixed_union.c:162-176, mixed_xor.c:196-205)
         ocard = olen = n;
         return;
