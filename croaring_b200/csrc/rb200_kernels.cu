@@ -168,7 +168,9 @@ cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uin
     }
 
     // ---- array x array union / xor whose result is known to stay an array: warp merge path ---
-    if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY && cA + cB <= 4064u) {
+    // (measured on B200: the two-pass merge costs ~1.25 instr/value + 200, the accumulator round
+    //  trip ~0.8 instr/value + 700 — the merge wins below ~1100 values, so it is used up to 1024)
+    if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY && cA + cB <= 1024u) {
         if (round16(2 * (cA + cB)) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
         const uint32_t n = (op == OP_OR) ? merge_arrays_split<false>(acc, pa, cA, pb, cB, out, lane)
                                          : merge_arrays_split<true>(acc, pa, cA, pb, cB, out, lane);
