@@ -460,16 +460,18 @@ __device__ __forceinline__ uint32_t acc_emit_array(const uint32_t *acc, uint16_t
         const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
         uint16_t *p = out + base + incl - c;
         const uint32_t hi = (uint32_t)(it * 32 + lane) << 7;
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t x = w[j];
-            const uint32_t h = hi | (j << 5);
-            while (x) {
-                const int b = __ffs(x) - 1;
-                x &= x - 1;
-                *p++ = (uint16_t)(h | b);
-            }
+        // (64-bit loops measured faster than four 32-bit ones: fewer divergent loop heads)
+        unsigned long long lo64 = ((unsigned long long)q.y << 32) | q.x;
+        unsigned long long hi64 = ((unsigned long long)q.w << 32) | q.z;
+        while (lo64) {
+            const int b = __ffsll((long long)lo64) - 1;
+            lo64 &= lo64 - 1;
+            *p++ = (uint16_t)(hi | b);
+        }
+        while (hi64) {
+            const int b = __ffsll((long long)hi64) - 1;
+            hi64 &= hi64 - 1;
+            *p++ = (uint16_t)(hi | 64 | b);
         }
         base += total;
     }
@@ -615,30 +617,6 @@ __device__ __forceinline__ uint32_t merge_arrays(uint32_t *acc, const uint8_t *p
     }
     __syncwarp();
     return count;
-}
-
-// Same for cA + cB up to 4064 values: the merged sequence is cut in two at its middle diagonal
-// (never between the two copies of a value present in both inputs) and each half goes through
-// the staged merge; the second half's output is appended to the first.
-template <bool IS_XOR>
-__device__ __forceinline__ uint32_t merge_arrays_split(uint32_t *acc, const uint8_t *pa, uint32_t n,
-                                                       const uint8_t *pb, uint32_t m, uint8_t *out,
-                                                       int lane) {
-    if (((n + 7) & ~7u) + ((m + 7) & ~7u) <= 2048u) return merge_arrays<IS_XOR>(acc, pa, n, pb, m, out, lane);
-    const uint16_t *a = reinterpret_cast<const uint16_t *>(pa), *b = reinterpret_cast<const uint16_t *>(pb);
-    const uint32_t d = (n + m) >> 1;
-    uint32_t lo = d > m ? d - m : 0u, hi = min(d, n);
-    while (lo < hi) {  // uniform across the warp
-        const uint32_t mid = (lo + hi) >> 1;
-        if (a[mid] <= b[d - 1 - mid]) lo = mid + 1;
-        else hi = mid;
-    }
-    const uint32_t i = lo;
-    uint32_t j = d - lo;
-    if (i > 0 && j < m && a[i - 1] == b[j]) j++;  // keep both copies of a shared value together
-    const uint32_t n1 = merge_arrays<IS_XOR>(acc, pa, i, pb, j, out, lane);
-    const uint32_t n2 = merge_arrays<IS_XOR>(acc, pa + 2 * i, n - i, pb + 2 * j, m - j, out + 2 * n1, lane);
-    return n1 + n2;
 }
 
 // ---------------------------------------------------------------- interval (run) algebra

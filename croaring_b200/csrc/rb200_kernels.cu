@@ -168,12 +168,13 @@ cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uin
     }
 
     // ---- array x array union / xor whose result is known to stay an array: warp merge path ---
-    // (measured on B200: the two-pass merge costs ~1.25 instr/value + 200, the accumulator round
-    //  trip ~0.8 instr/value + 700 — the merge wins below ~1100 values, so it is used up to 1024)
-    if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY && cA + cB <= 1024u) {
+    // (measured on B200, weather_sept_85 all-pairs OR: staging limit 2032 values -> 1.41 ms,
+    //  1024 -> 1.50 ms, split merge up to 4064 -> 2.06 ms; the accumulator round trip wins above)
+    if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY &&
+        ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= 2048u) {
         if (round16(2 * (cA + cB)) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-        const uint32_t n = (op == OP_OR) ? merge_arrays_split<false>(acc, pa, cA, pb, cB, out, lane)
-                                         : merge_arrays_split<true>(acc, pa, cA, pb, cB, out, lane);
+        const uint32_t n = (op == OP_OR) ? merge_arrays<false>(acc, pa, cA, pb, cB, out, lane)
+                                         : merge_arrays<true>(acc, pa, cA, pb, cB, out, lane);
         otype = n ? T_ARRAY : 0;  // cA + cB <= 4096 -> array (mixed_union.c:162-176, mixed_xor.c:196-205)
         ocard = olen = n;
         return;
