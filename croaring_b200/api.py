@@ -45,6 +45,8 @@ def lib():
         sig(f"roaring_bitmap_{op}", _P, _P, _P)
         sig(f"roaring_bitmap_{op}_cardinality", C.c_uint64, _P, _P)
     sig("roaring_bitmap_or_many", _P, C.c_size_t, C.POINTER(_P))
+    sig("roaring_bitmap_xor_many", _P, C.c_size_t, C.POINTER(_P))
+    sig("rb200_xor_many", _P, _P, _P, C.c_size_t)
     sig("roaring_bitmap_jaccard_index", C.c_double, _P, _P)
     sig("roaring_bitmap_intersect", C.c_bool, _P, _P)
     sig("rb200_bitmap_portable_deserialize_safe", _P, C.c_char_p, C.c_size_t)
@@ -198,6 +200,15 @@ def or_many(bitmaps):
     return Bitmap(p)
 
 
+def xor_many(bitmaps):
+    """roaring_bitmap_xor_many on host bitmaps (drop-in symbol)."""
+    arr = (_P * len(bitmaps))(*[b.ptr for b in bitmaps])
+    p = lib().roaring_bitmap_xor_many(len(bitmaps), arr)
+    if not p:
+        raise RB200Error(last_error())
+    return Bitmap(p)
+
+
 def batch_op_host(op, a, b):
     """out[k] = a[k] op b[k] through the device: one upload, one launch sequence, one download."""
     n = len(a)
@@ -280,6 +291,14 @@ class DeviceSet:
             assert card_per_key.dtype == np.uint32 and card_per_key.size == 65536
         p = lib().rb200_or_many_keyrange(self.ptr, ip, n, key_lo, key_hi, cp)
         return DeviceSet(p)
+
+    def xor_many(self, idx=None):
+        if idx is None:
+            ip, n = None, len(self)
+        else:
+            idx = _u32(idx)
+            ip, n = idx.ctypes.data, idx.size
+        return DeviceSet(lib().rb200_xor_many(self.ptr, ip, n))
 
     def cardinalities(self):
         out = np.zeros(len(self), dtype=np.uint64)

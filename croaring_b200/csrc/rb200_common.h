@@ -110,4 +110,8 @@ void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uin
                     uint32_t scratch_keys, SetOut out, uint32_t *card_per_key /*65536 or null*/,
                     OpStats *st, int sms, cudaStream_t s);
 
+void launch_xor_many(const SetView &S, const uint32_t *idx, uint32_t n, const uint16_t *keys,
+                     uint8_t *t_type, uint32_t *t_card, uint32_t *t_len, SetOut out, OpStats *st,
+                     int sms, cudaStream_t s);
+
 }  // namespace rb200

@@ -1193,6 +1193,74 @@ rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n) 
     return rb200_or_many_keyrange(S, idx, n, 0, 65535, nullptr);
 }
 
+// roaring_bitmap_xor_many (src/roaring.c:795-809) over S[idx[0..n)] (idx == NULL: all, in order).
+rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return nullptr;
+    if (idx == nullptr) n = S->n_bitmaps;
+    uint64_t tot = 0;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t b = idx ? idx[i] : (uint32_t)i;
+        if (b >= S->n_bitmaps) { g.err = "xor_many: index out of range"; return nullptr; }
+        tot += S->h_cnt[b];
+    }
+    const uint64_t maxk = std::min<uint64_t>(65536, tot);
+    rb200_set *R = set_new(1, maxk, maxk * BITSET_BYTES);
+    if (!R) return nullptr;
+    uint32_t *d_idx = nullptr, *h_idx = nullptr;
+    uint8_t *t_type = (uint8_t *)dev_alloc(maxk);
+    uint32_t *t_card = (uint32_t *)dev_alloc(4 * maxk), *t_len = (uint32_t *)dev_alloc(4 * maxk);
+    bool ok = t_type && t_card && t_len;
+    if (ok && idx && n) {
+        d_idx = (uint32_t *)dev_alloc(4 * n);
+        h_idx = (uint32_t *)pin_alloc(4 * n);
+        ok = d_idx && h_idx;
+        if (ok) {
+            memcpy(h_idx, idx, 4 * n);
+            ok = cudaMemcpyAsync(d_idx, h_idx, 4 * n, cudaMemcpyHostToDevice, g.stream) == cudaSuccess;
+        }
+    }
+    if (ok) {
+        cudaEventRecord(g.ev0, g.stream);
+        ok = stats_reset();
+        const SetView vs = S->view();
+        launch_many_mark(vs, d_idx, (uint32_t)n, 0, 65535, g.d_flags, g.stream);
+        launch_many_compact(g.d_flags, g.d_keys, g.d_stats, g.stream);
+        cudaEventRecord(g.evk0, g.stream);
+        launch_xor_many(vs, d_idx, (uint32_t)n, g.d_keys, t_type, t_card, t_len, R->out(), g.d_stats,
+                        g.sms, g.stream);
+        cudaEventRecord(g.evk1, g.stream);
+        cudaEventRecord(g.ev1, g.stream);
+        ok = ok && stats_fetch();
+        cudaError_t e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess) { g.err = std::string("xor_many: ") + cudaGetErrorString(e); ok = false; }
+        if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("xor_many launch: ") + cudaGetErrorString(e); ok = false; }
+    }
+    if (ok) {
+        cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+        cudaEventElapsedTime(&g.last_compute_ms, g.evk0, g.evk1);
+        const uint32_t live = (uint32_t)g.h_stats->dir_cursor;
+        R->n_containers = live;
+        R->slab_used = (uint64_t)g.h_stats->nk * BITSET_BYTES;
+        R->h_cnt[0] = live;
+        R->h_bytes[0] = (uint64_t)live * BITSET_BYTES;
+        uint8_t fl = 0;
+        for (size_t i = 0; i < n; i++) fl |= S->h_flags[idx ? idx[i] : i];
+        R->h_flags[0] = fl & FLAG_COW;
+        g.last_algo_bytes = (idx == nullptr) ? S->portable_bytes : 0;
+    }
+    dev_free(d_idx, 4 * n);
+    pin_free(h_idx, 4 * n);
+    dev_free(t_type, maxk);
+    dev_free(t_card, 4 * maxk);
+    dev_free(t_len, 4 * maxk);
+    if (!ok) {
+        set_delete(R);
+        return nullptr;
+    }
+    return R;
+}
+
 int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return -1;
@@ -1715,6 +1783,20 @@ roaring_bitmap_t *roaring_bitmap_or_many(size_t number, const roaring_bitmap_t *
     rb200_set *S = rb200_set_upload(rs, number);
     if (!S) return nullptr;
     rb200_set *R = rb200_or_many(S, nullptr, number);
+    roaring_bitmap_t *out = nullptr;
+    if (R) {
+        out = rb200_set_download(R, 0);
+        set_delete(R);
+    }
+    set_delete(S);
+    return out;
+}
+
+roaring_bitmap_t *roaring_bitmap_xor_many(size_t number, const roaring_bitmap_t **rs) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    rb200_set *S = rb200_set_upload(rs, number);
+    if (!S) return nullptr;
+    rb200_set *R = rb200_xor_many(S, nullptr, number);
     roaring_bitmap_t *out = nullptr;
     if (R) {
         out = rb200_set_download(R, 0);

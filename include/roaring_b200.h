@@ -63,6 +63,8 @@ roaring_bitmap_t *roaring_bitmap_xor(const roaring_bitmap_t *r1, const roaring_b
 roaring_bitmap_t *roaring_bitmap_andnot(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 /* include/roaring/roaring.h:304  (src/roaring.c:775) */
 roaring_bitmap_t *roaring_bitmap_or_many(size_t number, const roaring_bitmap_t **rs);
+/* include/roaring/roaring.h:334  (src/roaring.c:795) */
+roaring_bitmap_t *roaring_bitmap_xor_many(size_t number, const roaring_bitmap_t **rs);
 /* include/roaring/roaring.h:231  (src/roaring.c:3048) */
 uint64_t roaring_bitmap_and_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 /* include/roaring/roaring.h:258-271 (src/roaring.c:3086-3107): inclusion-exclusion on the above */
@@ -128,6 +130,9 @@ int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, cons
 /* roaring_bitmap_or_many over S[idx[0..n)] (idx == NULL: all bitmaps in order).
  * Returns a device-resident set holding ONE bitmap. */
 rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n);
+
+/* roaring_bitmap_xor_many over S[idx[0..n)] (idx == NULL: all bitmaps in order): ONE result bitmap. */
+rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n);
 
 /* Key-sharded form used for multi-GPU aggregation: only containers whose high-16 key lies in
  * [key_lo, key_hi] take part; per-key result cardinalities are ADDED into card_per_key[65536]
