@@ -117,11 +117,13 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
 
 // ------------------------------------------------------------------------------ grid cells
 // Evaluate one matched cell on the warp's accumulator and write the result payload.
+template <int OP>
 __device__ __forceinline__ void
-cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
+cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
              uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
              int lane, int &otype, uint32_t &ocard, uint32_t &olen, unsigned int *err) {
     // ---- run x run / array x run with few intervals: boundary sweep, no accumulator ---------
+    constexpr int op = OP;
     if ((tA == T_RUN || tB == T_RUN) && tA != T_BITSET && tB != T_BITSET &&
         (tA == T_RUN ? lA : cA) + (tB == T_RUN ? lB : cB) <= 512u) {
         if (interval_cell(acc, op, tA, tB, pa, pb, cA, cB, lA, lB, out, cap, lane, otype, ocard, olen))
@@ -234,8 +236,9 @@ cell_compute(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uin
     olen = len;
 }
 
+template <int OP>
 __global__ void __launch_bounds__(128)
-k_compute_items(SetView A, SetView B, Items it, uint64_t W, int op, uint8_t *slab,
+k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 uint64_t slab_cap, OpStats *st) {
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
     const int lane = threadIdx.x & 31;
@@ -261,7 +264,7 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, int op, uint8_t *sla
                 if (lane == 0) atomicExch(&st->error, 2u);
             } else if (kind == K_COMPUTE) {
                 const uint32_t ca = it.ca[item], cb = it.cb[item];
-                cell_compute(acc, op, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
+                cell_compute<OP>(acc, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
                              B.payload + B.c_off[cb], A.c_card[ca], B.c_card[cb], A.c_len[ca],
                              B.c_len[cb], slab + off, cap, lane, otype, ocard, olen, &st->error);
             } else {
@@ -602,7 +605,12 @@ void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t
                           uint8_t *slab, uint64_t slab_cap, OpStats *st, cudaStream_t s) {
     if (!W) return;
     const uint32_t g = blocks_for_warps((W + 3) / 4, 4, sm_count() * 6);
-    k_compute_items<<<g, 128, 0, s>>>(A, B, it, W, op, slab, slab_cap, st);
+    switch (op) {
+        case OP_AND: k_compute_items<OP_AND><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st); break;
+        case OP_OR: k_compute_items<OP_OR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st); break;
+        case OP_XOR: k_compute_items<OP_XOR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st); break;
+        default: k_compute_items<OP_ANDNOT><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st); break;
+    }
     g_launches++;
 }
 
