@@ -78,6 +78,9 @@ def lib():
     sig("rb200_set_download", _P, _P, C.c_size_t)
     sig("rb200_set_download_all", C.c_int, _P, C.POINTER(_P))
     sig("rb200_bitmaps_free", None, C.POINTER(_P), C.c_size_t)
+    sig("rb200_set_serialize", C.c_int, _P, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)),
+        C.POINTER(C.POINTER(C.c_uint64)))
+    sig("rb200_serialized_free", None, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     sig("rb200_download_begin", _P, _P, C.c_size_t)
     sig("rb200_download_chunk_capacity", C.c_size_t, _P)
     sig("rb200_download_next", C.c_size_t, _P, C.POINTER(_P))
@@ -321,6 +324,24 @@ class DeviceSet:
     @staticmethod
     def free_raw(arr, n=None):
         lib().rb200_bitmaps_free(arr, len(arr) if n is None else n)
+
+    def serialize_all(self, copy=True):
+        """Portable bytes of every bitmap, serialized ON THE DEVICE and brought back in one D2H.
+        copy=True -> list of bytes; copy=False -> (base pointer, offsets, lengths, release())"""
+        buf = C.c_void_p()
+        off = C.POINTER(C.c_uint64)()
+        ln = C.POINTER(C.c_uint64)()
+        if lib().rb200_set_serialize(self.ptr, C.byref(buf), C.byref(off), C.byref(ln)) != 0:
+            raise RB200Error(last_error())
+        n = len(self)
+
+        def release():
+            lib().rb200_serialized_free(buf, off, ln)
+        if not copy:
+            return buf, off, ln, release
+        out = [C.string_at(buf.value + off[i], ln[i]) for i in range(n)]
+        release()
+        return out
 
     def download_stream(self, chunk_bitmaps=1024):
         """Generator over (ctypes array of roaring_bitmap_t*, count): streaming download.  The

@@ -110,6 +110,12 @@ void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uin
                     uint32_t scratch_keys, SetOut out, uint32_t *card_per_key /*65536 or null*/,
                     OpStats *st, int sms, cudaStream_t s);
 
+void launch_pack_scan(const uint64_t *bytes, const uint32_t *cnts, uint32_t n, uint64_t *off,
+                      uint64_t *beg, cudaStream_t s);
+void launch_serialize_measure(const SetView &S, uint32_t n, uint64_t *sizes16, uint32_t *exact,
+                              uint32_t *hasrun, cudaStream_t s);
+void launch_serialize_write(const SetView &S, uint32_t n, const uint64_t *off, const uint32_t *hasrun,
+                            uint8_t *dst, cudaStream_t s);
 void launch_xor_many(const SetView &S, const uint32_t *idx, uint32_t n, const uint16_t *keys,
                      uint8_t *t_type, uint32_t *t_card, uint32_t *t_len, SetOut out, OpStats *st,
                      int sms, cudaStream_t s);

@@ -271,7 +271,7 @@ __device__ __forceinline__ void acc_apply_ranges(uint32_t *acc, uint32_t lo, uin
 
 // acc op= {run container}: one lane per run ("run-length expansion")
 template <int MODE, bool ATOMIC_INTERIOR>
-__device__ __forceinline__ void acc_apply_runs(uint32_t *acc, const uint8_t *src, uint32_t n,
+static __device__ __noinline__ void acc_apply_runs(uint32_t *acc, const uint8_t *src, uint32_t n,
                                                int lane) {
     const uint32_t *runs = reinterpret_cast<const uint32_t *>(src);
     for (uint32_t base = 0; base < n; base += 32) {
@@ -285,7 +285,7 @@ __device__ __forceinline__ void acc_apply_runs(uint32_t *acc, const uint8_t *src
 
 // acc &= {run container}: clear the n+1 gaps between / around the runs
 // (bitset_reset_range over the gaps, src/containers/mixed_intersection.c:171-182)
-__device__ __forceinline__ void acc_and_runs(uint32_t *acc, const uint8_t *src, uint32_t n,
+static __device__ __noinline__ void acc_and_runs(uint32_t *acc, const uint8_t *src, uint32_t n,
                                              int lane) {
     const uint32_t *runs = reinterpret_cast<const uint32_t *>(src);
     for (uint32_t base = 0; base <= n; base += 32) {
@@ -308,7 +308,7 @@ __device__ __forceinline__ void acc_and_runs(uint32_t *acc, const uint8_t *src, 
 }
 
 // acc &= {sorted array}: clear the gaps between consecutive values
-__device__ __forceinline__ void acc_and_array(uint32_t *acc, const uint8_t *src, uint32_t n,
+static __device__ __noinline__ void acc_and_array(uint32_t *acc, const uint8_t *src, uint32_t n,
                                               int lane) {
     const uint16_t *arr = reinterpret_cast<const uint16_t *>(src);
     for (uint32_t base = 0; base <= n; base += 32) {
@@ -480,7 +480,7 @@ __device__ __forceinline__ uint32_t acc_emit_array(const uint32_t *acc, uint16_t
 
 // acc -> run list {start, length-1}: pass 1 writes run starts, pass 2 run ends, pass 3 turns
 // ends into lengths.  Returns the number of runs.
-__device__ __forceinline__ uint32_t acc_emit_runs(const uint32_t *acc, uint16_t *out, int lane) {
+static __device__ __noinline__ uint32_t acc_emit_runs(const uint32_t *acc, uint16_t *out, int lane) {
     uint32_t nr = 0;
     for (int pass = 0; pass < 2; pass++) {
         uint32_t base = 0;
@@ -670,7 +670,7 @@ __device__ __forceinline__ uint32_t load_boundaries(uint32_t *pts, int type, con
     return nint;
 }
 
-__device__ __forceinline__ bool
+static __device__ __noinline__ bool
 interval_cell(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
               uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
               int lane, int &otype, uint32_t &ocard, uint32_t &olen) {

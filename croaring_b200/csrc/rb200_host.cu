@@ -110,6 +110,7 @@ struct Ctx {
     float last_ms = 0.f, last_compute_ms = 0.f;
     uint64_t last_download_bytes = 0;
 } g;
+std::map<uint8_t *, size_t> g_serialized_sizes;  // pinned blobs handed out by rb200_set_serialize
 
 #define CK(call)                                                                    \
     do {                                                                            \
@@ -1712,6 +1713,80 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
     dev_free(d_beg, 8 * (nb + 1));
     dev_free(d_cnt, 4 * nb);
     return ok ? 0 : -1;
+}
+
+// Device-side portable serialization of every bitmap of a set + one D2H copy.
+// *buf is pinned host memory owned by the library (release with rb200_serialized_free);
+// blob i = *buf + (*off)[i], (*len)[i] bytes, byte-identical to roaring_bitmap_portable_serialize.
+int rb200_set_serialize(const rb200_set_t *s, char **buf, uint64_t **off_out, uint64_t **len_out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    const size_t nb = s->n_bitmaps;
+    *buf = nullptr;
+    *off_out = (uint64_t *)malloc(8 * (nb + 1));
+    *len_out = (uint64_t *)malloc(8 * (nb + 1));
+    if (!*off_out || !*len_out) return -1;
+    (*off_out)[0] = 0;
+    if (nb == 0) return 0;
+    uint64_t *d_sz = (uint64_t *)dev_alloc(8 * nb), *d_off = (uint64_t *)dev_alloc(8 * (nb + 1)),
+             *d_dummy = (uint64_t *)dev_alloc(8 * (nb + 1));
+    uint32_t *d_exact = (uint32_t *)dev_alloc(4 * nb), *d_hasrun = (uint32_t *)dev_alloc(4 * nb);
+    uint8_t *h_meta = (uint8_t *)pin_alloc(8 * (nb + 1) + 4 * nb);
+    uint8_t *d_blob = nullptr, *h_blob = nullptr;
+    uint64_t total = 0;
+    bool ok = d_sz && d_off && d_dummy && d_exact && d_hasrun && h_meta;
+    if (ok) {
+        const SetView v = s->view();
+        launch_serialize_measure(v, (uint32_t)nb, d_sz, d_exact, d_hasrun, g.stream);
+        launch_pack_scan(d_sz, d_hasrun, (uint32_t)nb, d_off, d_dummy, g.stream);
+        ok = cudaMemcpyAsync(h_meta, d_off, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaMemcpyAsync(h_meta + 8 * (nb + 1), d_exact, 4 * nb, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaStreamSynchronize(g.stream) == cudaSuccess;
+    }
+    if (ok) {
+        const uint64_t *h_off = (const uint64_t *)h_meta;
+        const uint32_t *h_exact = (const uint32_t *)(h_meta + 8 * (nb + 1));
+        total = h_off[nb];
+        for (size_t i = 0; i < nb; i++) { (*off_out)[i] = h_off[i]; (*len_out)[i] = h_exact[i]; }
+        (*off_out)[nb] = total;
+        d_blob = (uint8_t *)dev_alloc(total);
+        h_blob = (uint8_t *)pin_alloc(total);
+        ok = d_blob && h_blob;
+    }
+    if (ok) {
+        launch_serialize_write(s->view(), (uint32_t)nb, d_off, d_hasrun, d_blob, g.stream);
+        ok = cudaMemcpyAsync(h_blob, d_blob, total, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaStreamSynchronize(g.stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    }
+    g.last_download_bytes = total;
+    dev_free(d_sz, 8 * nb);
+    dev_free(d_off, 8 * (nb + 1));
+    dev_free(d_dummy, 8 * (nb + 1));
+    dev_free(d_exact, 4 * nb);
+    dev_free(d_hasrun, 4 * nb);
+    dev_free(d_blob, total);
+    pin_free(h_meta, 8 * (nb + 1) + 4 * nb);
+    if (!ok) {
+        pin_free(h_blob, total);
+        if (g.err.empty()) g.err = "set_serialize failed";
+        return -1;
+    }
+    *buf = (char *)h_blob;
+    g_serialized_sizes[h_blob] = total;
+    return 0;
+}
+
+void rb200_serialized_free(char *buf, uint64_t *off, uint64_t *len) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (buf) {
+        auto it = g_serialized_sizes.find((uint8_t *)buf);
+        if (it != g_serialized_sizes.end()) {
+            pin_free(buf, it->second);
+            g_serialized_sizes.erase(it);
+        }
+    }
+    free(off);
+    free(len);
 }
 
 // Free many host bitmaps (results of rb200_set_download_all) with several threads.

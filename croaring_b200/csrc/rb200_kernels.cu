@@ -677,3 +677,156 @@ void launch_pack_copy(const SetView &S, uint32_t n, const uint64_t *off, const u
     g_launches++;
 }
 }  // namespace rb200
+
+// ------------------------------------------------------------------------------ serialization
+// Device-side roaring_bitmap_portable_serialize (src/roaring_array.c:469-531): every bitmap of a
+// set becomes its portable byte string inside one device buffer (blob starts 16-byte aligned),
+// so results can leave the device as bytes — one D2H, no per-container host allocation.
+namespace rb200 {
+
+__device__ __forceinline__ uint32_t ser_header_bytes(uint32_t n, bool hasrun) {
+    if (!hasrun) return 8u + 8u * n;
+    return 4u + ((n + 7u) >> 3) + (n < 4u ? 4u * n : 8u * n);
+}
+
+__global__ void __launch_bounds__(128)
+k_ser_measure(SetView S, uint32_t n, uint64_t *__restrict__ sizes16, uint32_t *__restrict__ exact,
+              uint32_t *__restrict__ hasrun_out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < n; b += nwarps) {
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        uint32_t bytes = 0, anyrun = 0;
+        for (uint32_t i = lane; i < nc; i += 32) {
+            const int t = S.c_type[c0 + i];
+            bytes += portable_bytes(t, S.c_len[c0 + i]);
+            anyrun |= (t == T_RUN) ? 1u : 0u;
+        }
+        bytes = __reduce_add_sync(FULLMASK, bytes);
+        anyrun = __reduce_or_sync(FULLMASK, anyrun);
+        if (lane == 0) {
+            const uint32_t tot = ser_header_bytes(nc, anyrun != 0) + bytes;
+            exact[b] = tot;
+            sizes16[b] = (uint64_t)round16(tot);
+            hasrun_out[b] = anyrun;
+        }
+    }
+}
+
+// byte-granular warp copy: src 4-byte aligned or not, dst arbitrary
+__device__ __forceinline__ void warp_copy_unaligned(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+    uint32_t head = (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    uint8_t *d = dst + head;
+    const uint8_t *s = src + head;
+    const uint32_t m = n - head, words = m >> 2;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3u) * 8u;
+    const uint32_t *sa = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+    uint32_t *dw = reinterpret_cast<uint32_t *>(d);
+    if (sh == 0) {
+        for (uint32_t w = lane; w < words; w += 32) dw[w] = sa[w];
+    } else {
+        for (uint32_t w = lane; w < words; w += 32) dw[w] = __funnelshift_r(sa[w], sa[w + 1], sh);
+    }
+    const uint32_t tail = m & 3u;
+    if ((uint32_t)lane < tail) d[4 * words + lane] = s[4 * words + lane];
+}
+
+__device__ __forceinline__ void store_u16(uint8_t *p, uint32_t v) {
+    p[0] = (uint8_t)v;
+    p[1] = (uint8_t)(v >> 8);
+}
+__device__ __forceinline__ void store_u32(uint8_t *p, uint32_t v) {
+    p[0] = (uint8_t)v;
+    p[1] = (uint8_t)(v >> 8);
+    p[2] = (uint8_t)(v >> 16);
+    p[3] = (uint8_t)(v >> 24);
+}
+
+__global__ void __launch_bounds__(128)
+k_ser_write(SetView S, uint32_t n, const uint64_t *__restrict__ off, const uint32_t *__restrict__ hasrun_in,
+            uint8_t *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < n; b += nwarps) {
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        const bool hasrun = hasrun_in[b] != 0;
+        uint8_t *o = dst + off[b];
+        const uint32_t hdr = ser_header_bytes(nc, hasrun);
+        uint8_t *kc, *offs = nullptr;
+        if (hasrun) {
+            if (lane == 0) store_u32(o, 12347u | ((nc - 1) << 16));  // SERIAL_COOKIE, roaring_array.h:35-40
+            const uint32_t nfb = (nc + 7) >> 3;
+            for (uint32_t j = lane; j < nfb; j += 32) {
+                uint32_t byte = 0;
+                for (uint32_t k = 0; k < 8 && 8 * j + k < nc; k++)
+                    byte |= (S.c_type[c0 + 8 * j + k] == T_RUN ? 1u : 0u) << k;
+                o[4 + j] = (uint8_t)byte;
+            }
+            kc = o + 4 + nfb;
+            if (nc >= 4) offs = kc + 4 * nc;  // NO_OFFSET_THRESHOLD
+        } else {
+            if (lane == 0) { store_u32(o, 12346u); store_u32(o + 4, nc); }
+            kc = o + 8;
+            offs = kc + 4 * nc;
+        }
+        uint32_t run = hdr;
+        for (uint32_t i0 = 0; i0 < nc; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t sz = 0, t = 0, len = 0;
+            uint64_t soff = 0;
+            if (i < nc) {
+                t = S.c_type[c0 + i];
+                len = S.c_len[c0 + i];
+                soff = S.c_off[c0 + i];
+                sz = portable_bytes(t, len);
+                store_u16(kc + 4 * i, S.c_key[c0 + i]);
+                store_u16(kc + 4 * i + 2, S.c_card[c0 + i] - 1);
+            }
+            const uint32_t incl = warp_incl_scan(sz, lane);
+            const uint32_t doff = run + incl - sz;
+            if (i < nc && offs) store_u32(offs + 4 * i, doff);
+            const uint32_t m = nc - i0 < 32 ? nc - i0 : 32;
+            for (uint32_t k = 0; k < m; k++) {
+                const uint64_t so = __shfl_sync(FULLMASK, soff, k);
+                const uint32_t d_o = __shfl_sync(FULLMASK, doff, k);
+                const uint32_t tt = __shfl_sync(FULLMASK, t, k), ll = __shfl_sync(FULLMASK, len, k);
+                uint8_t *pd = o + d_o;
+                if (tt == T_RUN) {
+                    if (lane == 0) store_u16(pd, ll);
+                    warp_copy_unaligned(pd + 2, S.payload + so, 4 * ll, lane);
+                } else {
+                    warp_copy_unaligned(pd, S.payload + so, tt == T_BITSET ? (uint32_t)BITSET_BYTES : 2 * ll, lane);
+                }
+            }
+            run += __shfl_sync(FULLMASK, incl, 31);
+        }
+    }
+}
+
+void launch_serialize_measure(const SetView &S, uint32_t n, uint64_t *sizes16, uint32_t *exact,
+                              uint32_t *hasrun, cudaStream_t s) {
+    if (!n) return;
+    const uint32_t g = blocks_for_warps(n, 4, sm_count() * 16);
+    k_ser_measure<<<g, 128, 0, s>>>(S, n, sizes16, exact, hasrun);
+    g_launches++;
+}
+void launch_serialize_write(const SetView &S, uint32_t n, const uint64_t *off, const uint32_t *hasrun,
+                            uint8_t *dst, cudaStream_t s) {
+    if (!n) return;
+    const uint32_t g = blocks_for_warps(n, 4, sm_count() * 16);
+    k_ser_write<<<g, 128, 0, s>>>(S, n, off, hasrun, dst);
+    g_launches++;
+}
+}  // namespace rb200
+
+namespace rb200 {
+void launch_pack_scan(const uint64_t *bytes, const uint32_t *cnts, uint32_t n, uint64_t *off,
+                      uint64_t *beg, cudaStream_t s) {
+    k_pack_scan<<<1, 1024, 0, s>>>(bytes, cnts, n, off, beg);
+    g_launches++;
+}
+}  // namespace rb200

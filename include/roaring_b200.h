@@ -159,6 +159,12 @@ size_t rb200_download_chunk_capacity(const rb200_download_stream_t *st);
 size_t rb200_download_next(rb200_download_stream_t *st, roaring_bitmap_t **out);
 void rb200_download_end(rb200_download_stream_t *st);
 
+/* Device-side roaring_bitmap_portable_serialize of every bitmap of a set + one D2H copy:
+ * blob i = *buf + (*off)[i], (*len)[i] bytes (blob starts are 16-byte aligned).  *buf is pinned
+ * host memory owned by the library; release all three with rb200_serialized_free. */
+int rb200_set_serialize(const rb200_set_t *s, char **buf, uint64_t **off, uint64_t **len);
+void rb200_serialized_free(char *buf, uint64_t *off, uint64_t *len);
+
 /* Free n host bitmaps (e.g. the results of rb200_set_download_all) using several threads. */
 void rb200_bitmaps_free(roaring_bitmap_t **bitmaps, size_t n);
 
