@@ -286,6 +286,42 @@ def main():
                       "rb200_download_begin/next/end (every result as host roaring_bitmap_t in the "
                       "reference layout, chunks of <=4096 bitmaps / 64 MB) -> rb200_bitmaps_free"}
 
+    # ---- e2e, bytes flavour: portable-serialized bitmaps in -> portable-serialized results out
+    # (device-side serialization, one D2H per op, no per-container host allocation)
+    e2e_ser = None
+    if not args.no_e2e:
+        ser_bytes = 0
+
+        def e2e_ser_step():
+            nonlocal ser_bytes
+            ser_bytes = 0
+            for ds in DATASETS:
+                S = rb.DeviceSet.from_serialized(blobs[ds])        # host parse + H2D
+                ia, ib = pairs[ds]
+                for op in OPS:
+                    r = S.batch(op, S, ia, ib)
+                    _buf, _off, _len, release = r.serialize_all(copy=False)
+                    ser_bytes += int(rb.api.lib().rb200_last_download_bytes())
+                    release()
+                    r.free()
+                S.free()
+
+        e2e_ser_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_ser_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ser = {"value": world * ops_per_step * args.e2e_steps / float(t.item()), "unit": "set-ops/s",
+                   "h2d_bytes_per_step": int(sum(sum(map(len, blobs[ds])) for ds in DATASETS)),
+                   "d2h_bytes_per_step": int(ser_bytes),
+                   "api": "rb200_set_upload_serialized(portable bytes) -> rb200_batch_op -> "
+                          "rb200_set_serialize (portable bytes of every result in pinned host memory)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -349,6 +385,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": e2e,
+        "e2e_serialized": e2e_ser,
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "successive": {"workload": "realdata_successive (configs[1] literal: 199 pairs x 3 ops x 3 datasets)",
