@@ -33,6 +33,28 @@ OPS = ["and", "or", "xor"]
 METRIC = "set-ops/sec (AND/OR/XOR over realdata suite)"
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Only the JSON line may reach stdout: libraries (NCCL prints its version banner there) are
+    sent to stderr for the rest of the run."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def all_pairs(n):
     i, j = np.triu_indices(n, 1)
     return i.astype(np.uint32), j.astype(np.uint32)
@@ -143,7 +165,7 @@ def run_reference(args, rank, world):
                                    "pairs split statically over all host threads"},
         "e2e": {"value": val, "unit": "set-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -157,6 +179,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,21 +273,23 @@ def main():
     if not args.no_e2e:
         host = {ds: [rb.Bitmap.deserialize(b) for b in blobs[ds]] for ds in DATASETS}
         h2d = d2h = 0
+        e2e_chk = [0]
 
         def e2e_step():
             nonlocal h2d, d2h
             h2d = d2h = 0
+            e2e_chk[0] = 0
             for ds in DATASETS:
                 S = rb.DeviceSet.upload(host[ds])                 # H2D inside the timed region
                 h2d += S.payload_bytes
                 ia, ib = pairs[ds]
                 for op in OPS:
                     r = S.batch(op, S, ia, ib)
-                    # streaming D2H + host materialisation; every result bitmap is built in the
-                    # reference layout, handed to the caller, then freed (as the reference's
-                    # benchmark loop does with each result, microbenchmarks/bench.cpp:85-96)
-                    for arr, n in r.download_stream(4096):
-                        rb.DeviceSet.free_raw(arr, n)
+                    # streaming D2H + host materialisation: every result bitmap is built in the
+                    # reference layout, its cardinality read with the host function, then freed —
+                    # the body of the reference's benchmark loop (microbenchmarks/bench.cpp:85-96),
+                    # run per result by the library's worker threads
+                    e2e_chk[0] += r.foreach_sum_cardinality()
                     d2h += int(rb.api.lib().rb200_last_download_bytes())
                     r.free()
                 S.free()
@@ -282,9 +307,10 @@ def main():
         e2e = {"value": world * ops_per_step * args.e2e_steps / float(t.item()), "unit": "set-ops/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": args.e2e_steps, "host_threads": host_threads(),
+               "checksum_sum_card": e2e_chk[0],
                "api": "rb200_set_upload(host roaring_bitmap_t[]) -> rb200_batch_op -> "
-                      "rb200_download_begin/next/end (every result as host roaring_bitmap_t in the "
-                      "reference layout, chunks of <=4096 bitmaps / 64 MB) -> rb200_bitmaps_free"}
+                      "rb200_download_foreach (every result materialised as a host roaring_bitmap_t in "
+                      "the reference layout, cardinality read on the host, freed)"}
 
     # ---- e2e, bytes flavour: portable-serialized bitmaps in -> portable-serialized results out
     # (device-side serialization, one D2H per op, no per-container host allocation)
@@ -392,7 +418,7 @@ def main():
                        "value": succ_val, "unit": "set-ops/s", "set_ops_per_step": succ_ops,
                        "ms_per_step": succ_ms / max(args.steps, 20)},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

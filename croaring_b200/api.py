@@ -85,6 +85,7 @@ def lib():
     sig("rb200_download_chunk_capacity", C.c_size_t, _P)
     sig("rb200_download_next", C.c_size_t, _P, C.POINTER(_P))
     sig("rb200_download_end", None, _P)
+    sig("rb200_download_foreach", C.c_int, _P, _P, _P)
     sig("rb200_batch_op_host", C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_size_t,
         C.POINTER(_P))
     _lib = L
@@ -324,6 +325,16 @@ class DeviceSet:
     @staticmethod
     def free_raw(arr, n=None):
         lib().rb200_bitmaps_free(arr, len(arr) if n is None else n)
+
+    def foreach_sum_cardinality(self):
+        """Materialise every bitmap on the host (reference layout), read its cardinality with the
+        host function and free it — the reference benchmark loop body, run by the library's worker
+        threads (rb200_download_foreach + rb200_visit_sum_cardinality)."""
+        acc = C.c_uint64(0)
+        fn = C.cast(lib().rb200_visit_sum_cardinality, _P)
+        if lib().rb200_download_foreach(self.ptr, fn, C.byref(acc)) != 0:
+            raise RB200Error(last_error())
+        return int(acc.value)
 
     def serialize_all(self, copy=True):
         """Portable bytes of every bitmap, serialized ON THE DEVICE and brought back in one D2H.

@@ -1569,6 +1569,63 @@ void rb200_download_end(rb200_download_stream_t *st) {
     stream_free(st);
 }
 
+// Visitor form of the streaming download: every bitmap of the set is materialised as a host
+// roaring_bitmap_t (reference layout), handed to `fn` ON A WORKER THREAD, and freed right after
+// unless fn returns non-zero (then the callee owns it).  Building, consuming and freeing a result
+// on the same thread is what the reference's own loops do (create, use, roaring_bitmap_free —
+// microbenchmarks/bench.cpp:85-96): the allocator recycles hot blocks instead of touching
+// gigabytes of fresh memory.  Returns 0 on success.
+int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    rb200_download_stream *st = rb200_download_begin(s, 4096);
+    if (!st) return -1;
+    std::atomic<int> failed(0);
+    while (st->next_build < st->chunk_end.size()) {
+        const size_t k = st->next_build;
+        const size_t p0 = k ? st->chunk_end[k - 1] : 0, p1 = st->chunk_end[k];
+        if (cudaEventSynchronize(st->ev[k & 1]) != cudaSuccess) { failed = 1; break; }
+        const uint8_t *buf = st->hbuf[k & 1];
+        const uint64_t bias = st->h_ob[p0];
+        const size_t n = p1 - p0;
+        std::atomic<size_t> next(0);
+        const rb200_set *P = st->P;
+        std::function<void()> work = [&]() {
+            for (;;) {
+                const size_t i0 = next.fetch_add(8);
+                if (i0 >= n) break;
+                const size_t i1 = std::min(n, i0 + 8);
+                for (size_t i = i0; i < i1; i++) {
+                    roaring_bitmap_t *bm = build_bitmap(P, p0 + i, buf, bias);
+                    if (!bm) { failed = 1; continue; }
+                    if (fn(p0 + i, bm, ctx) == 0) bitmap_free_host(bm);
+                }
+            }
+        };
+        const uint64_t chunk_bytes = st->h_ob[p1] - st->h_ob[p0];
+        const uint64_t chunk_conts = st->h_ob[st->nb + 1 + p1] - st->h_ob[st->nb + 1 + p0];
+        uint64_t want = (chunk_bytes + 256 * chunk_conts + 512 * n) / (128 << 10) + 1;
+        unsigned T = host_workers();
+        if (want < T) T = (unsigned)want;
+        if ((size_t)T * 8 > n) T = (unsigned)((n + 7) / 8);
+        pool().run(work, T);
+        st->next_build++;
+        if (!stream_enqueue(st)) { failed = 1; break; }
+    }
+    stream_free(st);
+    if (failed) {
+        if (g.err.empty()) g.err = "download_foreach: host allocation or copy failed";
+        return -1;
+    }
+    return 0;
+}
+
+// A ready-made visitor: *(uint64_t*)ctx += cardinality(bitmap) (atomic); the bitmap is released.
+int rb200_visit_sum_cardinality(size_t index, roaring_bitmap_t *bm, void *ctx) {
+    (void)index;
+    __atomic_fetch_add((uint64_t *)ctx, rb200_bitmap_get_cardinality(bm), __ATOMIC_RELAXED);
+    return 0;
+}
+
 roaring_bitmap_t *rb200_set_download(const rb200_set_t *cs, size_t i) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     rb200_set *s = const_cast<rb200_set *>(cs);

@@ -159,6 +159,14 @@ size_t rb200_download_chunk_capacity(const rb200_download_stream_t *st);
 size_t rb200_download_next(rb200_download_stream_t *st, roaring_bitmap_t **out);
 void rb200_download_end(rb200_download_stream_t *st);
 
+/* Visitor form: every bitmap of the set is materialised (reference layout) on a worker thread,
+ * passed to fn(index, bitmap, ctx) and freed right after unless fn returns non-zero (callee then
+ * owns it).  fn runs concurrently on several threads.  rb200_visit_sum_cardinality is a ready-made
+ * visitor: *(uint64_t*)ctx += roaring_bitmap_get_cardinality(bitmap). */
+typedef int (*rb200_visit_fn)(size_t index, roaring_bitmap_t *bitmap, void *ctx);
+int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx);
+int rb200_visit_sum_cardinality(size_t index, roaring_bitmap_t *bitmap, void *ctx);
+
 /* Device-side roaring_bitmap_portable_serialize of every bitmap of a set + one D2H copy:
  * blob i = *buf + (*off)[i], (*len)[i] bytes (blob starts are 16-byte aligned).  *buf is pinned
  * host memory owned by the library; release all three with rb200_serialized_free. */
