@@ -8,7 +8,10 @@
 //   container structs                          include/roaring/containers/{array,bitset,run}.h
 //   ownership of returned bitmaps              src/roaring.c:552-560, src/containers/containers.c:58-77
 //   portable format                            src/roaring_array.c:469-531, :633-813
+#include <ctype.h>
 #include <dlfcn.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -1345,7 +1348,7 @@ class Pool {
     void run(const std::function<void()> &fn, unsigned T) {
         if (T <= 1) { fn(); return; }
         std::unique_lock<std::mutex> lk(mu_);
-        while (workers_.size() < T - 1) workers_.emplace_back([this]() { loop(); });
+        while (workers_.size() < T - 1) workers_.emplace_back([this]() { bind_to_local_cpus(); loop(); });
         fn_ = &fn;
         want_ = T - 1;
         started_ = 0;
@@ -1387,12 +1390,48 @@ Pool &pool() {
     static Pool *p = new Pool();  // intentionally leaked: workers are detached for process life
     return *p;
 }
+// CPUs local to the GPU's PCIe root (sysfs local_cpulist); empty when unknown.
+std::vector<int> &local_cpus() {
+    static std::vector<int> cpus;
+    static bool done = false;
+    if (done) return cpus;
+    done = true;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), g.device) != cudaSuccess) return cpus;
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return cpus;
+    char line[1024] = {0};
+    if (fgets(line, sizeof(line), f)) {
+        for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; c++) cpus.push_back(c); }
+            else if (sscanf(tok, "%d", &a) == 1) cpus.push_back(a);
+        }
+    }
+    fclose(f);
+    return cpus;
+}
+void bind_to_local_cpus() {
+    const std::vector<int> &cpus = local_cpus();
+    if (cpus.empty()) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : cpus) if (c < CPU_SETSIZE) CPU_SET(c, &set);
+    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+}
+// Host worker threads for materialisation.  Measured on the 2 x 32-core host of this pool
+// (profiles/r1c/e2e_threads.txt): the stream is PCIe bound from 8 threads on, 24 is the sweet spot,
+// 40+ threads LOSE 20-80 % (remote-socket traffic on the pinned staging buffers), so the default
+// is 24 threads bound to the CPUs of the GPU's NUMA node.  RB200_HOST_THREADS overrides.
 unsigned host_workers() {
     static unsigned T = 0;
     if (!T) {
         const char *e = getenv("RB200_HOST_THREADS");
-        T = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
-        if (T > 64) T = 64;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        T = e ? (unsigned)atoi(e) : std::min(24u, std::max(1u, hw / 2));
+        if (T > 256) T = 256;
         if (T < 1) T = 1;
     }
     return T;
