@@ -1343,6 +1343,8 @@ namespace {
 
 // Persistent host worker pool (materialisation / bulk free).  run(fn, T) executes fn() on T
 // threads (the caller is one of them); fn pulls its own work from a shared atomic counter.
+void bind_to_local_cpus();
+
 class Pool {
    public:
     void run(const std::function<void()> &fn, unsigned T) {
