@@ -67,6 +67,7 @@ def lib():
     sig("rb200_set_upload", _P, C.POINTER(_P), C.c_size_t)
     sig("rb200_set_upload_serialized", _P, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t)
     sig("rb200_set_free", None, _P)
+    sig("rb200_set_bind_host", C.c_int, _P, C.c_int)
     sig("rb200_set_count", C.c_size_t, _P)
     sig("rb200_set_container_count", C.c_uint64, _P)
     sig("rb200_set_payload_bytes", C.c_uint64, _P)
@@ -255,6 +256,13 @@ class DeviceSet:
             self.free()
         except Exception:
             pass
+
+    def bind_host(self, enable=True):
+        """Promise that the host bitmaps this set was uploaded from outlive the downloads of its
+        results (pass-through containers are then not transferred back)."""
+        if lib().rb200_set_bind_host(self.ptr, 1 if enable else 0) != 0:
+            raise RB200Error(last_error())
+        return self
 
     def __len__(self):
         return int(lib().rb200_set_count(self.ptr))

@@ -24,7 +24,10 @@ enum Op { OP_AND = 0, OP_OR = 1, OP_XOR = 2, OP_ANDNOT = 3 };
 constexpr int K_HOLE = 0;     // nothing to do (slot kept so item order == key order)
 constexpr int K_COMPUTE = 1;  // matched key: run the (typeA,typeB) grid cell
 constexpr int K_COPY_A = 2;   // pass-through of an unmatched container of the left bitmap
-constexpr int K_COPY_B = 3;   // pass-through of an unmatched container of the right bitmap
+constexpr int K_COPY_B = 3;
+
+// c_src encoding: container index in the left parent, or SRC_B | index in the right parent
+constexpr uint32_t SRC_NONE = 0xffffffffu, SRC_B = 0x80000000u;   // pass-through of an unmatched container of the right bitmap
 
 // Device view of a resident set: SoA container directory + one payload slab.
 // Payload of container c starts at payload + c_off[c] (16-byte aligned, padded to 16 B):
@@ -38,6 +41,7 @@ struct SetView {
     const uint32_t *c_card;
     const uint32_t *c_len;
     const uint64_t *c_off;
+    const uint32_t *c_src;   // provenance of pass-through containers (SRC_NONE = computed here)
     const uint8_t *payload;
 };
 
@@ -51,6 +55,7 @@ struct SetOut {
     uint32_t *c_card;
     uint32_t *c_len;
     uint64_t *c_off;
+    uint32_t *c_src;
     uint8_t *payload;
 };
 
@@ -96,9 +101,11 @@ void launch_finalize_cards(Items it, const uint64_t *item_off, uint32_t npairs, 
 void launch_set_cardinalities(const SetView &S, uint32_t n_bitmaps, uint64_t *out, cudaStream_t s);
 
 // packing for download: measure+scan (off/beg have n+1 entries), then copy
-void launch_pack(const SetView &S, uint32_t n, uint64_t *bytes, uint32_t *cnts, uint64_t *off,
+// elide bit 0 / 1: payloads that are pass-through copies of the left / right parent are NOT packed
+// (the host rebuilds them from its own copy of the inputs)
+void launch_pack(const SetView &S, uint32_t n, int elide, uint64_t *bytes, uint32_t *cnts, uint64_t *off,
                  uint64_t *beg, cudaStream_t s);
-void launch_pack_copy(const SetView &S, uint32_t n, const uint64_t *off, const uint64_t *beg,
+void launch_pack_copy(const SetView &S, uint32_t n, int elide, const uint64_t *off, const uint64_t *beg,
                       SetOut out, cudaStream_t s);
 
 // or_many: mark -> compact keys -> reduce per key

@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <thread>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -215,7 +216,7 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Directory arrays carved out of one block (device and, mirrored, pinned host).
 struct DirLayout {
-    size_t o_beg, o_cnt, o_bcard, o_key, o_type, o_card, o_len, o_off, total;
+    size_t o_beg, o_cnt, o_bcard, o_key, o_type, o_card, o_len, o_off, o_src, total;
     void compute(size_t nb, size_t nc) {
         size_t o = 0;
         o_beg = o; o += al256(4 * nb);
@@ -224,6 +225,7 @@ struct DirLayout {
         o_off = o; o += al256(8 * nc);
         o_card = o; o += al256(4 * nc);
         o_len = o; o += al256(4 * nc);
+        o_src = o; o += al256(4 * nc);
         o_key = o; o += al256(2 * nc);
         o_type = o; o += al256(nc);
         total = o ? o : 256;
@@ -243,6 +245,11 @@ struct rb200_set {
     uint8_t *d_slab = nullptr;
     std::vector<uint32_t> h_cnt;    // host mirror: containers per bitmap
     std::vector<uint64_t> h_card;   // host mirror: cardinality per bitmap (empty = not cached)
+    // payload address of every container in the caller's host bitmaps (sets made by
+    // rb200_set_upload; valid while the caller keeps those bitmaps alive) and, for a batch result,
+    // the tables of its two parents: pass-through containers can then be rebuilt on the host from
+    // the inputs instead of crossing PCIe again
+    std::shared_ptr<std::vector<const void *>> h_ptr_all, h_ptr, parentA, parentB;  // h_ptr: bound (opt-in)
     std::vector<uint64_t> h_bytes;  // host mirror: upper bound of stored payload bytes per bitmap
     std::vector<uint8_t> h_flags;   // per bitmap: COW flag to propagate
     // lazily downloaded host mirror (pinned)
@@ -257,6 +264,7 @@ struct rb200_set {
         v.c_card = (const uint32_t *)(d_dir + L.o_card);
         v.c_len = (const uint32_t *)(d_dir + L.o_len);
         v.c_off = (const uint64_t *)(d_dir + L.o_off);
+        v.c_src = (const uint32_t *)(d_dir + L.o_src);
         v.payload = d_slab;
         return v;
     }
@@ -270,6 +278,7 @@ struct rb200_set {
         v.c_card = (uint32_t *)(d_dir + L.o_card);
         v.c_len = (uint32_t *)(d_dir + L.o_len);
         v.c_off = (uint64_t *)(d_dir + L.o_off);
+        v.c_src = (uint32_t *)(d_dir + L.o_src);
         v.payload = d_slab;
         return v;
     }
@@ -773,6 +782,8 @@ rb200_set *upload_impl(const PackSrc &src) {
         uint8_t *c_type = hd + s->L.o_type;
         uint32_t *c_card = (uint32_t *)(hd + s->L.o_card), *c_len = (uint32_t *)(hd + s->L.o_len);
         uint64_t *c_off = (uint64_t *)(hd + s->L.o_off);
+        uint32_t *c_src = (uint32_t *)(hd + s->L.o_src);
+        if (src.bms) s->h_ptr_all = std::make_shared<std::vector<const void *>>(nc);
         uint64_t ci = 0, off = 0, chunk_base = 0;
         int cur = 0;
         size_t used = 0;
@@ -837,6 +848,8 @@ rb200_set *upload_impl(const PackSrc &src) {
                 c_card[ci] = card;
                 c_len[ci] = len;
                 c_off[ci] = off;
+                c_src[ci] = SRC_NONE;
+                if (s->h_ptr_all) (*s->h_ptr_all)[ci] = p;
                 off += sb16;
                 bcard += card;
                 bbytes += sb16;
@@ -886,6 +899,16 @@ rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *
     src.views = &views;
     src.n = n;
     return upload_impl(src);
+}
+
+// Declare that the host bitmaps this set was uploaded from stay alive (and unmodified) for as long
+// as results derived from it are downloaded: pass-through containers of OR / XOR / ANDNOT results
+// are then rebuilt from the caller's own memory instead of crossing PCIe a second time.
+int rb200_set_bind_host(rb200_set_t *s, int enable) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (enable && !s->h_ptr_all) { g.err = "bind_host: set was not uploaded from host bitmaps"; return -1; }
+    s->h_ptr = enable ? s->h_ptr_all : nullptr;
+    return 0;
 }
 
 void rb200_set_free(rb200_set_t *s) {
@@ -1036,6 +1059,8 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         g.last_algo_bytes = g.h_stats->algo_bytes;
         R->n_containers = g.h_stats->dir_cursor;
         R->slab_used = g.h_stats->slab_cursor;
+        R->parentA = A->h_ptr;
+        R->parentB = B->h_ptr;
         R->portable_bytes = 0;
         const uint64_t *h_card = (const uint64_t *)((const uint8_t *)h_cnt + (R->L.o_bcard - R->L.o_cnt));
         R->h_card.assign(h_card, h_card + np);
@@ -1306,6 +1331,8 @@ bool ensure_mirror(rb200_set *s) {
 
 roaring_bitmap_t *build_bitmap(const rb200_set *s, size_t i, const uint8_t *slab = nullptr, uint64_t bias = 0) {
     if (!slab) slab = s->m_slab;
+    const uint32_t *c_src = (const uint32_t *)(s->m_dir + s->L.o_src);
+    const std::vector<const void *> *tabA = s->parentA.get(), *tabB = s->parentB.get();
     const uint32_t *bm_beg = (const uint32_t *)(s->m_dir + s->L.o_beg);
     const uint32_t *bm_cnt = (const uint32_t *)(s->m_dir + s->L.o_cnt);
     const uint16_t *c_key = (const uint16_t *)(s->m_dir + s->L.o_key);
@@ -1320,7 +1347,12 @@ roaring_bitmap_t *build_bitmap(const rb200_set *s, size_t i, const uint8_t *slab
     ra->flags = s->h_flags[i] & FLAG_COW;  // roaring.c:738,890
     for (uint32_t k = 0; k < cnt; k++) {
         const uint32_t c = beg + k;
-        void *hc = container_from_payload(c_type[c], c_card[c], c_len[c], slab + (c_off[c] - bias));
+        const uint8_t *pay = slab + (c_off[c] - bias);
+        if (tabA || tabB) {  // pass-through container elided from the download: copy from the input
+            const uint32_t sr = c_src[c];
+            if (sr != SRC_NONE) pay = (const uint8_t *)((sr & SRC_B) ? (*tabB)[sr & ~SRC_B] : (*tabA)[sr]);
+        }
+        void *hc = container_from_payload(c_type[c], c_card[c], c_len[c], pay);
         if (!hc) {
             bitmap_free_host(r);
             return nullptr;
@@ -1504,7 +1536,8 @@ rb200_download_stream_t *rb200_download_begin(const rb200_set_t *s, size_t chunk
     st->h_ob = (uint64_t *)pin_alloc(16 * (nb + 1));
     bool ok = d_bytes && d_off && d_beg && d_cnt && st->h_ob;
     if (ok) {
-        launch_pack(s->view(), (uint32_t)nb, d_bytes, d_cnt, d_off, d_beg, g.stream);
+        const int elide = (s->parentA ? 1 : 0) | (s->parentB ? 2 : 0);
+        launch_pack(s->view(), (uint32_t)nb, elide, d_bytes, d_cnt, d_off, d_beg, g.stream);
         ok = cudaMemcpyAsync(st->h_ob, d_off, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
              cudaMemcpyAsync(st->h_ob + nb + 1, d_beg, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
              cudaStreamSynchronize(g.stream) == cudaSuccess;
@@ -1519,7 +1552,10 @@ rb200_download_stream_t *rb200_download_begin(const rb200_set_t *s, size_t chunk
         P->n_containers = h_beg[nb];
         P->slab_used = h_off[nb];
         P->h_flags = s->h_flags;
-        launch_pack_copy(s->view(), (uint32_t)nb, d_off, d_beg, P->out(), g.stream);
+        P->parentA = s->parentA;
+        P->parentB = s->parentB;
+        launch_pack_copy(s->view(), (uint32_t)nb, (s->parentA ? 1 : 0) | (s->parentB ? 2 : 0), d_off, d_beg,
+                         P->out(), g.stream);
         P->m_dir = (uint8_t *)pin_alloc(P->L.total);
         ok = P->m_dir != nullptr &&
              cudaMemcpyAsync(P->m_dir, P->d_dir, P->L.total, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
@@ -1702,7 +1738,8 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
     std::vector<cudaEvent_t> evs;
     bool ok = d_bytes && d_off && d_beg && d_cnt && h_ob;
     if (ok) {
-        launch_pack(s->view(), (uint32_t)nb, d_bytes, d_cnt, d_off, d_beg, g.stream);
+        const int elide = (s->parentA ? 1 : 0) | (s->parentB ? 2 : 0);
+        launch_pack(s->view(), (uint32_t)nb, elide, d_bytes, d_cnt, d_off, d_beg, g.stream);
         ok = cudaMemcpyAsync(h_ob, d_off, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
              cudaMemcpyAsync(h_ob + nb + 1, d_beg, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
              cudaStreamSynchronize(g.stream) == cudaSuccess;
@@ -1717,7 +1754,10 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
         P->n_containers = h_beg[nb];
         P->slab_used = h_off[nb];
         P->h_flags = s->h_flags;
-        launch_pack_copy(s->view(), (uint32_t)nb, d_off, d_beg, P->out(), g.stream);
+        P->parentA = s->parentA;
+        P->parentB = s->parentB;
+        launch_pack_copy(s->view(), (uint32_t)nb, (s->parentA ? 1 : 0) | (s->parentB ? 2 : 0), d_off, d_beg,
+                         P->out(), g.stream);
         // ---- (2) directory, then payload chunks
         P->m_dir = (uint8_t *)pin_alloc(P->L.total);
         hp_bytes = P->slab_used;
@@ -1921,6 +1961,7 @@ int rb200_batch_op_host(int op, const roaring_bitmap_t *const *a, const roaring_
     }
     rb200_set *S = rb200_set_upload(all.data(), all.size());
     if (!S) return -1;
+    rb200_set_bind_host(S, 1);  // the inputs outlive this call
     rb200_set *R = batch_op_impl(op, S, S, ia.data(), ib.data(), np);
     int rc = -1;
     if (R) {

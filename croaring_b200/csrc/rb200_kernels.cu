@@ -403,6 +403,8 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
                 out.c_card[o] = it.ocard[idx];
                 out.c_len[o] = it.olen[idx];
                 out.c_off[o] = it.slot_off[idx];
+                const int kd = it.kind[idx];
+                out.c_src[o] = kd == K_COPY_A ? it.ca[idx] : (kd == K_COPY_B ? (SRC_B | it.cb[idx]) : SRC_NONE);
             }
             done += __popc(m);
         }
@@ -478,15 +480,18 @@ k_many_compact(const uint32_t *__restrict__ flags, uint16_t *__restrict__ keys, 
 // without slot slack, so that any range of bitmaps is one directory range + one payload range
 // (chunked D2H overlapped with host materialisation).
 __global__ void __launch_bounds__(128)
-k_pack_measure(SetView S, uint32_t n, uint64_t *__restrict__ bytes, uint32_t *__restrict__ cnts) {
+k_pack_measure(SetView S, uint32_t n, int elide, uint64_t *__restrict__ bytes, uint32_t *__restrict__ cnts) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t b = warp; b < n; b += nwarps) {
         const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
         unsigned long long v = 0;
-        for (uint32_t i = lane; i < nc; i += 32)
-            v += round16(stored_bytes(S.c_type[c0 + i], S.c_len[c0 + i]));
+        for (uint32_t i = lane; i < nc; i += 32) {
+            const uint32_t src = elide ? S.c_src[c0 + i] : SRC_NONE;
+            const bool skip = src != SRC_NONE && ((src & SRC_B) ? (elide & 2) : (elide & 1));
+            if (!skip) v += round16(stored_bytes(S.c_type[c0 + i], S.c_len[c0 + i]));
+        }
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
         if (lane == 0) {
             bytes[b] = v;
@@ -535,7 +540,7 @@ k_pack_scan(const uint64_t *__restrict__ bytes, const uint32_t *__restrict__ cnt
 }
 
 __global__ void __launch_bounds__(128)
-k_pack_copy(SetView S, uint32_t n, const uint64_t *__restrict__ off_in,
+k_pack_copy(SetView S, uint32_t n, int elide, const uint64_t *__restrict__ off_in,
             const uint64_t *__restrict__ beg_in, SetOut out) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -547,14 +552,17 @@ k_pack_copy(SetView S, uint32_t n, const uint64_t *__restrict__ off_in,
         unsigned long long card = 0;
         for (uint32_t i0 = 0; i0 < nc; i0 += 32) {
             const uint32_t i = i0 + lane;
-            uint32_t sz = 0, t = 0, len = 0, cd = 0;
+            uint32_t sz = 0, t = 0, len = 0, cd = 0, src = SRC_NONE;
             uint64_t soff = 0;
             if (i < nc) {
                 t = S.c_type[c0 + i];
                 len = S.c_len[c0 + i];
                 cd = S.c_card[c0 + i];
                 soff = S.c_off[c0 + i];
-                sz = round16(stored_bytes(t, len));
+                src = elide ? S.c_src[c0 + i] : SRC_NONE;
+                const bool skip = src != SRC_NONE && ((src & SRC_B) ? (elide & 2) : (elide & 1));
+                if (!skip) src = SRC_NONE;  // payload travels: the host needs no provenance
+                sz = skip ? 0u : round16(stored_bytes(t, len));
             }
             const uint32_t incl = warp_incl_scan(sz, lane);
             const uint64_t doff = run + incl - sz;
@@ -564,6 +572,7 @@ k_pack_copy(SetView S, uint32_t n, const uint64_t *__restrict__ off_in,
                 out.c_card[nb + i] = cd;
                 out.c_len[nb + i] = len;
                 out.c_off[nb + i] = doff;
+                out.c_src[nb + i] = src;
                 card += cd;
             }
             // the warp copies the (up to 32) payloads one after the other
@@ -571,7 +580,7 @@ k_pack_copy(SetView S, uint32_t n, const uint64_t *__restrict__ off_in,
             for (uint32_t k = 0; k < m; k++) {
                 const uint64_t so = __shfl_sync(FULLMASK, soff, k), d_o = __shfl_sync(FULLMASK, doff, k);
                 const uint32_t bytes = __shfl_sync(FULLMASK, sz, k);
-                warp_copy16(out.payload + d_o, S.payload + so, bytes, lane);
+                if (bytes) warp_copy16(out.payload + d_o, S.payload + so, bytes, lane);
             }
             run += __shfl_sync(FULLMASK, incl, 31);
         }
@@ -662,18 +671,18 @@ void launch_many_compact(const uint32_t *flags, uint16_t *keys_out, OpStats *st,
 }  // namespace rb200
 
 namespace rb200 {
-void launch_pack(const SetView &S, uint32_t n, uint64_t *bytes, uint32_t *cnts, uint64_t *off,
+void launch_pack(const SetView &S, uint32_t n, int elide, uint64_t *bytes, uint32_t *cnts, uint64_t *off,
                  uint64_t *beg, cudaStream_t s) {
     const uint32_t g = blocks_for_warps(n ? n : 1, 4, sm_count() * 16);
-    k_pack_measure<<<g, 128, 0, s>>>(S, n, bytes, cnts);
+    k_pack_measure<<<g, 128, 0, s>>>(S, n, elide, bytes, cnts);
     k_pack_scan<<<1, 1024, 0, s>>>(bytes, cnts, n, off, beg);
     g_launches += 2;
 }
-void launch_pack_copy(const SetView &S, uint32_t n, const uint64_t *off, const uint64_t *beg,
+void launch_pack_copy(const SetView &S, uint32_t n, int elide, const uint64_t *off, const uint64_t *beg,
                       SetOut out, cudaStream_t s) {
     if (!n) return;
     const uint32_t g = blocks_for_warps(n, 4, sm_count() * 16);
-    k_pack_copy<<<g, 128, 0, s>>>(S, n, off, beg, out);
+    k_pack_copy<<<g, 128, 0, s>>>(S, n, elide, off, beg, out);
     g_launches++;
 }
 }  // namespace rb200

@@ -454,6 +454,7 @@ or_many_body(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
             out.c_card[ki] = (uint32_t)card;
             out.c_len[ki] = olen;
             out.c_off[ki] = off;
+            out.c_src[ki] = SRC_NONE;
             if (card_per_key) card_per_key[key] = (uint32_t)card;
         }
         __syncthreads();
@@ -679,6 +680,7 @@ k_compact_dir(const uint16_t *__restrict__ keys, const uint8_t *__restrict__ t_t
             out.c_card[o] = t_card[i];
             out.c_len[o] = t_len[i];
             out.c_off[o] = (uint64_t)i * BITSET_BYTES;
+            out.c_src[o] = SRC_NONE;
             csum += t_card[i];
         }
         __syncthreads();

@@ -114,6 +114,11 @@ rb200_set_t *rb200_set_upload(const roaring_bitmap_t *const *bitmaps, size_t n);
 /* Same from portable-serialized bytes ("identical serialized inputs"). */
 rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *lens, size_t n);
 void rb200_set_free(rb200_set_t *s);
+/* Opt-in for sets made by rb200_set_upload: promise that the host bitmaps stay alive and unmodified
+ * while results derived from the set are downloaded.  Pass-through containers of batch results
+ * (unmatched keys of OR / XOR / ANDNOT) are then rebuilt on the host from the caller's own memory
+ * instead of crossing PCIe again.  enable = 0 revokes the promise for later ops. */
+int rb200_set_bind_host(rb200_set_t *s, int enable);
 size_t rb200_set_count(const rb200_set_t *s);              /* number of bitmaps */
 uint64_t rb200_set_container_count(const rb200_set_t *s);   /* total containers */
 uint64_t rb200_set_payload_bytes(const rb200_set_t *s);     /* container_size_in_bytes summed */
