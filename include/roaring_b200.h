@@ -167,7 +167,7 @@ void rb200_download_end(rb200_download_stream_t *st);
 /* Visitor form: every bitmap of the set is materialised (reference layout) on a worker thread,
  * passed to fn(index, bitmap, ctx) and freed right after unless fn returns non-zero (callee then
  * owns it).  fn runs concurrently on several threads.  rb200_visit_sum_cardinality is a ready-made
- * visitor: *(uint64_t*)ctx += roaring_bitmap_get_cardinality(bitmap). */
+ * visitor: *(uint64_t*)ctx += cardinality of the bitmap. */
 typedef int (*rb200_visit_fn)(size_t index, roaring_bitmap_t *bitmap, void *ctx);
 int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx);
 int rb200_visit_sum_cardinality(size_t index, roaring_bitmap_t *bitmap, void *ctx);
