@@ -42,6 +42,7 @@ def lib():
         f.argtypes = list(args)
 
     for op in ("and", "or", "xor", "andnot"):
+        sig(f"roaring_bitmap_{op}_inplace", None, _P, _P)
         sig(f"roaring_bitmap_{op}", _P, _P, _P)
         sig(f"roaring_bitmap_{op}_cardinality", C.c_uint64, _P, _P)
     sig("roaring_bitmap_or_many", _P, C.c_size_t, C.POINTER(_P))
@@ -72,6 +73,7 @@ def lib():
     sig("rb200_set_container_count", C.c_uint64, _P)
     sig("rb200_set_payload_bytes", C.c_uint64, _P)
     sig("rb200_batch_op", _P, C.c_int, _P, _P, _P, _P, C.c_size_t)
+    sig("rb200_batch_op_ex", _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t)
     sig("rb200_batch_and_cardinality", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
     sig("rb200_or_many", _P, _P, _P, C.c_size_t)
     sig("rb200_or_many_keyrange", _P, _P, _P, C.c_size_t, C.c_uint32, C.c_uint32, _P)
@@ -183,6 +185,11 @@ class Bitmap:
     def __xor__(self, o): return self._pair("xor", o)
     def __sub__(self, o): return self._pair("andnot", o)
 
+    def inplace(self, name, other):
+        """roaring_bitmap_{and,or,xor,andnot}_inplace(self, other)."""
+        getattr(lib(), f"roaring_bitmap_{name}_inplace")(self.ptr, other.ptr)
+        return self
+
     def and_cardinality(self, o) -> int:
         v = int(lib().roaring_bitmap_and_cardinality(self.ptr, o.ptr))
         if v == 2 ** 64 - 1:
@@ -275,12 +282,13 @@ class DeviceSet:
     def payload_bytes(self):
         return int(lib().rb200_set_payload_bytes(self.ptr))
 
-    def batch(self, op, other, ia, ib):
+    def batch(self, op, other, ia, ib, inplace_rules=False):
         """result[k] = self[ia[k]] op other[ib[k]] as a new DeviceSet."""
         ia, ib = _u32(ia), _u32(ib)
         assert ia.shape == ib.shape
         code = OPS[op] if isinstance(op, str) else op
-        p = lib().rb200_batch_op(code, self.ptr, other.ptr, ia.ctypes.data, ib.ctypes.data, ia.size)
+        p = lib().rb200_batch_op_ex(code, 1 if inplace_rules else 0, self.ptr, other.ptr,
+                                    ia.ctypes.data, ib.ctypes.data, ia.size)
         return DeviceSet(p)
 
     def and_cardinality(self, other, ia, ib):

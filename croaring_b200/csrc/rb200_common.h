@@ -91,7 +91,8 @@ void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, c
                        const uint64_t *item_off, uint32_t npairs, int op, bool card_only,
                        Items it, OpStats *st, cudaStream_t s);
 void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
-                          uint8_t *slab, uint64_t slab_cap, OpStats *st, cudaStream_t s);
+                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int inplace_rules,
+                          cudaStream_t s);
 void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W, OpStats *st,
                        cudaStream_t s);
 void launch_finalize_pairs(const SetView &A, const SetView &B, Items it, const uint64_t *item_off,

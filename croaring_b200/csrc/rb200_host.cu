@@ -1013,7 +1013,7 @@ bool stats_fetch() {
 }
 
 rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const uint32_t *ia,
-                         const uint32_t *ib, size_t np) {
+                         const uint32_t *ib, size_t np, int inplace_rules = 0) {
     if (!ctx_init()) return nullptr;
     if (op < 0 || op > 3) { g.err = "bad op"; return nullptr; }
     if (np > 0xffffffffull) { g.err = "too many pairs"; return nullptr; }
@@ -1037,7 +1037,7 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, ib_.it,
                           g.d_stats, g.stream);
         cudaEventRecord(g.evk0, g.stream);
-        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, g.stream);
+        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, inplace_rules, g.stream);
         cudaEventRecord(g.evk1, g.stream);
         launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
         cudaEventRecord(g.ev1, g.stream);
@@ -1089,6 +1089,12 @@ rb200_set_t *rb200_batch_op(int op, const rb200_set_t *A, const rb200_set_t *B, 
                             const uint32_t *ib, size_t npairs) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     return batch_op_impl(op, A, B, ia, ib, npairs);
+}
+
+rb200_set_t *rb200_batch_op_ex(int op, int flags, const rb200_set_t *A, const rb200_set_t *B,
+                               const uint32_t *ia, const uint32_t *ib, size_t npairs) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return batch_op_impl(op, A, B, ia, ib, npairs, flags & 1);
 }
 
 int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
@@ -2005,6 +2011,39 @@ roaring_bitmap_t *roaring_bitmap_or_many(size_t number, const roaring_bitmap_t *
     set_delete(S);
     return out;
 }
+
+// In-place twins (src/roaring.c:812 and_inplace, :1063 or_inplace, :1200 xor_inplace, :1342
+// andnot_inplace): the result is computed on the device with the in-place type rules and then
+// swapped into x1 (its old containers and directory are released, its flags kept).
+static void dropin_inplace(int op, roaring_bitmap_t *x1, const roaring_bitmap_t *x2) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const roaring_bitmap_t *both[2] = {x1, x2};
+    rb200_set *S = rb200_set_upload(both, 2);
+    if (!S) return;
+    rb200_set_bind_host(S, 1);
+    const uint32_t ia = 0, ib = 1;
+    rb200_set *R = batch_op_impl(op, S, S, &ia, &ib, 1, 1);
+    roaring_bitmap_t *out = R ? rb200_set_download(R, 0) : nullptr;
+    set_delete(R);
+    set_delete(S);
+    if (!out) return;  // CUDA failure: x1 is left untouched, rb200_last_error() tells why
+    roaring_array_t *ra = &x1->high_low_container, *rn = &out->high_low_container;
+    const uint8_t flags = ra->flags;
+    if (!(flags & FLAG_FROZEN)) {
+        for (int32_t i = 0; i < ra->size; i++) container_free_host(ra->containers[i], ra->typecodes[i]);
+        h_free(ra->containers);
+    }
+    *ra = *rn;
+    ra->flags = flags;
+    h_free(out);
+}
+void roaring_bitmap_and_inplace(roaring_bitmap_t *x1, const roaring_bitmap_t *x2) {
+    if (x1 == x2) return;  // roaring.c:814
+    dropin_inplace(OP_AND, x1, x2);
+}
+void roaring_bitmap_or_inplace(roaring_bitmap_t *x1, const roaring_bitmap_t *x2) { dropin_inplace(OP_OR, x1, x2); }
+void roaring_bitmap_xor_inplace(roaring_bitmap_t *x1, const roaring_bitmap_t *x2) { dropin_inplace(OP_XOR, x1, x2); }
+void roaring_bitmap_andnot_inplace(roaring_bitmap_t *x1, const roaring_bitmap_t *x2) { dropin_inplace(OP_ANDNOT, x1, x2); }
 
 roaring_bitmap_t *roaring_bitmap_xor_many(size_t number, const roaring_bitmap_t **rs) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);

@@ -121,7 +121,8 @@ template <int OP>
 __device__ __forceinline__ void
 cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
              uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
-             int lane, int &otype, uint32_t &ocard, uint32_t &olen, unsigned int *err) {
+             int lane, int &otype, uint32_t &ocard, uint32_t &olen, unsigned int *err,
+             bool inplace_rules) {
     // ---- run x run / array x run with few intervals: boundary sweep, no accumulator ---------
     constexpr int op = OP;
     if ((tA == T_RUN || tB == T_RUN) && tA != T_BITSET && tB != T_BITSET &&
@@ -222,6 +223,13 @@ cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb
     if (card < 0 || want_runs) acc_count(acc, lane, want_runs, card, nruns);
     if (card == 0) { otype = 0; ocard = olen = 0; return; }
     int t = decide_type(op, tA, tB, cA, cB, lA, lB, card, nruns);
+    if (OP == OP_OR && inplace_rules) {
+        // roaring_bitmap_or_inplace: a full left container is left untouched (roaring.c:1081-1083)
+        // and container_ior turns a saturated bitset|bitset into the full run (containers.h:1234-1242)
+        const bool a_full = is_full_run(tA, lA, cA) || (tA == T_BITSET && cA == 65536u);
+        if (a_full) t = tA;
+        else if (tA == T_BITSET && tB == T_BITSET && card == 65536) t = T_RUN;
+    }
     if (t == T_RUN && !want_runs) {  // bitset OR full-run -> [0,65535]
         nruns = 1;
     }
@@ -239,7 +247,7 @@ cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb
 template <int OP>
 __global__ void __launch_bounds__(128)
 k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
-                uint64_t slab_cap, OpStats *st) {
+                uint64_t slab_cap, OpStats *st, int inplace_rules) {
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
     const int lane = threadIdx.x & 31;
     uint32_t *acc = s_acc[threadIdx.x >> 5];
@@ -266,7 +274,8 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 const uint32_t ca = it.ca[item], cb = it.cb[item];
                 cell_compute<OP>(acc, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
                              B.payload + B.c_off[cb], A.c_card[ca], B.c_card[cb], A.c_len[ca],
-                             B.c_len[cb], slab + off, cap, lane, otype, ocard, olen, &st->error);
+                             B.c_len[cb], slab + off, cap, lane, otype, ocard, olen, &st->error,
+                             inplace_rules != 0);
             } else {
                 const SetView &S = (kind == K_COPY_A) ? A : B;
                 const uint32_t c = (kind == K_COPY_A) ? it.ca[item] : it.cb[item];
@@ -611,14 +620,15 @@ void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, c
 }
 
 void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
-                          uint8_t *slab, uint64_t slab_cap, OpStats *st, cudaStream_t s) {
+                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int inplace_rules,
+                          cudaStream_t s) {
     if (!W) return;
     const uint32_t g = blocks_for_warps((W + 3) / 4, 4, sm_count() * 6);
     switch (op) {
-        case OP_AND: k_compute_items<OP_AND><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st); break;
-        case OP_OR: k_compute_items<OP_OR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st); break;
-        case OP_XOR: k_compute_items<OP_XOR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st); break;
-        default: k_compute_items<OP_ANDNOT><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st); break;
+        case OP_AND: k_compute_items<OP_AND><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
+        case OP_OR: k_compute_items<OP_OR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
+        case OP_XOR: k_compute_items<OP_XOR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
+        default: k_compute_items<OP_ANDNOT><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
     }
     g_launches++;
 }

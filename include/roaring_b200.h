@@ -63,6 +63,13 @@ roaring_bitmap_t *roaring_bitmap_xor(const roaring_bitmap_t *r1, const roaring_b
 roaring_bitmap_t *roaring_bitmap_andnot(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 /* include/roaring/roaring.h:304  (src/roaring.c:775) */
 roaring_bitmap_t *roaring_bitmap_or_many(size_t number, const roaring_bitmap_t **rs);
+/* In-place twins, include/roaring/roaring.h:280,296,328,348 (src/roaring.c:812, 1063, 1200, 1342):
+ * same cells with the in-place type rules (container_ior: a saturated bitset|bitset becomes the
+ * full run, a full left container is kept as is); the result replaces the contents of r1. */
+void roaring_bitmap_and_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+void roaring_bitmap_or_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+void roaring_bitmap_xor_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+void roaring_bitmap_andnot_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 /* include/roaring/roaring.h:334  (src/roaring.c:795) */
 roaring_bitmap_t *roaring_bitmap_xor_many(size_t number, const roaring_bitmap_t **rs);
 /* include/roaring/roaring.h:231  (src/roaring.c:3048) */
@@ -127,6 +134,12 @@ uint64_t rb200_set_payload_bytes(const rb200_set_t *s);     /* container_size_in
  * Returns a new device-resident set of npairs bitmaps (NULL on error).  A may equal B. */
 rb200_set_t *rb200_batch_op(int op, const rb200_set_t *A, const rb200_set_t *B,
                             const uint32_t *ia, const uint32_t *ib, size_t npairs);
+
+/* Same with flags: RB200_INPLACE_RULES applies the type rules of the in-place twins
+ * (roaring_bitmap_or_inplace ...) to every pair; the results are still new bitmaps. */
+enum { RB200_INPLACE_RULES = 1 };
+rb200_set_t *rb200_batch_op_ex(int op, int flags, const rb200_set_t *A, const rb200_set_t *B,
+                               const uint32_t *ia, const uint32_t *ib, size_t npairs);
 
 /* out[k] = |A[ia[k]] AND B[ib[k]]|  (roaring_bitmap_and_cardinality per pair); 0 on success. */
 int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,

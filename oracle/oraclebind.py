@@ -6,7 +6,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "liboracle.so")
 
-OPS = {"and": 0, "or": 1, "xor": 2, "andnot": 3}
+OPS = {"and": 0, "or": 1, "xor": 2, "andnot": 3,
+       "and_inplace": 4, "or_inplace": 5, "xor_inplace": 6, "andnot_inplace": 7}
 MANY = {"or_many": 0, "xor_many": 1}
 
 

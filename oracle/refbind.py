@@ -121,6 +121,17 @@ class RefLib:
             self.free(x)
         return out
 
+    def op_inplace_bytes(self, name, a: bytes, b: bytes) -> bytes:
+        """roaring_bitmap_<name>_inplace(x1, x2) on fresh deserializations; returns x1's bytes."""
+        ra, rb = self.deserialize(a), self.deserialize(b)
+        getattr(self.L, f"roaring_bitmap_{name}_inplace")(ra, rb)
+        out = self.serialize(ra)
+        ok, why = self.validate(ra)
+        assert ok, why
+        self.free(ra)
+        self.free(rb)
+        return out
+
     def many_bytes(self, name, blobs) -> bytes:
         rs = [self.deserialize(b) for b in blobs]
         r = self.many(name, rs)

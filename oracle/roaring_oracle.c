@@ -616,7 +616,26 @@ static size_t bm_serialize(const obm_t *b, uint8_t *out, size_t cap) {
 }
 
 /* roaring_bitmap_and :731, _or :877, _xor :1121, _andnot :1275 (all src/roaring.c) */
+/* container_ior differs from container_or in one cell (containers.h:1226-1320): bitset|bitset
+ * that saturates becomes the full run (OR_BITSET_CONVERSION_TO_FULL, :1234-1242), and
+ * roaring_bitmap_or_inplace leaves a full left container untouched (roaring.c:1081-1083).
+ * iand / ixor / iandnot apply the same type rules as their functional twins. */
+static oc_t cell_ior(const oc_t *c1, const oc_t *c2) {
+    if (oc_is_full(c1)) return oc_clone(c1);
+    oc_t r = cell_or(c1, c2);
+    if (c1->type == T_BITSET && c2->type == T_BITSET && r.type == T_BITSET && r.card == 65536) {
+        oc_free(&r);
+        oc_t f = {T_RUN, 0, 1, (uint16_t *)malloc(4), NULL};
+        f.v[0] = 0;
+        f.v[1] = 0xFFFF;
+        return f;
+    }
+    return r;
+}
+
 static void bm_pair(int op, const obm_t *x1, const obm_t *x2, obm_t *ans) {
+    const int inplace = op >= 4;
+    op &= 3;
     bm_init(ans, x1->n + x2->n);
     int p1 = 0, p2 = 0;
     while (p1 < x1->n && p2 < x2->n) {
@@ -625,7 +644,7 @@ static void bm_pair(int op, const obm_t *x1, const obm_t *x2, obm_t *ans) {
             oc_t c;
             switch (op) {
                 case ORC_AND: c = cell_and(&x1->c[p1], &x2->c[p2]); break;
-                case ORC_OR: c = cell_or(&x1->c[p1], &x2->c[p2]); break;
+                case ORC_OR: c = inplace ? cell_ior(&x1->c[p1], &x2->c[p2]) : cell_or(&x1->c[p1], &x2->c[p2]); break;
                 case ORC_XOR: c = cell_xor(&x1->c[p1], &x2->c[p2]); break;
                 default: c = cell_andnot(&x1->c[p1], &x2->c[p2]); break;
             }
