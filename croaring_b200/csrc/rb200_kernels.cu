@@ -253,7 +253,8 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
     uint32_t *acc = s_acc[threadIdx.x >> 5];
     // dynamic scheduling: a ticket is TICKET consecutive items; the next ticket is requested
     // before the current one is processed so its latency hides behind the work.
-    constexpr unsigned long long TICKET = 4;
+    // (small batches: tickets of 1 so that every warp of the grid gets work at once)
+    const unsigned long long TICKET = (W >= 8ull * ((unsigned long long)gridDim.x * 4)) ? 4ull : 1ull;
     unsigned long long tk = 0;
     if (lane == 0) tk = atomicAdd(&st->work_counter, TICKET);
     tk = __shfl_sync(FULLMASK, tk, 0);
@@ -623,7 +624,7 @@ void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t
                           uint8_t *slab, uint64_t slab_cap, OpStats *st, int inplace_rules,
                           cudaStream_t s) {
     if (!W) return;
-    const uint32_t g = blocks_for_warps((W + 3) / 4, 4, sm_count() * 6);
+    const uint32_t g = blocks_for_warps(W, 4, sm_count() * 6);
     switch (op) {
         case OP_AND: k_compute_items<OP_AND><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
         case OP_OR: k_compute_items<OP_OR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
