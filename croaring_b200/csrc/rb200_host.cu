@@ -245,6 +245,7 @@ struct rb200_set {
     uint8_t *d_slab = nullptr;
     std::vector<uint32_t> h_cnt;    // host mirror: containers per bitmap
     std::vector<uint64_t> h_card;   // host mirror: cardinality per bitmap (empty = not cached)
+    bool mirrors_pending = false;   // batch results: h_cnt / h_bytes / h_card are fetched on first use
     // payload address of every container in the caller's host bitmaps (sets made by
     // rb200_set_upload; valid while the caller keeps those bitmaps alive) and, for a batch result,
     // the tables of its two parents: pass-through containers can then be rebuilt on the host from
@@ -924,6 +925,33 @@ uint64_t rb200_set_payload_bytes(const rb200_set_t *s) { return s->portable_byte
 // =================================================================== batched pairwise ops
 namespace {
 
+// Host mirrors of a batch result (containers / cardinality per bitmap) are fetched lazily: a
+// result that is only measured, chained on the device or downloaded never pays this D2H.
+bool ensure_mirrors(const rb200_set *cs) {
+    rb200_set *s = const_cast<rb200_set *>(cs);
+    if (!s->mirrors_pending) return true;
+    const size_t nb = s->n_bitmaps;
+    const size_t bytes = (s->L.o_bcard - s->L.o_cnt) + 8 * nb;
+    uint8_t *h = (uint8_t *)pin_alloc(bytes);
+    if (!h) return false;
+    bool ok = cudaMemcpyAsync(h, s->d_dir + s->L.o_cnt, bytes, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+              cudaStreamSynchronize(g.stream) == cudaSuccess;
+    if (ok) {
+        const uint32_t *cnt = (const uint32_t *)h;
+        const uint64_t *card = (const uint64_t *)(h + (s->L.o_bcard - s->L.o_cnt));
+        s->h_card.assign(card, card + nb);
+        for (size_t p = 0; p < nb; p++) {
+            s->h_cnt[p] = cnt[p];
+            s->h_bytes[p] = (uint64_t)cnt[p] * BITSET_BYTES;  // upper bound: every container <= 8 KiB
+        }
+        s->mirrors_pending = false;
+    } else {
+        g.err = "fetching result directory failed";
+    }
+    pin_free(h, bytes);
+    return ok;
+}
+
 struct ItemsBuf {
     uint8_t *block = nullptr;
     size_t bytes = 0;
@@ -965,6 +993,7 @@ struct PairBuf {
     uint64_t W = 0, slab_bound = 0;
     bool build(const rb200_set *A, const rb200_set *B, const uint32_t *ia, const uint32_t *ib,
                size_t np, bool and_like) {
+        if (!ensure_mirrors(A) || !ensure_mirrors(B)) return false;
         const size_t o_off = 0, o_ia = al256(8 * (np + 1)), o_ib = o_ia + al256(4 * np);
         bytes = o_ib + al256(4 * np);
         h = (uint8_t *)pin_alloc(bytes);
@@ -1020,16 +1049,12 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
     PairBuf pb;
     ItemsBuf ib_;
     rb200_set *R = nullptr;
-    uint32_t *h_cnt = nullptr;
     bool ok = pb.build(A, B, ia, ib, np, op == OP_AND);
     if (ok) ok = ib_.alloc(pb.W);
     if (ok) {
         R = set_new((uint32_t)np, pb.W, pb.slab_bound);
         ok = R != nullptr;
     }
-    // bm_cnt and bm_card are adjacent in the directory block: one D2H brings both
-    const size_t cnt_bytes = R ? (R->L.o_bcard - R->L.o_cnt) + 8 * np : 0;
-    if (ok) { h_cnt = (uint32_t *)pin_alloc(cnt_bytes); ok = h_cnt != nullptr; }
     if (ok) {
         cudaEventRecord(g.ev0, g.stream);
         ok = stats_reset();
@@ -1042,9 +1067,6 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
         cudaEventRecord(g.ev1, g.stream);
         ok = ok && stats_fetch();
-        if (np) {
-            ok = ok && cudaMemcpyAsync(h_cnt, R->d_dir + R->L.o_cnt, cnt_bytes, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
-        }
         cudaError_t e = cudaStreamSynchronize(g.stream);
         if (e != cudaSuccess) { g.err = std::string("batch op: ") + cudaGetErrorString(e); ok = false; }
         if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("batch op launch: ") + cudaGetErrorString(e); ok = false; }
@@ -1062,16 +1084,9 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         R->parentA = A->h_ptr;
         R->parentB = B->h_ptr;
         R->portable_bytes = 0;
-        const uint64_t *h_card = (const uint64_t *)((const uint8_t *)h_cnt + (R->L.o_bcard - R->L.o_cnt));
-        R->h_card.assign(h_card, h_card + np);
-        for (size_t p = 0; p < np; p++) {
-            R->h_cnt[p] = h_cnt[p];
-            // stored-bytes upper bound for chained ops: every container <= 8 KiB
-            R->h_bytes[p] = (uint64_t)h_cnt[p] * BITSET_BYTES;
-            R->h_flags[p] = (A->h_flags[ia[p]] | B->h_flags[ib[p]]) & FLAG_COW;
-        }
+        R->mirrors_pending = np > 0;  // h_cnt / h_bytes / h_card: see ensure_mirrors()
+        for (size_t p = 0; p < np; p++) R->h_flags[p] = (A->h_flags[ia[p]] | B->h_flags[ib[p]]) & FLAG_COW;
     }
-    pin_free(h_cnt, cnt_bytes);
     pb.release();
     ib_.release();
     if (!ok) {
@@ -1141,6 +1156,7 @@ rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, s
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return nullptr;
     if (key_hi > 65535) key_hi = 65535;
+    if (!ensure_mirrors(S)) return nullptr;
     if (idx == nullptr) n = S->n_bitmaps;
     uint64_t tot = 0;
     for (size_t i = 0; i < n; i++) {
@@ -1232,6 +1248,7 @@ rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n) 
 rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return nullptr;
+    if (!ensure_mirrors(S)) return nullptr;
     if (idx == nullptr) n = S->n_bitmaps;
     uint64_t tot = 0;
     for (size_t i = 0; i < n; i++) {
@@ -1301,6 +1318,7 @@ int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out) {
     if (!ctx_init()) return -1;
     const size_t nb = s->n_bitmaps;
     if (!nb) return 0;
+    if (!ensure_mirrors(s)) return -1;
     if (s->h_card.size() == nb) {  // cached by the op that produced this set
         memcpy(out, s->h_card.data(), 8 * nb);
         return 0;
