@@ -146,6 +146,39 @@ def bench_ormany(a):
         S.free()
 
 
+def bench_xormany(a):
+    """roaring_bitmap_xor_many on the three real-data sets (200 bitmaps each) vs the reference."""
+    from oracle.refbind import ref
+    import time as _t
+    R = ref()
+    for ds in ("census1881", "weather_sept_85", "wikileaks-noquotes"):
+        blobs = rb.load_realdata(ds)
+        S = rb.DeviceSet.from_serialized(blobs)
+        ms = []
+        for it in range(a.warmup + a.steps):
+            r = S.xor_many()
+            if it >= a.warmup:
+                ms.append(rb.last_device_ms())
+            got = r.serialize_all()[0] if it == a.warmup + a.steps - 1 else None
+            r.free()
+        rs = [R.deserialize(b) for b in blobs]
+        best = 1e9
+        for _ in range(5):
+            t0 = _t.perf_counter()
+            x = R.many("xor_many", rs)
+            best = min(best, _t.perf_counter() - t0)
+            exp = R.serialize(x)
+            R.free(x)
+        for x in rs:
+            R.free(x)
+        print(json.dumps({"workload": "xor_many_realdata", "dataset": ds, "bitmaps": len(blobs),
+                          "device_ms": float(np.median(ms)), "value": 1.0 / (np.median(ms) * 1e-3),
+                          "unit": "set-ops/s", "input_bytes": S.payload_bytes,
+                          "cpu_baseline": {"kind": "reference", "cores": 1, "ms": best * 1e3,
+                                           "parity": "bytes identical" if exp == got else "MISMATCH"}}), flush=True)
+        assert exp == got
+
+
 def bench_sharded(a):
     """configs[4]: 10^8-universe, many-bitmap OR sharded by high-16 key range across ranks, one NCCL
     all-reduce of the per-key cardinalities.  Strong scaling: total work fixed."""
@@ -230,7 +263,7 @@ def bench_sharded(a):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["card", "ormany", "sharded"])
+    ap.add_argument("what", choices=["card", "ormany", "sharded", "xormany"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=10000)
@@ -241,4 +274,4 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.what != "sharded":
         rb.init(0)
-    {"card": bench_card, "ormany": bench_ormany, "sharded": bench_sharded}[a.what](a)
+    {"card": bench_card, "ormany": bench_ormany, "sharded": bench_sharded, "xormany": bench_xormany}[a.what](a)
