@@ -81,6 +81,9 @@ def lib():
     sig("rb200_set_download", _P, _P, C.c_size_t)
     sig("rb200_set_download_all", C.c_int, _P, C.POINTER(_P))
     sig("rb200_bitmaps_free", None, C.POINTER(_P), C.c_size_t)
+    sig("rb200_set_run_optimize", _P, _P, C.c_int)
+    sig("rb200_set_to_uint32", C.c_int, _P, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint64)))
+    sig("rb200_values_free", None, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64))
     sig("rb200_set_serialize", C.c_int, _P, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)),
         C.POINTER(C.POINTER(C.c_uint64)))
     sig("rb200_serialized_free", None, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
@@ -351,6 +354,23 @@ class DeviceSet:
         if lib().rb200_download_foreach(self.ptr, fn, C.byref(acc)) != 0:
             raise RB200Error(last_error())
         return int(acc.value)
+
+    def run_optimize(self, remove_runs=False):
+        """roaring_bitmap_run_optimize (or remove_run_compression) of every bitmap, on the device."""
+        return DeviceSet(lib().rb200_set_run_optimize(self.ptr, 0 if remove_runs else 1))
+
+    def to_uint32_arrays(self):
+        """roaring_bitmap_to_uint32_array of every bitmap: list of numpy uint32 arrays."""
+        vals = C.POINTER(C.c_uint32)()
+        off = C.POINTER(C.c_uint64)()
+        if lib().rb200_set_to_uint32(self.ptr, C.byref(vals), C.byref(off)) != 0:
+            raise RB200Error(last_error())
+        n = len(self)
+        total = off[n] if n else 0
+        flat = np.ctypeslib.as_array(vals, shape=(total,)).copy() if total else np.zeros(0, np.uint32)
+        out = [flat[off[i]:off[i + 1]] for i in range(n)]
+        lib().rb200_values_free(vals, off)
+        return out
 
     def serialize_all(self, copy=True):
         """Portable bytes of every bitmap, serialized ON THE DEVICE and brought back in one D2H.

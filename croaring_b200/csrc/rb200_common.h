@@ -124,6 +124,12 @@ void launch_serialize_measure(const SetView &S, uint32_t n, uint64_t *sizes16, u
                               uint32_t *hasrun, cudaStream_t s);
 void launch_serialize_write(const SetView &S, uint32_t n, const uint64_t *off, const uint32_t *hasrun,
                             uint8_t *dst, cudaStream_t s);
+void launch_run_optimize(const SetView &S, uint32_t nb, uint64_t nc, int mode, SetOut out, OpStats *st,
+                         cudaStream_t s);
+void launch_values_measure(const SetView &S, uint32_t nb, uint64_t *bm_vals, uint32_t *dummy,
+                           uint64_t *c_start, uint32_t *c_bitmap, cudaStream_t s);
+void launch_values_write(const SetView &S, uint32_t nb, const uint64_t *bm_off, const uint64_t *c_start,
+                         const uint32_t *c_bitmap, uint64_t nc, uint32_t *out, cudaStream_t s);
 void launch_xor_many(const SetView &S, const uint32_t *idx, uint32_t n, const uint16_t *keys,
                      uint8_t *t_type, uint32_t *t_card, uint32_t *t_len, SetOut out, OpStats *st,
                      int sms, cudaStream_t s);

@@ -1877,6 +1877,91 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
     return ok ? 0 : -1;
 }
 
+// roaring_bitmap_run_optimize (mode 1) / roaring_bitmap_remove_run_compression (mode 0) applied
+// to every bitmap of a set on the device; returns a new resident set (same bitmaps, same keys).
+rb200_set_t *rb200_set_run_optimize(const rb200_set_t *S, int mode) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return nullptr;
+    const uint64_t nc = S->n_containers;
+    // mode 1 never grows a container by more than its 16-byte padding; mode 0 may expand runs
+    const uint64_t bound = S->slab_used + 16 * nc + (mode == 0 ? nc * (uint64_t)BITSET_BYTES : 0) + 512;
+    rb200_set *R = set_new(S->n_bitmaps, nc, bound);
+    if (!R) return nullptr;
+    bool ok = stats_reset();
+    launch_run_optimize(S->view(), S->n_bitmaps, nc, mode ? 1 : 0, R->out(), g.d_stats, g.stream);
+    ok = ok && stats_fetch();
+    cudaError_t e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+        g.err = std::string("run_optimize: ") + cudaGetErrorString(e);
+        ok = false;
+    }
+    if (!ok) { set_delete(R); return nullptr; }
+    R->n_containers = nc;
+    R->slab_used = g.h_stats->slab_cursor;
+    R->h_flags = S->h_flags;
+    if (!ensure_mirrors(S)) { set_delete(R); return nullptr; }
+    R->h_cnt = S->h_cnt;
+    for (size_t b = 0; b < R->n_bitmaps; b++) R->h_bytes[b] = (uint64_t)R->h_cnt[b] * BITSET_BYTES;
+    return R;
+}
+
+// roaring_bitmap_to_uint32_array for every bitmap of a set: *vals (pinned host memory owned by the
+// library) holds all values; bitmap i = vals[off[i] .. off[i+1]).  Release with rb200_values_free.
+int rb200_set_to_uint32(const rb200_set_t *S, uint32_t **vals, uint64_t **off_out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    const size_t nb = S->n_bitmaps;
+    const uint64_t nc = S->n_containers;
+    *vals = nullptr;
+    *off_out = (uint64_t *)malloc(8 * (nb + 1));
+    if (!*off_out) return -1;
+    (*off_out)[0] = 0;
+    if (nb == 0) return 0;
+    uint64_t *d_bv = (uint64_t *)dev_alloc(8 * nb), *d_off = (uint64_t *)dev_alloc(8 * (nb + 1)),
+             *d_dummy = (uint64_t *)dev_alloc(8 * (nb + 1)), *d_cstart = (uint64_t *)dev_alloc(8 * nc);
+    uint32_t *d_zero = (uint32_t *)dev_alloc(4 * nb), *d_cbm = (uint32_t *)dev_alloc(4 * nc);
+    uint64_t *h_off = (uint64_t *)pin_alloc(8 * (nb + 1));
+    uint32_t *d_vals = nullptr, *h_vals = nullptr;
+    uint64_t total = 0;
+    bool ok = d_bv && d_off && d_dummy && d_cstart && d_zero && d_cbm && h_off;
+    if (ok) {
+        launch_values_measure(S->view(), (uint32_t)nb, d_bv, d_zero, d_cstart, d_cbm, g.stream);
+        launch_pack_scan(d_bv, d_zero, (uint32_t)nb, d_off, d_dummy, g.stream);
+        ok = cudaMemcpyAsync(h_off, d_off, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaStreamSynchronize(g.stream) == cudaSuccess;
+    }
+    if (ok) {
+        total = h_off[nb];
+        memcpy(*off_out, h_off, 8 * (nb + 1));
+        d_vals = (uint32_t *)dev_alloc(4 * total);
+        h_vals = (uint32_t *)pin_alloc(4 * total);
+        ok = d_vals && h_vals;
+    }
+    if (ok) {
+        launch_values_write(S->view(), (uint32_t)nb, d_off, d_cstart, d_cbm, nc, d_vals, g.stream);
+        ok = cudaMemcpyAsync(h_vals, d_vals, 4 * total, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaStreamSynchronize(g.stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    }
+    dev_free(d_bv, 8 * nb);
+    dev_free(d_off, 8 * (nb + 1));
+    dev_free(d_dummy, 8 * (nb + 1));
+    dev_free(d_cstart, 8 * nc);
+    dev_free(d_zero, 4 * nb);
+    dev_free(d_cbm, 4 * nc);
+    dev_free(d_vals, 4 * total);
+    pin_free(h_off, 8 * (nb + 1));
+    if (!ok) {
+        pin_free(h_vals, 4 * total);
+        if (g.err.empty()) g.err = "set_to_uint32 failed";
+        return -1;
+    }
+    *vals = h_vals;
+    g_serialized_sizes[(uint8_t *)h_vals] = 4 * total;
+    return 0;
+}
+
+void rb200_values_free(uint32_t *vals, uint64_t *off) { rb200_serialized_free((char *)vals, off, nullptr); }
+
 // Device-side portable serialization of every bitmap of a set + one D2H copy.
 // *buf is pinned host memory owned by the library (release with rb200_serialized_free);
 // blob i = *buf + (*off)[i], (*len)[i] bytes, byte-identical to roaring_bitmap_portable_serialize.

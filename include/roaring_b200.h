@@ -191,6 +191,13 @@ int rb200_visit_sum_cardinality(size_t index, roaring_bitmap_t *bitmap, void *ct
 int rb200_set_serialize(const rb200_set_t *s, char **buf, uint64_t **off, uint64_t **len);
 void rb200_serialized_free(char *buf, uint64_t *off, uint64_t *len);
 
+/* Batch producers / consumers next to the path (device kernels over a whole set):
+ * mode 1 = roaring_bitmap_run_optimize [src/roaring.c:1530], mode 0 = remove_run_compression, and
+ * roaring_bitmap_to_uint32_array [src/roaring_array.c:426] for every bitmap of the set. */
+rb200_set_t *rb200_set_run_optimize(const rb200_set_t *s, int mode);
+int rb200_set_to_uint32(const rb200_set_t *s, uint32_t **vals, uint64_t **off);
+void rb200_values_free(uint32_t *vals, uint64_t *off);
+
 /* Free n host bitmaps (e.g. the results of rb200_set_download_all) using several threads. */
 void rb200_bitmaps_free(roaring_bitmap_t **bitmaps, size_t n);
 
