@@ -188,6 +188,7 @@ void dev_free(void *p, size_t n) {
     if (n == 0) n = 1;
     g.dpool.insert({bucket(n), p});
 }
+bool enter_local_cpus(cpu_set_t *saved);
 void *pin_alloc(size_t n) {
     if (n == 0) n = 1;
     const size_t b = bucket(n);
@@ -197,8 +198,15 @@ void *pin_alloc(size_t n) {
         g.hpool.erase(it);
         return p;
     }
+    // Staging buffers belong on the GPU's NUMA node: the D2H stream and the (node-bound) workers
+    // that read them then never cross the socket interconnect.  Pages are placed when they are
+    // pinned, in the calling thread's context, so the caller is moved to the local CPUs for the
+    // duration of the allocation.
+    cpu_set_t saved;
+    const bool moved = b >= (1u << 20) && enter_local_cpus(&saved);
     void *p = nullptr;
     cudaError_t e = cudaHostAlloc(&p, b, cudaHostAllocDefault);
+    if (moved) pthread_setaffinity_np(pthread_self(), sizeof(saved), &saved);
     if (e != cudaSuccess) {
         g.err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
         return nullptr;
@@ -1471,6 +1479,17 @@ std::vector<int> &local_cpus() {
     fclose(f);
     return cpus;
 }
+// Move the calling thread onto the GPU-local CPUs; *saved receives the previous mask.
+bool enter_local_cpus(cpu_set_t *saved) {
+    if (getenv("RB200_NO_NUMA")) return false;
+    const std::vector<int> &cpus = local_cpus();
+    if (cpus.empty()) return false;
+    if (pthread_getaffinity_np(pthread_self(), sizeof(*saved), saved) != 0) return false;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    for (int c : cpus) if (c < CPU_SETSIZE) CPU_SET(c, &set);
+    return pthread_setaffinity_np(pthread_self(), sizeof(set), &set) == 0;
+}
 void bind_to_local_cpus() {
     const std::vector<int> &cpus = local_cpus();
     if (cpus.empty()) return;
@@ -1678,13 +1697,24 @@ void rb200_download_end(rb200_download_stream_t *st) {
 // gigabytes of fresh memory.  Returns 0 on success.
 int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const auto t_enter = std::chrono::steady_clock::now();
     rb200_download_stream *st = rb200_download_begin(s, 4096);
     if (!st) return -1;
     std::atomic<int> failed(0);
+    const bool trace = getenv("RB200_TRACE") != nullptr;
+    double t_wait = 0, t_build = 0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+    const double t_pack = ms_since(t_enter);
     while (st->next_build < st->chunk_end.size()) {
         const size_t k = st->next_build;
         const size_t p0 = k ? st->chunk_end[k - 1] : 0, p1 = st->chunk_end[k];
+        const auto t0 = std::chrono::steady_clock::now();
         if (cudaEventSynchronize(st->ev[k & 1]) != cudaSuccess) { failed = 1; break; }
+        t_wait += ms_since(t0);
+        const auto t1 = std::chrono::steady_clock::now();
         const uint8_t *buf = st->hbuf[k & 1];
         const uint64_t bias = st->h_ob[p0];
         const size_t n = p1 - p0;
@@ -1709,9 +1739,13 @@ int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx) {
         if (want < T) T = (unsigned)want;
         if ((size_t)T * 8 > n) T = (unsigned)((n + 7) / 8);
         pool().run(work, T);
+        t_build += ms_since(t1);
         st->next_build++;
         if (!stream_enqueue(st)) { failed = 1; break; }
     }
+    if (trace)
+        fprintf(stderr, "rb200 foreach: %zu bitmaps %zu chunks %.1f MB | pack %.2f ms, copy-wait %.2f ms, build %.2f ms, loop %.2f ms\n",
+                st->nb, st->chunk_end.size(), st->total_bytes / 1e6, t_pack, t_wait, t_build, ms_since(t_begin));
     stream_free(st);
     if (failed) {
         if (g.err.empty()) g.err = "download_foreach: host allocation or copy failed";
