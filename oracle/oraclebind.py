@@ -28,6 +28,12 @@ class Oracle:
         L.oracle_many_op.restype = C.c_size_t
         L.oracle_many_op.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_char_p),
                                      C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+        L.oracle_lazy_fold.restype = C.c_size_t
+        L.oracle_lazy_fold.argtypes = [C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_char_p),
+                                       C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+        L.oracle_or_many_heap.restype = C.c_size_t
+        L.oracle_or_many_heap.argtypes = [C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+                                          C.c_char_p, C.c_size_t]
         L.oracle_and_cardinality.restype = C.c_uint64
         L.oracle_and_cardinality.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         L.oracle_cardinality.restype = C.c_uint64
@@ -53,6 +59,23 @@ class Oracle:
         got = self.L.oracle_many_op(MANY[name], n, arr, lens, buf, need)
         assert got == need
         return buf.raw
+
+    def _many(self, fn, head, blobs) -> bytes:
+        n = len(blobs)
+        arr = (C.c_char_p * n)(*blobs)
+        lens = (C.c_size_t * n)(*[len(b) for b in blobs])
+        need = fn(*head, n, arr, lens, None, 0)
+        if need == C.c_size_t(-1).value:
+            raise ValueError("oracle: malformed input")
+        buf = C.create_string_buffer(need)
+        assert fn(*head, n, arr, lens, buf, need) == need
+        return buf.raw
+
+    def lazy_fold_bytes(self, op: str, conv: bool, blobs) -> bytes:
+        return self._many(self.L.oracle_lazy_fold, (0 if op == "or" else 1, int(conv)), blobs)
+
+    def or_many_heap_bytes(self, blobs) -> bytes:
+        return self._many(self.L.oracle_or_many_heap, (), blobs)
 
     def and_cardinality(self, a: bytes, b: bytes) -> int:
         return int(self.L.oracle_and_cardinality(a, len(a), b, len(b)))

@@ -62,6 +62,11 @@ class RefLib:
         sig("roaring_bitmap_jaccard_index", C.c_double, P, P)               # roaring.h:252
         sig("roaring_bitmap_intersect", C.c_bool, P, P)                     # roaring.h:237
         sig("roaring_bitmap_statistics", None, P, C.c_void_p)
+        sig("roaring_bitmap_lazy_or", P, P, P, C.c_bool)                    # roaring.h:932
+        sig("roaring_bitmap_lazy_or_inplace", None, P, P, C.c_bool)         # roaring.h:943
+        sig("roaring_bitmap_lazy_xor", P, P, P)                             # roaring.h:963
+        sig("roaring_bitmap_lazy_xor_inplace", None, P, P)                  # roaring.h:970
+        sig("roaring_bitmap_repair_after_lazy", None, P)                    # roaring.h:952
 
     # ---- helpers -------------------------------------------------------------
     def from_values(self, vals, run_optimize=True):
@@ -130,6 +135,28 @@ class RefLib:
         assert ok, why
         self.free(ra)
         self.free(rb)
+        return out
+
+    def lazy_fold_bytes(self, op: str, conv: bool, blobs) -> bytes:
+        """repair_after_lazy(lazy_<op>(x0, x1) then lazy_<op>_inplace(acc, xi) for i >= 2)."""
+        rs = [self.deserialize(b) for b in blobs]
+        L = self.L
+        if len(rs) == 1:
+            acc = L.roaring_bitmap_copy(rs[0])
+        elif op == "or":
+            acc = L.roaring_bitmap_lazy_or(rs[0], rs[1], conv)
+            for x in rs[2:]:
+                L.roaring_bitmap_lazy_or_inplace(acc, x, conv)
+        else:
+            acc = L.roaring_bitmap_lazy_xor(rs[0], rs[1])
+            for x in rs[2:]:
+                L.roaring_bitmap_lazy_xor_inplace(acc, x)
+        L.roaring_bitmap_repair_after_lazy(acc)
+        ok, why = self.validate(acc)
+        assert ok, why
+        out = self.serialize(acc)
+        for x in rs + [acc]:
+            self.free(x)
         return out
 
     def many_bytes(self, name, blobs) -> bytes:

@@ -384,6 +384,37 @@ static void cell_lazy_ior_bitset(oc_t *acc, const oc_t *c2) {
     }
 }
 
+/* container_lazy_ior for every type pairing, containers.h:1333-1440.  Replaces *c1. */
+static void cell_lazy_ior(oc_t *c1, const oc_t *c2) {
+    if (c1->type == T_BITSET) { /* B,B / B,A / B,R */
+        cell_lazy_ior_bitset(c1, c2);
+        return;
+    }
+    uint64_t w1[WORDS], w2[WORDS];
+    oc_t r;
+    if (c1->type == T_RUN && c2->type == T_BITSET && run_is_full(c1)) return; /* :1409-1412 */
+    to_words(c1, w1);
+    to_words(c2, w2);
+    for (int i = 0; i < WORDS; i++) w1[i] |= w2[i];
+    switch (PAIR(c1->type, c2->type)) {
+        case PAIR(T_ARRAY, T_ARRAY): /* mixed_union.c:285-372 */
+            r = (c1->n + c2->n <= LAZY_LOWER) ? mk_array(w1) : mk_bitset(w1, -1);
+            break;
+        case PAIR(T_RUN, T_RUN): /* :1366-1370 union + convert_run_to_efficient_container */
+            r = eff_from_words(w1);
+            break;
+        case PAIR(T_ARRAY, T_BITSET): /* :1380-1388 */
+        case PAIR(T_RUN, T_BITSET):   /* :1413-1419 */
+            r = mk_bitset(w1, -1);
+            break;
+        default: /* A,R / R,A: left as RUN, :1421-1440 */
+            r = mk_run(w1);
+            break;
+    }
+    oc_free(c1);
+    *c1 = r;
+}
+
 /* container_is_full, containers.h:262-277 */
 static bool oc_is_full(const oc_t *c) {
     if (c->type == T_BITSET) return c->card == 65536;
@@ -674,8 +705,8 @@ static void bm_copy(const obm_t *x, obm_t *ans) {
     for (int i = 0; i < x->n; i++) bm_append(ans, x->keys[i], oc_clone(&x->c[i]));
 }
 
-/* roaring_bitmap_lazy_or(x1,x2,bitsetconversion=true), roaring.c:2509-2598 */
-static void bm_lazy_or(const obm_t *x1, const obm_t *x2, obm_t *ans) {
+/* roaring_bitmap_lazy_or(x1,x2,bitsetconversion), roaring.c:2509-2598 */
+static void bm_lazy_or(const obm_t *x1, const obm_t *x2, bool conv, obm_t *ans) {
     if (x1->n == 0) { bm_copy(x2, ans); return; }
     if (x2->n == 0) { bm_copy(x1, ans); return; }
     bm_init(ans, x1->n + x2->n);
@@ -685,7 +716,7 @@ static void bm_lazy_or(const obm_t *x1, const obm_t *x2, obm_t *ans) {
         if (s1 == s2) {
             const oc_t *c1 = &x1->c[p1], *c2 = &x2->c[p2];
             oc_t c;
-            if (c1->type != T_BITSET && c2->type != T_BITSET) { /* :2535-2545 */
+            if (conv && c1->type != T_BITSET && c2->type != T_BITSET) { /* :2535-2545 */
                 c = to_bitset(c1);
                 cell_lazy_ior_bitset(&c, c2);
             } else {
@@ -704,8 +735,8 @@ static void bm_lazy_or(const obm_t *x1, const obm_t *x2, obm_t *ans) {
     for (; p2 < x2->n; p2++) bm_append(ans, x2->keys[p2], oc_clone(&x2->c[p2]));
 }
 
-/* roaring_bitmap_lazy_or_inplace(x1,x2,true), roaring.c:2600-2682 */
-static void bm_lazy_or_inplace(obm_t *x1, const obm_t *x2) {
+/* roaring_bitmap_lazy_or_inplace(x1,x2,bitsetconversion), roaring.c:2600-2682 */
+static void bm_lazy_or_inplace(obm_t *x1, const obm_t *x2, bool conv) {
     if (x2->n == 0) return;
     if (x1->n == 0) {
         bm_free(x1);
@@ -718,12 +749,12 @@ static void bm_lazy_or_inplace(obm_t *x1, const obm_t *x2) {
         if (s1 == s2) {
             oc_t *c1 = &x1->c[p1];
             if (!oc_is_full(c1)) { /* :2621 */
-                if (c1->type != T_BITSET) { /* :2622-2633 */
+                if (conv && c1->type != T_BITSET) { /* :2622-2633 */
                     oc_t b = to_bitset(c1);
                     oc_free(c1);
                     *c1 = b;
                 }
-                cell_lazy_ior_bitset(c1, &x2->c[p2]);
+                cell_lazy_ior(c1, &x2->c[p2]);
             }
             p1++;
             p2++;
@@ -840,12 +871,12 @@ size_t oracle_many_op(int op, size_t n, const uint8_t *const *bufs, const size_t
             bm_copy(&xs[0], &ans);
         } else {
             if (op == ORC_OR_MANY)
-                bm_lazy_or(&xs[0], &xs[1], &ans);
+                bm_lazy_or(&xs[0], &xs[1], true, &ans);
             else
                 bm_lazy_xor(&xs[0], &xs[1], &ans);
             for (size_t i = 2; i < n; i++) {
                 if (op == ORC_OR_MANY)
-                    bm_lazy_or_inplace(&ans, &xs[i]);
+                    bm_lazy_or_inplace(&ans, &xs[i], true);
                 else
                     bm_lazy_xor_inplace(&ans, &xs[i]);
             }
@@ -886,4 +917,176 @@ uint64_t oracle_cardinality(const uint8_t *a, size_t na) { /* roaring.c:1436 */
     for (int i = 0; i < x.n; i++) s += (uint64_t)oc_card(&x.c[i]);
     bm_free(&x);
     return s;
+}
+
+/* A left fold of the public lazy API followed by one repair:
+ *   acc = lazy_op(x0, x1[, conv]); acc = lazy_op_inplace(acc, xi[, conv]) for i >= 2;
+ *   roaring_bitmap_repair_after_lazy(acc).
+ * op 0 = roaring_bitmap_lazy_or / _lazy_or_inplace (roaring.c:2509-2682, `conv` = their
+ * bitsetconversion argument), op 1 = roaring_bitmap_lazy_xor / _lazy_xor_inplace
+ * (roaring.c:2684-2843).  n == 1: repair(copy(x0)). */
+size_t oracle_lazy_fold(int op, int conv, size_t n, const uint8_t *const *bufs, const size_t *lens,
+                        uint8_t *out, size_t cap) {
+    obm_t ans;
+    if (n == 0) return (size_t)-1;
+    obm_t *xs = (obm_t *)malloc(sizeof(obm_t) * n);
+    for (size_t i = 0; i < n; i++)
+        if (!bm_parse(&xs[i], bufs[i], lens[i])) return (size_t)-1;
+    if (n == 1) {
+        bm_copy(&xs[0], &ans);
+    } else {
+        if (op == 0) bm_lazy_or(&xs[0], &xs[1], conv != 0, &ans);
+        else bm_lazy_xor(&xs[0], &xs[1], &ans);
+        for (size_t i = 2; i < n; i++) {
+            if (op == 0) bm_lazy_or_inplace(&ans, &xs[i], conv != 0);
+            else bm_lazy_xor_inplace(&ans, &xs[i]);
+        }
+    }
+    for (int i = 0; i < ans.n; i++) repair(&ans.c[i]); /* roaring.c:2845 */
+    for (size_t i = 0; i < n; i++) bm_free(&xs[i]);
+    free(xs);
+    size_t r = bm_serialize(&ans, out, cap);
+    bm_free(&ans);
+    return r;
+}
+
+/* roaring_bitmap_portable_size_in_bytes (roaring.c:1490 -> roaring_array.c:469-500) of a bitmap
+ * that may be in a lazy state: arrays count 2*card, bitsets 8192, runs 2+4*n_runs. */
+static uint64_t bm_portable_size(const obm_t *b) {
+    bool hasrun = false;
+    uint64_t sz = 0;
+    for (int i = 0; i < b->n; i++) {
+        if (b->c[i].type == T_RUN) hasrun = true;
+        sz += oc_bytes(&b->c[i]);
+    }
+    if (hasrun) {
+        sz += 4 + (uint64_t)(b->n + 7) / 8 + 4ull * b->n;
+        if (b->n >= NO_OFFSET_THRESHOLD) sz += 4ull * b->n;
+    } else {
+        sz += 4 + 4 + 8ull * b->n;
+    }
+    return sz;
+}
+
+/* lazy_or_from_lazy_inputs, roaring_priority_queue.c:99-181: container_lazy_ior on every
+ * matched key (no full-container short cut), unmatched containers moved.  Consumes x1, x2. */
+static void bm_lazy_or_from_lazy(obm_t *x1, obm_t *x2, obm_t *ans) {
+    if (x1->n == 0) { bm_free(x1); *ans = *x2; return; }
+    if (x2->n == 0) { bm_free(x2); *ans = *x1; return; }
+    bm_init(ans, x1->n + x2->n);
+    int p1 = 0, p2 = 0;
+    while (p1 < x1->n && p2 < x2->n) {
+        uint16_t s1 = x1->keys[p1], s2 = x2->keys[p2];
+        if (s1 == s2) {
+            oc_t *c1 = &x1->c[p1], *c2 = &x2->c[p2];
+            if (c2->type == T_BITSET && c1->type != T_BITSET) { /* :133-139 operands swapped */
+                cell_lazy_ior(c2, c1);
+                bm_append(ans, s1, oc_clone(c2));
+            } else {
+                cell_lazy_ior(c1, c2);
+                bm_append(ans, s1, oc_clone(c1));
+            }
+            p1++;
+            p2++;
+        } else if (s1 < s2) {
+            bm_append(ans, s1, oc_clone(&x1->c[p1++]));
+        } else {
+            bm_append(ans, s2, oc_clone(&x2->c[p2++]));
+        }
+    }
+    for (; p1 < x1->n; p1++) bm_append(ans, x1->keys[p1], oc_clone(&x1->c[p1]));
+    for (; p2 < x2->n; p2++) bm_append(ans, x2->keys[p2], oc_clone(&x2->c[p2]));
+    bm_free(x1);
+    bm_free(x2);
+}
+
+/* The binary min-heap of roaring_priority_queue.c:12-97 (ordering by portable size, ties
+ * resolved by heap position exactly as the reference's sift loops do). */
+typedef struct {
+    uint64_t size;
+    bool temp;
+    obm_t bm;
+} hp_t;
+
+static void hp_down(hp_t *e, uint32_t n, uint32_t i) { /* percolate_down :46-66 */
+    uint32_t half = n >> 1;
+    hp_t cur = e[i];
+    while (i < half) {
+        uint32_t child = 2 * i + 1;
+        if (child + 1 < n && e[child + 1].size < e[child].size) child++;
+        if (!(e[child].size < cur.size)) break;
+        e[i] = e[child];
+        i = child;
+    }
+    e[i] = cur;
+}
+static void hp_push(hp_t *e, uint32_t *n, hp_t t) { /* pq_add :31-42 */
+    uint32_t i = (*n)++;
+    while (i > 0) {
+        uint32_t parent = (i - 1) >> 1;
+        if (!(t.size < e[parent].size)) break;
+        e[i] = e[parent];
+        i = parent;
+    }
+    e[i] = t;
+}
+static hp_t hp_pop(hp_t *e, uint32_t *n) { /* pq_poll :84-95 */
+    hp_t top = e[0];
+    if (*n > 1) {
+        e[0] = e[--(*n)];
+        hp_down(e, *n, 0);
+    } else {
+        --(*n);
+    }
+    return top;
+}
+
+/* roaring_bitmap_or_many_heap, roaring_priority_queue.c:200-250 */
+size_t oracle_or_many_heap(size_t n, const uint8_t *const *bufs, const size_t *lens, uint8_t *out,
+                           size_t cap) {
+    obm_t ans;
+    if (n == 0) {
+        bm_init(&ans, 0);
+    } else {
+        hp_t *e = (hp_t *)malloc(sizeof(hp_t) * n);
+        for (size_t i = 0; i < n; i++) {
+            if (!bm_parse(&e[i].bm, bufs[i], lens[i])) return (size_t)-1;
+            e[i].temp = false;
+            e[i].size = bm_portable_size(&e[i].bm);
+        }
+        if (n == 1) {
+            bm_copy(&e[0].bm, &ans);
+            bm_free(&e[0].bm);
+        } else {
+            uint32_t cnt = (uint32_t)n;
+            for (int32_t i = (int32_t)(cnt >> 1); i >= 0; i--) hp_down(e, cnt, (uint32_t)i); /* create_pq :68-82 */
+            while (cnt > 1) {
+                hp_t a = hp_pop(e, &cnt), b = hp_pop(e, &cnt), r;
+                r.temp = true;
+                if (a.temp && b.temp) {
+                    bm_lazy_or_from_lazy(&a.bm, &b.bm, &r.bm);
+                } else if (b.temp) {
+                    bm_lazy_or_inplace(&b.bm, &a.bm, false);
+                    r.bm = b.bm;
+                    bm_free(&a.bm);
+                } else if (a.temp) {
+                    bm_lazy_or_inplace(&a.bm, &b.bm, false);
+                    r.bm = a.bm;
+                    bm_free(&b.bm);
+                } else {
+                    bm_lazy_or(&a.bm, &b.bm, false, &r.bm);
+                    bm_free(&a.bm);
+                    bm_free(&b.bm);
+                }
+                r.size = bm_portable_size(&r.bm);
+                hp_push(e, &cnt, r);
+            }
+            ans = hp_pop(e, &cnt).bm;
+            for (int i = 0; i < ans.n; i++) repair(&ans.c[i]);
+        }
+        free(e);
+    }
+    size_t r = bm_serialize(&ans, out, cap);
+    bm_free(&ans);
+    return r;
 }

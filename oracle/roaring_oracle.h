@@ -21,6 +21,15 @@ size_t oracle_pair_op(int op, const uint8_t *a, size_t na, const uint8_t *b, siz
 size_t oracle_many_op(int op, size_t n, const uint8_t *const *bufs, const size_t *lens,
                       uint8_t *out, size_t cap);
 
+/* repair_after_lazy(fold of the public lazy API): op 0 = lazy_or/lazy_or_inplace with
+ * bitsetconversion = conv, op 1 = lazy_xor/lazy_xor_inplace; inputs folded left to right. */
+size_t oracle_lazy_fold(int op, int conv, size_t n, const uint8_t *const *bufs, const size_t *lens,
+                        uint8_t *out, size_t cap);
+
+/* roaring_bitmap_or_many_heap (roaring_priority_queue.c:200-250). */
+size_t oracle_or_many_heap(size_t n, const uint8_t *const *bufs, const size_t *lens, uint8_t *out,
+                           size_t cap);
+
 /* roaring_bitmap_and_cardinality; (uint64_t)-1 on malformed input. */
 uint64_t oracle_and_cardinality(const uint8_t *a, size_t na, const uint8_t *b, size_t nb);
 

@@ -83,3 +83,27 @@ def test_reference_known_answers(R, O):
     assert out == R.op_bytes("and", R.serialize(x1), R.serialize(x2))
     for r in (r1, r2, x1, x2):
         R.free(r)
+
+
+@pytest.mark.parametrize("seed", [7, 4242])
+def test_oracle_lazy_api_and_heap_vs_reference(O, R, seed):
+    """The public lazy API (roaring.h:932-977) folded left to right then repaired, for both values
+    of `bitsetconversion`, and roaring_bitmap_or_many_heap (roaring_priority_queue.c:200)."""
+    blobs = synth_blobs(R, seed, 80)
+    rng = np.random.default_rng(seed)
+    for _ in range(150):
+        idx = rng.integers(0, len(blobs), int(rng.integers(1, 8)))
+        sub = [blobs[k] for k in idx]
+        for conv in (False, True):
+            assert O.lazy_fold_bytes("or", conv, sub) == R.lazy_fold_bytes("or", conv, sub), (conv, idx.tolist())
+        assert O.lazy_fold_bytes("xor", False, sub) == R.lazy_fold_bytes("xor", False, sub), idx.tolist()
+        assert O.or_many_heap_bytes(sub) == R.many_bytes("or_many_heap", sub), idx.tolist()
+    assert O.or_many_heap_bytes([]) == R.many_bytes("or_many_heap", [])
+
+
+@pytest.mark.parametrize("ds", ["census1881", "weather_sept_85", "wikileaks-noquotes", "uscensus2000"])
+def test_oracle_heap_vs_reference_realdata(O, R, ds):
+    blobs = dsm.load_realdata(ds)
+    assert O.or_many_heap_bytes(blobs) == R.many_bytes("or_many_heap", blobs)
+    assert O.or_many_heap_bytes(blobs[:37]) == R.many_bytes("or_many_heap", blobs[:37])
+    assert O.lazy_fold_bytes("or", False, blobs[:50]) == R.lazy_fold_bytes("or", False, blobs[:50])
