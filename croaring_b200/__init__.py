@@ -5,5 +5,5 @@ its Python mirror (ctypes) plus workload I/O helpers.  See DESIGN.md / INTEGRATI
 """
 from .api import (AND, ANDNOT, OR, XOR, Bitmap, DeviceSet, RB200Error, batch_op_host, init,  # noqa: F401
                   kernel_launches, last_algorithmic_bytes, last_device_ms, last_error, lib,
-                  or_many, set_stream, synchronize, xor_many)
+                  or_many, or_many_heap, set_stream, synchronize, xor_many)
 from .datasets import load_realdata, read_rbset, write_rbset  # noqa: F401

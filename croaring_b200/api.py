@@ -48,6 +48,14 @@ def lib():
     sig("roaring_bitmap_or_many", _P, C.c_size_t, C.POINTER(_P))
     sig("roaring_bitmap_xor_many", _P, C.c_size_t, C.POINTER(_P))
     sig("rb200_xor_many", _P, _P, _P, C.c_size_t)
+    sig("roaring_bitmap_or_many_heap", _P, C.c_uint32, C.POINTER(_P))
+    sig("rb200_or_many_heap", _P, _P, _P, C.c_size_t)
+    sig("rb200_set_repair_after_lazy", _P, _P)
+    sig("roaring_bitmap_lazy_or", _P, _P, _P, C.c_bool)
+    sig("roaring_bitmap_lazy_or_inplace", None, _P, _P, C.c_bool)
+    sig("roaring_bitmap_lazy_xor", _P, _P, _P)
+    sig("roaring_bitmap_lazy_xor_inplace", None, _P, _P)
+    sig("roaring_bitmap_repair_after_lazy", None, _P)
     sig("roaring_bitmap_jaccard_index", C.c_double, _P, _P)
     sig("roaring_bitmap_intersect", C.c_bool, _P, _P)
     sig("rb200_bitmap_portable_deserialize_safe", _P, C.c_char_p, C.c_size_t)
@@ -193,6 +201,31 @@ class Bitmap:
         getattr(lib(), f"roaring_bitmap_{name}_inplace")(self.ptr, other.ptr)
         return self
 
+    # -- public lazy API (roaring.h:932-977)
+    def lazy_or(self, o, bitsetconversion=False):
+        p = lib().roaring_bitmap_lazy_or(self.ptr, o.ptr, bool(bitsetconversion))
+        if not p:
+            raise RB200Error(last_error())
+        return Bitmap(p)
+
+    def lazy_or_inplace(self, o, bitsetconversion=False):
+        lib().roaring_bitmap_lazy_or_inplace(self.ptr, o.ptr, bool(bitsetconversion))
+        return self
+
+    def lazy_xor(self, o):
+        p = lib().roaring_bitmap_lazy_xor(self.ptr, o.ptr)
+        if not p:
+            raise RB200Error(last_error())
+        return Bitmap(p)
+
+    def lazy_xor_inplace(self, o):
+        lib().roaring_bitmap_lazy_xor_inplace(self.ptr, o.ptr)
+        return self
+
+    def repair_after_lazy(self):
+        lib().roaring_bitmap_repair_after_lazy(self.ptr)
+        return self
+
     def and_cardinality(self, o) -> int:
         v = int(lib().roaring_bitmap_and_cardinality(self.ptr, o.ptr))
         if v == 2 ** 64 - 1:
@@ -210,6 +243,15 @@ def or_many(bitmaps):
     """roaring_bitmap_or_many on host bitmaps (drop-in symbol)."""
     arr = (_P * len(bitmaps))(*[b.ptr for b in bitmaps])
     p = lib().roaring_bitmap_or_many(len(bitmaps), arr)
+    if not p:
+        raise RB200Error(last_error())
+    return Bitmap(p)
+
+
+def or_many_heap(bitmaps):
+    """roaring_bitmap_or_many_heap on host bitmaps (drop-in symbol)."""
+    arr = (_P * len(bitmaps))(*[b.ptr for b in bitmaps])
+    p = lib().roaring_bitmap_or_many_heap(len(bitmaps), arr)
     if not p:
         raise RB200Error(last_error())
     return Bitmap(p)
@@ -285,14 +327,29 @@ class DeviceSet:
     def payload_bytes(self):
         return int(lib().rb200_set_payload_bytes(self.ptr))
 
-    def batch(self, op, other, ia, ib, inplace_rules=False):
-        """result[k] = self[ia[k]] op other[ib[k]] as a new DeviceSet."""
+    def batch(self, op, other, ia, ib, inplace_rules=False, lazy=False, bitsetconversion=False,
+              from_lazy_inputs=False):
+        """result[k] = self[ia[k]] op other[ib[k]] as a new DeviceSet.  lazy=True: the lazy OR/XOR
+        variants (result set in a lazy state: chain further lazy ops, then repair_after_lazy())."""
         ia, ib = _u32(ia), _u32(ib)
         assert ia.shape == ib.shape
         code = OPS[op] if isinstance(op, str) else op
-        p = lib().rb200_batch_op_ex(code, 1 if inplace_rules else 0, self.ptr, other.ptr,
+        flags = (1 if inplace_rules else 0) | (2 if lazy else 0) | (4 if bitsetconversion else 0) | \
+                (8 if from_lazy_inputs else 0)
+        p = lib().rb200_batch_op_ex(code, flags, self.ptr, other.ptr,
                                     ia.ctypes.data, ib.ctypes.data, ia.size)
         return DeviceSet(p)
+
+    def repair_after_lazy(self):
+        return DeviceSet(lib().rb200_set_repair_after_lazy(self.ptr))
+
+    def or_many_heap(self, idx=None):
+        if idx is None:
+            ip, n = None, len(self)
+        else:
+            idx = _u32(idx)
+            ip, n = idx.ctypes.data, idx.size
+        return DeviceSet(lib().rb200_or_many_heap(self.ptr, ip, n))
 
     def and_cardinality(self, other, ia, ib):
         ia, ib = _u32(ia), _u32(ib)

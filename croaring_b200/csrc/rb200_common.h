@@ -29,6 +29,20 @@ constexpr int K_COPY_B = 3;
 // c_src encoding: container index in the left parent, or SRC_B | index in the right parent
 constexpr uint32_t SRC_NONE = 0xffffffffu, SRC_B = 0x80000000u;   // pass-through of an unmatched container of the right bitmap
 
+// c_card of a BITSET container produced by a lazy op: the reference leaves its cardinality field
+// at BITSET_UNKNOWN_CARDINALITY (bitset.h:42), which later lazy steps can observe
+// (container_is_full, containers.h:262-277).  We keep the true cardinality in the low bits and
+// the "unknown to the reference" state in the top bit.  Only sets marked lazy carry the bit.
+constexpr uint32_t CARD_UNKNOWN = 0x80000000u, CARD_MASK = 0x7fffffffu;
+
+// type-rule variants of the pairwise kernel (bit set):
+//   RULES_INPLACE          container_i* outcomes (roaring_bitmap_*_inplace)
+//   RULES_LAZY             roaring_bitmap_lazy_or / lazy_xor (+ INPLACE: the _inplace twins)
+//   RULES_CONV             lazy_or's bitsetconversion argument
+//   RULES_NOFULL           lazy_or_from_lazy_inputs (roaring_priority_queue.c:99): lazy_ior on
+//                          every matched key, without lazy_or_inplace's full-container short cut
+constexpr int RULES_INPLACE = 1, RULES_LAZY = 2, RULES_CONV = 4, RULES_NOFULL = 8;
+
 // Device view of a resident set: SoA container directory + one payload slab.
 // Payload of container c starts at payload + c_off[c] (16-byte aligned, padded to 16 B):
 //   bitset: 1024 x u64;  array: c_len x u16 (sorted);  run: c_len x {u16 start,u16 len-1}.
@@ -88,10 +102,10 @@ struct OpStats {
 extern unsigned long long g_launches;
 
 void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, const uint32_t *ib,
-                       const uint64_t *item_off, uint32_t npairs, int op, bool card_only,
+                       const uint64_t *item_off, uint32_t npairs, int op, bool card_only, int rules,
                        Items it, OpStats *st, cudaStream_t s);
 void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
-                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int inplace_rules,
+                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int rules,
                           cudaStream_t s);
 void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W, OpStats *st,
                        cudaStream_t s);

@@ -42,7 +42,8 @@ __device__ __forceinline__ int array_nruns_global(const uint8_t *p, uint32_t n, 
     return __reduce_add_sync(FULLMASK, r);
 }
 
-// mode 1: run_optimize; mode 0: remove_run_compression
+// mode 1: run_optimize; mode 0: remove_run_compression; mode 2: roaring_bitmap_repair_after_lazy
+// (roaring.c:2845 -> container_repair_after_lazy, containers.h:344-371)
 __global__ void __launch_bounds__(128)
 k_run_optimize(SetView S, uint64_t nc, int mode, SetOut out, OpStats *st) {
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
@@ -52,7 +53,7 @@ k_run_optimize(SetView S, uint64_t nc, int mode, SetOut out, OpStats *st) {
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t c = warp; c < nc; c += nwarps) {
         const int t = S.c_type[c];
-        const uint32_t len = S.c_len[c], card = S.c_card[c];
+        const uint32_t len = S.c_len[c], card = S.c_card[c] & CARD_MASK;
         const uint8_t *p = S.payload + S.c_off[c];
         int nt = t;       // new type
         int nruns = 0;
@@ -66,6 +67,9 @@ k_run_optimize(SetView S, uint64_t nc, int mode, SetOut out, OpStats *st) {
                 nruns = bitset_nruns_global(p, lane);
                 nt = (BITSET_BYTES <= 2 + 4 * nruns) ? T_BITSET : T_RUN;
             }
+        } else if (mode == 2) {  // bitset: recount, <= 4096 -> array; run: efficient container; array: as is
+            if (t == T_BITSET) nt = rule_ab((int)card);
+            else if (t == T_RUN) nt = rule_eff((int)card, (int)len);
         } else {  // remove_run_compression: runs -> array / bitset by cardinality (roaring.c:1490-1528)
             if (t == T_RUN) nt = rule_ab((int)card);
         }
@@ -102,7 +106,7 @@ __global__ void k_copy_bitmap_dir(SetView S, uint32_t nb, SetOut out) {
         out.bm_cnt[i] = S.bm_cnt[i];
         unsigned long long card = 0;
         const uint32_t c0 = S.bm_beg[i], n = S.bm_cnt[i];
-        for (uint32_t k = 0; k < n; k++) card += S.c_card[c0 + k];
+        for (uint32_t k = 0; k < n; k++) card += S.c_card[c0 + k] & CARD_MASK;
         out.bm_card[i] = card;
     }
 }

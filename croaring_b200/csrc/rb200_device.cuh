@@ -162,6 +162,92 @@ __host__ __device__ inline uint32_t slot_bound(int op, int tA, int tB, uint32_t 
     return round16(b);
 }
 
+// Slot bound of a matched cell under the lazy rules: unions / symmetric differences left as RUN
+// (array x run, containers.h:1189-1207) are not capped by the bitset size.
+__host__ __device__ inline uint32_t slot_bound_lazy(int tA, int tB, uint32_t cA, uint32_t cB,
+                                                    uint32_t lA, uint32_t lB) {
+    uint32_t b = BITSET_BYTES;
+    if (tA != T_BITSET && tB != T_BITSET && (tA == T_RUN || tB == T_RUN)) {
+        const uint32_t nA = (tA == T_ARRAY) ? cA : lA, nB = (tB == T_ARRAY) ? cB : lB;
+        const uint32_t r = 4 * (nA + nB);
+        if (r > b) b = r;
+    }
+    return round16(b);
+}
+
+// Result type of a matched cell under the public lazy API.  `unknown` = the reference leaves the
+// result bitset's cardinality dirty.  Mirrors oracle/roaring_oracle.c cell_lazy_or / cell_lazy_ior /
+// cell_lazy_xor / bm_lazy_*  (container_lazy_or containers.h:1113-1215, container_lazy_ior
+// :1333-1440, container_lazy_xor :1570-1654, container_lazy_ixor :1749-1776; bitmap level
+// roaring.c:2509-2843).  unkA: the left bitset's cardinality is already dirty.
+__host__ __device__ inline int decide_type_lazy(int op, int rules, int tA, int tB, uint32_t cA,
+                                                uint32_t cB, uint32_t lA, uint32_t lB, bool unkA,
+                                                int card, int nruns, bool &unknown) {
+    unknown = false;
+    const bool inplace = (rules & RULES_INPLACE) != 0;
+    if (op == OP_XOR) {
+        if (tA == T_BITSET && tB == T_BITSET) { unknown = true; return T_BITSET; }  // xor_nocard
+        if (inplace) return decide_type(OP_XOR, tA, tB, cA, cB, lA, lB, card, nruns);  // container_ixor
+        if (tA == T_ARRAY && tB == T_ARRAY) {  // mixed_xor.c:221-252
+            if (cA + cB <= 1024u) return T_ARRAY;
+            unknown = true;
+            return T_BITSET;
+        }
+        if (tA == T_RUN && tB == T_RUN) return rule_eff(card, nruns);
+        if (tA == T_BITSET || tB == T_BITSET) { unknown = true; return T_BITSET; }
+        return T_RUN;  // array x run left as RUN (mixed_xor.c:145-174)
+    }
+    // OP_OR
+    const bool fullA = is_full_run(tA, lA, cA), fullB = is_full_run(tB, lB, cB);
+    if (inplace && !(rules & RULES_NOFULL)) {  // roaring.c:2621 container_is_full(c1): untouched
+        if (fullA || (tA == T_BITSET && !unkA && cA == 65536u)) return tA;
+    }
+    int a = tA;
+    bool ior = inplace;
+    if (rules & RULES_CONV) {  // roaring.c:2535-2545, 2622-2633: c1 -> bitset, then lazy_ior
+        if (inplace) { if (tA != T_BITSET) a = T_BITSET; }
+        else if (tA != T_BITSET && tB != T_BITSET) { a = T_BITSET; ior = true; }
+    }
+    if (ior) {
+        if (a == T_BITSET) {
+            if (tB == T_BITSET) return card == 65536 ? T_RUN : T_BITSET;  // :1342-1352, card computed
+            if (tB == T_RUN && fullB) return T_RUN;                      // :1394-1399
+            unknown = true;
+            return T_BITSET;
+        }
+        if (a == T_ARRAY) {
+            if (tB == T_ARRAY) {  // mixed_union.c:285-372
+                if (cA + cB <= 1024u) return T_ARRAY;
+                unknown = true;
+                return T_BITSET;
+            }
+            if (tB == T_BITSET) { unknown = true; return T_BITSET; }
+            return T_RUN;
+        }
+        // a == RUN
+        if (tB == T_RUN) return rule_eff(card, nruns);
+        if (tB == T_BITSET) {
+            if (fullA) return T_RUN;  // :1409-1412
+            unknown = true;
+            return T_BITSET;
+        }
+        return T_RUN;
+    }
+    // container_lazy_or
+    if (tA == T_ARRAY && tB == T_ARRAY) {  // mixed_union.c:247-283
+        if (cA + cB <= 1024u) return T_ARRAY;
+        unknown = true;
+        return T_BITSET;
+    }
+    if (tA == T_RUN && tB == T_RUN) return rule_eff(card, nruns);
+    if (tA == T_BITSET || tB == T_BITSET) {
+        if (fullA || fullB) return T_RUN;  // :1165-1170, :1180-1185 copy of the full run
+        unknown = true;
+        return T_BITSET;
+    }
+    return T_RUN;  // array x run left as RUN (:1189-1207)
+}
+
 // ---------------------------------------------------------------- accumulator primitives
 __device__ __forceinline__ void acc_zero(uint32_t *acc, int lane) {
     const uint4 z = make_uint4(0, 0, 0, 0);

@@ -254,6 +254,7 @@ struct rb200_set {
     std::vector<uint32_t> h_cnt;    // host mirror: containers per bitmap
     std::vector<uint64_t> h_card;   // host mirror: cardinality per bitmap (empty = not cached)
     bool mirrors_pending = false;   // batch results: h_cnt / h_bytes / h_card are fetched on first use
+    bool lazy = false;              // produced by a lazy op: needs rb200_set_repair_after_lazy
     // payload address of every container in the caller's host bitmaps (sets made by
     // rb200_set_upload; valid while the caller keeps those bitmaps alive) and, for a batch result,
     // the tables of its two parents: pass-through containers can then be rebuilt on the host from
@@ -415,7 +416,7 @@ void *container_from_payload(uint8_t type, uint32_t card, uint32_t len, const ui
         b->words = (uint64_t *)h_aligned_malloc(64, BITSET_BYTES);
         if (!b->words) { h_free(b); return nullptr; }
         memcpy(b->words, p, BITSET_BYTES);
-        b->cardinality = (int32_t)card;
+        b->cardinality = (card & CARD_UNKNOWN) ? -1 : (int32_t)card;  // bitset.h:42 BITSET_UNKNOWN_CARDINALITY
         return b;
     }
     if (type == T_ARRAY) {
@@ -828,9 +829,20 @@ rb200_set *upload_impl(const PackSrc &src) {
                     const void *c = unwrap_shared(ra->containers[i], t);
                     key = ra->keys[i];
                     card = host_container_card(c, t);
-                    if (t == T_BITSET) { len = 1024; p = (const uint8_t *)((const bitset_container_t *)c)->words; }
+                    if (t == T_BITSET) {
+                        len = 1024;
+                        p = (const uint8_t *)((const bitset_container_t *)c)->words;
+                        if (((const bitset_container_t *)c)->cardinality < 0) {  // lazy state
+                            card |= CARD_UNKNOWN;
+                            s->lazy = true;
+                        }
+                    }
                     else if (t == T_ARRAY) { len = card; p = (const uint8_t *)((const array_container_t *)c)->array; }
-                    else { len = (uint32_t)((const run_container_t *)c)->n_runs; p = (const uint8_t *)((const run_container_t *)c)->runs; }
+                    else {
+                        len = (uint32_t)((const run_container_t *)c)->n_runs;
+                        p = (const uint8_t *)((const run_container_t *)c)->runs;
+                        if (4 * (uint64_t)len > BITSET_BYTES) s->lazy = true;  // only lazy unions leave such runs
+                    }
                 } else {
                     t = pv->type[i];
                     key = pv->key[i];
@@ -860,7 +872,7 @@ rb200_set *upload_impl(const PackSrc &src) {
                 c_src[ci] = SRC_NONE;
                 if (s->h_ptr_all) (*s->h_ptr_all)[ci] = p;
                 off += sb16;
-                bcard += card;
+                bcard += card & CARD_MASK;
                 bbytes += sb16;
                 s->portable_bytes += portable_bytes(t, len);
             }
@@ -951,6 +963,8 @@ bool ensure_mirrors(const rb200_set *cs) {
         for (size_t p = 0; p < nb; p++) {
             s->h_cnt[p] = cnt[p];
             s->h_bytes[p] = (uint64_t)cnt[p] * BITSET_BYTES;  // upper bound: every container <= 8 KiB
+            if (s->lazy)  // ... except runs left unconverted by lazy unions (<= 128 KiB each)
+                s->h_bytes[p] = std::min<uint64_t>((uint64_t)cnt[p] * 16 * BITSET_BYTES, s->slab_used);
         }
         s->mirrors_pending = false;
     } else {
@@ -1000,7 +1014,7 @@ struct PairBuf {
     uint64_t *d_off = nullptr;
     uint64_t W = 0, slab_bound = 0;
     bool build(const rb200_set *A, const rb200_set *B, const uint32_t *ia, const uint32_t *ib,
-               size_t np, bool and_like) {
+               size_t np, bool and_like, bool lazy = false) {
         if (!ensure_mirrors(A) || !ensure_mirrors(B)) return false;
         const size_t o_off = 0, o_ia = al256(8 * (np + 1)), o_ib = o_ia + al256(4 * np);
         bytes = o_ib + al256(4 * np);
@@ -1024,6 +1038,8 @@ struct PairBuf {
             // upper bound of the result slab: pass-through bytes + 8 KiB per possible match
             const uint64_t m = na < nb ? na : nb;
             sb += (and_like ? 0 : A->h_bytes[a] + B->h_bytes[b]) + m * (uint64_t)BITSET_BYTES + 512;
+            // lazy array x run unions stay runs: up to 4 bytes per input value / run on top
+            if (lazy) sb += 2 * (A->h_bytes[a] + B->h_bytes[b]);
         }
         off[np] = w;
         W = w;
@@ -1049,15 +1065,28 @@ bool stats_fetch() {
     return true;
 }
 
+bool reject_lazy(const rb200_set *s, const char *what) {
+    if (!s->lazy) return false;
+    g.err = std::string(what) + ": the set is in a lazy state, call rb200_set_repair_after_lazy first";
+    return true;
+}
+
 rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const uint32_t *ia,
-                         const uint32_t *ib, size_t np, int inplace_rules = 0) {
+                         const uint32_t *ib, size_t np, int rules = 0) {
     if (!ctx_init()) return nullptr;
     if (op < 0 || op > 3) { g.err = "bad op"; return nullptr; }
+    if (rules & RULES_LAZY) {
+        if (op != OP_OR && op != OP_XOR) { g.err = "lazy rules exist for OR and XOR only"; return nullptr; }
+        if (op == OP_XOR && (rules & (RULES_CONV | RULES_NOFULL))) { g.err = "bad lazy flags for XOR"; return nullptr; }
+    } else {
+        if (rules & ~RULES_INPLACE) { g.err = "bad flags"; return nullptr; }
+        if (reject_lazy(A, "batch op") || reject_lazy(B, "batch op")) return nullptr;
+    }
     if (np > 0xffffffffull) { g.err = "too many pairs"; return nullptr; }
     PairBuf pb;
     ItemsBuf ib_;
     rb200_set *R = nullptr;
-    bool ok = pb.build(A, B, ia, ib, np, op == OP_AND);
+    bool ok = pb.build(A, B, ia, ib, np, op == OP_AND, (rules & RULES_LAZY) != 0);
     if (ok) ok = ib_.alloc(pb.W);
     if (ok) {
         R = set_new((uint32_t)np, pb.W, pb.slab_bound);
@@ -1067,10 +1096,10 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         cudaEventRecord(g.ev0, g.stream);
         ok = stats_reset();
         const SetView va = A->view(), vb = B->view();
-        launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, ib_.it,
+        launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, rules, ib_.it,
                           g.d_stats, g.stream);
         cudaEventRecord(g.evk0, g.stream);
-        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, inplace_rules, g.stream);
+        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, g.stream);
         cudaEventRecord(g.evk1, g.stream);
         launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
         cudaEventRecord(g.ev1, g.stream);
@@ -1093,6 +1122,7 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         R->parentB = B->h_ptr;
         R->portable_bytes = 0;
         R->mirrors_pending = np > 0;  // h_cnt / h_bytes / h_card: see ensure_mirrors()
+        R->lazy = (rules & RULES_LAZY) != 0;
         for (size_t p = 0; p < np; p++) R->h_flags[p] = (A->h_flags[ia[p]] | B->h_flags[ib[p]]) & FLAG_COW;
     }
     pb.release();
@@ -1117,7 +1147,7 @@ rb200_set_t *rb200_batch_op(int op, const rb200_set_t *A, const rb200_set_t *B, 
 rb200_set_t *rb200_batch_op_ex(int op, int flags, const rb200_set_t *A, const rb200_set_t *B,
                                const uint32_t *ia, const uint32_t *ib, size_t npairs) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
-    return batch_op_impl(op, A, B, ia, ib, npairs, flags & 1);
+    return batch_op_impl(op, A, B, ia, ib, npairs, flags);
 }
 
 int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
@@ -1125,6 +1155,7 @@ int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, cons
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return -1;
     if (np == 0) return 0;
+    if (reject_lazy(A, "and_cardinality") || reject_lazy(B, "and_cardinality")) return -1;
     PairBuf pb;
     ItemsBuf ib_;
     uint64_t *d_out = nullptr, *h_out = nullptr;
@@ -1135,7 +1166,7 @@ int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, cons
         cudaEventRecord(g.ev0, g.stream);
         ok = stats_reset();
         const SetView va = A->view(), vb = B->view();
-        launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, OP_AND, true, ib_.it,
+        launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, OP_AND, true, 0, ib_.it,
                           g.d_stats, g.stream);
         cudaEventRecord(g.evk0, g.stream);
         launch_card_items(va, vb, ib_.it, pb.W, g.d_stats, g.stream);
@@ -1164,6 +1195,7 @@ rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, s
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return nullptr;
     if (key_hi > 65535) key_hi = 65535;
+    if (reject_lazy(S, "or_many")) return nullptr;
     if (!ensure_mirrors(S)) return nullptr;
     if (idx == nullptr) n = S->n_bitmaps;
     uint64_t tot = 0;
@@ -1256,6 +1288,7 @@ rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n) 
 rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return nullptr;
+    if (reject_lazy(S, "xor_many")) return nullptr;
     if (!ensure_mirrors(S)) return nullptr;
     if (idx == nullptr) n = S->n_bitmaps;
     uint64_t tot = 0;
@@ -1913,8 +1946,20 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
 
 // roaring_bitmap_run_optimize (mode 1) / roaring_bitmap_remove_run_compression (mode 0) applied
 // to every bitmap of a set on the device; returns a new resident set (same bitmaps, same keys).
+static rb200_set *convert_impl(const rb200_set *S, int mode);
 rb200_set_t *rb200_set_run_optimize(const rb200_set_t *S, int mode) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (reject_lazy(S, "run_optimize")) return nullptr;
+    return convert_impl(S, mode ? 1 : 0);
+}
+// roaring_bitmap_repair_after_lazy (src/roaring.c:2845) on every bitmap of a set produced by lazy
+// ops: bitsets are recounted (<= 4096 values -> array), runs go through the efficient-container
+// rule, arrays stay.  Returns a new, ordinary (non-lazy) set.
+rb200_set_t *rb200_set_repair_after_lazy(const rb200_set_t *S) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return convert_impl(S, 2);
+}
+static rb200_set *convert_impl(const rb200_set *S, int mode) {
     if (!ctx_init()) return nullptr;
     const uint64_t nc = S->n_containers;
     // mode 1 never grows a container by more than its 16-byte padding; mode 0 may expand runs
@@ -1922,7 +1967,7 @@ rb200_set_t *rb200_set_run_optimize(const rb200_set_t *S, int mode) {
     rb200_set *R = set_new(S->n_bitmaps, nc, bound);
     if (!R) return nullptr;
     bool ok = stats_reset();
-    launch_run_optimize(S->view(), S->n_bitmaps, nc, mode ? 1 : 0, R->out(), g.d_stats, g.stream);
+    launch_run_optimize(S->view(), S->n_bitmaps, nc, mode, R->out(), g.d_stats, g.stream);
     ok = ok && stats_fetch();
     cudaError_t e = cudaStreamSynchronize(g.stream);
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
@@ -2002,6 +2047,7 @@ void rb200_values_free(uint32_t *vals, uint64_t *off) { rb200_serialized_free((c
 int rb200_set_serialize(const rb200_set_t *s, char **buf, uint64_t **off_out, uint64_t **len_out) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return -1;
+    if (reject_lazy(s, "serialize")) return -1;
     const size_t nb = s->n_bitmaps;
     *buf = nullptr;
     *off_out = (uint64_t *)malloc(8 * (nb + 1));
@@ -2152,18 +2198,23 @@ roaring_bitmap_t *roaring_bitmap_or_many(size_t number, const roaring_bitmap_t *
 // In-place twins (src/roaring.c:812 and_inplace, :1063 or_inplace, :1200 xor_inplace, :1342
 // andnot_inplace): the result is computed on the device with the in-place type rules and then
 // swapped into x1 (its old containers and directory are released, its flags kept).
-static void dropin_inplace(int op, roaring_bitmap_t *x1, const roaring_bitmap_t *x2) {
+// replace x1's directory and containers by those of `out` (consumed); x1 keeps its flags
+static void swap_into(roaring_bitmap_t *x1, roaring_bitmap_t *out);
+static void dropin_inplace(int op, roaring_bitmap_t *x1, const roaring_bitmap_t *x2, int rules = RULES_INPLACE) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     const roaring_bitmap_t *both[2] = {x1, x2};
     rb200_set *S = rb200_set_upload(both, 2);
     if (!S) return;
     rb200_set_bind_host(S, 1);
     const uint32_t ia = 0, ib = 1;
-    rb200_set *R = batch_op_impl(op, S, S, &ia, &ib, 1, 1);
+    rb200_set *R = batch_op_impl(op, S, S, &ia, &ib, 1, rules);
     roaring_bitmap_t *out = R ? rb200_set_download(R, 0) : nullptr;
     set_delete(R);
     set_delete(S);
     if (!out) return;  // CUDA failure: x1 is left untouched, rb200_last_error() tells why
+    swap_into(x1, out);
+}
+static void swap_into(roaring_bitmap_t *x1, roaring_bitmap_t *out) {
     roaring_array_t *ra = &x1->high_low_container, *rn = &out->high_low_container;
     const uint8_t flags = ra->flags;
     if (!(flags & FLAG_FROZEN)) {
@@ -2232,6 +2283,182 @@ double roaring_bitmap_jaccard_index(const roaring_bitmap_t *r1, const roaring_bi
 bool roaring_bitmap_intersect(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
     const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
     return inter != 0 && inter != UINT64_MAX;
+}
+
+// ---- public lazy API (include/roaring/roaring.h:932-977) ------------------------------------
+// The lazy state lives in ordinary host bitmaps exactly as the reference leaves it (bitsets with
+// cardinality -1, unconverted runs), so the reference's own functions accept what we return.
+static roaring_bitmap_t *dropin_lazy_pair(int op, const roaring_bitmap_t *r1, const roaring_bitmap_t *r2, int rules) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const roaring_bitmap_t *both[2] = {r1, r2};
+    rb200_set *S = rb200_set_upload(both, 2);
+    if (!S) return nullptr;
+    rb200_set_bind_host(S, 1);
+    const uint32_t ia = 0, ib = 1;
+    rb200_set *R = batch_op_impl(op, S, S, &ia, &ib, 1, rules);
+    roaring_bitmap_t *out = R ? rb200_set_download(R, 0) : nullptr;
+    set_delete(R);
+    set_delete(S);
+    return out;
+}
+roaring_bitmap_t *roaring_bitmap_lazy_or(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2, const bool bitsetconversion) {
+    return dropin_lazy_pair(OP_OR, r1, r2, RULES_LAZY | (bitsetconversion ? RULES_CONV : 0));
+}
+void roaring_bitmap_lazy_or_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2, const bool bitsetconversion) {
+    dropin_inplace(OP_OR, r1, r2, RULES_LAZY | RULES_INPLACE | (bitsetconversion ? RULES_CONV : 0));
+}
+roaring_bitmap_t *roaring_bitmap_lazy_xor(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    return dropin_lazy_pair(OP_XOR, r1, r2, RULES_LAZY);
+}
+void roaring_bitmap_lazy_xor_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    dropin_inplace(OP_XOR, r1, r2, RULES_LAZY | RULES_INPLACE);
+}
+void roaring_bitmap_repair_after_lazy(roaring_bitmap_t *r1) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const roaring_bitmap_t *one[1] = {r1};
+    rb200_set *S = rb200_set_upload(one, 1);
+    if (!S) return;
+    rb200_set *R = rb200_set_repair_after_lazy(S);
+    roaring_bitmap_t *out = R ? rb200_set_download(R, 0) : nullptr;
+    set_delete(R);
+    set_delete(S);
+    if (out) swap_into(r1, out);
+}
+
+// ---- roaring_bitmap_or_many_heap (src/roaring_priority_queue.c:200-250) ------------------------
+// The reference orders pairwise LAZY unions with a binary min-heap keyed by
+// roaring_bitmap_portable_size_in_bytes; the result TYPES depend on that order, so the same heap
+// (same sift loops, same tie behaviour) is replayed here and every union runs on the device:
+// lazy_or (both inputs), lazy_or_inplace (one temporary) or lazy_or_from_lazy_inputs (two).
+namespace {
+struct HeapEl {
+    uint64_t size;
+    bool temp;
+    rb200_set *set;
+    uint32_t index;
+};
+void heap_down(std::vector<HeapEl> &e, uint32_t n, uint32_t i) {  // percolate_down :46-66
+    const uint32_t half = n >> 1;
+    const HeapEl cur = e[i];
+    while (i < half) {
+        uint32_t child = 2 * i + 1;
+        if (child + 1 < n && e[child + 1].size < e[child].size) child++;
+        if (!(e[child].size < cur.size)) break;
+        e[i] = e[child];
+        i = child;
+    }
+    e[i] = cur;
+}
+void heap_push(std::vector<HeapEl> &e, uint32_t &n, const HeapEl &t) {  // pq_add :31-42
+    uint32_t i = n++;
+    while (i > 0) {
+        const uint32_t parent = (i - 1) >> 1;
+        if (!(t.size < e[parent].size)) break;
+        e[i] = e[parent];
+        i = parent;
+    }
+    e[i] = t;
+}
+HeapEl heap_pop(std::vector<HeapEl> &e, uint32_t &n) {  // pq_poll :84-95
+    const HeapEl top = e[0];
+    if (n > 1) {
+        e[0] = e[--n];
+        heap_down(e, n, 0);
+    } else {
+        --n;
+    }
+    return top;
+}
+// portable sizes (header + containers) of every bitmap of a set, lazy state included
+bool portable_sizes(const rb200_set *S, std::vector<uint32_t> &out) {
+    const size_t nb = S->n_bitmaps;
+    out.assign(nb, 0);
+    if (!nb) return true;
+    uint64_t *d16 = (uint64_t *)dev_alloc(8 * nb);
+    uint32_t *dex = (uint32_t *)dev_alloc(4 * nb), *dhr = (uint32_t *)dev_alloc(4 * nb);
+    uint32_t *h = (uint32_t *)pin_alloc(4 * nb);
+    bool ok = d16 && dex && dhr && h;
+    if (ok) {
+        launch_serialize_measure(S->view(), (uint32_t)nb, d16, dex, dhr, g.stream);
+        ok = cudaMemcpyAsync(h, dex, 4 * nb, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
+             cudaStreamSynchronize(g.stream) == cudaSuccess;
+        if (ok) out.assign(h, h + nb);
+    }
+    dev_free(d16, 8 * nb);
+    dev_free(dex, 4 * nb);
+    dev_free(dhr, 4 * nb);
+    pin_free(h, 4 * nb);
+    if (!ok && g.err.empty()) g.err = "portable_sizes failed";
+    return ok;
+}
+}  // namespace
+
+rb200_set_t *rb200_or_many_heap(const rb200_set_t *S, const uint32_t *idx, size_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return nullptr;
+    if (reject_lazy(S, "or_many_heap")) return nullptr;
+    if (idx == nullptr) n = S->n_bitmaps;
+    for (size_t i = 0; i < n; i++)
+        if (idx && idx[i] >= S->n_bitmaps) { g.err = "or_many_heap: index out of range"; return nullptr; }
+    if (n == 0) return rb200_or_many(S, idx, 0);
+    if (n == 1) {  // roaring_bitmap_copy: union with an empty bitmap = pass-through of every container
+        roaring_bitmap_t *e = bitmap_alloc(0);
+        if (!e) return nullptr;
+        const roaring_bitmap_t *one[1] = {e};
+        rb200_set *E = rb200_set_upload(one, 1);
+        bitmap_free_host(e);
+        if (!E) return nullptr;
+        const uint32_t a = idx ? idx[0] : 0u, z = 0;
+        rb200_set *R = batch_op_impl(OP_OR, S, E, &a, &z, 1, 0);
+        set_delete(E);
+        return R;
+    }
+    std::vector<uint32_t> sz;
+    if (!portable_sizes(S, sz)) return nullptr;
+    std::vector<HeapEl> e(n);
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t b = idx ? idx[i] : (uint32_t)i;
+        e[i] = HeapEl{sz[b], false, const_cast<rb200_set *>(S), b};
+    }
+    uint32_t cnt = (uint32_t)n;
+    for (int32_t i = (int32_t)(cnt >> 1); i >= 0; i--) heap_down(e, cnt, (uint32_t)i);  // create_pq :68-82
+    bool ok = true;
+    while (cnt > 1 && ok) {
+        const HeapEl a = heap_pop(e, cnt), b = heap_pop(e, cnt);
+        rb200_set *R;
+        if (a.temp && b.temp)
+            R = batch_op_impl(OP_OR, a.set, b.set, &a.index, &b.index, 1, RULES_LAZY | RULES_INPLACE | RULES_NOFULL);
+        else if (b.temp)  // roaring_bitmap_lazy_or_inplace(x2, x1, false)
+            R = batch_op_impl(OP_OR, b.set, a.set, &b.index, &a.index, 1, RULES_LAZY | RULES_INPLACE);
+        else if (a.temp)
+            R = batch_op_impl(OP_OR, a.set, b.set, &a.index, &b.index, 1, RULES_LAZY | RULES_INPLACE);
+        else
+            R = batch_op_impl(OP_OR, a.set, b.set, &a.index, &b.index, 1, RULES_LAZY);
+        if (a.temp) set_delete(a.set);
+        if (b.temp) set_delete(b.set);
+        std::vector<uint32_t> rs;
+        if (!R || !portable_sizes(R, rs)) { set_delete(R); ok = false; break; }
+        heap_push(e, cnt, HeapEl{rs[0], true, R, 0});
+    }
+    if (!ok) {
+        for (uint32_t i = 0; i < cnt; i++) if (e[i].temp) set_delete(e[i].set);
+        return nullptr;
+    }
+    const HeapEl top = heap_pop(e, cnt);
+    rb200_set *out = convert_impl(top.set, 2);  // roaring_bitmap_repair_after_lazy
+    set_delete(top.set);
+    return out;
+}
+
+roaring_bitmap_t *roaring_bitmap_or_many_heap(uint32_t number, const roaring_bitmap_t **rs) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    rb200_set *S = rb200_set_upload(rs, number);
+    if (!S) return nullptr;
+    rb200_set *R = rb200_or_many_heap(S, nullptr, number);
+    roaring_bitmap_t *out = R ? rb200_set_download(R, 0) : nullptr;
+    set_delete(R);
+    set_delete(S);
+    return out;
 }
 
 }  // extern "C"

@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t upper_bound_u16(const uint16_t *a, uint32_t 
 __global__ void __launch_bounds__(128)
 k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
              const uint32_t *__restrict__ ib, const uint64_t *__restrict__ item_off,
-             uint32_t npairs, int op, bool card_only, Items it, OpStats *st) {
+             uint32_t npairs, int op, bool card_only, int rules, Items it, OpStats *st) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -73,9 +73,12 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
                     if (matched) {
                         cb = b0 + lb;
                         kind = K_COMPUTE;
-                        if (!card_only)
-                            cap = slot_bound(op, A.c_type[ca], B.c_type[cb], A.c_card[ca],
-                                             B.c_card[cb], A.c_len[ca], B.c_len[cb]);
+                        if (!card_only) {
+                            const uint32_t cA = A.c_card[ca] & CARD_MASK, cB = B.c_card[cb] & CARD_MASK;
+                            cap = (rules & RULES_LAZY)
+                                      ? slot_bound_lazy(A.c_type[ca], B.c_type[cb], cA, cB, A.c_len[ca], B.c_len[cb])
+                                      : slot_bound(op, A.c_type[ca], B.c_type[cb], cA, cB, A.c_len[ca], B.c_len[cb]);
+                        }
                     } else if (op != OP_AND && !card_only) {
                         kind = K_COPY_A;
                         cap = round16(stored_bytes(A.c_type[ca], A.c_len[ca]));
@@ -117,15 +120,17 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
 
 // ------------------------------------------------------------------------------ grid cells
 // Evaluate one matched cell on the warp's accumulator and write the result payload.
-template <int OP>
+template <int OP, bool LAZY>
 __device__ __forceinline__ void
 cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
              uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
              int lane, int &otype, uint32_t &ocard, uint32_t &olen, unsigned int *err,
-             bool inplace_rules) {
+             int rules, bool unkA) {
     // ---- run x run / array x run with few intervals: boundary sweep, no accumulator ---------
     constexpr int op = OP;
-    if ((tA == T_RUN || tB == T_RUN) && tA != T_BITSET && tB != T_BITSET &&
+    const bool inplace_rules = (rules & RULES_INPLACE) != 0;
+    constexpr bool lazy = LAZY && (OP == OP_OR || OP == OP_XOR);
+    if (!lazy && (tA == T_RUN || tB == T_RUN) && tA != T_BITSET && tB != T_BITSET &&
         (tA == T_RUN ? lA : cA) + (tB == T_RUN ? lB : cB) <= 512u) {
         if (interval_cell(acc, op, tA, tB, pa, pb, cA, cB, lA, lB, out, cap, lane, otype, ocard, olen))
             return;
@@ -173,8 +178,11 @@ cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb
     // ---- array x array union / xor whose result is known to stay an array: warp merge path ---
     // (measured on B200, weather_sept_85 all-pairs OR: staging limit 2032 values -> 1.41 ms,
     //  1024 -> 1.50 ms, split merge up to 4064 -> 2.06 ms; the accumulator round trip wins above)
+    // (lazy rules: only unions / xors of at most ARRAY_LAZY_LOWERBOUND values stay arrays)
+    const bool lazy_eager = lazy && OP == OP_XOR && inplace_rules;  // container_lazy_ixor A,A is eager
     if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY &&
-        ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= 2048u) {
+        ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= 2048u &&
+        (!lazy || lazy_eager || (cA + cB <= 1024u && !(rules & RULES_CONV)))) {
         if (round16(2 * (cA + cB)) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
         const uint32_t n = (op == OP_OR) ? merge_arrays<false>(acc, pa, cA, pb, cB, out, lane)
                                          : merge_arrays<true>(acc, pa, cA, pb, cB, out, lane);
@@ -219,11 +227,14 @@ cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb
         }
         __syncwarp();
     }
-    const bool want_runs = cell_needs_runs(op, tA, tB);
+    const bool want_runs = lazy ? ((tA == T_RUN || tB == T_RUN) && tA != T_BITSET && tB != T_BITSET)
+                                : cell_needs_runs(op, tA, tB);
     if (card < 0 || want_runs) acc_count(acc, lane, want_runs, card, nruns);
     if (card == 0) { otype = 0; ocard = olen = 0; return; }
-    int t = decide_type(op, tA, tB, cA, cB, lA, lB, card, nruns);
-    if (OP == OP_OR && inplace_rules) {
+    bool unknown = false;
+    int t = lazy ? decide_type_lazy(op, rules, tA, tB, cA, cB, lA, lB, unkA, card, nruns, unknown)
+                 : decide_type(op, tA, tB, cA, cB, lA, lB, card, nruns);
+    if (OP == OP_OR && inplace_rules && !lazy) {
         // roaring_bitmap_or_inplace: a full left container is left untouched (roaring.c:1081-1083)
         // and container_ior turns a saturated bitset|bitset into the full run (containers.h:1234-1242)
         const bool a_full = is_full_run(tA, lA, cA) || (tA == T_BITSET && cA == 65536u);
@@ -240,14 +251,14 @@ cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb
     else acc_emit_runs(acc, reinterpret_cast<uint16_t *>(out), lane);
     __syncwarp();
     otype = t;
-    ocard = (uint32_t)card;
+    ocard = (uint32_t)card | (unknown ? CARD_UNKNOWN : 0u);
     olen = len;
 }
 
-template <int OP>
+template <int OP, bool LAZY>
 __global__ void __launch_bounds__(128)
 k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
-                uint64_t slab_cap, OpStats *st, int inplace_rules) {
+                uint64_t slab_cap, OpStats *st, int rules) {
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
     const int lane = threadIdx.x & 31;
     uint32_t *acc = s_acc[threadIdx.x >> 5];
@@ -273,10 +284,11 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 if (lane == 0) atomicExch(&st->error, 2u);
             } else if (kind == K_COMPUTE) {
                 const uint32_t ca = it.ca[item], cb = it.cb[item];
-                cell_compute<OP>(acc, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
-                             B.payload + B.c_off[cb], A.c_card[ca], B.c_card[cb], A.c_len[ca],
-                             B.c_len[cb], slab + off, cap, lane, otype, ocard, olen, &st->error,
-                             inplace_rules != 0);
+                const uint32_t rawA = A.c_card[ca];
+                cell_compute<OP, LAZY>(acc, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
+                             B.payload + B.c_off[cb], rawA & CARD_MASK, B.c_card[cb] & CARD_MASK,
+                             A.c_len[ca], B.c_len[cb], slab + off, cap, lane, otype, ocard, olen,
+                             &st->error, rules, (rawA & CARD_UNKNOWN) != 0);
             } else {
                 const SetView &S = (kind == K_COPY_A) ? A : B;
                 const uint32_t c = (kind == K_COPY_A) ? it.ca[item] : it.cb[item];
@@ -383,7 +395,7 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
             }
             if (ot) {
                 cnt++;
-                card += it.ocard[i];
+                card += it.ocard[i] & CARD_MASK;
             }
         }
         cnt = __reduce_add_sync(FULLMASK, cnt);
@@ -444,7 +456,7 @@ __global__ void k_set_cardinalities(SetView S, uint32_t n, uint64_t *__restrict_
     for (uint32_t b = warp; b < n; b += nwarps) {
         const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
         unsigned long long card = 0;
-        for (uint32_t i = lane; i < nc; i += 32) card += S.c_card[c0 + i];
+        for (uint32_t i = lane; i < nc; i += 32) card += S.c_card[c0 + i] & CARD_MASK;
         for (int d = 16; d > 0; d >>= 1) card += __shfl_xor_sync(FULLMASK, card, d);
         if (lane == 0) out[b] = card;
     }
@@ -612,24 +624,30 @@ static inline uint32_t blocks_for_warps(uint64_t warps, int warps_per_block, int
 }
 
 void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, const uint32_t *ib,
-                       const uint64_t *item_off, uint32_t npairs, int op, bool card_only,
+                       const uint64_t *item_off, uint32_t npairs, int op, bool card_only, int rules,
                        Items it, OpStats *st, cudaStream_t s) {
     if (!npairs) return;
     const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * 16);
-    k_plan_pairs<<<g, 128, 0, s>>>(A, B, ia, ib, item_off, npairs, op, card_only, it, st);
+    k_plan_pairs<<<g, 128, 0, s>>>(A, B, ia, ib, item_off, npairs, op, card_only, rules, it, st);
     g_launches++;
 }
 
 void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
-                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int inplace_rules,
+                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int rules,
                           cudaStream_t s) {
     if (!W) return;
     const uint32_t g = blocks_for_warps(W, 4, sm_count() * 6);
     switch (op) {
-        case OP_AND: k_compute_items<OP_AND><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
-        case OP_OR: k_compute_items<OP_OR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
-        case OP_XOR: k_compute_items<OP_XOR><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
-        default: k_compute_items<OP_ANDNOT><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, inplace_rules); break;
+        case OP_AND: k_compute_items<OP_AND, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules); break;
+        case OP_OR:
+            if (rules & RULES_LAZY) k_compute_items<OP_OR, true><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules);
+            else k_compute_items<OP_OR, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules);
+            break;
+        case OP_XOR:
+            if (rules & RULES_LAZY) k_compute_items<OP_XOR, true><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules);
+            else k_compute_items<OP_XOR, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules);
+            break;
+        default: k_compute_items<OP_ANDNOT, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules); break;
     }
     g_launches++;
 }

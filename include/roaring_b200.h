@@ -72,6 +72,19 @@ void roaring_bitmap_xor_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2
 void roaring_bitmap_andnot_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 /* include/roaring/roaring.h:334  (src/roaring.c:795) */
 roaring_bitmap_t *roaring_bitmap_xor_many(size_t number, const roaring_bitmap_t **rs);
+/* include/roaring/roaring.h:312  (src/roaring_priority_queue.c:200): pairwise lazy unions in the
+ * order of the reference's size-keyed binary heap (the result TYPES depend on that order). */
+roaring_bitmap_t *roaring_bitmap_or_many_heap(uint32_t number, const roaring_bitmap_t **rs);
+/* Public lazy API, include/roaring/roaring.h:932-977 (src/roaring.c:2509, 2600, 2684, 2763, 2845).
+ * The lazy state is kept in ordinary host bitmaps exactly as the reference keeps it (bitset
+ * cardinality -1, unconverted runs), so these calls and the reference's own can be mixed. */
+roaring_bitmap_t *roaring_bitmap_lazy_or(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2,
+                                         const bool bitsetconversion);
+void roaring_bitmap_lazy_or_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2,
+                                    const bool bitsetconversion);
+roaring_bitmap_t *roaring_bitmap_lazy_xor(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+void roaring_bitmap_lazy_xor_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+void roaring_bitmap_repair_after_lazy(roaring_bitmap_t *r1);
 /* include/roaring/roaring.h:231  (src/roaring.c:3048) */
 uint64_t roaring_bitmap_and_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 /* include/roaring/roaring.h:258-271 (src/roaring.c:3086-3107): inclusion-exclusion on the above */
@@ -135,9 +148,18 @@ uint64_t rb200_set_payload_bytes(const rb200_set_t *s);     /* container_size_in
 rb200_set_t *rb200_batch_op(int op, const rb200_set_t *A, const rb200_set_t *B,
                             const uint32_t *ia, const uint32_t *ib, size_t npairs);
 
-/* Same with flags: RB200_INPLACE_RULES applies the type rules of the in-place twins
- * (roaring_bitmap_or_inplace ...) to every pair; the results are still new bitmaps. */
-enum { RB200_INPLACE_RULES = 1 };
+/* Same with flags (the results are always new bitmaps):
+ *   RB200_INPLACE_RULES    type rules of the in-place twins (roaring_bitmap_or_inplace ...)
+ *   RB200_LAZY_RULES       OR / XOR only: the lazy variants (roaring.h:932-977); the result set is
+ *                          in a LAZY state — feed it to further lazy ops, download it (the host
+ *                          bitmaps carry the reference's lazy representation) or repair it with
+ *                          rb200_set_repair_after_lazy; every other entry point refuses it.
+ *                          | RB200_INPLACE_RULES = the lazy in-place twins
+ *   RB200_LAZY_BITSET_CONVERSION   the `bitsetconversion` argument of the lazy OR functions
+ *   RB200_LAZY_FROM_LAZY_INPUTS    with LAZY|INPLACE: no full-container short cut (the heap's
+ *                          union of two temporaries, roaring_priority_queue.c:99) */
+enum { RB200_INPLACE_RULES = 1, RB200_LAZY_RULES = 2, RB200_LAZY_BITSET_CONVERSION = 4,
+       RB200_LAZY_FROM_LAZY_INPUTS = 8 };
 rb200_set_t *rb200_batch_op_ex(int op, int flags, const rb200_set_t *A, const rb200_set_t *B,
                                const uint32_t *ia, const uint32_t *ib, size_t npairs);
 
@@ -151,6 +173,13 @@ rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n);
 
 /* roaring_bitmap_xor_many over S[idx[0..n)] (idx == NULL: all bitmaps in order): ONE result bitmap. */
 rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n);
+
+/* roaring_bitmap_or_many_heap over S[idx[0..n)]: ONE result bitmap.  Sequential by construction
+ * (every union's operands depend on the sizes of the previous results): n-1 single-pair lazy ops. */
+rb200_set_t *rb200_or_many_heap(const rb200_set_t *S, const uint32_t *idx, size_t n);
+
+/* roaring_bitmap_repair_after_lazy on every bitmap of a set in a lazy state; returns a new set. */
+rb200_set_t *rb200_set_repair_after_lazy(const rb200_set_t *S);
 
 /* Key-sharded form used for multi-GPU aggregation: only containers whose high-16 key lies in
  * [key_lo, key_hi] take part; per-key result cardinalities are ADDED into card_per_key[65536]

@@ -1,4 +1,4 @@
-python tools/pcie_probe.py > gpurun_out/pcie_probe.txt 2>&1
-RB200_TRACE=1 python tools/e2e_breakdown.py > gpurun_out/e2e_numa.txt 2>&1
-RB200_NO_NUMA=1 RB200_TRACE=1 python tools/e2e_breakdown.py > gpurun_out/e2e_nonuma.txt 2>&1
-cat gpurun_out/pcie_probe.txt; grep -v "^rb200 foreach" gpurun_out/e2e_numa.txt | tail -10;  grep -v "^rb200 foreach" gpurun_out/e2e_nonuma.txt | tail -2
+timeout 900 python -m pytest tests/test_gpu_lazy.py -x -q -m gpu --timeout 600 2>&1 | tail -25 > gpurun_out/lazy.log
+cat gpurun_out/lazy.log
+timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 --deselect tests/test_gpu_lazy.py 2>&1 | tail -5
+python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | head -c 300
