@@ -94,7 +94,7 @@ struct OpStats {
     unsigned long long algo_bytes;    // SURVEY.md §8(d) algorithmic bytes
     unsigned long long work_counter;  // dynamic scheduler for the compute kernel
     unsigned long long work_counter2;
-    unsigned int error;               // 0 = ok; 1 = slot overflow; 2 = slab overflow
+    unsigned int error;               // 0 = ok; 1 = slot overflow; 2 = slab overflow; 3 = malformed blob
     unsigned int nk;                  // or_many: number of distinct keys
 };
 
@@ -138,6 +138,10 @@ void launch_serialize_measure(const SetView &S, uint32_t n, uint64_t *sizes16, u
                               uint32_t *hasrun, cudaStream_t s);
 void launch_serialize_write(const SetView &S, uint32_t n, const uint64_t *off, const uint32_t *hasrun,
                             uint8_t *dst, cudaStream_t s);
+// device-side roaring_bitmap_portable_deserialize_safe of nb blobs staged in `raw`
+void launch_deserialize(const uint8_t *raw, const uint64_t *roff, const uint64_t *rlen,
+                        const uint64_t *slab_base, uint32_t nb, uint64_t nc, SetOut out,
+                        uint64_t *src_pos, OpStats *st, cudaStream_t s);
 void launch_run_optimize(const SetView &S, uint32_t nb, uint64_t nc, int mode, SetOut out, OpStats *st,
                          cudaStream_t s);
 void launch_values_measure(const SetView &S, uint32_t nb, uint64_t *bm_vals, uint32_t *dummy,

@@ -125,6 +125,9 @@ std::map<uint8_t *, size_t> g_serialized_sizes;  // pinned blobs handed out by r
         }                                                                           \
     } while (0)
 
+bool stats_reset();
+bool stats_fetch();
+
 size_t bucket(size_t n) {
     size_t b = 512;
     while (b < n) b <<= 1;
@@ -908,18 +911,136 @@ rb200_set_t *rb200_set_upload(const roaring_bitmap_t *const *bitmaps, size_t n) 
     return upload_impl(src);
 }
 
+// Portable-serialized inputs are parsed ON THE DEVICE (src/roaring_array.c:633-813 restated as
+// k_deser_dir / k_deser_copy): the host only reads each blob's cookie (to size the directory) and
+// streams the raw bytes through pinned staging chunks; no per-container host work.
 rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *lens, size_t n) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
-    std::vector<PView> views(n);
-    for (size_t i = 0; i < n; i++)
-        if (!parse_portable((const uint8_t *)bufs[i], lens[i], views[i])) {
+    if (!ctx_init()) return nullptr;
+    if (n > 0xffffffffull) { g.err = "too many bitmaps"; return nullptr; }
+    // pass 1 (host): container count of every blob from its cookie; staging offsets
+    uint64_t nc = 0, raw_total = 0, slab_total = 0;
+    std::vector<uint32_t> cnt(n);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t cookie = 0, size = 0;
+        bool ok = lens[i] >= 4;
+        if (ok) {
+            memcpy(&cookie, bufs[i], 4);
+            if ((cookie & 0xFFFF) == SERIAL_COOKIE) size = (cookie >> 16) + 1;
+            else if (cookie == SERIAL_COOKIE_NO_RUN && lens[i] >= 8) memcpy(&size, bufs[i] + 4, 4);
+            else ok = false;
+        }
+        if (!ok || size > 65536 || 4ull * size > lens[i]) {
             g.err = "malformed portable bitmap at index " + std::to_string(i);
             return nullptr;
         }
-    PackSrc src;
-    src.views = &views;
-    src.n = n;
-    return upload_impl(src);
+        cnt[i] = size;
+        nc += size;
+        raw_total += (lens[i] + 15) & ~(uint64_t)15;
+        slab_total += ((lens[i] + 15) & ~(uint64_t)15) + 16ull * size;   // payload <= blob bytes, + 16-byte padding per container
+    }
+    rb200_set *s = set_new((uint32_t)n, nc, slab_total + 16);
+    if (!s) return nullptr;
+    s->n_containers = nc;
+    s->slab_used = slab_total;
+    // per-bitmap tables: [roff | rlen | slab_base] for the kernels, bm_beg / bm_cnt into the directory
+    const size_t tb = 24 * (n ? n : 1);
+    uint64_t *h_tab = (uint64_t *)pin_alloc(tb), *d_tab = (uint64_t *)dev_alloc(tb);
+    uint32_t *h_bc = (uint32_t *)pin_alloc(8 * (n ? n : 1));
+    uint8_t *d_raw = (uint8_t *)dev_alloc(raw_total ? raw_total : 16);
+    uint64_t *d_src = (uint64_t *)dev_alloc(8 * (nc ? nc : 1));
+    const size_t CH = (size_t)32 << 20;
+    uint8_t *chunk[2] = {(uint8_t *)pin_alloc(CH), (uint8_t *)pin_alloc(CH)};
+    cudaEvent_t cev[2] = {nullptr, nullptr};
+    bool cev_used[2] = {false, false};
+    bool ok = h_tab && d_tab && h_bc && d_raw && d_src && chunk[0] && chunk[1];
+    for (int k = 0; k < 2 && ok; k++) ok = cudaEventCreateWithFlags(&cev[k], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {
+        uint64_t ro = 0, so = 0, cb = 0;
+        for (size_t i = 0; i < n; i++) {
+            h_tab[i] = ro;
+            h_tab[n + i] = lens[i];
+            h_tab[2 * n + i] = so;
+            h_bc[i] = (uint32_t)cb;
+            h_bc[n + i] = cnt[i];
+            s->h_cnt[i] = cnt[i];
+            s->h_bytes[i] = lens[i] + 16ull * cnt[i];
+            const uint64_t hdr = ((cnt[i] && (((uint8_t)bufs[i][0] | ((uint8_t)bufs[i][1] << 8)) == SERIAL_COOKIE))
+                                     ? 4 + (cnt[i] + 7) / 8 + (cnt[i] < (uint32_t)NO_OFFSET_THRESHOLD ? 4ull : 8ull) * cnt[i]
+                                     : 8 + 8ull * cnt[i]);
+            s->portable_bytes += lens[i] > hdr ? lens[i] - hdr : 0;
+            ro += (lens[i] + 15) & ~(uint64_t)15;
+            so += ((lens[i] + 15) & ~(uint64_t)15) + 16ull * cnt[i];
+            cb += cnt[i];
+        }
+        ok = cudaMemcpyAsync(d_tab, h_tab, tb, cudaMemcpyHostToDevice, g.stream) == cudaSuccess &&
+             (n == 0 ||
+              (cudaMemcpyAsync(s->d_dir + s->L.o_beg, h_bc, 4 * n, cudaMemcpyHostToDevice, g.stream) == cudaSuccess &&
+               cudaMemcpyAsync(s->d_dir + s->L.o_cnt, h_bc + n, 4 * n, cudaMemcpyHostToDevice, g.stream) == cudaSuccess));
+        // raw bytes as one stream through the two pinned chunks
+        int cur = 0;
+        size_t used = 0;
+        uint64_t base = 0;
+        auto flush = [&]() -> bool {
+            if (used) {
+                if (cudaMemcpyAsync(d_raw + base, chunk[cur], used, cudaMemcpyHostToDevice, g.stream) != cudaSuccess)
+                    return false;
+                cudaEventRecord(cev[cur], g.stream);
+                cev_used[cur] = true;
+            }
+            base += used;
+            used = 0;
+            cur ^= 1;
+            if (cev_used[cur]) cudaEventSynchronize(cev[cur]);
+            return true;
+        };
+        for (size_t i = 0; i < n && ok; i++) {
+            size_t done = 0;
+            const size_t padded = (lens[i] + 15) & ~(size_t)15;
+            while (done < padded && ok) {
+                if (used == CH) ok = flush();
+                const size_t room = CH - used, want = padded - done;
+                const size_t take = room < want ? room : want;
+                const size_t real = done < lens[i] ? std::min(take, lens[i] - done) : 0;
+                if (real) memcpy(chunk[cur] + used, bufs[i] + done, real);
+                if (take > real) memset(chunk[cur] + used + real, 0, take - real);
+                used += take;
+                done += take;
+            }
+        }
+        if (ok) ok = flush();
+    }
+    if (ok) {
+        ok = stats_reset();
+        launch_deserialize(d_raw, d_tab, d_tab + n, d_tab + 2 * n, (uint32_t)n, nc, s->out(), d_src, g.d_stats,
+                           g.stream);
+        ok = ok && stats_fetch();
+        cudaError_t e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+            g.err = std::string("deserialize: ") + cudaGetErrorString(e);
+            ok = false;
+        }
+        if (ok && g.h_stats->error) {
+            g.err = "malformed portable bitmap at index " + std::to_string((uint64_t)n - g.h_stats->nk);
+            ok = false;
+        }
+    } else {
+        cudaStreamSynchronize(g.stream);
+    }
+    for (int k = 0; k < 2; k++) if (cev[k]) cudaEventDestroy(cev[k]);
+    pin_free(chunk[0], CH);
+    pin_free(chunk[1], CH);
+    pin_free(h_tab, tb);
+    pin_free(h_bc, 8 * (n ? n : 1));
+    dev_free(d_tab, tb);
+    dev_free(d_raw, raw_total ? raw_total : 16);
+    dev_free(d_src, 8 * (nc ? nc : 1));
+    if (!ok) {
+        if (g.err.empty()) g.err = "upload_serialized failed";
+        set_delete(s);
+        return nullptr;
+    }
+    return s;
 }
 
 // Declare that the host bitmaps this set was uploaded from stay alive (and unmodified) for as long

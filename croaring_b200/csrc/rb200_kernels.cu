@@ -861,6 +861,162 @@ void launch_serialize_write(const SetView &S, uint32_t n, const uint64_t *off, c
 }
 }  // namespace rb200
 
+// ------------------------------------------------------------------------------ deserialization
+// roaring_bitmap_portable_deserialize_safe (src/roaring_array.c:633-813) of every blob of a batch,
+// on the device: the raw bytes arrive in one staging buffer (blob b at raw + roff[b], 16-byte
+// aligned); k_deser_dir walks the headers (warp per bitmap) and fills the directory, k_deser_copy
+// moves the payloads into the 16-byte aligned slab (warp per container) and counts run cardinalities.
+namespace rb200 {
+
+__device__ __forceinline__ uint32_t ld_u16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return ld_u16(p) | (ld_u16(p + 2) << 16); }
+
+__global__ void __launch_bounds__(128)
+k_deser_dir(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ roff,
+            const uint64_t *__restrict__ rlen, const uint64_t *__restrict__ slab_base, uint32_t nb,
+            SetOut out, uint64_t *__restrict__ src_pos, OpStats *st) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < nb; b += nwarps) {
+        const uint8_t *buf = raw + roff[b];
+        const uint64_t len = rlen[b];
+        const uint32_t c0 = out.bm_beg[b], want = out.bm_cnt[b];  // filled by the host from the cookies
+        bool bad = len < 4;
+        uint32_t size = 0;
+        uint64_t pos = 4;
+        bool hasrun = false;
+        const uint8_t *runflags = nullptr;
+        if (!bad) {
+            const uint32_t cookie = ld_u32(buf);
+            if ((cookie & 0xFFFFu) == 12347u) {          // SERIAL_COOKIE, roaring_array.h:35-40
+                size = (cookie >> 16) + 1;
+                hasrun = true;
+                runflags = buf + 4;
+                pos = 4 + ((size + 7) >> 3);
+            } else if (cookie == 12346u && len >= 8) {   // SERIAL_COOKIE_NO_RUN
+                size = ld_u32(buf + 4);
+                pos = 8;
+            } else {
+                bad = true;
+            }
+        }
+        if (!bad && (size != want || size > 65536u || pos + 4ull * size > len)) bad = true;
+        const uint8_t *kc = buf + pos;
+        if (!bad) {
+            pos += 4ull * size;
+            if (!hasrun || size >= 4u) pos += 4ull * size;   // offset header (NO_OFFSET_THRESHOLD), not trusted
+        }
+        uint64_t off = slab_base[b];
+        int prev_key = -1;
+        for (uint32_t chunk = 0; chunk < size && !bad; chunk += 32) {
+            const uint32_t i = chunk + lane;
+            const bool valid = i < size;
+            uint32_t key = 0, card = 0, known = 0;
+            bool isrun = false;
+            if (valid) {
+                key = ld_u16(kc + 4 * i);
+                card = ld_u16(kc + 4 * i + 2) + 1;
+                isrun = hasrun && ((runflags[i >> 3] >> (i & 7)) & 1);
+                known = isrun ? 0u : (card > (uint32_t)MAX_ARRAY ? (uint32_t)BITSET_BYTES : 2u * card);
+            }
+            // keys strictly increasing (roaring.c:496-503)
+            int left = __shfl_up_sync(FULLMASK, (int)key, 1);
+            if (lane == 0) left = prev_key;
+            if (__any_sync(FULLMASK, valid && (int)key <= left)) { bad = true; break; }
+            prev_key = __shfl_sync(FULLMASK, (int)key, 31);
+            // sequential walk over the chunk: a run container's size is in its first two bytes
+            uint64_t mypos = 0;
+            uint32_t mylen = 0, mystored = 0;
+            const uint32_t cnt = size - chunk < 32u ? size - chunk : 32u;
+            for (uint32_t j = 0; j < cnt; j++) {
+                const bool isr = __shfl_sync(FULLMASK, isrun ? 1 : 0, j) != 0;
+                uint32_t sz = __shfl_sync(FULLMASK, known, j), nr = 0, skip = 0;
+                if (isr) {
+                    if (pos + 2 > len) { bad = true; break; }
+                    nr = ld_u16(buf + pos);
+                    sz = 2u + 4u * nr;
+                    skip = 2;
+                }
+                if (pos + sz > len) { bad = true; break; }
+                if (lane == (int)j) { mypos = pos + skip; mylen = isr ? nr : 0u; mystored = sz - skip; }
+                pos += sz;
+            }
+            if (bad) break;
+            const uint32_t r16 = valid ? round16(mystored) : 0u;
+            const uint32_t incl = warp_incl_scan(r16, lane);
+            if (valid) {
+                const uint64_t c = (uint64_t)c0 + i;
+                const int t = isrun ? T_RUN : (card > (uint32_t)MAX_ARRAY ? T_BITSET : T_ARRAY);
+                out.c_key[c] = (uint16_t)key;
+                out.c_type[c] = (uint8_t)t;
+                out.c_card[c] = card;                      // runs: recounted by k_deser_copy
+                out.c_len[c] = t == T_BITSET ? 1024u : (t == T_ARRAY ? card : mylen);
+                out.c_off[c] = off + incl - r16;
+                out.c_src[c] = SRC_NONE;
+                src_pos[c] = roff[b] + mypos;
+            }
+            off += __shfl_sync(FULLMASK, incl, 31);
+        }
+        if (bad && lane == 0) {
+            atomicExch(&st->error, 3u);
+            atomicMax(&st->nk, nb - b);  // host: first malformed blob = nb - nk
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_deser_copy(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ src_pos, uint64_t nc,
+             SetOut out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t c = warp; c < nc; c += nwarps) {
+        const int t = out.c_type[c];
+        const uint32_t len = out.c_len[c];
+        const uint32_t n = stored_bytes(t, len);
+        uint8_t *dst = out.payload + out.c_off[c];
+        const uint8_t *src = raw + src_pos[c];
+        warp_copy_unaligned(dst, src, n, lane);
+        const uint32_t pad = round16(n) - n;
+        if ((uint32_t)lane < pad) dst[n + lane] = 0;
+        if (t == T_RUN) {  // run_container_cardinality (run.c:1077)
+            uint32_t card = 0;
+            for (uint32_t k = lane; k < len; k += 32) card += ld_u16(src + 4 * k + 2) + 1u;
+            card = __reduce_add_sync(FULLMASK, card);
+            if (lane == 0) out.c_card[c] = card;
+        }
+    }
+}
+
+__global__ void k_deser_bitmap_cards(SetOut out, uint32_t nb) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < nb; b += nwarps) {
+        const uint32_t c0 = out.bm_beg[b], n = out.bm_cnt[b];
+        unsigned long long card = 0;
+        for (uint32_t i = lane; i < n; i += 32) card += out.c_card[c0 + i];
+        for (int d = 16; d > 0; d >>= 1) card += __shfl_xor_sync(FULLMASK, card, d);
+        if (lane == 0) out.bm_card[b] = card;
+    }
+}
+
+void launch_deserialize(const uint8_t *raw, const uint64_t *roff, const uint64_t *rlen,
+                        const uint64_t *slab_base, uint32_t nb, uint64_t nc, SetOut out,
+                        uint64_t *src_pos, OpStats *st, cudaStream_t s) {
+    if (!nb) return;
+    k_deser_dir<<<blocks_for_warps(nb, 4, sm_count() * 16), 128, 0, s>>>(raw, roff, rlen, slab_base, nb, out, src_pos, st);
+    g_launches++;
+    if (nc) {
+        k_deser_copy<<<blocks_for_warps(nc, 4, sm_count() * 16), 128, 0, s>>>(raw, src_pos, nc, out);
+        g_launches++;
+    }
+    k_deser_bitmap_cards<<<blocks_for_warps(nb, 4, sm_count() * 16), 128, 0, s>>>(out, nb);
+    g_launches++;
+}
+}  // namespace rb200
+
 namespace rb200 {
 void launch_pack_scan(const uint64_t *bytes, const uint32_t *cnts, uint32_t n, uint64_t *off,
                       uint64_t *beg, cudaStream_t s) {

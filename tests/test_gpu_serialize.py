@@ -28,3 +28,67 @@ def test_serialize_batch_results(rb, R, ds):
         for k in range(0, len(got), 97):
             assert got[k] == R.op_bytes(op, blobs[i[k]], blobs[j[k]]), (ds, op, k)
         assert got == [b.serialize() for b in res.download_all()]
+
+
+def test_device_deserialize_shapes(rb, R):
+    """Device-side parse (k_deser_dir / k_deser_copy): odd payload alignment (run cookie with
+    1-3 containers: no offset header, 5/6/7-byte preamble), > 32 containers per bitmap (chunked
+    walk), empty bitmaps, and the values decode to what the reference holds."""
+    vals = []
+    rng = np.random.default_rng(3)
+    for nkeys in (1, 2, 3, 4, 5, 33, 64, 100):
+        v = []
+        for k in range(nkeys):
+            base = (k * 3 + 1) << 16
+            if k % 3 == 0:
+                v.append(base + np.arange(100, 100 + 700 * (k % 5 + 1)))          # run
+            elif k % 3 == 1:
+                v.append(base + np.sort(rng.choice(65536, 300 + 11 * k, replace=False)))   # array
+            else:
+                v.append(base + np.sort(rng.choice(65536, 20000, replace=False)))  # bitset
+        vals.append(np.concatenate(v).astype(np.uint32))
+    vals.append(np.zeros(0, np.uint32))
+    blobs = []
+    for v in vals:
+        for ro in (True, False):
+            r = R.from_values(v, run_optimize=ro)
+            blobs.append(R.serialize(r))
+            R.free(r)
+    S = rb.DeviceSet.from_serialized(blobs)
+    assert S.serialize_all() == blobs
+    arrs = S.to_uint32_arrays()
+    for k, v in enumerate(vals):
+        assert np.array_equal(arrs[2 * k], v) and np.array_equal(arrs[2 * k + 1], v)
+    assert S.cardinalities().tolist() == [len(v) for v in vals for _ in (0, 1)]
+
+
+def test_device_deserialize_rejects_malformed(rb, R):
+    good = rb.load_realdata("wikileaks-noquotes")[:6]
+    r = R.from_values(np.arange(0, 300000, 7, dtype=np.uint32), run_optimize=True)
+    runblob = R.serialize(r)
+    R.free(r)
+    bad_cases = {
+        "truncated payload": good[2][: len(good[2]) - 5],
+        "truncated header": good[1][:10],
+        "bad cookie": b"\x01\x02\x03\x04" + good[0][4:],
+        "run count overflows": None,
+        "keys not increasing": None,
+    }
+    # corrupt the first run container's n_runs field to something huge
+    import struct
+    n = (struct.unpack_from("<I", runblob, 0)[0] >> 16) + 1
+    hdr = 4 + (n + 7) // 8 + 4 * n + (4 * n if n >= 4 else 0)
+    bad_cases["run count overflows"] = runblob[:hdr] + b"\xff\xff" + runblob[hdr + 2:]
+    # swap two keys of a no-run blob
+    g = bytearray(good[3])
+    if struct.unpack_from("<I", g, 0)[0] == 12346 and struct.unpack_from("<I", g, 4)[0] >= 2:
+        g[8:10], g[12:14] = g[12:14], g[8:10]
+        bad_cases["keys not increasing"] = bytes(g)
+    else:
+        del bad_cases["keys not increasing"]
+    for name, blob in bad_cases.items():
+        with pytest.raises(rb.RB200Error) as ei:
+            rb.DeviceSet.from_serialized(good[:2] + [blob] + good[4:])
+        assert "malformed portable bitmap at index 2" in str(ei.value), (name, str(ei.value))
+    # the library keeps working afterwards
+    assert rb.DeviceSet.from_serialized(good).serialize_all() == good
