@@ -94,6 +94,7 @@ struct OpStats {
     unsigned long long algo_bytes;    // SURVEY.md §8(d) algorithmic bytes
     unsigned long long work_counter;  // dynamic scheduler for the compute kernel
     unsigned long long work_counter2;
+    unsigned long long out_portable;  // sum over result bitmaps of roaring_bitmap_portable_size_in_bytes
     unsigned int error;               // 0 = ok; 1 = slot overflow; 2 = slab overflow; 3 = malformed blob
     unsigned int nk;                  // or_many: number of distinct keys
 };

@@ -113,6 +113,7 @@ struct Ctx {
     uint64_t last_algo_bytes = 0;
     float last_ms = 0.f, last_compute_ms = 0.f;
     uint64_t last_download_bytes = 0;
+    uint64_t last_out_portable = 0;  // portable bytes of the last batch's results (all pairs)
 } g;
 std::map<uint8_t *, size_t> g_serialized_sizes;  // pinned blobs handed out by rb200_set_serialize
 
@@ -1243,6 +1244,12 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         R->parentB = B->h_ptr;
         R->portable_bytes = 0;
         R->mirrors_pending = np > 0;  // h_cnt / h_bytes / h_card: see ensure_mirrors()
+        g.last_out_portable = g.h_stats->out_portable;
+        if (np == 1) {  // a single result: its mirrors are the op's counters, no extra D2H
+            R->h_cnt[0] = (uint32_t)R->n_containers;
+            R->h_bytes[0] = R->slab_used;
+            R->mirrors_pending = false;
+        }
         R->lazy = (rules & RULES_LAZY) != 0;
         for (size_t p = 0; p < np; p++) R->h_flags[p] = (A->h_flags[ia[p]] | B->h_flags[ib[p]]) & FLAG_COW;
     }
@@ -2557,9 +2564,8 @@ rb200_set_t *rb200_or_many_heap(const rb200_set_t *S, const uint32_t *idx, size_
             R = batch_op_impl(OP_OR, a.set, b.set, &a.index, &b.index, 1, RULES_LAZY);
         if (a.temp) set_delete(a.set);
         if (b.temp) set_delete(b.set);
-        std::vector<uint32_t> rs;
-        if (!R || !portable_sizes(R, rs)) { set_delete(R); ok = false; break; }
-        heap_push(e, cnt, HeapEl{rs[0], true, R, 0});
+        if (!R) { ok = false; break; }
+        heap_push(e, cnt, HeapEl{g.last_out_portable, true, R, 0});  // size measured by k_finalize_pairs
     }
     if (!ok) {
         for (uint32_t i = 0; i < cnt; i++) if (e[i].temp) set_delete(e[i].set);

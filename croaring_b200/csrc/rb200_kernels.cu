@@ -370,6 +370,12 @@ k_card_items(SetView A, SetView B, Items it, uint64_t W, OpStats *st) {
 }
 
 // ------------------------------------------------------------------------------ finalize
+// header bytes of the portable format (roaring_array.c:469-500)
+__device__ __forceinline__ uint32_t portable_header_bytes(uint32_t n, bool hasrun) {
+    if (!hasrun) return 8u + 8u * n;
+    return 4u + ((n + 7u) >> 3) + (n < 4u ? 4u * n : 8u * n);
+}
+
 __global__ void __launch_bounds__(128)
 k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ item_off,
                  uint32_t npairs, SetOut out, OpStats *st) {
@@ -379,13 +385,15 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
     for (uint32_t p = warp; p < npairs; p += nwarps) {
         const uint64_t i0 = item_off[p], i1 = item_off[p + 1];
         // pass 1: count surviving containers, cardinality and algorithmic bytes
-        uint32_t cnt = 0;
-        unsigned long long card = 0, bytes = 0;
+        uint32_t cnt = 0, anyrun = 0;
+        unsigned long long card = 0, bytes = 0, outb = 0;
         for (uint64_t i = i0 + lane; i < i1; i += 32) {
             const int kind = it.kind[i];
             if (kind == K_HOLE) continue;
             const int ot = it.otype[i];
             const uint32_t osz = ot ? portable_bytes(ot, it.olen[i]) : 0u;
+            outb += osz;
+            anyrun |= (ot == T_RUN) ? 1u : 0u;
             if (kind == K_COMPUTE) {
                 const uint32_t ca = it.ca[i], cb = it.cb[i];
                 bytes += portable_bytes(A.c_type[ca], A.c_len[ca]) +
@@ -399,14 +407,17 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
             }
         }
         cnt = __reduce_add_sync(FULLMASK, cnt);
+        anyrun = __reduce_or_sync(FULLMASK, anyrun);
         for (int d = 16; d > 0; d >>= 1) {
             card += __shfl_xor_sync(FULLMASK, card, d);
             bytes += __shfl_xor_sync(FULLMASK, bytes, d);
+            outb += __shfl_xor_sync(FULLMASK, outb, d);
         }
         unsigned long long base = 0;
         if (lane == 0) {
             base = atomicAdd(&st->dir_cursor, (unsigned long long)cnt);
             atomicAdd(&st->algo_bytes, bytes);
+            atomicAdd(&st->out_portable, outb + portable_header_bytes(cnt, anyrun != 0));
             out.bm_beg[p] = (uint32_t)base;
             out.bm_cnt[p] = cnt;
             out.bm_card[p] = card;
@@ -967,7 +978,8 @@ k_deser_dir(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ roff,
 
 __global__ void __launch_bounds__(128)
 k_deser_copy(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ src_pos, uint64_t nc,
-             SetOut out) {
+             SetOut out, const OpStats *st) {
+    if (st->error) return;  // a malformed blob leaves directory entries unwritten: nothing to move
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -989,7 +1001,8 @@ k_deser_copy(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ src_p
     }
 }
 
-__global__ void k_deser_bitmap_cards(SetOut out, uint32_t nb) {
+__global__ void k_deser_bitmap_cards(SetOut out, uint32_t nb, const OpStats *st) {
+    if (st->error) return;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1009,10 +1022,10 @@ void launch_deserialize(const uint8_t *raw, const uint64_t *roff, const uint64_t
     k_deser_dir<<<blocks_for_warps(nb, 4, sm_count() * 16), 128, 0, s>>>(raw, roff, rlen, slab_base, nb, out, src_pos, st);
     g_launches++;
     if (nc) {
-        k_deser_copy<<<blocks_for_warps(nc, 4, sm_count() * 16), 128, 0, s>>>(raw, src_pos, nc, out);
+        k_deser_copy<<<blocks_for_warps(nc, 4, sm_count() * 16), 128, 0, s>>>(raw, src_pos, nc, out, st);
         g_launches++;
     }
-    k_deser_bitmap_cards<<<blocks_for_warps(nb, 4, sm_count() * 16), 128, 0, s>>>(out, nb);
+    k_deser_bitmap_cards<<<blocks_for_warps(nb, 4, sm_count() * 16), 128, 0, s>>>(out, nb, st);
     g_launches++;
 }
 }  // namespace rb200

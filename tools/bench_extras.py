@@ -179,6 +179,129 @@ def bench_xormany(a):
         assert exp == got
 
 
+def bench_heap(a):
+    """roaring_bitmap_or_many_heap on the three real-data sets (200 bitmaps each) vs the reference.
+    Sequential by construction (199 dependent single-pair lazy unions): a parity row, not a
+    throughput row — the wall time per call is reported next to the reference's."""
+    from oracle.refbind import ref
+    import time as _t
+    R = ref()
+    for ds in ("census1881", "weather_sept_85", "wikileaks-noquotes"):
+        blobs = rb.load_realdata(ds)
+        S = rb.DeviceSet.from_serialized(blobs)
+        ms = []
+        got = None
+        for it in range(a.warmup + a.steps):
+            rb.synchronize()
+            t0 = _t.perf_counter()
+            r = S.or_many_heap()
+            rb.synchronize()
+            if it >= a.warmup:
+                ms.append((_t.perf_counter() - t0) * 1e3)
+            got = r.serialize_all()[0]
+            r.free()
+        rs = [R.deserialize(b) for b in blobs]
+        best = 1e9
+        for _ in range(5):
+            t0 = _t.perf_counter()
+            x = R.many("or_many_heap", rs)
+            best = min(best, _t.perf_counter() - t0)
+            exp = R.serialize(x)
+            R.free(x)
+        for x in rs:
+            R.free(x)
+        print(json.dumps({"workload": "or_many_heap_realdata", "dataset": ds, "bitmaps": len(blobs),
+                          "wall_ms": float(np.median(ms)), "steps_per_call": len(blobs) - 1,
+                          "cpu_baseline": {"kind": "reference", "cores": 1, "ms": best * 1e3,
+                                           "parity": "bytes identical" if exp == got else "MISMATCH"}}), flush=True)
+        assert exp == got
+
+
+def bench_lazy(a):
+    """Batched lazy unions: all 19 900 pairs of a real-data set through roaring_bitmap_lazy_or
+    (bitsetconversion off) + roaring_bitmap_repair_after_lazy, device-resident, vs the reference
+    doing the same two calls per pair on one host thread (sampled)."""
+    from oracle.refbind import ref
+    import time as _t
+    R = ref()
+    for ds in ("census1881", "weather_sept_85", "wikileaks-noquotes"):
+        blobs = rb.load_realdata(ds)
+        S = rb.DeviceSet.from_serialized(blobs)
+        i, j = np.triu_indices(len(blobs), 1)
+        ia, ib = i.astype(np.uint32), j.astype(np.uint32)
+        ms = []
+        for it in range(a.warmup + a.steps):
+            rb.synchronize()
+            t0 = _t.perf_counter()
+            lz = S.batch("or", S, ia, ib, lazy=True)
+            rep = lz.repair_after_lazy()
+            rb.synchronize()
+            if it >= a.warmup:
+                ms.append((_t.perf_counter() - t0) * 1e3)
+            cards = rep.cardinalities() if it == a.warmup + a.steps - 1 else None
+            lz.free()
+            if cards is None:
+                rep.free()
+        sample = np.arange(0, len(ia), 20)
+        rs = [R.deserialize(b) for b in blobs]
+        t0 = _t.perf_counter()
+        ok = True
+        for k in sample:
+            x = R.L.roaring_bitmap_lazy_or(rs[ia[k]], rs[ib[k]], False)
+            R.L.roaring_bitmap_repair_after_lazy(x)
+            ok = ok and int(R.card(x)) == int(cards[k])
+            R.free(x)
+        cpu_ms = (_t.perf_counter() - t0) * 1e3
+        got = rep.serialize_all()
+        for k in sample[::10]:
+            ok = ok and got[k] == R.lazy_fold_bytes("or", False, [blobs[ia[k]], blobs[ib[k]]])
+        rep.free()
+        for x in rs:
+            R.free(x)
+        med = float(np.median(ms))
+        print(json.dumps({"workload": "lazy_or+repair all pairs", "dataset": ds, "pairs": int(len(ia)),
+                          "wall_ms": med, "value": len(ia) / (med * 1e-3), "unit": "set-ops/s",
+                          "cpu_baseline": {"kind": "reference", "cores": 1, "sample_pairs": int(len(sample)),
+                                           "value": len(sample) / (cpu_ms * 1e-3),
+                                           "parity": "cardinalities + sampled bytes identical" if ok else "MISMATCH"}}),
+              flush=True)
+        assert ok
+
+
+def bench_deser(a):
+    """Device-side portable deserialization: host blobs -> resident set (H2D of the raw bytes +
+    header walk + payload move), vs roaring_bitmap_portable_deserialize_safe on one host thread."""
+    from oracle.refbind import ref
+    import time as _t
+    R = ref()
+    for ds in ("census1881", "weather_sept_85", "wikileaks-noquotes"):
+        blobs = rb.load_realdata(ds) * 8            # 1600 bitmaps per call
+        nbytes = sum(map(len, blobs))
+        ms = []
+        for it in range(a.warmup + a.steps):
+            rb.synchronize()
+            t0 = _t.perf_counter()
+            S = rb.DeviceSet.from_serialized(blobs)
+            rb.synchronize()
+            if it >= a.warmup:
+                ms.append((_t.perf_counter() - t0) * 1e3)
+            if it == a.warmup + a.steps - 1:
+                assert S.serialize_all() == blobs
+            S.free()
+        t0 = _t.perf_counter()
+        rs = [R.deserialize(b) for b in blobs]
+        cpu_ms = (_t.perf_counter() - t0) * 1e3
+        for x in rs:
+            R.free(x)
+        med = float(np.median(ms))
+        print(json.dumps({"workload": "portable deserialize -> resident set", "dataset": ds,
+                          "bitmaps": len(blobs), "bytes": nbytes, "wall_ms": med,
+                          "GBps": nbytes / (med * 1e-3) / 1e9,
+                          "cpu_baseline": {"kind": "reference", "cores": 1, "ms": cpu_ms,
+                                           "GBps": nbytes / (cpu_ms * 1e-3) / 1e9,
+                                           "parity": "round trip bytes identical"}}), flush=True)
+
+
 def bench_sharded(a):
     """configs[4]: 10^8-universe, many-bitmap OR sharded by high-16 key range across ranks, one NCCL
     all-reduce of the per-key cardinalities.  Strong scaling: total work fixed."""
@@ -263,7 +386,7 @@ def bench_sharded(a):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["card", "ormany", "sharded", "xormany"])
+    ap.add_argument("what", choices=["card", "ormany", "sharded", "xormany", "heap", "lazy", "deser"])
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=10000)
@@ -274,4 +397,5 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.what != "sharded":
         rb.init(0)
-    {"card": bench_card, "ormany": bench_ormany, "sharded": bench_sharded, "xormany": bench_xormany}[a.what](a)
+    {"card": bench_card, "ormany": bench_ormany, "sharded": bench_sharded, "xormany": bench_xormany,
+     "heap": bench_heap, "lazy": bench_lazy, "deser": bench_deser}[a.what](a)

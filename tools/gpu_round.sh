@@ -10,6 +10,9 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 timeout 600 python tools/bench_extras.py card > gpurun_out/extras_card.json 2> gpurun_out/extras_card.err
 timeout 900 python tools/bench_extras.py ormany > gpurun_out/extras_ormany.json 2> gpurun_out/extras_ormany.err
 timeout 600 python tools/bench_extras.py xormany > gpurun_out/extras_xormany.json 2> gpurun_out/extras_xormany.err
+for w in heap lazy deser; do
+  timeout 600 python tools/bench_extras.py $w --steps 5 > gpurun_out/extras_$w.json 2> gpurun_out/extras_$w.err
+done
 timeout 900 python tools/bench_extras.py sharded --bitmaps ${SHARD_BITMAPS:-200} > gpurun_out/extras_sharded_n1.json 2> gpurun_out/extras_sharded_n1.err
 for w in pairs card many; do
   timeout 300 python tools/profile_target.py $w 3 > gpurun_out/target_$w.log 2>&1
