@@ -100,6 +100,7 @@ def lib():
     sig("rb200_download_next", C.c_size_t, _P, C.POINTER(_P))
     sig("rb200_download_end", None, _P)
     sig("rb200_download_foreach", C.c_int, _P, _P, _P)
+    sig("rb200_download_foreach_many", C.c_int, C.POINTER(_P), C.c_size_t, _P, _P)
     sig("rb200_batch_op_host", C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_size_t,
         C.POINTER(_P))
     _lib = L
@@ -264,6 +265,26 @@ def xor_many(bitmaps):
     if not p:
         raise RB200Error(last_error())
     return Bitmap(p)
+
+
+VISIT_FN = C.CFUNCTYPE(C.c_int, C.c_size_t, _P, _P)
+
+
+def foreach_many(sets, fn=None):
+    """rb200_download_foreach_many: several result sets as one pipelined D2H stream.  fn=None:
+    the built-in visitor (sum of host-side cardinalities, every bitmap freed) — returns the sum;
+    otherwise fn(index, bitmap_ptr) is called on worker threads (return non-zero to keep the bitmap)."""
+    arr = (_P * len(sets))(*[s.ptr for s in sets])
+    if fn is None:
+        acc = C.c_uint64(0)
+        cb = C.cast(lib().rb200_visit_sum_cardinality, _P)
+        if lib().rb200_download_foreach_many(arr, len(sets), cb, C.byref(acc)) != 0:
+            raise RB200Error(last_error())
+        return int(acc.value)
+    cb = VISIT_FN(lambda i, p, _ctx: int(fn(i, p) or 0))
+    if lib().rb200_download_foreach_many(arr, len(sets), C.cast(cb, _P), None) != 0:
+        raise RB200Error(last_error())
+    return None
 
 
 def batch_op_host(op, a, b):

@@ -1726,8 +1726,13 @@ void stream_free(rb200_download_stream *st) {
 
 extern "C" {
 
+static rb200_download_stream *download_begin_impl(const rb200_set *s, size_t chunk_bitmaps, bool defer);
 rb200_download_stream_t *rb200_download_begin(const rb200_set_t *s, size_t chunk_bitmaps) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return download_begin_impl(s, chunk_bitmaps, false);
+}
+// defer: pack only; the caller owns the staging ring and enqueues the copies itself
+static rb200_download_stream *download_begin_impl(const rb200_set *s, size_t chunk_bitmaps, bool defer) {
     if (!ctx_init()) return nullptr;
     const size_t nb = s->n_bitmaps;
     rb200_download_stream *st = new rb200_download_stream();
@@ -1775,13 +1780,13 @@ rb200_download_stream_t *rb200_download_begin(const rb200_set_t *s, size_t chunk
             p0 = p1;
         }
         st->hbuf_bytes = maxb;
-        for (int k = 0; k < 2 && ok; k++) {
+        for (int k = 0; k < 2 && ok && !defer; k++) {
             st->hbuf[k] = (uint8_t *)pin_alloc(maxb);
             ok = st->hbuf[k] != nullptr && cudaEventCreateWithFlags(&st->ev[k], cudaEventDisableTiming) == cudaSuccess;
         }
         st->total_bytes = P->L.total + P->slab_used;
         g.last_download_bytes = st->total_bytes;
-        ok = ok && stream_enqueue(st) && stream_enqueue(st);
+        if (!defer) ok = ok && stream_enqueue(st) && stream_enqueue(st);
     }
     dev_free(d_bytes, 8 * nb);
     dev_free(d_off, 8 * (nb + 1));
@@ -1910,6 +1915,111 @@ int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx) {
     stream_free(st);
     if (failed) {
         if (g.err.empty()) g.err = "download_foreach: host allocation or copy failed";
+        return -1;
+    }
+    return 0;
+}
+
+// Visitor download of SEVERAL result sets as one pipelined stream: every set is packed on the
+// device first, then all their chunks cross PCIe back to back through one staging ring while the
+// workers materialise the previous chunk — the copy engine never idles between sets, and the
+// builds of small / host-bound sets hide behind the transfers of the large ones.  fn receives a
+// running index (set 0's bitmaps first).  Returns 0 on success.
+int rb200_download_foreach_many(const rb200_set_t *const *sets, size_t nsets, rb200_visit_fn fn, void *ctx) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    std::vector<rb200_download_stream *> sts(nsets, nullptr);
+    struct Ref { size_t set; size_t k; };
+    std::vector<Ref> order;
+    std::vector<size_t> first_index(nsets, 0);
+    size_t ring_bytes = 0, running = 0;
+    uint64_t total = 0;
+    bool ok = true;
+    for (size_t i = 0; i < nsets && ok; i++) {
+        sts[i] = download_begin_impl(sets[i], 4096, true);
+        ok = sts[i] != nullptr;
+        if (!ok) break;
+        first_index[i] = running;
+        running += sts[i]->nb;
+        ring_bytes = std::max(ring_bytes, sts[i]->hbuf_bytes);
+        total += sts[i]->total_bytes;
+        for (size_t k = 0; k < sts[i]->chunk_end.size(); k++) order.push_back(Ref{i, k});
+    }
+    // staging ring: RING buffers, so the copy engine can run up to RING-1 chunks ahead of the
+    // builders (chunks alternate between copy-bound and build-bound; 2 buffers stall either side)
+    constexpr int RING = 4;
+    uint8_t *ring[RING] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t rev[RING] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < RING && ok; k++) {
+        ring[k] = (uint8_t *)pin_alloc(ring_bytes ? ring_bytes : 16);
+        ok = ring[k] != nullptr && cudaEventCreateWithFlags(&rev[k], cudaEventDisableTiming) == cudaSuccess;
+    }
+    auto enqueue = [&](size_t gidx) -> bool {
+        if (gidx >= order.size()) return true;
+        const rb200_download_stream *st = sts[order[gidx].set];
+        const size_t k = order[gidx].k;
+        const size_t p0 = k ? st->chunk_end[k - 1] : 0, p1 = st->chunk_end[k];
+        const uint64_t b0 = st->h_ob[p0], b1 = st->h_ob[p1];
+        if (b1 > b0 && cudaMemcpyAsync(ring[gidx % RING], st->P->d_slab + b0, b1 - b0, cudaMemcpyDeviceToHost,
+                                       g.stream) != cudaSuccess)
+            return false;
+        return cudaEventRecord(rev[gidx % RING], g.stream) == cudaSuccess;
+    };
+    std::atomic<int> failed(0);
+    const bool trace = getenv("RB200_TRACE") != nullptr;
+    double t_wait = 0, t_build = 0;
+    auto ms_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
+    const auto t_begin = std::chrono::steady_clock::now();
+    for (int k = 0; k < RING && ok; k++) ok = enqueue((size_t)k);
+    for (size_t gidx = 0; gidx < order.size() && ok; gidx++) {
+        const rb200_download_stream *st = sts[order[gidx].set];
+        const size_t k = order[gidx].k, base_index = first_index[order[gidx].set];
+        const size_t p0 = k ? st->chunk_end[k - 1] : 0, p1 = st->chunk_end[k];
+        const auto t0 = std::chrono::steady_clock::now();
+        if (cudaEventSynchronize(rev[gidx % RING]) != cudaSuccess) { ok = false; break; }
+        t_wait += ms_since(t0);
+        const auto t1 = std::chrono::steady_clock::now();
+        const uint8_t *buf = ring[gidx % RING];
+        const uint64_t bias = st->h_ob[p0];
+        const size_t n = p1 - p0;
+        std::atomic<size_t> next(0);
+        const rb200_set *P = st->P;
+        std::function<void()> work = [&]() {
+            for (;;) {
+                const size_t i0 = next.fetch_add(8);
+                if (i0 >= n) break;
+                const size_t i1 = std::min(n, i0 + 8);
+                for (size_t i = i0; i < i1; i++) {
+                    roaring_bitmap_t *bm = build_bitmap(P, p0 + i, buf, bias);
+                    if (!bm) { failed = 1; continue; }
+                    if (fn(base_index + p0 + i, bm, ctx) == 0) bitmap_free_host(bm);
+                }
+            }
+        };
+        const uint64_t chunk_bytes = st->h_ob[p1] - st->h_ob[p0];
+        const uint64_t chunk_conts = st->h_ob[st->nb + 1 + p1] - st->h_ob[st->nb + 1 + p0];
+        uint64_t want = (chunk_bytes + 256 * chunk_conts + 512 * n) / (128 << 10) + 1;
+        unsigned T = host_workers();
+        if (want < T) T = (unsigned)want;
+        if ((size_t)T * 8 > n) T = (unsigned)((n + 7) / 8);
+        pool().run(work, T);
+        t_build += ms_since(t1);
+        ok = enqueue(gidx + RING);
+    }
+    if (trace)
+        fprintf(stderr, "rb200 foreach_many: %zu sets %zu chunks %.1f MB | copy-wait %.2f ms, build %.2f ms, loop %.2f ms\n",
+                nsets, order.size(), total / 1e6, t_wait, t_build, ms_since(t_begin));
+    cudaStreamSynchronize(g.stream);
+    for (int k = 0; k < RING; k++) {
+        if (rev[k]) cudaEventDestroy(rev[k]);
+        pin_free(ring[k], ring_bytes ? ring_bytes : 16);
+    }
+    for (auto st : sts) if (st) stream_free(st);
+    g.last_download_bytes = total;
+    if (!ok || failed) {
+        if (g.err.empty()) g.err = "download_foreach_many: host allocation or copy failed";
         return -1;
     }
     return 0;

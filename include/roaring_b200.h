@@ -212,6 +212,9 @@ void rb200_download_end(rb200_download_stream_t *st);
  * visitor: *(uint64_t*)ctx += cardinality of the bitmap. */
 typedef int (*rb200_visit_fn)(size_t index, roaring_bitmap_t *bitmap, void *ctx);
 int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx);
+/* The same over several result sets as ONE pipelined stream (all sets packed first, their chunks
+ * cross PCIe back to back; the index passed to fn keeps running across the sets). */
+int rb200_download_foreach_many(const rb200_set_t *const *sets, size_t nsets, rb200_visit_fn fn, void *ctx);
 int rb200_visit_sum_cardinality(size_t index, roaring_bitmap_t *bitmap, void *ctx);
 
 /* Device-side roaring_bitmap_portable_serialize of every bitmap of a set + one D2H copy:

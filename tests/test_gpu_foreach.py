@@ -14,3 +14,37 @@ def test_foreach_sum_cardinality(rb, golden):
         assert r.foreach_sum_cardinality() == golden["weather_sept_85"]["run_optimized"][op]["sum_card"]
     e = S.batch("and", S, np.zeros(0, np.uint32), np.zeros(0, np.uint32))
     assert e.foreach_sum_cardinality() == 0
+
+
+def test_foreach_many_pipelined(rb, R, golden):
+    """Several result sets through one pipelined stream: built-in visitor checksum, then a Python
+    visitor that keeps every bitmap and checks index -> content against the reference."""
+    import threading
+    sets, exp_sum, exp_bytes = [], 0, []
+    keep = []
+    for ds in ("wikileaks-noquotes", "census1881"):
+        blobs = rb.load_realdata(ds)[:60]
+        host = [rb.Bitmap.deserialize(b) for b in blobs]
+        keep.append(host)
+        S = rb.DeviceSet.upload(host).bind_host()
+        ia = np.arange(59, dtype=np.uint32)
+        for op in ("and", "or", "xor", "andnot"):
+            sets.append(S.batch(op, S, ia, ia + 1))
+            for k in range(59):
+                b = R.op_bytes(op, blobs[k], blobs[k + 1])
+                exp_bytes.append(b)
+    exp_sum = sum(int(s.cardinalities().sum()) for s in sets)
+    assert rb.foreach_many(sets) == exp_sum
+    got, lock = {}, threading.Lock()
+
+    def visit(i, p):
+        bm = rb.Bitmap(p)                      # we keep it (return 1): freed by the wrapper later
+        with lock:
+            got[i] = bm
+        return 1
+
+    rb.foreach_many(sets, visit)
+    assert sorted(got) == list(range(len(exp_bytes)))
+    for i, b in enumerate(exp_bytes):
+        assert got[i].serialize() == b, i
+    assert rb.foreach_many([]) == 0
