@@ -101,6 +101,8 @@ def lib():
     sig("rb200_download_end", None, _P)
     sig("rb200_download_foreach", C.c_int, _P, _P, _P)
     sig("rb200_download_foreach_many", C.c_int, C.POINTER(_P), C.c_size_t, _P, _P)
+    sig("rb200_download_foreach_async", C.c_int, _P, _P, _P)
+    sig("rb200_download_wait", C.c_int)
     sig("rb200_batch_op_host", C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_size_t,
         C.POINTER(_P))
     _lib = L
@@ -287,6 +289,24 @@ def foreach_many(sets, fn=None):
     return None
 
 
+class CardinalitySum:
+    """Accumulator for the built-in visitor (sum of host-side cardinalities); must outlive the
+    downloads it is passed to."""
+
+    def __init__(self):
+        self.acc = C.c_uint64(0)
+
+    @property
+    def value(self):
+        return int(self.acc.value)
+
+
+def download_wait():
+    """rb200_download_wait: drain every download queued with DeviceSet.foreach_async."""
+    if lib().rb200_download_wait() != 0:
+        raise RB200Error(last_error())
+
+
 def batch_op_host(op, a, b):
     """out[k] = a[k] op b[k] through the device: one upload, one launch sequence, one download."""
     n = len(a)
@@ -432,6 +452,14 @@ class DeviceSet:
         if lib().rb200_download_foreach(self.ptr, fn, C.byref(acc)) != 0:
             raise RB200Error(last_error())
         return int(acc.value)
+
+    def foreach_async(self, acc: "CardinalitySum", fn=None):
+        """rb200_download_foreach_async: queue this set for the background downloader (built-in
+        visitor adding into `acc`, or a VISIT_FN kept alive by the caller) and return at once."""
+        cb = C.cast(lib().rb200_visit_sum_cardinality, _P) if fn is None else C.cast(fn, _P)
+        ctx = C.byref(acc.acc) if fn is None else None
+        if lib().rb200_download_foreach_async(self.ptr, cb, ctx) != 0:
+            raise RB200Error(last_error())
 
     def run_optimize(self, remove_runs=False):
         """roaring_bitmap_run_optimize (or remove_run_compression) of every bitmap, on the device."""

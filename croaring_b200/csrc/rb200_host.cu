@@ -19,6 +19,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <stdio.h>
 #include <thread>
@@ -110,6 +111,7 @@ struct Ctx {
     uint32_t *d_many_acc = nullptr, *d_many_tickets = nullptr;  // split-key scratch (kept zeroed)
     int sms = 148;
     std::multimap<size_t, void *> dpool, hpool;
+    std::mutex alloc_mu;  // dpool / hpool are also used by the background downloader thread
     uint64_t last_algo_bytes = 0;
     float last_ms = 0.f, last_compute_ms = 0.f;
     uint64_t last_download_bytes = 0;
@@ -165,6 +167,7 @@ bool ctx_init(int device = -1) {
 }
 
 void *dev_alloc(size_t n) {
+    std::lock_guard<std::mutex> alk(g.alloc_mu);
     if (n == 0) n = 1;
     const size_t b = bucket(n);
     auto it = g.dpool.find(b);
@@ -189,11 +192,13 @@ void *dev_alloc(size_t n) {
 }
 void dev_free(void *p, size_t n) {
     if (!p) return;
+    std::lock_guard<std::mutex> alk(g.alloc_mu);
     if (n == 0) n = 1;
     g.dpool.insert({bucket(n), p});
 }
 bool enter_local_cpus(cpu_set_t *saved);
 void *pin_alloc(size_t n) {
+    std::lock_guard<std::mutex> alk(g.alloc_mu);
     if (n == 0) n = 1;
     const size_t b = bucket(n);
     auto it = g.hpool.find(b);
@@ -219,6 +224,7 @@ void *pin_alloc(size_t n) {
 }
 void pin_free(void *p, size_t n) {
     if (!p) return;
+    std::lock_guard<std::mutex> alk(g.alloc_mu);
     if (n == 0) n = 1;
     g.hpool.insert({bucket(n), p});
 }
@@ -1574,6 +1580,7 @@ class Pool {
    public:
     void run(const std::function<void()> &fn, unsigned T) {
         if (T <= 1) { fn(); return; }
+        std::lock_guard<std::mutex> one_run(run_mu_);  // callers: API threads and the downloader
         std::unique_lock<std::mutex> lk(mu_);
         while (workers_.size() < T - 1) workers_.emplace_back([this]() { bind_to_local_cpus(); loop(); });
         fn_ = &fn;
@@ -1606,7 +1613,7 @@ class Pool {
             if (started_ == want_ && running_ == 0) done_cv_.notify_all();
         }
     }
-    std::mutex mu_;
+    std::mutex mu_, run_mu_;
     std::condition_variable cv_, done_cv_;
     std::vector<std::thread> workers_;
     const std::function<void()> *fn_ = nullptr;
@@ -1706,9 +1713,9 @@ bool stream_enqueue(rb200_download_stream *st) {
     return true;
 }
 
-void stream_free(rb200_download_stream *st) {
+void stream_free(rb200_download_stream *st, bool sync = true) {
     if (!st) return;
-    cudaStreamSynchronize(g.stream);
+    if (sync) cudaStreamSynchronize(g.stream);
     for (int k = 0; k < 2; k++) {
         if (st->ev[k]) cudaEventDestroy(st->ev[k]);
         pin_free(st->hbuf[k], st->hbuf_bytes);
@@ -2020,6 +2027,189 @@ int rb200_download_foreach_many(const rb200_set_t *const *sets, size_t nsets, rb
     g.last_download_bytes = total;
     if (!ok || failed) {
         if (g.err.empty()) g.err = "download_foreach_many: host allocation or copy failed";
+        return -1;
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- asynchronous visitor download ---------------------------------------------------------
+// rb200_download_foreach_async packs the set on the caller's thread (device kernels on the library
+// stream) and hands the packed copy to ONE background downloader thread, which owns a second CUDA
+// stream and a 4-deep pinned staging ring: chunks of all queued sets cross PCIe back to back while
+// the worker pool materialises the previous chunk — and while the caller goes on uploading and
+// launching the next ops.  rb200_download_wait drains the queue.
+namespace {
+struct DlJob {
+    rb200_download_stream *st = nullptr;
+    rb200_visit_fn fn = nullptr;
+    void *ctx = nullptr;
+    cudaEvent_t ready = nullptr;  // recorded on the library stream after the pack
+    size_t next_copy = 0, built = 0;
+};
+struct Downloader {
+    std::mutex mu;
+    std::condition_variable cv, idle_cv;
+    std::deque<DlJob *> q;
+    size_t active = 0;  // jobs queued or in progress
+    bool started = false;
+    int failed = 0;
+    std::string err;
+    uint64_t bytes = 0;
+    void loop();
+};
+Downloader &dl() {
+    static Downloader *d = new Downloader();  // leaked on purpose: the thread lives as long as the process
+    return *d;
+}
+
+void Downloader::loop() {
+    cudaSetDevice(g.device);
+    bind_to_local_cpus();
+    constexpr int RING = 4;
+    cudaStream_t stream = nullptr;
+    cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    uint8_t *ring[RING] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t rev[RING];
+    for (int k = 0; k < RING; k++) cudaEventCreateWithFlags(&rev[k], cudaEventDisableTiming);
+    size_t ring_bytes = 0;
+    struct Flight { DlJob *job; size_t k; int slot; };
+    std::deque<Flight> inflight;
+    std::deque<DlJob *> jobs;  // taken from q, not yet fully enqueued
+    uint64_t nslot = 0;
+    auto fail = [&](const char *why) {
+        std::lock_guard<std::mutex> lk(mu);
+        failed = 1;
+        if (err.empty()) err = why;
+    };
+    auto finish = [&](DlJob *j) {
+        cudaEventDestroy(j->ready);
+        stream_free(j->st, false);
+        delete j;
+        std::lock_guard<std::mutex> lk(mu);
+        if (--active == 0) idle_cv.notify_all();
+    };
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            if (jobs.empty() && inflight.empty()) cv.wait(lk, [&]() { return !q.empty(); });
+            while (!q.empty()) { jobs.push_back(q.front()); q.pop_front(); }
+        }
+        // keep the copy engine up to RING chunks ahead
+        while ((int)inflight.size() < RING && !jobs.empty()) {
+            DlJob *j = jobs.front();
+            const rb200_download_stream *st = j->st;
+            if (st->chunk_end.empty()) { jobs.pop_front(); finish(j); continue; }
+            if (st->hbuf_bytes > ring_bytes) {  // grow the ring (only with nothing in flight)
+                if (!inflight.empty()) break;
+                for (int k = 0; k < RING; k++) { pin_free(ring[k], ring_bytes); ring[k] = (uint8_t *)pin_alloc(st->hbuf_bytes); }
+                ring_bytes = st->hbuf_bytes;
+                if (!ring[0] || !ring[1] || !ring[2] || !ring[3]) { fail("downloader: pinned allocation failed"); ring_bytes = 0; }
+            }
+            const size_t k = j->next_copy;
+            if (k == 0) cudaStreamWaitEvent(stream, j->ready, 0);
+            const size_t p0 = k ? st->chunk_end[k - 1] : 0, p1 = st->chunk_end[k];
+            const uint64_t b0 = st->h_ob[p0], b1 = st->h_ob[p1];
+            const int slot = (int)(nslot++ % RING);
+            if (ring_bytes && b1 > b0 &&
+                cudaMemcpyAsync(ring[slot], st->P->d_slab + b0, b1 - b0, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+                fail("downloader: D2H copy failed");
+            cudaEventRecord(rev[slot], stream);
+            inflight.push_back(Flight{j, k, slot});
+            if (++j->next_copy == st->chunk_end.size()) jobs.pop_front();
+        }
+        if (inflight.empty()) continue;
+        const Flight f = inflight.front();
+        inflight.pop_front();
+        if (cudaEventSynchronize(rev[f.slot]) != cudaSuccess) fail("downloader: copy failed");
+        const rb200_download_stream *st = f.job->st;
+        const size_t p0 = f.k ? st->chunk_end[f.k - 1] : 0, p1 = st->chunk_end[f.k];
+        if (ring_bytes) {
+            const uint8_t *buf = ring[f.slot];
+            const uint64_t bias = st->h_ob[p0];
+            const size_t n = p1 - p0;
+            std::atomic<size_t> next(0);
+            std::atomic<int> bad(0);
+            const rb200_set *P = st->P;
+            const rb200_visit_fn fn = f.job->fn;
+            void *ctx = f.job->ctx;
+            std::function<void()> work = [&]() {
+                for (;;) {
+                    const size_t i0 = next.fetch_add(8);
+                    if (i0 >= n) break;
+                    const size_t i1 = std::min(n, i0 + 8);
+                    for (size_t i = i0; i < i1; i++) {
+                        roaring_bitmap_t *bm = build_bitmap(P, p0 + i, buf, bias);
+                        if (!bm) { bad = 1; continue; }
+                        if (fn(p0 + i, bm, ctx) == 0) bitmap_free_host(bm);
+                    }
+                }
+            };
+            const uint64_t chunk_bytes = st->h_ob[p1] - st->h_ob[p0];
+            const uint64_t chunk_conts = st->h_ob[st->nb + 1 + p1] - st->h_ob[st->nb + 1 + p0];
+            uint64_t want = (chunk_bytes + 256 * chunk_conts + 512 * n) / (128 << 10) + 1;
+            unsigned T = host_workers();
+            if (want < T) T = (unsigned)want;
+            if ((size_t)T * 8 > n) T = (unsigned)((n + 7) / 8);
+            pool().run(work, T);
+            if (bad) fail("downloader: host allocation failed");
+        }
+        if (++f.job->built == st->chunk_end.size()) finish(f.job);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+// Enqueue the visitor download of `s` and return at once (the set may be freed right away: the
+// job owns a packed device copy).  fn runs on worker threads with the index of the bitmap in `s`.
+int rb200_download_foreach_async(const rb200_set_t *s, rb200_visit_fn fn, void *ctx) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    DlJob *j = new DlJob();
+    j->st = download_begin_impl(s, 4096, true);
+    if (!j->st) { delete j; return -1; }
+    j->fn = fn;
+    j->ctx = ctx;
+    if (cudaEventCreateWithFlags(&j->ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventRecord(j->ready, g.stream) != cudaSuccess) {
+        g.err = "download_foreach_async: event failed";
+        stream_free(j->st);
+        delete j;
+        return -1;
+    }
+    Downloader &d = dl();
+    {
+        std::lock_guard<std::mutex> dk(d.mu);
+        d.bytes += j->st->total_bytes;
+        d.active++;
+        d.q.push_back(j);
+        if (!d.started) {
+            d.started = true;
+            std::thread([&d]() { d.loop(); }).detach();
+        }
+    }
+    d.cv.notify_one();
+    return 0;
+}
+
+// Wait for every queued download; 0 on success.  rb200_last_download_bytes() then reports the
+// bytes that crossed PCIe since the previous wait.
+int rb200_download_wait(void) {
+    Downloader &d = dl();
+    std::unique_lock<std::mutex> dk(d.mu);
+    d.idle_cv.wait(dk, [&]() { return d.active == 0; });
+    const int failed = d.failed;
+    const std::string why = d.err;
+    g.last_download_bytes = d.bytes;
+    d.bytes = 0;
+    d.failed = 0;
+    d.err.clear();
+    dk.unlock();
+    if (failed) {
+        std::lock_guard<std::recursive_mutex> lk(g.mu);
+        g.err = why.empty() ? "asynchronous download failed" : why;
         return -1;
     }
     return 0;

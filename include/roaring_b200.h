@@ -215,6 +215,11 @@ int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx);
 /* The same over several result sets as ONE pipelined stream (all sets packed first, their chunks
  * cross PCIe back to back; the index passed to fn keeps running across the sets). */
 int rb200_download_foreach_many(const rb200_set_t *const *sets, size_t nsets, rb200_visit_fn fn, void *ctx);
+/* Asynchronous form: pack `s` now, stream and materialise it on a background thread (own CUDA
+ * stream, 4-deep pinned ring) while the caller keeps uploading / launching ops; `s` may be freed
+ * as soon as the call returns.  rb200_download_wait() drains every queued download (0 = ok). */
+int rb200_download_foreach_async(const rb200_set_t *s, rb200_visit_fn fn, void *ctx);
+int rb200_download_wait(void);
 int rb200_visit_sum_cardinality(size_t index, roaring_bitmap_t *bitmap, void *ctx);
 
 /* Device-side roaring_bitmap_portable_serialize of every bitmap of a set + one D2H copy:
