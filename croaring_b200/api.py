@@ -84,6 +84,9 @@ def lib():
     sig("rb200_batch_op_ex", _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t)
     sig("rb200_batch_and_cardinality", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
     sig("rb200_or_many", _P, _P, _P, C.c_size_t)
+    sig("rb200_batch_relations", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
+    for rel in ("equals", "is_subset", "is_strict_subset"):
+        sig(f"roaring_bitmap_{rel}", C.c_bool, _P, _P)
     sig("rb200_or_many_keyrange", _P, _P, _P, C.c_size_t, C.c_uint32, C.c_uint32, _P)
     sig("rb200_set_cardinalities", C.c_int, _P, _P)
     sig("rb200_set_download", _P, _P, C.c_size_t)
@@ -95,6 +98,9 @@ def lib():
     sig("rb200_set_serialize", C.c_int, _P, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)),
         C.POINTER(C.POINTER(C.c_uint64)))
     sig("rb200_serialized_free", None, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+    sig("rb200_set_serialize_frozen", C.c_int, _P, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)),
+        C.POINTER(C.POINTER(C.c_uint64)))
+    sig("rb200_set_upload_frozen", _P, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t)
     sig("rb200_download_begin", _P, _P, C.c_size_t)
     sig("rb200_download_chunk_capacity", C.c_size_t, _P)
     sig("rb200_download_next", C.c_size_t, _P, C.POINTER(_P))
@@ -240,6 +246,9 @@ class Bitmap:
     def andnot_cardinality(self, o): return int(lib().roaring_bitmap_andnot_cardinality(self.ptr, o.ptr))
     def jaccard_index(self, o): return float(lib().roaring_bitmap_jaccard_index(self.ptr, o.ptr))
     def intersect(self, o): return bool(lib().roaring_bitmap_intersect(self.ptr, o.ptr))
+    def equals(self, o): return bool(lib().roaring_bitmap_equals(self.ptr, o.ptr))
+    def is_subset(self, o): return bool(lib().roaring_bitmap_is_subset(self.ptr, o.ptr))
+    def is_strict_subset(self, o): return bool(lib().roaring_bitmap_is_strict_subset(self.ptr, o.ptr))
 
 
 def or_many(bitmaps):
@@ -339,6 +348,14 @@ class DeviceSet:
         lens = (C.c_size_t * n)(*[len(b) for b in blobs])
         return cls(lib().rb200_set_upload_serialized(arr, lens, n))
 
+    @classmethod
+    def from_frozen(cls, blobs):
+        """Resident set from roaring_bitmap_frozen_serialize blobs (parsed on the device)."""
+        n = len(blobs)
+        arr = (C.c_char_p * n)(*blobs)
+        lens = (C.c_size_t * n)(*[len(b) for b in blobs])
+        return cls(lib().rb200_set_upload_frozen(arr, lens, n))
+
     def free(self):
         if self.ptr:
             lib().rb200_set_free(self.ptr)
@@ -398,6 +415,15 @@ class DeviceSet:
         rc = lib().rb200_batch_and_cardinality(self.ptr, other.ptr, ia.ctypes.data, ib.ctypes.data,
                                                ia.size, out.ctypes.data)
         if rc != 0:
+            raise RB200Error(last_error())
+        return out
+
+    def relations(self, other, ia, ib):
+        """uint8 per pair: bit 0 equals, bit 1 is_subset, bit 2 is_strict_subset."""
+        ia, ib = _u32(ia), _u32(ib)
+        out = np.zeros(ia.size, dtype=np.uint8)
+        if lib().rb200_batch_relations(self.ptr, other.ptr, ia.ctypes.data, ib.ctypes.data, ia.size,
+                                       out.ctypes.data) != 0:
             raise RB200Error(last_error())
         return out
 
@@ -478,13 +504,14 @@ class DeviceSet:
         lib().rb200_values_free(vals, off)
         return out
 
-    def serialize_all(self, copy=True):
-        """Portable bytes of every bitmap, serialized ON THE DEVICE and brought back in one D2H.
-        copy=True -> list of bytes; copy=False -> (base pointer, offsets, lengths, release())"""
+    def serialize_all(self, copy=True, frozen=False):
+        """Portable (or frozen) bytes of every bitmap, serialized ON THE DEVICE and brought back in
+        one D2H.  copy=True -> list of bytes; copy=False -> (base pointer, offsets, lengths, release())"""
         buf = C.c_void_p()
         off = C.POINTER(C.c_uint64)()
         ln = C.POINTER(C.c_uint64)()
-        if lib().rb200_set_serialize(self.ptr, C.byref(buf), C.byref(off), C.byref(ln)) != 0:
+        fn = lib().rb200_set_serialize_frozen if frozen else lib().rb200_set_serialize
+        if fn(self.ptr, C.byref(buf), C.byref(off), C.byref(ln)) != 0:
             raise RB200Error(last_error())
         n = len(self)
 

@@ -143,6 +143,14 @@ void launch_serialize_write(const SetView &S, uint32_t n, const uint64_t *off, c
 void launch_deserialize(const uint8_t *raw, const uint64_t *roff, const uint64_t *rlen,
                         const uint64_t *slab_base, uint32_t nb, uint64_t nc, SetOut out,
                         uint64_t *src_pos, OpStats *st, cudaStream_t s);
+void launch_deserialize_frozen(const uint8_t *raw, const uint64_t *roff, const uint64_t *rlen,
+                               const uint64_t *slab_base, uint32_t nb, uint64_t nc, SetOut out,
+                               uint64_t *src_pos, OpStats *st, cudaStream_t s);
+// frozen format emit: sizes32 = blob bytes rounded up to 32 (blob starts stay 32-byte aligned)
+void launch_frozen_measure(const SetView &S, uint32_t n, uint64_t *sizes32, uint32_t *exact, uint32_t *cnt,
+                           cudaStream_t s);
+void launch_frozen_write(const SetView &S, uint32_t n, uint64_t nc, const uint64_t *off, uint8_t *dst,
+                         uint64_t *c_dst, cudaStream_t s);
 void launch_run_optimize(const SetView &S, uint32_t nb, uint64_t nc, int mode, SetOut out, OpStats *st,
                          cudaStream_t s);
 void launch_values_measure(const SetView &S, uint32_t nb, uint64_t *bm_vals, uint32_t *dummy,

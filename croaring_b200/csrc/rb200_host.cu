@@ -921,8 +921,18 @@ rb200_set_t *rb200_set_upload(const roaring_bitmap_t *const *bitmaps, size_t n) 
 // Portable-serialized inputs are parsed ON THE DEVICE (src/roaring_array.c:633-813 restated as
 // k_deser_dir / k_deser_copy): the host only reads each blob's cookie (to size the directory) and
 // streams the raw bytes through pinned staging chunks; no per-container host work.
+static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens, size_t n, bool frozen);
 rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *lens, size_t n) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return upload_blobs_impl(bufs, lens, n, false);
+}
+// The same for the FROZEN format (roaring_bitmap_frozen_serialize output, src/roaring.c:3180-3456);
+// the blobs need no particular alignment here (frozen_view's 32-byte rule is about in-place use).
+rb200_set_t *rb200_set_upload_frozen(const char *const *bufs, const size_t *lens, size_t n) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return upload_blobs_impl(bufs, lens, n, true);
+}
+static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens, size_t n, bool frozen) {
     if (!ctx_init()) return nullptr;
     if (n > 0xffffffffull) { g.err = "too many bitmaps"; return nullptr; }
     // pass 1 (host): container count of every blob from its cookie; staging offsets
@@ -931,14 +941,18 @@ rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *
     for (size_t i = 0; i < n; i++) {
         uint32_t cookie = 0, size = 0;
         bool ok = lens[i] >= 4;
-        if (ok) {
+        if (ok && frozen) {
+            memcpy(&cookie, bufs[i] + lens[i] - 4, 4);   // the header is the LAST word
+            size = cookie >> 15;
+            ok = (cookie & 0x7FFF) == 13766 /* FROZEN_COOKIE */ && 5ull * size + 4 <= lens[i];
+        } else if (ok) {
             memcpy(&cookie, bufs[i], 4);
             if ((cookie & 0xFFFF) == SERIAL_COOKIE) size = (cookie >> 16) + 1;
             else if (cookie == SERIAL_COOKIE_NO_RUN && lens[i] >= 8) memcpy(&size, bufs[i] + 4, 4);
             else ok = false;
         }
         if (!ok || size > 65536 || 4ull * size > lens[i]) {
-            g.err = "malformed portable bitmap at index " + std::to_string(i);
+            g.err = std::string(frozen ? "malformed frozen bitmap at index " : "malformed portable bitmap at index ") + std::to_string(i);
             return nullptr;
         }
         cnt[i] = size;
@@ -975,7 +989,7 @@ rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *
             const uint64_t hdr = ((cnt[i] && (((uint8_t)bufs[i][0] | ((uint8_t)bufs[i][1] << 8)) == SERIAL_COOKIE))
                                      ? 4 + (cnt[i] + 7) / 8 + (cnt[i] < (uint32_t)NO_OFFSET_THRESHOLD ? 4ull : 8ull) * cnt[i]
                                      : 8 + 8ull * cnt[i]);
-            s->portable_bytes += lens[i] > hdr ? lens[i] - hdr : 0;
+            s->portable_bytes += frozen ? lens[i] - 4 - 5ull * cnt[i] + 0 : (lens[i] > hdr ? lens[i] - hdr : 0);
             ro += (lens[i] + 15) & ~(uint64_t)15;
             so += ((lens[i] + 15) & ~(uint64_t)15) + 16ull * cnt[i];
             cb += cnt[i];
@@ -1019,8 +1033,12 @@ rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *
     }
     if (ok) {
         ok = stats_reset();
-        launch_deserialize(d_raw, d_tab, d_tab + n, d_tab + 2 * n, (uint32_t)n, nc, s->out(), d_src, g.d_stats,
-                           g.stream);
+        if (frozen)
+            launch_deserialize_frozen(d_raw, d_tab, d_tab + n, d_tab + 2 * n, (uint32_t)n, nc, s->out(), d_src,
+                                      g.d_stats, g.stream);
+        else
+            launch_deserialize(d_raw, d_tab, d_tab + n, d_tab + 2 * n, (uint32_t)n, nc, s->out(), d_src, g.d_stats,
+                               g.stream);
         ok = ok && stats_fetch();
         cudaError_t e = cudaStreamSynchronize(g.stream);
         if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
@@ -1028,7 +1046,8 @@ rb200_set_t *rb200_set_upload_serialized(const char *const *bufs, const size_t *
             ok = false;
         }
         if (ok && g.h_stats->error) {
-            g.err = "malformed portable bitmap at index " + std::to_string((uint64_t)n - g.h_stats->nk);
+            g.err = std::string(frozen ? "malformed frozen bitmap at index " : "malformed portable bitmap at index ") +
+                    std::to_string((uint64_t)n - g.h_stats->nk);
             ok = false;
         }
     } else {
@@ -2472,8 +2491,18 @@ void rb200_values_free(uint32_t *vals, uint64_t *off) { rb200_serialized_free((c
 // Device-side portable serialization of every bitmap of a set + one D2H copy.
 // *buf is pinned host memory owned by the library (release with rb200_serialized_free);
 // blob i = *buf + (*off)[i], (*len)[i] bytes, byte-identical to roaring_bitmap_portable_serialize.
+static int serialize_impl(const rb200_set *s, char **buf, uint64_t **off_out, uint64_t **len_out, bool frozen);
 int rb200_set_serialize(const rb200_set_t *s, char **buf, uint64_t **off_out, uint64_t **len_out) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return serialize_impl(s, buf, off_out, len_out, false);
+}
+// Device-side roaring_bitmap_frozen_serialize (src/roaring.c:3246-3330) of every bitmap of the set:
+// blob starts are 32-byte aligned inside *buf, so roaring_bitmap_frozen_view works on them in place.
+int rb200_set_serialize_frozen(const rb200_set_t *s, char **buf, uint64_t **off_out, uint64_t **len_out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return serialize_impl(s, buf, off_out, len_out, true);
+}
+static int serialize_impl(const rb200_set *s, char **buf, uint64_t **off_out, uint64_t **len_out, bool frozen) {
     if (!ctx_init()) return -1;
     if (reject_lazy(s, "serialize")) return -1;
     const size_t nb = s->n_bitmaps;
@@ -2492,7 +2521,8 @@ int rb200_set_serialize(const rb200_set_t *s, char **buf, uint64_t **off_out, ui
     bool ok = d_sz && d_off && d_dummy && d_exact && d_hasrun && h_meta;
     if (ok) {
         const SetView v = s->view();
-        launch_serialize_measure(v, (uint32_t)nb, d_sz, d_exact, d_hasrun, g.stream);
+        if (frozen) launch_frozen_measure(v, (uint32_t)nb, d_sz, d_exact, d_hasrun, g.stream);
+        else launch_serialize_measure(v, (uint32_t)nb, d_sz, d_exact, d_hasrun, g.stream);
         launch_pack_scan(d_sz, d_hasrun, (uint32_t)nb, d_off, d_dummy, g.stream);
         ok = cudaMemcpyAsync(h_meta, d_off, 8 * (nb + 1), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
              cudaMemcpyAsync(h_meta + 8 * (nb + 1), d_exact, 4 * nb, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
@@ -2509,7 +2539,14 @@ int rb200_set_serialize(const rb200_set_t *s, char **buf, uint64_t **off_out, ui
         ok = d_blob && h_blob;
     }
     if (ok) {
-        launch_serialize_write(s->view(), (uint32_t)nb, d_off, d_hasrun, d_blob, g.stream);
+        if (frozen) {
+            uint64_t *d_cdst = (uint64_t *)dev_alloc(8 * (s->n_containers ? s->n_containers : 1));
+            ok = d_cdst != nullptr;
+            if (ok) launch_frozen_write(s->view(), (uint32_t)nb, s->n_containers, d_off, d_blob, d_cdst, g.stream);
+            dev_free(d_cdst, 8 * (s->n_containers ? s->n_containers : 1));  // stream-ordered reuse only
+        } else {
+            launch_serialize_write(s->view(), (uint32_t)nb, d_off, d_hasrun, d_blob, g.stream);
+        }
         ok = cudaMemcpyAsync(h_blob, d_blob, total, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
              cudaStreamSynchronize(g.stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
     }
@@ -2711,6 +2748,48 @@ double roaring_bitmap_jaccard_index(const roaring_bitmap_t *r1, const roaring_bi
 bool roaring_bitmap_intersect(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
     const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
     return inter != 0 && inter != UINT64_MAX;
+}
+
+// ---- equality / subset relations (src/roaring.c:2128-2200, 3172; cells mixed_equal.c,
+// mixed_subset.c): A == B  <=>  |A| = |B| = |A and B|;  A subset of B  <=>  |A and B| = |A|.
+// One k_card_items sweep over the pair list + the per-bitmap cardinalities already on the device.
+// out[k]: bit 0 = equals, bit 1 = is_subset(a, b), bit 2 = is_strict_subset(a, b).
+int rb200_batch_relations(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
+                          const uint32_t *ib, size_t np, uint8_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (np == 0) return 0;
+    std::vector<uint64_t> inter(np), ca(A->n_bitmaps), cb(B->n_bitmaps);
+    if (rb200_batch_and_cardinality(A, B, ia, ib, np, inter.data()) != 0) return -1;
+    if (rb200_set_cardinalities(A, ca.data()) != 0 || rb200_set_cardinalities(B, cb.data()) != 0) return -1;
+    for (size_t k = 0; k < np; k++) {
+        const uint64_t a = ca[ia[k]], b = cb[ib[k]], x = inter[k];
+        const bool sub = x == a;
+        out[k] = (uint8_t)((sub && a == b ? 1 : 0) | (sub ? 2 : 0) | (sub && b > a ? 4 : 0));
+    }
+    return 0;
+}
+static int dropin_relation(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const roaring_bitmap_t *both[2] = {r1, r2};
+    rb200_set *S = rb200_set_upload(both, 2);
+    if (!S) return -1;
+    const uint32_t ia = 0, ib = 1;
+    uint8_t out = 0;
+    const int rc = rb200_batch_relations(S, S, &ia, &ib, 1, &out);
+    set_delete(S);
+    return rc != 0 ? -1 : out;
+}
+bool roaring_bitmap_equals(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    const int r = dropin_relation(r1, r2);
+    return r > 0 && (r & 1);
+}
+bool roaring_bitmap_is_subset(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    const int r = dropin_relation(r1, r2);
+    return r > 0 && (r & 2);
+}
+bool roaring_bitmap_is_strict_subset(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
+    const int r = dropin_relation(r1, r2);
+    return r > 0 && (r & 4);
 }
 
 // ---- public lazy API (include/roaring/roaring.h:932-977) ------------------------------------

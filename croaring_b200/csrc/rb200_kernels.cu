@@ -1015,6 +1015,205 @@ __global__ void k_deser_bitmap_cards(SetOut out, uint32_t nb, const OpStats *st)
     }
 }
 
+// ------------------------------------------------------------------------------ frozen format
+// roaring_bitmap_frozen_serialize / roaring_bitmap_frozen_view (src/roaring.c:3180-3456): zones
+// [bitset words | runs | array values | keys u16 | counts u16 | typecodes u8 | header u32], the
+// header LAST: (n_containers << 15) | FROZEN_COOKIE (13766).  counts = cardinality-1 (bitset,
+// array) or n_runs (run).  Blob starts are 32-byte aligned so frozen_view accepts them in place.
+constexpr uint32_t FROZEN_COOKIE = 13766u;
+
+__global__ void __launch_bounds__(128)
+k_frozen_measure(SetView S, uint32_t n, uint64_t *__restrict__ sizes32, uint32_t *__restrict__ exact,
+                 uint32_t *__restrict__ cnt_out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < n; b += nwarps) {
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        unsigned long long bytes = 0;
+        for (uint32_t i = lane; i < nc; i += 32) bytes += stored_bytes(S.c_type[c0 + i], S.c_len[c0 + i]);
+        for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(FULLMASK, bytes, d);
+        if (lane == 0) {
+            const unsigned long long tot = bytes + 5ull * nc + 4ull;
+            exact[b] = (uint32_t)tot;
+            sizes32[b] = (tot + 31ull) & ~31ull;
+            cnt_out[b] = nc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_frozen_dir(SetView S, uint32_t n, const uint64_t *__restrict__ off, uint8_t *__restrict__ dst,
+             uint64_t *__restrict__ c_dst) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < n; b += nwarps) {
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        unsigned long long zb = 0, zr = 0, za = 0;
+        for (uint32_t i = lane; i < nc; i += 32) {
+            const int t = S.c_type[c0 + i];
+            const uint32_t sz = stored_bytes(t, S.c_len[c0 + i]);
+            if (t == T_BITSET) zb += sz; else if (t == T_RUN) zr += sz; else za += sz;
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            zb += __shfl_xor_sync(FULLMASK, zb, d);
+            zr += __shfl_xor_sync(FULLMASK, zr, d);
+            za += __shfl_xor_sync(FULLMASK, za, d);
+        }
+        uint8_t *base = dst + off[b];
+        const unsigned long long k0 = zb + zr + za, n0 = k0 + 2ull * nc, t0 = n0 + 2ull * nc, h0 = t0 + nc;
+        unsigned long long pb = 0, pr = zb, pa = zb + zr;  // running write cursors of the three zones
+        for (uint32_t chunk = 0; chunk < nc; chunk += 32) {
+            const uint32_t i = chunk + lane;
+            const bool valid = i < nc;
+            int t = 0;
+            uint32_t sz = 0, card = 0, len = 0;
+            if (valid) {
+                t = S.c_type[c0 + i];
+                len = S.c_len[c0 + i];
+                card = S.c_card[c0 + i] & CARD_MASK;
+                sz = stored_bytes(t, len);
+            }
+            const uint32_t sb = t == T_BITSET ? sz : 0u, sr = t == T_RUN ? sz : 0u, sa = t == T_ARRAY ? sz : 0u;
+            const uint32_t ib = warp_incl_scan(sb, lane), ir = warp_incl_scan(sr, lane), ia = warp_incl_scan(sa, lane);
+            if (valid) {
+                const unsigned long long d = t == T_BITSET ? pb + ib - sb : (t == T_RUN ? pr + ir - sr : pa + ia - sa);
+                c_dst[c0 + i] = off[b] + d;
+                store_u16(base + k0 + 2ull * i, S.c_key[c0 + i]);
+                store_u16(base + n0 + 2ull * i, t == T_RUN ? len : card - 1u);
+                base[t0 + i] = (uint8_t)t;
+            }
+            pb += __shfl_sync(FULLMASK, ib, 31);
+            pr += __shfl_sync(FULLMASK, ir, 31);
+            pa += __shfl_sync(FULLMASK, ia, 31);
+        }
+        if (lane == 0) store_u32(base + h0, (nc << 15) | FROZEN_COOKIE);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_frozen_copy(SetView S, uint64_t nc, const uint64_t *__restrict__ c_dst, uint8_t *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t c = warp; c < nc; c += nwarps)
+        warp_copy_unaligned(dst + c_dst[c], S.payload + S.c_off[c], stored_bytes(S.c_type[c], S.c_len[c]), lane);
+}
+
+void launch_frozen_measure(const SetView &S, uint32_t n, uint64_t *sizes32, uint32_t *exact, uint32_t *cnt,
+                           cudaStream_t s) {
+    if (!n) return;
+    k_frozen_measure<<<blocks_for_warps(n, 4, sm_count() * 16), 128, 0, s>>>(S, n, sizes32, exact, cnt);
+    g_launches++;
+}
+void launch_frozen_write(const SetView &S, uint32_t n, uint64_t nc, const uint64_t *off, uint8_t *dst,
+                         uint64_t *c_dst, cudaStream_t s) {
+    if (!n) return;
+    k_frozen_dir<<<blocks_for_warps(n, 4, sm_count() * 16), 128, 0, s>>>(S, n, off, dst, c_dst);
+    g_launches++;
+    if (nc) {
+        k_frozen_copy<<<blocks_for_warps(nc, 4, sm_count() * 16), 128, 0, s>>>(S, nc, c_dst, dst);
+        g_launches++;
+    }
+}
+
+// frozen blobs -> directory (the zones make every payload offset a prefix sum: no sequential walk)
+__global__ void __launch_bounds__(128)
+k_frozen_parse_dir(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ roff,
+                   const uint64_t *__restrict__ rlen, const uint64_t *__restrict__ slab_base, uint32_t nb,
+                   SetOut out, uint64_t *__restrict__ src_pos, OpStats *st) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < nb; b += nwarps) {
+        const uint8_t *buf = raw + roff[b];
+        const uint64_t len = rlen[b];
+        const uint32_t c0 = out.bm_beg[b], want = out.bm_cnt[b];
+        bool bad = len < 4;
+        uint32_t nc = 0;
+        if (!bad) {
+            const uint32_t header = ld_u32(buf + len - 4);
+            nc = header >> 15;
+            bad = (header & 0x7FFFu) != FROZEN_COOKIE || nc != want || len < 4ull + 5ull * nc;
+        }
+        const uint8_t *tz = buf + len - 4 - nc, *nz = tz - 2ull * nc, *kz = nz - 2ull * nc;
+        unsigned long long zb = 0, zr = 0, za = 0;
+        if (!bad) {
+            for (uint32_t i = lane; i < nc; i += 32) {
+                const int t = tz[i];
+                const uint32_t cnt = ld_u16(nz + 2ull * i);
+                if (t == T_BITSET) zb += BITSET_BYTES;
+                else if (t == T_RUN) zr += 4ull * cnt;
+                else if (t == T_ARRAY) za += 2ull * (cnt + 1);
+                else bad = true;
+            }
+            bad = __any_sync(FULLMASK, bad);
+            for (int d = 16; d > 0; d >>= 1) {
+                zb += __shfl_xor_sync(FULLMASK, zb, d);
+                zr += __shfl_xor_sync(FULLMASK, zr, d);
+                za += __shfl_xor_sync(FULLMASK, za, d);
+            }
+            if (zb + zr + za + 5ull * nc + 4ull != len) bad = true;   // roaring.c:3425-3429 exact length
+        }
+        unsigned long long pb = 0, pr = zb, pa = zb + zr, off = slab_base[b];
+        int prev_key = -1;
+        for (uint32_t chunk = 0; chunk < nc && !bad; chunk += 32) {
+            const uint32_t i = chunk + lane;
+            const bool valid = i < nc;
+            int t = 0;
+            uint32_t key = 0, cnt = 0, sz = 0;
+            if (valid) {
+                t = tz[i];
+                key = ld_u16(kz + 2ull * i);
+                cnt = ld_u16(nz + 2ull * i);
+                sz = t == T_BITSET ? (uint32_t)BITSET_BYTES : (t == T_RUN ? 4u * cnt : 2u * (cnt + 1u));
+            }
+            int left = __shfl_up_sync(FULLMASK, (int)key, 1);
+            if (lane == 0) left = prev_key;
+            if (__any_sync(FULLMASK, valid && (int)key <= left)) { bad = true; break; }
+            prev_key = __shfl_sync(FULLMASK, (int)key, 31);
+            const uint32_t sb = t == T_BITSET ? sz : 0u, sr = t == T_RUN ? sz : 0u, sa = t == T_ARRAY ? sz : 0u;
+            const uint32_t ib = warp_incl_scan(sb, lane), ir = warp_incl_scan(sr, lane), ia = warp_incl_scan(sa, lane);
+            const uint32_t r16 = valid ? round16(sz) : 0u;
+            const uint32_t incl = warp_incl_scan(r16, lane);
+            if (valid) {
+                const uint64_t c = (uint64_t)c0 + i;
+                const unsigned long long d = t == T_BITSET ? pb + ib - sb : (t == T_RUN ? pr + ir - sr : pa + ia - sa);
+                out.c_key[c] = (uint16_t)key;
+                out.c_type[c] = (uint8_t)t;
+                out.c_card[c] = cnt + 1u;                    // runs: recounted by k_deser_copy
+                out.c_len[c] = t == T_BITSET ? 1024u : (t == T_ARRAY ? cnt + 1u : cnt);
+                out.c_off[c] = off + incl - r16;
+                out.c_src[c] = SRC_NONE;
+                src_pos[c] = roff[b] + d;
+            }
+            pb += __shfl_sync(FULLMASK, ib, 31);
+            pr += __shfl_sync(FULLMASK, ir, 31);
+            pa += __shfl_sync(FULLMASK, ia, 31);
+            off += __shfl_sync(FULLMASK, incl, 31);
+        }
+        if (bad && lane == 0) {
+            atomicExch(&st->error, 3u);
+            atomicMax(&st->nk, nb - b);
+        }
+    }
+}
+
+void launch_deserialize_frozen(const uint8_t *raw, const uint64_t *roff, const uint64_t *rlen,
+                               const uint64_t *slab_base, uint32_t nb, uint64_t nc, SetOut out,
+                               uint64_t *src_pos, OpStats *st, cudaStream_t s) {
+    if (!nb) return;
+    k_frozen_parse_dir<<<blocks_for_warps(nb, 4, sm_count() * 16), 128, 0, s>>>(raw, roff, rlen, slab_base, nb, out, src_pos, st);
+    g_launches++;
+    if (nc) {
+        k_deser_copy<<<blocks_for_warps(nc, 4, sm_count() * 16), 128, 0, s>>>(raw, src_pos, nc, out, st);
+        g_launches++;
+    }
+    k_deser_bitmap_cards<<<blocks_for_warps(nb, 4, sm_count() * 16), 128, 0, s>>>(out, nb, st);
+    g_launches++;
+}
+
 void launch_deserialize(const uint8_t *raw, const uint64_t *roff, const uint64_t *rlen,
                         const uint64_t *slab_base, uint32_t nb, uint64_t nc, SetOut out,
                         uint64_t *src_pos, OpStats *st, cudaStream_t s) {

@@ -95,6 +95,11 @@ uint64_t roaring_bitmap_xor_cardinality(const roaring_bitmap_t *r1, const roarin
 double roaring_bitmap_jaccard_index(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 /* include/roaring/roaring.h:237  (src/roaring.c:2998) */
 bool roaring_bitmap_intersect(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+/* include/roaring/roaring.h:899, 905, 912 (src/roaring.c:2128, 2151, 3172): decided from
+ * |r1 and r2|, |r1|, |r2| (same answers as the reference's early-exit container cells). */
+bool roaring_bitmap_equals(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+bool roaring_bitmap_is_subset(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
+bool roaring_bitmap_is_strict_subset(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 
 /* ---------------------------------------------------------------------------------------
  * Stand-alone helpers (our own implementations of the steps either side of the path, so the
@@ -167,6 +172,11 @@ rb200_set_t *rb200_batch_op_ex(int op, int flags, const rb200_set_t *A, const rb
 int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
                                 const uint32_t *ib, size_t npairs, uint64_t *out);
 
+/* out[k]: bit 0 = roaring_bitmap_equals, bit 1 = is_subset, bit 2 = is_strict_subset of
+ * (A[ia[k]], B[ib[k]]); one cardinality sweep on the device.  0 on success. */
+int rb200_batch_relations(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
+                          const uint32_t *ib, size_t npairs, uint8_t *out);
+
 /* roaring_bitmap_or_many over S[idx[0..n)] (idx == NULL: all bitmaps in order).
  * Returns a device-resident set holding ONE bitmap. */
 rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n);
@@ -227,6 +237,11 @@ int rb200_visit_sum_cardinality(size_t index, roaring_bitmap_t *bitmap, void *ct
  * host memory owned by the library; release all three with rb200_serialized_free. */
 int rb200_set_serialize(const rb200_set_t *s, char **buf, uint64_t **off, uint64_t **len);
 void rb200_serialized_free(char *buf, uint64_t *off, uint64_t *len);
+/* Frozen format (src/roaring.c:3180-3456) on the device, both directions: emit every bitmap of a
+ * set as roaring_bitmap_frozen_serialize would (blob starts 32-byte aligned: frozen_view works on
+ * them in place; release with rb200_serialized_free), and build a resident set from frozen blobs. */
+int rb200_set_serialize_frozen(const rb200_set_t *s, char **buf, uint64_t **off, uint64_t **len);
+rb200_set_t *rb200_set_upload_frozen(const char *const *bufs, const size_t *lens, size_t n);
 
 /* Batch producers / consumers next to the path (device kernels over a whole set):
  * mode 1 = roaring_bitmap_run_optimize [src/roaring.c:1530], mode 0 = remove_run_compression, and

@@ -49,6 +49,8 @@ class RefLib:
         sig("roaring_bitmap_portable_deserialize_safe", P, C.c_char_p, C.c_size_t)
         sig("roaring_bitmap_internal_validate", C.c_bool, P, C.POINTER(C.c_char_p))
         sig("roaring_bitmap_equals", C.c_bool, P, P)
+        sig("roaring_bitmap_is_subset", C.c_bool, P, P)                     # roaring.h:905
+        sig("roaring_bitmap_is_strict_subset", C.c_bool, P, P)              # roaring.h:912
         sig("roaring_bitmap_to_uint32_array", None, P, C.c_void_p)
         sig("roaring_bitmap_set_copy_on_write", None, P, C.c_bool)
         for op in ("and", "or", "xor", "andnot"):                          # roaring.h:225,288,320,342
@@ -62,6 +64,9 @@ class RefLib:
         sig("roaring_bitmap_jaccard_index", C.c_double, P, P)               # roaring.h:252
         sig("roaring_bitmap_intersect", C.c_bool, P, P)                     # roaring.h:237
         sig("roaring_bitmap_statistics", None, P, C.c_void_p)
+        sig("roaring_bitmap_frozen_size_in_bytes", C.c_size_t, P)           # roaring.h:831
+        sig("roaring_bitmap_frozen_serialize", None, P, C.c_void_p)         # roaring.h:846
+        sig("roaring_bitmap_frozen_view", P, C.c_void_p, C.c_size_t)        # roaring.h:864
         sig("roaring_bitmap_lazy_or", P, P, P, C.c_bool)                    # roaring.h:932
         sig("roaring_bitmap_lazy_or_inplace", None, P, P, C.c_bool)         # roaring.h:943
         sig("roaring_bitmap_lazy_xor", P, P, P)                             # roaring.h:963
@@ -136,6 +141,15 @@ class RefLib:
         self.free(ra)
         self.free(rb)
         return out
+
+    def frozen_bytes(self, blob: bytes) -> bytes:
+        """roaring_bitmap_frozen_serialize of the bitmap held in a portable blob."""
+        r = self.deserialize(blob)
+        n = self.L.roaring_bitmap_frozen_size_in_bytes(r)
+        buf = C.create_string_buffer(n)
+        self.L.roaring_bitmap_frozen_serialize(r, buf)
+        self.free(r)
+        return buf.raw[:n]
 
     def lazy_fold_bytes(self, op: str, conv: bool, blobs) -> bytes:
         """repair_after_lazy(lazy_<op>(x0, x1) then lazy_<op>_inplace(acc, xi) for i >= 2)."""

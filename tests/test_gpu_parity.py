@@ -313,3 +313,43 @@ def test_streaming_download_matches(rb, R):
     # empty set streams nothing
     e = S.batch("and", S, np.zeros(0, np.uint32), np.zeros(0, np.uint32))
     assert list(e.download_stream()) == []
+
+
+def test_relations_equals_subset(rb, R):
+    """roaring_bitmap_equals / is_subset / is_strict_subset (roaring.h:899-912), batched and as
+    drop-in symbols, vs the reference — on pairs built to be equal, nested, and unrelated."""
+    blobs = synth_blobs(R, 77, 40, key_space=5, max_keys=6)
+    rs = [R.deserialize(b) for b in blobs]
+    # derived bitmaps: unions (supersets), intersections (subsets), copies (equal, other encoding)
+    extra = []
+    for k in range(0, 38, 2):
+        extra.append(R.op_bytes("or", blobs[k], blobs[k + 1]))
+        extra.append(R.op_bytes("and", blobs[k], blobs[k + 1]))
+    twins = []
+    for b in blobs[:20]:
+        r = R.deserialize(b)
+        R.L.roaring_bitmap_remove_run_compression(r)
+        twins.append(R.serialize(r))
+        R.free(r)
+    allb = blobs + extra + twins
+    ra = [R.deserialize(b) for b in allb]
+    S = rb.DeviceSet.from_serialized(allb)
+    rng = np.random.default_rng(5)
+    ia = np.concatenate([rng.integers(0, len(allb), 600), np.arange(20), np.arange(0, 38, 2), np.arange(40, 78)]).astype(np.uint32)
+    ib = np.concatenate([rng.integers(0, len(allb), 600), np.arange(78, 98), np.arange(40, 78, 2), np.repeat(np.arange(0, 38, 2), 2)]).astype(np.uint32)
+    got = S.relations(S, ia, ib)
+    seen = set()
+    for k in range(len(ia)):
+        a, b = ra[ia[k]], ra[ib[k]]
+        exp = (1 if R.L.roaring_bitmap_equals(a, b) else 0) | (2 if R.L.roaring_bitmap_is_subset(a, b) else 0) | \
+              (4 if R.L.roaring_bitmap_is_strict_subset(a, b) else 0)
+        assert got[k] == exp, (k, int(ia[k]), int(ib[k]))
+        seen.add(exp)
+    assert {0, 3, 6} <= seen
+    ha, hb = rb.Bitmap.deserialize(allb[0]), rb.Bitmap.deserialize(allb[78])
+    assert ha.equals(hb) and ha.is_subset(hb) and not ha.is_strict_subset(hb)
+    hu = rb.Bitmap.deserialize(extra[0])
+    assert ha.is_subset(hu) == bool(R.L.roaring_bitmap_is_subset(ra[0], ra[40]))
+    assert ha.is_strict_subset(hu) == bool(R.L.roaring_bitmap_is_strict_subset(ra[0], ra[40]))
+    for x in rs + ra:
+        R.free(x)

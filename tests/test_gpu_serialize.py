@@ -92,3 +92,40 @@ def test_device_deserialize_rejects_malformed(rb, R):
         assert "malformed portable bitmap at index 2" in str(ei.value), (name, str(ei.value))
     # the library keeps working afterwards
     assert rb.DeviceSet.from_serialized(good).serialize_all() == good
+
+
+def test_frozen_format_both_ways(rb, R):
+    """Device-side frozen format (roaring.c:3180-3456): emitted bytes equal
+    roaring_bitmap_frozen_serialize; the reference's frozen_view accepts our 32-byte aligned blobs
+    IN PLACE; frozen blobs parse on the device back to the same bitmaps; malformed ones are refused."""
+    blobs = rb.load_realdata("weather_sept_85")[:25] + rb.load_realdata("census1881")[:25] + synth_blobs(R, 91, 50)
+    r0 = R.from_values(np.zeros(0, np.uint32), False)
+    blobs.append(R.serialize(r0))
+    R.free(r0)
+    exp = [R.frozen_bytes(b) for b in blobs]
+    S = rb.DeviceSet.from_serialized(blobs)
+    assert S.serialize_all(frozen=True) == exp
+    # in place: hand the pinned buffer to the reference's zero-copy view
+    buf, off, ln, release = S.serialize_all(copy=False, frozen=True)
+    for i in range(0, len(blobs), 7):
+        assert (buf.value + off[i]) % 32 == 0
+        view = R.L.roaring_bitmap_frozen_view(buf.value + off[i], ln[i])
+        assert view, i
+        assert R.serialize(view) == blobs[i]
+        R.free(view)
+    release()
+    # results of an op, frozen
+    i, j = np.triu_indices(40, 1)
+    res = S.batch("xor", S, i.astype(np.uint32), j.astype(np.uint32))
+    fz = res.serialize_all(frozen=True)
+    for k in range(0, len(fz), 53):
+        assert fz[k] == R.frozen_bytes(R.op_bytes("xor", blobs[i[k]], blobs[j[k]])), k
+    # parse
+    F = rb.DeviceSet.from_frozen(exp)
+    assert F.serialize_all() == blobs
+    assert F.cardinalities().tolist() == S.cardinalities().tolist()
+    for name, bad in {"truncated": exp[3][:-9], "cookie": exp[3][:-4] + b"\\x00\\x00\\x00\\x00",
+                      "length": exp[3][:100] + b"\\x00\\x00" + exp[3][100:]}.items():
+        with pytest.raises(rb.RB200Error) as ei:
+            rb.DeviceSet.from_frozen(exp[:2] + [bad] + exp[4:6])
+        assert "malformed frozen bitmap at index 2" in str(ei.value), (name, str(ei.value))
