@@ -85,6 +85,9 @@ def lib():
     sig("rb200_batch_and_cardinality", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
     sig("rb200_or_many", _P, _P, _P, C.c_size_t)
     sig("rb200_batch_relations", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
+    sig("rb200_batch_flip", _P, _P, _P, C.c_size_t, C.c_uint64, C.c_uint64)
+    sig("roaring_bitmap_flip", _P, _P, C.c_uint64, C.c_uint64)
+    sig("roaring_bitmap_flip_inplace", None, _P, C.c_uint64, C.c_uint64)
     for rel in ("equals", "is_subset", "is_strict_subset"):
         sig(f"roaring_bitmap_{rel}", C.c_bool, _P, _P)
     sig("rb200_or_many_keyrange", _P, _P, _P, C.c_size_t, C.c_uint32, C.c_uint32, _P)
@@ -246,6 +249,16 @@ class Bitmap:
     def andnot_cardinality(self, o): return int(lib().roaring_bitmap_andnot_cardinality(self.ptr, o.ptr))
     def jaccard_index(self, o): return float(lib().roaring_bitmap_jaccard_index(self.ptr, o.ptr))
     def intersect(self, o): return bool(lib().roaring_bitmap_intersect(self.ptr, o.ptr))
+    def flip(self, start, end):
+        p = lib().roaring_bitmap_flip(self.ptr, int(start), int(end))
+        if not p:
+            raise RB200Error(last_error())
+        return Bitmap(p)
+
+    def flip_inplace(self, start, end):
+        lib().roaring_bitmap_flip_inplace(self.ptr, int(start), int(end))
+        return self
+
     def equals(self, o): return bool(lib().roaring_bitmap_equals(self.ptr, o.ptr))
     def is_subset(self, o): return bool(lib().roaring_bitmap_is_subset(self.ptr, o.ptr))
     def is_strict_subset(self, o): return bool(lib().roaring_bitmap_is_strict_subset(self.ptr, o.ptr))
@@ -417,6 +430,15 @@ class DeviceSet:
         if rc != 0:
             raise RB200Error(last_error())
         return out
+
+    def flip(self, range_start, range_end, idx=None):
+        """roaring_bitmap_flip of every (or the selected) bitmap over [range_start, range_end)."""
+        if idx is None:
+            ip, n = None, len(self)
+        else:
+            idx = _u32(idx)
+            ip, n = idx.ctypes.data, idx.size
+        return DeviceSet(lib().rb200_batch_flip(self.ptr, ip, n, int(range_start), int(range_end)))
 
     def relations(self, other, ia, ib):
         """uint8 per pair: bit 0 equals, bit 1 is_subset, bit 2 is_strict_subset."""

@@ -41,7 +41,10 @@ constexpr uint32_t CARD_UNKNOWN = 0x80000000u, CARD_MASK = 0x7fffffffu;
 //   RULES_CONV             lazy_or's bitsetconversion argument
 //   RULES_NOFULL           lazy_or_from_lazy_inputs (roaring_priority_queue.c:99): lazy_ior on
 //                          every matched key, without lazy_or_inplace's full-container short cut
-constexpr int RULES_INPLACE = 1, RULES_LAZY = 2, RULES_CONV = 4, RULES_NOFULL = 8;
+//   RULES_FLIP             (with RULES_LAZY's kernel instantiation, op XOR) roaring_bitmap_flip: the
+//                          right operand is the range as run containers, types follow the
+//                          negation cells (mixed_negation.c), see decide_type_lazy
+constexpr int RULES_INPLACE = 1, RULES_LAZY = 2, RULES_CONV = 4, RULES_NOFULL = 8, RULES_FLIP = 16;
 
 // Device view of a resident set: SoA container directory + one payload slab.
 // Payload of container c starts at payload + c_off[c] (16-byte aligned, padded to 16 B):

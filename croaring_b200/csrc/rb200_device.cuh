@@ -184,6 +184,9 @@ __host__ __device__ inline int decide_type_lazy(int op, int rules, int tA, int t
                                                 uint32_t cB, uint32_t lA, uint32_t lB, bool unkA,
                                                 int card, int nruns, bool &unknown) {
     unknown = false;
+    // negation (container_not_range, containers.h:2039-2073; mixed_negation.c:79-256): bitset / array
+    // input -> by cardinality, run input -> efficient container
+    if (rules & RULES_FLIP) return tA == T_RUN ? rule_eff(card, nruns) : rule_ab(card);
     const bool inplace = (rules & RULES_INPLACE) != 0;
     if (op == OP_XOR) {
         if (tA == T_BITSET && tB == T_BITSET) { unknown = true; return T_BITSET; }  // xor_nocard

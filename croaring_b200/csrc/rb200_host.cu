@@ -1225,6 +1225,7 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
     if (rules & RULES_LAZY) {
         if (op != OP_OR && op != OP_XOR) { g.err = "lazy rules exist for OR and XOR only"; return nullptr; }
         if (op == OP_XOR && (rules & (RULES_CONV | RULES_NOFULL))) { g.err = "bad lazy flags for XOR"; return nullptr; }
+        if ((rules & RULES_FLIP) && op != OP_XOR) { g.err = "bad flags"; return nullptr; }
     } else {
         if (rules & ~RULES_INPLACE) { g.err = "bad flags"; return nullptr; }
         if (reject_lazy(A, "batch op") || reject_lazy(B, "batch op")) return nullptr;
@@ -1275,7 +1276,7 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
             R->h_bytes[0] = R->slab_used;
             R->mirrors_pending = false;
         }
-        R->lazy = (rules & RULES_LAZY) != 0;
+        R->lazy = (rules & RULES_LAZY) != 0 && !(rules & RULES_FLIP);
         for (size_t p = 0; p < np; p++) R->h_flags[p] = (A->h_flags[ia[p]] | B->h_flags[ib[p]]) & FLAG_COW;
     }
     pb.release();
@@ -1300,7 +1301,7 @@ rb200_set_t *rb200_batch_op(int op, const rb200_set_t *A, const rb200_set_t *B, 
 rb200_set_t *rb200_batch_op_ex(int op, int flags, const rb200_set_t *A, const rb200_set_t *B,
                                const uint32_t *ia, const uint32_t *ib, size_t npairs) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
-    return batch_op_impl(op, A, B, ia, ib, npairs, flags);
+    return batch_op_impl(op, A, B, ia, ib, npairs, flags & (RULES_INPLACE | RULES_LAZY | RULES_CONV | RULES_NOFULL));
 }
 
 int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
@@ -1568,7 +1569,10 @@ roaring_bitmap_t *build_bitmap(const rb200_set *s, size_t i, const uint8_t *slab
         const uint8_t *pay = slab + (c_off[c] - bias);
         if (tabA || tabB) {  // pass-through container elided from the download: copy from the input
             const uint32_t sr = c_src[c];
-            if (sr != SRC_NONE) pay = (const uint8_t *)((sr & SRC_B) ? (*tabB)[sr & ~SRC_B] : (*tabA)[sr]);
+            if (sr != SRC_NONE) {  // elided only when THAT parent is host-bound (same mask as k_pack_*)
+                const std::vector<const void *> *tab = (sr & SRC_B) ? tabB : tabA;
+                if (tab) pay = (const uint8_t *)(*tab)[sr & ~SRC_B];
+            }
         }
         void *hc = container_from_payload(c_type[c], c_card[c], c_len[c], pay);
         if (!hc) {
@@ -2790,6 +2794,76 @@ bool roaring_bitmap_is_subset(const roaring_bitmap_t *r1, const roaring_bitmap_t
 bool roaring_bitmap_is_strict_subset(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
     const int r = dropin_relation(r1, r2);
     return r > 0 && (r & 4);
+}
+
+// ---- negation: roaring_bitmap_flip (src/roaring.c:2289-2349) ------------------------------------
+// result[k] = S[idx[k]] with [range_start, range_end) negated.  The range is materialised as ONE
+// tiny bitmap of run containers (one {lo, hi-lo} run per key it touches) and every flip is a
+// symmetric difference with it under the negation type rules (RULES_FLIP), batched like any op.
+rb200_set_t *rb200_batch_flip(const rb200_set_t *S, const uint32_t *idx, size_t n, uint64_t range_start,
+                              uint64_t range_end) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return nullptr;
+    if (reject_lazy(S, "flip")) return nullptr;
+    if (idx == nullptr) n = S->n_bitmaps;
+    std::vector<uint32_t> ia(n), ib(n, 0);
+    for (size_t i = 0; i < n; i++) ia[i] = idx ? idx[i] : (uint32_t)i;
+    std::vector<uint8_t> blob;
+    const bool noop = range_start >= range_end || range_start > (uint64_t)UINT32_MAX + 1;  // roaring.c:2292
+    if (noop) {  // copy: symmetric difference with the empty bitmap
+        const uint32_t hdr[2] = {SERIAL_COOKIE_NO_RUN, 0};
+        blob.assign((const uint8_t *)hdr, (const uint8_t *)hdr + 8);
+    } else {
+        const uint32_t first = (uint32_t)range_start, last = (uint32_t)(range_end - 1);
+        const uint32_t hb0 = first >> 16, hb1 = last >> 16, nk = hb1 - hb0 + 1;
+        const size_t nfb = (nk + 7) / 8, hdr = 4 + nfb + 4 * (size_t)nk + (nk >= (uint32_t)NO_OFFSET_THRESHOLD ? 4 * (size_t)nk : 0);
+        blob.assign(hdr + 6 * (size_t)nk, 0);
+        const uint32_t cookie = SERIAL_COOKIE | ((nk - 1) << 16);
+        memcpy(blob.data(), &cookie, 4);
+        memset(blob.data() + 4, 0xFF, nfb);  // every container is a run
+        if (nk & 7) blob[4 + nfb - 1] = (uint8_t)((1u << (nk & 7)) - 1);
+        uint8_t *kc = blob.data() + 4 + nfb, *offs = kc + 4 * (size_t)nk, *pay = blob.data() + hdr;
+        for (uint32_t k = 0; k < nk; k++) {
+            const uint32_t hb = hb0 + k, lo = hb == hb0 ? (first & 0xFFFF) : 0, hi = hb == hb1 ? (last & 0xFFFF) : 0xFFFF;
+            const uint16_t key = (uint16_t)hb, cm1 = (uint16_t)(hi - lo), one = 1, v0 = (uint16_t)lo;
+            memcpy(kc + 4 * (size_t)k, &key, 2);
+            memcpy(kc + 4 * (size_t)k + 2, &cm1, 2);
+            if (nk >= (uint32_t)NO_OFFSET_THRESHOLD) {
+                const uint32_t o = (uint32_t)(hdr + 6 * (size_t)k);
+                memcpy(offs + 4 * (size_t)k, &o, 4);
+            }
+            memcpy(pay + 6 * (size_t)k, &one, 2);
+            memcpy(pay + 6 * (size_t)k + 2, &v0, 2);
+            memcpy(pay + 6 * (size_t)k + 4, &cm1, 2);
+        }
+    }
+    const char *bp = (const char *)blob.data();
+    const size_t bl = blob.size();
+    rb200_set *Rg = upload_blobs_impl(&bp, &bl, 1, false);
+    if (!Rg) return nullptr;
+    rb200_set *R = batch_op_impl(OP_XOR, S, Rg, ia.data(), ib.data(), n, noop ? 0 : (RULES_LAZY | RULES_FLIP));
+    set_delete(Rg);
+    return R;
+}
+roaring_bitmap_t *roaring_bitmap_flip(const roaring_bitmap_t *r1, uint64_t range_start, uint64_t range_end) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    const roaring_bitmap_t *one[1] = {r1};
+    rb200_set *S = rb200_set_upload(one, 1);
+    if (!S) return nullptr;
+    rb200_set_bind_host(S, 1);
+    rb200_set *R = rb200_batch_flip(S, nullptr, 1, range_start, range_end);
+    roaring_bitmap_t *out = R ? rb200_set_download(R, 0) : nullptr;
+    set_delete(R);
+    set_delete(S);
+    return out;
+}
+void roaring_bitmap_flip_inplace(roaring_bitmap_t *r1, uint64_t range_start, uint64_t range_end) {
+    if (range_start >= range_end || range_start > (uint64_t)UINT32_MAX + 1) return;  // roaring.c:2353
+    roaring_bitmap_t *out = roaring_bitmap_flip(r1, range_start, range_end);
+    if (out) {
+        std::lock_guard<std::recursive_mutex> lk(g.mu);
+        swap_into(r1, out);
+    }
 }
 
 // ---- public lazy API (include/roaring/roaring.h:932-977) ------------------------------------

@@ -295,6 +295,12 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 otype = S.c_type[c];
                 ocard = S.c_card[c];
                 olen = S.c_len[c];
+                // roaring_bitmap_flip on an absent key: container_range_of_ones (containers.h:300-312)
+                // makes a one-value range an ARRAY; {start, 0} and {start} share their first 2 bytes
+                if (LAZY && (rules & RULES_FLIP) && kind == K_COPY_B && (ocard & CARD_MASK) == 1u) {
+                    otype = T_ARRAY;
+                    olen = 1;
+                }
                 warp_copy16(slab + off, S.payload + S.c_off[c], stored_bytes(otype, olen), lane);
             }
             if (lane == 0) {

@@ -85,6 +85,10 @@ void roaring_bitmap_lazy_or_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t
 roaring_bitmap_t *roaring_bitmap_lazy_xor(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 void roaring_bitmap_lazy_xor_inplace(roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 void roaring_bitmap_repair_after_lazy(roaring_bitmap_t *r1);
+/* include/roaring/roaring.h:986, 1004 (src/roaring.c:2289, 2351): negation of [range_start,
+ * range_end) — the negation cells of mixed_negation.c as one more rule set of the pairwise kernel. */
+roaring_bitmap_t *roaring_bitmap_flip(const roaring_bitmap_t *r1, uint64_t range_start, uint64_t range_end);
+void roaring_bitmap_flip_inplace(roaring_bitmap_t *r1, uint64_t range_start, uint64_t range_end);
 /* include/roaring/roaring.h:231  (src/roaring.c:3048) */
 uint64_t roaring_bitmap_and_cardinality(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2);
 /* include/roaring/roaring.h:258-271 (src/roaring.c:3086-3107): inclusion-exclusion on the above */
@@ -176,6 +180,10 @@ int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, cons
  * (A[ia[k]], B[ib[k]]); one cardinality sweep on the device.  0 on success. */
 int rb200_batch_relations(const rb200_set_t *A, const rb200_set_t *B, const uint32_t *ia,
                           const uint32_t *ib, size_t npairs, uint8_t *out);
+
+/* result[k] = roaring_bitmap_flip(S[idx[k]], range_start, range_end) (idx == NULL: every bitmap). */
+rb200_set_t *rb200_batch_flip(const rb200_set_t *S, const uint32_t *idx, size_t n, uint64_t range_start,
+                              uint64_t range_end);
 
 /* roaring_bitmap_or_many over S[idx[0..n)] (idx == NULL: all bitmaps in order).
  * Returns a device-resident set holding ONE bitmap. */

@@ -34,6 +34,8 @@ class Oracle:
         L.oracle_or_many_heap.restype = C.c_size_t
         L.oracle_or_many_heap.argtypes = [C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
                                           C.c_char_p, C.c_size_t]
+        L.oracle_flip.restype = C.c_size_t
+        L.oracle_flip.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_char_p, C.c_size_t]
         L.oracle_and_cardinality.restype = C.c_uint64
         L.oracle_and_cardinality.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         L.oracle_cardinality.restype = C.c_uint64
@@ -76,6 +78,14 @@ class Oracle:
 
     def or_many_heap_bytes(self, blobs) -> bytes:
         return self._many(self.L.oracle_or_many_heap, (), blobs)
+
+    def flip_bytes(self, a: bytes, start: int, end: int) -> bytes:
+        need = self.L.oracle_flip(a, len(a), start, end, None, 0)
+        if need == C.c_size_t(-1).value:
+            raise ValueError("oracle: malformed input")
+        buf = C.create_string_buffer(need)
+        assert self.L.oracle_flip(a, len(a), start, end, buf, need) == need
+        return buf.raw
 
     def and_cardinality(self, a: bytes, b: bytes) -> int:
         return int(self.L.oracle_and_cardinality(a, len(a), b, len(b)))

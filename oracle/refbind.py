@@ -67,6 +67,8 @@ class RefLib:
         sig("roaring_bitmap_frozen_size_in_bytes", C.c_size_t, P)           # roaring.h:831
         sig("roaring_bitmap_frozen_serialize", None, P, C.c_void_p)         # roaring.h:846
         sig("roaring_bitmap_frozen_view", P, C.c_void_p, C.c_size_t)        # roaring.h:864
+        sig("roaring_bitmap_flip", P, P, C.c_uint64, C.c_uint64)            # roaring.h:986
+        sig("roaring_bitmap_flip_inplace", None, P, C.c_uint64, C.c_uint64) # roaring.h:1004
         sig("roaring_bitmap_lazy_or", P, P, P, C.c_bool)                    # roaring.h:932
         sig("roaring_bitmap_lazy_or_inplace", None, P, P, C.c_bool)         # roaring.h:943
         sig("roaring_bitmap_lazy_xor", P, P, P)                             # roaring.h:963
@@ -141,6 +143,21 @@ class RefLib:
         self.free(ra)
         self.free(rb)
         return out
+
+    def flip_bytes(self, blob: bytes, start: int, end: int, inplace=False) -> bytes:
+        r = self.deserialize(blob)
+        if inplace:
+            self.L.roaring_bitmap_flip_inplace(r, start, end)
+            out = r
+        else:
+            out = self.L.roaring_bitmap_flip(r, start, end)
+        ok, why = self.validate(out)
+        assert ok, why
+        b = self.serialize(out)
+        if out != r:
+            self.free(out)
+        self.free(r)
+        return b
 
     def frozen_bytes(self, blob: bytes) -> bytes:
         """roaring_bitmap_frozen_serialize of the bitmap held in a portable blob."""

@@ -1090,3 +1090,58 @@ size_t oracle_or_many_heap(size_t n, const uint8_t *const *bufs, const size_t *l
     bm_free(&ans);
     return r;
 }
+
+/* roaring_bitmap_flip (roaring.c:2289-2349): negation of [range_start, range_end) — containers
+ * outside the range are copied, keys inside it go through container_not_range / container_not
+ * (containers.h:2009-2073; mixed_negation.c) or, when absent, container_range_of_ones
+ * (containers.h:300-312).  Type rules: bitset / array input -> array if card <= 4096 else bitset
+ * (mixed_negation.c:79-160, 182-203; a fully negated array is always a bitset, :26-37, which the
+ * same rule yields); run input -> convert_run_to_efficient_container (:226-256); empty results
+ * are dropped (roaring.c:2199-2204). */
+size_t oracle_flip(const uint8_t *a, size_t na, uint64_t range_start, uint64_t range_end, uint8_t *out,
+                   size_t cap) {
+    obm_t x, ans;
+    if (!bm_parse(&x, a, na)) return (size_t)-1;
+    if (range_start >= range_end || range_start > (uint64_t)0xFFFFFFFFu + 1) { /* :2292-2294 */
+        size_t r0 = bm_serialize(&x, out, cap);
+        bm_free(&x);
+        return r0;
+    }
+    const uint32_t first = (uint32_t)range_start, last = (uint32_t)(range_end - 1);
+    const uint32_t hb0 = first >> 16, hb1 = last >> 16;
+    bm_init(&ans, x.n + (int)(hb1 - hb0) + 1);
+    int p = 0;
+    for (; p < x.n && x.keys[p] < hb0; p++) bm_append(&ans, x.keys[p], oc_clone(&x.c[p]));
+    for (uint32_t hb = hb0; hb <= hb1; hb++) {
+        const uint32_t lo = hb == hb0 ? (first & 0xFFFF) : 0, hi = hb == hb1 ? (last & 0xFFFF) : 0xFFFF;
+        if (p < x.n && x.keys[p] == hb) {
+            uint64_t w[WORDS], rng[WORDS];
+            to_words(&x.c[p], w);
+            memset(rng, 0, sizeof(rng));
+            words_set_range(rng, lo, hi);
+            for (int i = 0; i < WORDS; i++) w[i] ^= rng[i];
+            oc_t c = x.c[p].type == T_RUN ? eff_from_words(w) : ab_from_words(w);
+            if (oc_card(&c) > 0) bm_append(&ans, (uint16_t)hb, c);
+            else oc_free(&c);
+            p++;
+        } else { /* container_range_of_ones: one value -> array, else a run */
+            oc_t c;
+            if (hi == lo) {
+                c.type = T_ARRAY; c.card = 0; c.n = 1; c.w = NULL;
+                c.v = (uint16_t *)malloc(2);
+                c.v[0] = (uint16_t)lo;
+            } else {
+                c.type = T_RUN; c.card = 0; c.n = 1; c.w = NULL;
+                c.v = (uint16_t *)malloc(4);
+                c.v[0] = (uint16_t)lo;
+                c.v[1] = (uint16_t)(hi - lo);
+            }
+            bm_append(&ans, (uint16_t)hb, c);
+        }
+    }
+    for (; p < x.n; p++) bm_append(&ans, x.keys[p], oc_clone(&x.c[p]));
+    size_t r = bm_serialize(&ans, out, cap);
+    bm_free(&x);
+    bm_free(&ans);
+    return r;
+}

@@ -30,6 +30,10 @@ size_t oracle_lazy_fold(int op, int conv, size_t n, const uint8_t *const *bufs, 
 size_t oracle_or_many_heap(size_t n, const uint8_t *const *bufs, const size_t *lens, uint8_t *out,
                            size_t cap);
 
+/* roaring_bitmap_flip(x, range_start, range_end) (roaring.c:2289). */
+size_t oracle_flip(const uint8_t *a, size_t na, uint64_t range_start, uint64_t range_end, uint8_t *out,
+                   size_t cap);
+
 /* roaring_bitmap_and_cardinality; (uint64_t)-1 on malformed input. */
 uint64_t oracle_and_cardinality(const uint8_t *a, size_t na, const uint8_t *b, size_t nb);
 

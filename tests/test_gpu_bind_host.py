@@ -31,3 +31,21 @@ def test_bind_host_results_identical_and_smaller(rb, R):
         c0 = r0.batch("xor", S0, k, ib)
         c1 = r1.batch("xor", S1, k, ib)
         assert [x.serialize() for x in c0.download_all()][::97] == [x.serialize() for x in c1.download_all()][::97]
+
+
+def test_only_one_parent_bound(rb, R):
+    """A result whose LEFT parent is host-bound and whose right parent is not (and vice versa):
+    pass-through containers of the unbound side travel over PCIe, the bound side's are rebuilt."""
+    import numpy as np
+    from helpers import synth_blobs
+    blobs = synth_blobs(R, 71, 30, key_space=8, max_keys=8)
+    host = [rb.Bitmap.deserialize(b) for b in blobs]
+    A = rb.DeviceSet.upload(host).bind_host()
+    B = rb.DeviceSet.from_serialized(blobs)
+    ia = np.arange(29, dtype=np.uint32)
+    for left, right in ((A, B), (B, A)):
+        for op in ("or", "xor", "andnot"):
+            res = left.batch(op, right, ia, ia + 1)
+            exp = [R.op_bytes(op, blobs[k], blobs[k + 1]) for k in range(29)]
+            assert [b.serialize() for b in res.download_all()] == exp
+            assert res.download(5).serialize() == exp[5]

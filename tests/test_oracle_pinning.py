@@ -107,3 +107,20 @@ def test_oracle_heap_vs_reference_realdata(O, R, ds):
     assert O.or_many_heap_bytes(blobs) == R.many_bytes("or_many_heap", blobs)
     assert O.or_many_heap_bytes(blobs[:37]) == R.many_bytes("or_many_heap", blobs[:37])
     assert O.lazy_fold_bytes("or", False, blobs[:50]) == R.lazy_fold_bytes("or", False, blobs[:50])
+
+
+FLIP_RANGES = [(0, 1), (5, 6), (5, 7), (0, 65536), (0, 65537), (65535, 65537), (100, 70000), (65536, 131072),
+               (1 << 16, (5 << 16) + 17), (3, 3), (9, 4), (0, 1 << 32), ((1 << 32) - 1, 1 << 32), ((1 << 32) - 70000, 1 << 32),
+               (123456, 654321), (2 << 16, (2 << 16) + 4097), ((1 << 32) + 1, (1 << 32) + 5)]
+
+
+@pytest.mark.parametrize("seed", [17, 18])
+def test_oracle_flip_vs_reference(O, R, seed):
+    blobs = synth_blobs(R, seed, 40, key_space=6, max_keys=6)
+    rng = np.random.default_rng(seed)
+    for b in blobs:
+        ranges = FLIP_RANGES + [tuple(sorted(rng.integers(0, 7 << 16, 2).tolist())) for _ in range(6)]
+        for (s, e) in ranges:
+            exp = R.flip_bytes(b, s, e)
+            assert O.flip_bytes(b, s, e) == exp, (s, e)
+            assert R.flip_bytes(b, s, e, inplace=True) == exp, ("inplace twin differs", s, e)

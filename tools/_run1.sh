@@ -1,2 +1,1 @@
-timeout 900 python -m pytest tests/test_gpu_serialize.py tests/test_gpu_parity.py -x -q -m gpu --timeout 300 -k "frozen or relations or deserialize" 2>&1 | tail -15
-timeout 900 python -m pytest tests -x -q -m gpu --timeout 600 2>&1 | tail -3
+timeout 900 python -X faulthandler -m pytest tests/test_gpu_flip.py tests/test_gpu_bind_host.py -x -q -m gpu --timeout 300 2>&1 | tail -6
