@@ -86,6 +86,11 @@ def lib():
     sig("rb200_or_many", _P, _P, _P, C.c_size_t)
     sig("rb200_batch_relations", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
     sig("rb200_batch_flip", _P, _P, _P, C.c_size_t, C.c_uint64, C.c_uint64)
+    sig("rb200_r64_batch_op_serialized", C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+        C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, _P, _P, C.c_size_t,
+        C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.POINTER(C.c_uint64)))
+    sig("rb200_r64_batch_and_cardinality_serialized", C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+        C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, _P, _P, C.c_size_t, _P)
     sig("roaring_bitmap_flip", _P, _P, C.c_uint64, C.c_uint64)
     sig("roaring_bitmap_flip_inplace", None, _P, C.c_uint64, C.c_uint64)
     for rel in ("equals", "is_subset", "is_strict_subset"):
@@ -327,6 +332,37 @@ def download_wait():
     """rb200_download_wait: drain every download queued with DeviceSet.foreach_async."""
     if lib().rb200_download_wait() != 0:
         raise RB200Error(last_error())
+
+
+def _blob_args(blobs):
+    n = len(blobs)
+    return (C.c_char_p * n)(*blobs), (C.c_size_t * n)(*[len(b) for b in blobs]), n
+
+
+def r64_batch_op(op, a_blobs, b_blobs, ia, ib):
+    """roaring64 and/or/xor/andnot on 64-bit portable blobs: list of result blobs (bytes)."""
+    ia, ib = _u32(ia), _u32(ib)
+    pa, la, na = _blob_args(a_blobs)
+    pb, lb, nb = _blob_args(b_blobs)
+    buf, off, ln = C.c_void_p(), C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+    code = OPS[op] if isinstance(op, str) else op
+    if lib().rb200_r64_batch_op_serialized(code, pa, la, na, pb, lb, nb, ia.ctypes.data, ib.ctypes.data, ia.size,
+                                           C.byref(buf), C.byref(off), C.byref(ln)) != 0:
+        raise RB200Error(last_error())
+    out = [C.string_at(buf.value + off[k], ln[k]) for k in range(ia.size)]
+    lib().rb200_serialized_free(buf, off, ln)
+    return out
+
+
+def r64_and_cardinality(a_blobs, b_blobs, ia, ib):
+    ia, ib = _u32(ia), _u32(ib)
+    pa, la, na = _blob_args(a_blobs)
+    pb, lb, nb = _blob_args(b_blobs)
+    out = np.zeros(ia.size, dtype=np.uint64)
+    if lib().rb200_r64_batch_and_cardinality_serialized(pa, la, na, pb, lb, nb, ia.ctypes.data, ib.ctypes.data,
+                                                        ia.size, out.ctypes.data) != 0:
+        raise RB200Error(last_error())
+    return out
 
 
 def batch_op_host(op, a, b):

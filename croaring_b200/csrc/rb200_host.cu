@@ -2866,6 +2866,215 @@ void roaring_bitmap_flip_inplace(roaring_bitmap_t *r1, uint64_t range_start, uin
     }
 }
 
+// ---- 64-bit bitmaps through their portable format (src/roaring64.c) -------------------------
+// roaring64_bitmap_{and,or,xor,andnot} (roaring64.c:1332, 1541, 1663, 1809) apply the same
+// container cells to equal high-48-bit keys; the 64-bit portable format (roaring64.c:2262-2395)
+// stores one ordinary 32-bit portable bitmap per high-32 "bucket".  Here every bucket of every
+// input becomes one bitmap of ONE resident set, matching buckets of a pair become one pair of the
+// batched kernel (unmatched ones are paired with an empty bitmap = pass-through), and the result
+// buckets are serialized on the device and stitched back into 64-bit blobs.
+namespace {
+struct R64Bucket { uint32_t high; const char *ptr; size_t len; };
+// length of the 32-bit portable bitmap starting at buf (0 = malformed); header walk only
+size_t portable_length(const uint8_t *buf, size_t maxlen) {
+    if (maxlen < 4) return 0;
+    uint32_t cookie;
+    memcpy(&cookie, buf, 4);
+    size_t pos = 4, size;
+    const uint8_t *runflags = nullptr;
+    if ((cookie & 0xFFFF) == SERIAL_COOKIE) {
+        size = (cookie >> 16) + 1;
+        runflags = buf + 4;
+        pos += (size + 7) / 8;
+    } else if (cookie == SERIAL_COOKIE_NO_RUN && maxlen >= 8) {
+        uint32_t sz;
+        memcpy(&sz, buf + 4, 4);
+        size = sz;
+        pos = 8;
+    } else {
+        return 0;
+    }
+    if (size > 65536 || pos + 4 * size > maxlen) return 0;
+    const uint8_t *kc = buf + pos;
+    pos += 4 * size;
+    if (!runflags || size >= (size_t)NO_OFFSET_THRESHOLD) pos += 4 * size;
+    for (size_t i = 0; i < size; i++) {
+        uint16_t cm1;
+        memcpy(&cm1, kc + 4 * i + 2, 2);
+        if (runflags && ((runflags[i / 8] >> (i % 8)) & 1)) {
+            if (pos + 2 > maxlen) return 0;
+            uint16_t nr;
+            memcpy(&nr, buf + pos, 2);
+            pos += 2 + 4 * (size_t)nr;
+        } else {
+            pos += (uint32_t)cm1 + 1 > (uint32_t)MAX_ARRAY ? (size_t)BITSET_BYTES : 2 * ((size_t)cm1 + 1);
+        }
+        if (pos > maxlen) return 0;
+    }
+    return pos;
+}
+bool parse_r64(const char *buf, size_t len, std::vector<R64Bucket> &out) {
+    out.clear();
+    if (len < 8) return false;
+    uint64_t n;
+    memcpy(&n, buf, 8);
+    if (n > UINT32_MAX) return false;
+    size_t pos = 8;
+    for (uint64_t i = 0; i < n; i++) {
+        if (pos + 4 > len) return false;
+        R64Bucket b;
+        memcpy(&b.high, buf + pos, 4);
+        pos += 4;
+        if (i && b.high <= out.back().high) return false;
+        b.ptr = buf + pos;
+        b.len = portable_length((const uint8_t *)buf + pos, len - pos);
+        if (!b.len) return false;
+        pos += b.len;
+        out.push_back(b);
+    }
+    return true;
+}
+struct R64Plan {
+    rb200_set *S = nullptr;                 // every bucket of every input + one empty bitmap (last)
+    std::vector<uint32_t> pa, pb, high;     // bucket pairs and their high-32 value
+    std::vector<size_t> first;              // per 64-bit pair: its bucket pairs are [first[p], first[p+1])
+};
+// op < 0: cardinality planning (matched buckets only)
+bool plan_r64(int op, const char *const *a, const size_t *alen, size_t na, const char *const *b,
+              const size_t *blen, size_t nb, const uint32_t *ia, const uint32_t *ib, size_t np, R64Plan &P) {
+    std::vector<std::vector<R64Bucket>> A(na), B(nb);
+    std::vector<size_t> baseA(na), baseB(nb);
+    std::vector<const char *> ptrs;
+    std::vector<size_t> lens;
+    for (size_t i = 0; i < na; i++) {
+        if (!parse_r64(a[i], alen[i], A[i])) { g.err = "malformed 64-bit portable bitmap (left) at index " + std::to_string(i); return false; }
+        baseA[i] = ptrs.size();
+        for (auto &x : A[i]) { ptrs.push_back(x.ptr); lens.push_back(x.len); }
+    }
+    for (size_t i = 0; i < nb; i++) {
+        if (!parse_r64(b[i], blen[i], B[i])) { g.err = "malformed 64-bit portable bitmap (right) at index " + std::to_string(i); return false; }
+        baseB[i] = ptrs.size();
+        for (auto &x : B[i]) { ptrs.push_back(x.ptr); lens.push_back(x.len); }
+    }
+    static const uint32_t empty_blob[2] = {SERIAL_COOKIE_NO_RUN, 0};
+    const uint32_t EMPTY = (uint32_t)ptrs.size();
+    ptrs.push_back((const char *)empty_blob);
+    lens.push_back(8);
+    P.first.assign(1, 0);
+    for (size_t p = 0; p < np; p++) {
+        if (ia[p] >= na || ib[p] >= nb) { g.err = "pair index out of range"; return false; }
+        const auto &x = A[ia[p]], &y = B[ib[p]];
+        size_t i = 0, j = 0;
+        while (i < x.size() || j < y.size()) {
+            const bool only1 = j >= y.size() || (i < x.size() && x[i].high < y[j].high);
+            const bool only2 = !only1 && (i >= x.size() || y[j].high < x[i].high);
+            const bool keep = only1 ? (op == OP_OR || op == OP_XOR || op == OP_ANDNOT)
+                              : only2 ? (op == OP_OR || op == OP_XOR) : true;
+            if (keep) {
+                P.pa.push_back(only2 ? EMPTY : (uint32_t)(baseA[ia[p]] + i));
+                P.pb.push_back(only1 ? EMPTY : (uint32_t)(baseB[ib[p]] + j));
+                P.high.push_back(only2 ? y[j].high : x[i].high);
+            }
+            if (!only2) i++;
+            if (!only1) j++;
+        }
+        P.first.push_back(P.pa.size());
+    }
+    P.S = upload_blobs_impl(ptrs.data(), lens.data(), ptrs.size(), false);
+    return P.S != nullptr;
+}
+}  // namespace
+
+// result[k] = roaring64 op of (a[ia[k]], b[ib[k]]), all in the 64-bit portable format.  *out is
+// pinned memory owned by the library (blob k at *out + (*off)[k], (*len)[k] bytes); release with
+// rb200_serialized_free.
+int rb200_r64_batch_op_serialized(int op, const char *const *a, const size_t *alen, size_t na,
+                                  const char *const *b, const size_t *blen, size_t nb, const uint32_t *ia,
+                                  const uint32_t *ib, size_t np, char **out, uint64_t **off_out, uint64_t **len_out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    if (op < 0 || op > 3) { g.err = "bad op"; return -1; }
+    *out = nullptr;
+    *off_out = *len_out = nullptr;
+    R64Plan P;
+    if (!plan_r64(op, a, alen, na, b, blen, nb, ia, ib, np, P)) return -1;
+    rb200_set *R = batch_op_impl(op, P.S, P.S, P.pa.data(), P.pb.data(), P.pa.size());
+    char *sbuf = nullptr;
+    uint64_t *soff = nullptr, *slen = nullptr;
+    int rc = R ? serialize_impl(R, &sbuf, &soff, &slen, false) : -1;
+    set_delete(R);
+    set_delete(P.S);
+    if (rc != 0) return -1;
+    // stitch: u64 bucket count, then per non-empty bucket u32 high32 + 32-bit blob
+    uint64_t *off = (uint64_t *)malloc(8 * (np + 1)), *len = (uint64_t *)malloc(8 * (np + 1));
+    uint64_t total = 0;
+    auto empty_bucket = [&](size_t q) {
+        uint32_t w[2];
+        if (slen[q] != 8) return false;
+        memcpy(w, sbuf + soff[q], 8);
+        return w[0] == SERIAL_COOKIE_NO_RUN && w[1] == 0;
+    };
+    if (off && len) {
+        for (size_t p = 0; p < np; p++) {
+            uint64_t sz = 8;
+            for (size_t q = P.first[p]; q < P.first[p + 1]; q++)
+                if (!empty_bucket(q)) sz += 4 + slen[q];
+            off[p] = total;
+            len[p] = sz;
+            total += (sz + 15) & ~(uint64_t)15;
+        }
+        off[np] = total;
+    }
+    uint8_t *dst = (off && len) ? (uint8_t *)pin_alloc(total ? total : 16) : nullptr;
+    if (dst) {
+        for (size_t p = 0; p < np; p++) {
+            uint8_t *o = dst + off[p];
+            uint64_t kept = 0;
+            size_t pos = 8;
+            for (size_t q = P.first[p]; q < P.first[p + 1]; q++) {
+                if (empty_bucket(q)) continue;
+                memcpy(o + pos, &P.high[q], 4);
+                memcpy(o + pos + 4, sbuf + soff[q], slen[q]);
+                pos += 4 + slen[q];
+                kept++;
+            }
+            memcpy(o, &kept, 8);
+        }
+        g_serialized_sizes[dst] = total ? total : 16;
+    }
+    rb200_serialized_free(sbuf, soff, slen);
+    if (!dst) {
+        free(off);
+        free(len);
+        g.err = "r64 batch op: host allocation failed";
+        return -1;
+    }
+    *out = (char *)dst;
+    *off_out = off;
+    *len_out = len;
+    return 0;
+}
+
+// out[k] = roaring64_bitmap_and_cardinality(a[ia[k]], b[ib[k]]) (roaring64.c:1375)
+int rb200_r64_batch_and_cardinality_serialized(const char *const *a, const size_t *alen, size_t na,
+                                               const char *const *b, const size_t *blen, size_t nb,
+                                               const uint32_t *ia, const uint32_t *ib, size_t np, uint64_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    R64Plan P;
+    if (!plan_r64(OP_AND, a, alen, na, b, blen, nb, ia, ib, np, P)) return -1;
+    std::vector<uint64_t> c(P.pa.size());
+    const int rc = P.pa.empty() ? 0 : rb200_batch_and_cardinality(P.S, P.S, P.pa.data(), P.pb.data(), P.pa.size(), c.data());
+    set_delete(P.S);
+    if (rc != 0) return -1;
+    for (size_t p = 0; p < np; p++) {
+        uint64_t s = 0;
+        for (size_t q = P.first[p]; q < P.first[p + 1]; q++) s += c[q];
+        out[p] = s;
+    }
+    return 0;
+}
+
 // ---- public lazy API (include/roaring/roaring.h:932-977) ------------------------------------
 // The lazy state lives in ordinary host bitmaps exactly as the reference leaves it (bitsets with
 // cardinality -1, unconverted runs), so the reference's own functions accept what we return.

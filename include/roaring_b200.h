@@ -185,6 +185,20 @@ int rb200_batch_relations(const rb200_set_t *A, const rb200_set_t *B, const uint
 rb200_set_t *rb200_batch_flip(const rb200_set_t *S, const uint32_t *idx, size_t n, uint64_t range_start,
                               uint64_t range_end);
 
+/* 64-bit bitmaps (src/roaring64.c) through their portable format: result[k] =
+ * roaring64_bitmap_{and,or,xor,andnot}(a[ia[k]], b[ib[k]]) — the same container grid per
+ * high-32 bucket.  *out (pinned, owned by the library; blob k at *out + (*off)[k], (*len)[k]
+ * bytes) is released with rb200_serialized_free.  The in-memory roaring64_bitmap_t (ART) is not
+ * bound: bytes in, bytes out. */
+int rb200_r64_batch_op_serialized(int op, const char *const *a, const size_t *alen, size_t na,
+                                  const char *const *b, const size_t *blen, size_t nb,
+                                  const uint32_t *ia, const uint32_t *ib, size_t npairs, char **out,
+                                  uint64_t **off, uint64_t **len);
+int rb200_r64_batch_and_cardinality_serialized(const char *const *a, const size_t *alen, size_t na,
+                                               const char *const *b, const size_t *blen, size_t nb,
+                                               const uint32_t *ia, const uint32_t *ib, size_t npairs,
+                                               uint64_t *out);
+
 /* roaring_bitmap_or_many over S[idx[0..n)] (idx == NULL: all bitmaps in order).
  * Returns a device-resident set holding ONE bitmap. */
 rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n);

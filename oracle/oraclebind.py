@@ -36,6 +36,9 @@ class Oracle:
                                           C.c_char_p, C.c_size_t]
         L.oracle_flip.restype = C.c_size_t
         L.oracle_flip.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_char_p, C.c_size_t]
+        L.oracle_r64_pair_op.restype = C.c_size_t
+        L.oracle_r64_pair_op.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
+                                         C.c_char_p, C.c_size_t]
         L.oracle_and_cardinality.restype = C.c_uint64
         L.oracle_and_cardinality.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
         L.oracle_cardinality.restype = C.c_uint64
@@ -78,6 +81,14 @@ class Oracle:
 
     def or_many_heap_bytes(self, blobs) -> bytes:
         return self._many(self.L.oracle_or_many_heap, (), blobs)
+
+    def r64_op_bytes(self, name: str, a: bytes, b: bytes) -> bytes:
+        need = self.L.oracle_r64_pair_op(OPS[name], a, len(a), b, len(b), None, 0)
+        if need == C.c_size_t(-1).value:
+            raise ValueError("oracle: malformed 64-bit input")
+        buf = C.create_string_buffer(need)
+        assert self.L.oracle_r64_pair_op(OPS[name], a, len(a), b, len(b), buf, need) == need
+        return buf.raw
 
     def flip_bytes(self, a: bytes, start: int, end: int) -> bytes:
         need = self.L.oracle_flip(a, len(a), start, end, None, 0)

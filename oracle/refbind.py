@@ -67,6 +67,18 @@ class RefLib:
         sig("roaring_bitmap_frozen_size_in_bytes", C.c_size_t, P)           # roaring.h:831
         sig("roaring_bitmap_frozen_serialize", None, P, C.c_void_p)         # roaring.h:846
         sig("roaring_bitmap_frozen_view", P, C.c_void_p, C.c_size_t)        # roaring.h:864
+        V = C.c_void_p                                                      # roaring64_bitmap_t*
+        sig("roaring64_bitmap_of_ptr", V, C.c_size_t, C.c_void_p)           # roaring64.h:92
+        sig("roaring64_bitmap_free", None, V)                               # roaring64.h:69
+        sig("roaring64_bitmap_run_optimize", C.c_bool, V)                   # roaring64.h:364
+        sig("roaring64_bitmap_get_cardinality", C.c_uint64, V)              # roaring64.h:326
+        sig("roaring64_bitmap_internal_validate", C.c_bool, V, C.POINTER(C.c_char_p))
+        sig("roaring64_bitmap_portable_size_in_bytes", C.c_size_t, V)
+        sig("roaring64_bitmap_portable_serialize", C.c_size_t, V, C.c_char_p)
+        sig("roaring64_bitmap_portable_deserialize_safe", V, C.c_char_p, C.c_size_t)
+        for op in ("and", "or", "xor", "andnot"):                          # roaring64.h:423-530
+            sig(f"roaring64_bitmap_{op}", V, V, V)
+        sig("roaring64_bitmap_and_cardinality", C.c_uint64, V, V)           # roaring64.h:429
         sig("roaring_bitmap_flip", P, P, C.c_uint64, C.c_uint64)            # roaring.h:986
         sig("roaring_bitmap_flip_inplace", None, P, C.c_uint64, C.c_uint64) # roaring.h:1004
         sig("roaring_bitmap_lazy_or", P, P, P, C.c_bool)                    # roaring.h:932
@@ -143,6 +155,44 @@ class RefLib:
         self.free(ra)
         self.free(rb)
         return out
+
+    # ---- 64-bit bitmaps (roaring64.h), through their portable format
+    def r64_from_values(self, vals, run_optimize=True) -> bytes:
+        v = np.ascontiguousarray(vals, dtype=np.uint64)
+        r = self.L.roaring64_bitmap_of_ptr(v.size, v.ctypes.data)
+        if run_optimize:
+            self.L.roaring64_bitmap_run_optimize(r)
+        b = self.r64_serialize(r)
+        self.L.roaring64_bitmap_free(r)
+        return b
+
+    def r64_serialize(self, r) -> bytes:
+        n = self.L.roaring64_bitmap_portable_size_in_bytes(r)
+        buf = C.create_string_buffer(n)
+        assert self.L.roaring64_bitmap_portable_serialize(r, buf) == n
+        return buf.raw[:n]
+
+    def r64_deserialize(self, b: bytes):
+        r = self.L.roaring64_bitmap_portable_deserialize_safe(b, len(b))
+        assert r, "reference refused a 64-bit blob"
+        return r
+
+    def r64_op_bytes(self, name: str, a: bytes, b: bytes) -> bytes:
+        ra, rb = self.r64_deserialize(a), self.r64_deserialize(b)
+        r = getattr(self.L, f"roaring64_bitmap_{name}")(ra, rb)
+        why = C.c_char_p()
+        assert self.L.roaring64_bitmap_internal_validate(r, C.byref(why)), why.value
+        out = self.r64_serialize(r)
+        for x in (ra, rb, r):
+            self.L.roaring64_bitmap_free(x)
+        return out
+
+    def r64_and_cardinality(self, a: bytes, b: bytes) -> int:
+        ra, rb = self.r64_deserialize(a), self.r64_deserialize(b)
+        v = int(self.L.roaring64_bitmap_and_cardinality(ra, rb))
+        self.L.roaring64_bitmap_free(ra)
+        self.L.roaring64_bitmap_free(rb)
+        return v
 
     def flip_bytes(self, blob: bytes, start: int, end: int, inplace=False) -> bytes:
         r = self.deserialize(blob)

@@ -1145,3 +1145,78 @@ size_t oracle_flip(const uint8_t *a, size_t na, uint64_t range_start, uint64_t r
     bm_free(&ans);
     return r;
 }
+
+/* ------------------------------------------------------------------ 64-bit bitmaps
+ * roaring64_bitmap_{and,or,xor,andnot} (src/roaring64.c:1332, 1541, 1663, 1809) walk two ARTs in
+ * high-48-bit key order and apply the SAME container cells (container_and / _or / _xor / _andnot)
+ * to equal keys; the portable format (roaring64.c:2262-2395) groups the containers of one high-32
+ * value into an ordinary 32-bit portable bitmap:  u64 n_buckets, then per bucket u32 high32 +
+ * 32-bit blob.  So a 64-bit op is the 32-bit op per matching bucket, unmatched buckets passing
+ * through (or / xor: both sides, andnot: left side), buckets left without containers dropped. */
+typedef struct {
+    uint64_t n;
+    uint32_t *high;
+    obm_t *bm;
+} o64_t;
+
+static void o64_free(o64_t *x) {
+    for (uint64_t i = 0; i < x->n; i++) bm_free(&x->bm[i]);
+    free(x->high);
+    free(x->bm);
+}
+static bool o64_parse(o64_t *x, const uint8_t *buf, size_t len) {
+    if (len < 8) return false;
+    uint64_t n = (uint64_t)rd32(buf) | ((uint64_t)rd32(buf + 4) << 32);
+    if (n > 0xFFFFFFFFull) return false;
+    x->n = 0;
+    x->high = (uint32_t *)malloc(4 * (size_t)(n ? n : 1));
+    x->bm = (obm_t *)malloc(sizeof(obm_t) * (size_t)(n ? n : 1));
+    size_t pos = 8;
+    for (uint64_t i = 0; i < n; i++) {
+        if (pos + 4 > len) return false;
+        x->high[i] = rd32(buf + pos);
+        pos += 4;
+        if (!bm_parse(&x->bm[i], buf + pos, len - pos)) return false;
+        x->n = i + 1;
+        pos += bm_serialize(&x->bm[i], NULL, 0);
+        if (pos > len) return false;
+    }
+    return true;
+}
+
+size_t oracle_r64_pair_op(int op, const uint8_t *a, size_t na, const uint8_t *b, size_t nb, uint8_t *out,
+                          size_t cap) {
+    o64_t x1, x2;
+    if (!o64_parse(&x1, a, na) || !o64_parse(&x2, b, nb)) return (size_t)-1;
+    obm_t empty;
+    bm_init(&empty, 0);
+    size_t pos = 8;
+    uint64_t kept = 0, p1 = 0, p2 = 0;
+    while (p1 < x1.n || p2 < x2.n) {
+        const bool only1 = p2 >= x2.n || (p1 < x1.n && x1.high[p1] < x2.high[p2]);
+        const bool only2 = !only1 && (p1 >= x1.n || x2.high[p2] < x1.high[p1]);
+        const uint32_t high = only2 ? x2.high[p2] : x1.high[p1];
+        obm_t ans;
+        bm_pair(op, only2 ? &empty : &x1.bm[p1], only1 ? &empty : &x2.bm[p2], &ans);
+        if (!only2) p1++;
+        if (!only1) p2++;
+        if (ans.n > 0) {
+            const size_t sz = bm_serialize(&ans, NULL, 0);
+            if (out && pos + 4 + sz <= cap) {
+                wr32(out + pos, high);
+                bm_serialize(&ans, out + pos + 4, sz);
+            }
+            pos += 4 + sz;
+            kept++;
+        }
+        bm_free(&ans);
+    }
+    if (out && cap >= 8) {
+        wr32(out, (uint32_t)kept);
+        wr32(out + 4, (uint32_t)(kept >> 32));
+    }
+    o64_free(&x1);
+    o64_free(&x2);
+    bm_free(&empty);
+    return pos;
+}

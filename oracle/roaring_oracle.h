@@ -34,6 +34,11 @@ size_t oracle_or_many_heap(size_t n, const uint8_t *const *bufs, const size_t *l
 size_t oracle_flip(const uint8_t *a, size_t na, uint64_t range_start, uint64_t range_end, uint8_t *out,
                    size_t cap);
 
+/* roaring64_bitmap_{and,or,xor,andnot} on the 64-bit portable format (roaring64.c:1332-1895,
+ * 2262-2395); op codes 0-3 as oracle_pair_op. */
+size_t oracle_r64_pair_op(int op, const uint8_t *a, size_t na, const uint8_t *b, size_t nb, uint8_t *out,
+                          size_t cap);
+
 /* roaring_bitmap_and_cardinality; (uint64_t)-1 on malformed input. */
 uint64_t oracle_and_cardinality(const uint8_t *a, size_t na, const uint8_t *b, size_t nb);
 

@@ -47,3 +47,20 @@ def check_result_bitmap(R, bm, expect_bytes, what=""):
     ok, why = R.validate(bm.ptr)           # the reference's own validator on OUR object
     assert ok, f"{what}: reference validate failed: {why}"
     assert R.serialize(bm.ptr) == expect_bytes, f"{what}: reference serializer disagrees on our object"
+
+
+def synth_blobs64(R, seed, n, highs=(0, 1, 7, 0x10000, 0xFFFFFFFF), key_space=5, max_keys=5, profiles=None):
+    """n seeded 64-bit bitmaps (portable format, serialized by the reference): every bitmap owns a
+    random subset of the high-32 buckets, each filled like a synthetic 32-bit bitmap."""
+    rng = np.random.default_rng(seed)
+    blobs = []
+    for i in range(n):
+        parts = []
+        for h in highs:
+            if rng.random() < 0.6:
+                v = synth.random_bitmap(rng, n_keys=int(rng.integers(0, max_keys)), key_space=key_space,
+                                        profiles=profiles)
+                parts.append(v.astype(np.uint64) + (np.uint64(h) << np.uint64(32)))
+        vals = np.concatenate(parts) if parts else np.zeros(0, np.uint64)
+        blobs.append(R.r64_from_values(vals, run_optimize=bool(i % 3)))
+    return blobs

@@ -124,3 +124,16 @@ def test_oracle_flip_vs_reference(O, R, seed):
             exp = R.flip_bytes(b, s, e)
             assert O.flip_bytes(b, s, e) == exp, (s, e)
             assert R.flip_bytes(b, s, e, inplace=True) == exp, ("inplace twin differs", s, e)
+
+
+@pytest.mark.parametrize("seed", [64, 65])
+def test_oracle_r64_vs_reference(O, R, seed):
+    """64-bit bitmaps through their portable format: the oracle's per-bucket restatement vs
+    roaring64_bitmap_{and,or,xor,andnot} (roaring64.c:1332-1895)."""
+    from helpers import synth_blobs64
+    blobs = synth_blobs64(R, seed, 30)
+    rng = np.random.default_rng(seed)
+    for _ in range(120):
+        i, j = rng.integers(0, len(blobs), 2)
+        for op in OPS:
+            assert O.r64_op_bytes(op, blobs[i], blobs[j]) == R.r64_op_bytes(op, blobs[i], blobs[j]), (op, i, j)
