@@ -162,6 +162,7 @@ bool ctx_init(int device = -1) {
     CK(cudaMemset(g.d_many_acc, 0, (size_t)MANY_SCRATCH_KEYS * BITSET_BYTES));
     CK(cudaMemset(g.d_many_tickets, 0, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
     CK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, g.device));
+    g_halloc.look();  // resolve the host allocator once, before any worker thread exists
     g.inited = true;
     return true;
 }
@@ -1649,25 +1650,28 @@ Pool &pool() {
 }
 // CPUs local to the GPU's PCIe root (sysfs local_cpulist); empty when unknown.
 std::vector<int> &local_cpus() {
-    static std::vector<int> cpus;
-    static bool done = false;
-    if (done) return cpus;
-    done = true;
-    char bus[32] = {0};
-    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), g.device) != cudaSuccess) return cpus;
-    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
-    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
-    FILE *f = fopen(path.c_str(), "r");
-    if (!f) return cpus;
-    char line[1024] = {0};
-    if (fgets(line, sizeof(line), f)) {
-        for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
-            int a = 0, b = 0;
-            if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; c++) cpus.push_back(c); }
-            else if (sscanf(tok, "%d", &a) == 1) cpus.push_back(a);
+    // function-local static: initialised once, thread-safe (API threads, pool workers and the
+    // downloader may all get here first)
+    static std::vector<int> cpus = []() {
+        std::vector<int> v;
+        char bus[32] = {0};
+        if (cudaDeviceGetPCIBusId(bus, sizeof(bus), g.device) != cudaSuccess) return v;
+        for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+        std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+        FILE *f = fopen(path.c_str(), "r");
+        if (!f) return v;
+        char line[1024] = {0};
+        if (fgets(line, sizeof(line), f)) {
+            char *save = nullptr;
+            for (char *tok = strtok_r(line, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
+                int lo = 0, hi = 0;
+                if (sscanf(tok, "%d-%d", &lo, &hi) == 2) { for (int c = lo; c <= hi; c++) v.push_back(c); }
+                else if (sscanf(tok, "%d", &lo) == 1) v.push_back(lo);
+            }
         }
-    }
-    fclose(f);
+        fclose(f);
+        return v;
+    }();
     return cpus;
 }
 // Move the calling thread onto the GPU-local CPUs; *saved receives the previous mask.
