@@ -2568,6 +2568,9 @@ static int serialize_impl(const rb200_set *s, char **buf, uint64_t **off_out, ui
     pin_free(h_meta, 8 * (nb + 1) + 4 * nb);
     if (!ok) {
         pin_free(h_blob, total);
+        free(*off_out);
+        free(*len_out);
+        *off_out = *len_out = nullptr;
         if (g.err.empty()) g.err = "set_serialize failed";
         return -1;
     }
