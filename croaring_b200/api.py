@@ -85,6 +85,7 @@ def lib():
     sig("rb200_batch_and_cardinality", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
     sig("rb200_or_many", _P, _P, _P, C.c_size_t)
     sig("rb200_batch_relations", C.c_int, _P, _P, _P, _P, C.c_size_t, _P)
+    sig("rb200_set_op_stats", C.c_int, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64))
     sig("rb200_batch_flip", _P, _P, _P, C.c_size_t, C.c_uint64, C.c_uint64)
     sig("rb200_r64_batch_op_serialized", C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
         C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, _P, _P, C.c_size_t,
@@ -475,6 +476,13 @@ class DeviceSet:
             idx = _u32(idx)
             ip, n = idx.ctypes.data, idx.size
         return DeviceSet(lib().rb200_batch_flip(self.ptr, ip, n, int(range_start), int(range_end)))
+
+    def op_stats(self):
+        """(device_ms, compute_kernel_ms, algorithmic_bytes) of the batch op that produced this set."""
+        ms, cms, ab = C.c_float(), C.c_float(), C.c_uint64()
+        if lib().rb200_set_op_stats(self.ptr, C.byref(ms), C.byref(cms), C.byref(ab)) != 0:
+            raise RB200Error(last_error())
+        return float(ms.value), float(cms.value), int(ab.value)
 
     def relations(self, other, ia, ib):
         """uint8 per pair: bit 0 equals, bit 1 is_subset, bit 2 is_strict_subset."""

@@ -116,6 +116,8 @@ struct Ctx {
     float last_ms = 0.f, last_compute_ms = 0.f;
     uint64_t last_download_bytes = 0;
     uint64_t last_out_portable = 0;  // portable bytes of the last batch's results (all pairs)
+    std::vector<cudaEvent_t> evpool;  // timing events recycled between batch ops (under alloc_mu)
+    struct rb200_set *last_op = nullptr;  // result of the most recent batch op (counters may be pending)
 } g;
 std::map<uint8_t *, size_t> g_serialized_sizes;  // pinned blobs handed out by rb200_set_serialize
 
@@ -266,6 +268,16 @@ struct rb200_set {
     std::vector<uint64_t> h_card;   // host mirror: cardinality per bitmap (empty = not cached)
     bool mirrors_pending = false;   // batch results: h_cnt / h_bytes / h_card are fetched on first use
     bool lazy = false;              // produced by a lazy op: needs rb200_set_repair_after_lazy
+    // Deferred counters of the batch op that produced this set: the op returns as soon as its
+    // kernels and the D2H copy of its counters are queued; resolve() waits for them on first use,
+    // so consecutive batch calls pipeline on the stream without a host round trip.
+    bool pending = false, failed = false;
+    OpStats *pstats = nullptr;                  // pinned
+    uint8_t *staging = nullptr;                 // pinned pair list of the op (alive until it ran)
+    size_t staging_bytes = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // op start, kernel start, kernel end, op end
+    float ms = 0.f, compute_ms = 0.f;
+    uint64_t algo_bytes = 0, out_portable = 0;
     // payload address of every container in the caller's host bitmaps (sets made by
     // rb200_set_upload; valid while the caller keeps those bitmaps alive) and, for a batch result,
     // the tables of its two parents: pass-through containers can then be rebuilt on the host from
@@ -333,8 +345,78 @@ void set_drop_mirror(rb200_set *s) {
     s->m_dir = s->m_slab = nullptr;
 }
 
+cudaEvent_t ev_get() {
+    {
+        std::lock_guard<std::mutex> alk(g.alloc_mu);
+        if (!g.evpool.empty()) {
+            cudaEvent_t e = g.evpool.back();
+            g.evpool.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void ev_put(cudaEvent_t e) {
+    if (!e) return;
+    std::lock_guard<std::mutex> alk(g.alloc_mu);
+    g.evpool.push_back(e);
+}
+
+// Wait for the op that produced `cs` (if it is still in flight) and take over its counters.
+// false: the op failed (g.err says why); the set must not be used.
+bool resolve(const rb200_set *cs) {
+    rb200_set *s = const_cast<rb200_set *>(cs);
+    if (!s->pending) {
+        if (s->failed && g.err.empty()) g.err = "the operation that produced this set failed";
+        return !s->failed;
+    }
+    s->pending = false;
+    cudaError_t e = cudaEventSynchronize(s->ev[3]);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g.err = std::string("batch op: ") + cudaGetErrorString(e);
+        s->failed = true;
+    } else if (s->pstats->error) {
+        g.err = s->pstats->error == 2 ? "internal: result slab bound exceeded" : "internal: result slot bound exceeded";
+        s->failed = true;
+    } else {
+        cudaEventElapsedTime(&s->ms, s->ev[0], s->ev[3]);
+        cudaEventElapsedTime(&s->compute_ms, s->ev[1], s->ev[2]);
+        s->algo_bytes = s->pstats->algo_bytes;
+        s->out_portable = s->pstats->out_portable;
+        s->n_containers = s->pstats->dir_cursor;
+        s->slab_used = s->pstats->slab_cursor;
+        if (s->n_bitmaps == 1) {  // a single result: its mirrors are the op's counters, no extra D2H
+            s->h_cnt[0] = (uint32_t)s->n_containers;
+            s->h_bytes[0] = s->slab_used;
+            s->mirrors_pending = false;
+        }
+    }
+    for (int k = 0; k < 4; k++) { ev_put(s->ev[k]); s->ev[k] = nullptr; }
+    pin_free(s->pstats, sizeof(OpStats));
+    pin_free(s->staging, s->staging_bytes);
+    s->pstats = nullptr;
+    s->staging = nullptr;
+    if (g.last_op == s) {
+        g.last_ms = s->ms;
+        g.last_compute_ms = s->compute_ms;
+        g.last_algo_bytes = s->algo_bytes;
+        g.last_out_portable = s->out_portable;
+    }
+    return !s->failed;
+}
+
 void set_delete(rb200_set *s) {
     if (!s) return;
+    if (s->pending) resolve(s);  // pinned staging / counters must not be recycled under a pending DMA
+    for (int k = 0; k < 4; k++) { ev_put(s->ev[k]); s->ev[k] = nullptr; }  // (only set if the enqueue failed half way)
+    pin_free(s->pstats, sizeof(OpStats));
+    pin_free(s->staging, s->staging_bytes);
+    s->pstats = nullptr;
+    s->staging = nullptr;
+    if (g.last_op == s) g.last_op = nullptr;
     set_drop_mirror(s);
     dev_free(s->d_dir, s->L.total);
     dev_free(s->d_slab, s->slab_cap);
@@ -472,9 +554,13 @@ extern "C" {
 
 const char *rb200_last_error(void) { return g.err.c_str(); }
 uint64_t rb200_kernel_launches(void) { return g_launches; }
-uint64_t rb200_last_algorithmic_bytes(void) { return g.last_algo_bytes; }
-float rb200_last_device_ms(void) { return g.last_ms; }
-float rb200_last_compute_ms(void) { return g.last_compute_ms; }
+static void settle_last_op() {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (g.last_op && g.last_op->pending) resolve(g.last_op);
+}
+uint64_t rb200_last_algorithmic_bytes(void) { settle_last_op(); return g.last_algo_bytes; }
+float rb200_last_device_ms(void) { settle_last_op(); return g.last_ms; }
+float rb200_last_compute_ms(void) { settle_last_op(); return g.last_compute_ms; }
 uint64_t rb200_last_download_bytes(void) { return g.last_download_bytes; }
 
 int rb200_init(int device) {
@@ -1085,7 +1171,21 @@ void rb200_set_free(rb200_set_t *s) {
     set_delete(s);
 }
 size_t rb200_set_count(const rb200_set_t *s) { return s->n_bitmaps; }
-uint64_t rb200_set_container_count(const rb200_set_t *s) { return s->n_containers; }
+// Counters of the batch op that produced `s` (waits for it if it is still in flight): device time
+// of the whole op and of its compute kernel (CUDA events on the library stream), algorithmic bytes.
+int rb200_set_op_stats(const rb200_set_t *s, float *device_ms, float *compute_ms, uint64_t *algorithmic_bytes) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!resolve(s)) return -1;
+    if (device_ms) *device_ms = s->ms;
+    if (compute_ms) *compute_ms = s->compute_ms;
+    if (algorithmic_bytes) *algorithmic_bytes = s->algo_bytes;
+    return 0;
+}
+uint64_t rb200_set_container_count(const rb200_set_t *s) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    resolve(s);
+    return s->n_containers;
+}
 uint64_t rb200_set_payload_bytes(const rb200_set_t *s) { return s->portable_bytes; }
 
 }  // extern "C"
@@ -1097,6 +1197,7 @@ namespace {
 // result that is only measured, chained on the device or downloaded never pays this D2H.
 bool ensure_mirrors(const rb200_set *cs) {
     rb200_set *s = const_cast<rb200_set *>(cs);
+    if (!resolve(cs)) return false;
     if (!s->mirrors_pending) return true;
     const size_t nb = s->n_bitmaps;
     const size_t bytes = (s->L.o_bcard - s->L.o_cnt) + 8 * nb;
@@ -1242,47 +1343,39 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         ok = R != nullptr;
     }
     if (ok) {
-        cudaEventRecord(g.ev0, g.stream);
+        for (int k = 0; k < 4; k++) R->ev[k] = ev_get();
+        R->pstats = (OpStats *)pin_alloc(sizeof(OpStats));
+        ok = R->pstats && R->ev[0] && R->ev[1] && R->ev[2] && R->ev[3];
+    }
+    if (ok) {
+        cudaEventRecord(R->ev[0], g.stream);
         ok = stats_reset();
         const SetView va = A->view(), vb = B->view();
         launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, rules, ib_.it,
                           g.d_stats, g.stream);
-        cudaEventRecord(g.evk0, g.stream);
+        cudaEventRecord(R->ev[1], g.stream);
         launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, g.stream);
-        cudaEventRecord(g.evk1, g.stream);
+        cudaEventRecord(R->ev[2], g.stream);
         launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
-        cudaEventRecord(g.ev1, g.stream);
-        ok = ok && stats_fetch();
-        cudaError_t e = cudaStreamSynchronize(g.stream);
-        if (e != cudaSuccess) { g.err = std::string("batch op: ") + cudaGetErrorString(e); ok = false; }
-        if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("batch op launch: ") + cudaGetErrorString(e); ok = false; }
-    }
-    if (ok && g.h_stats->error) {
-        g.err = g.h_stats->error == 2 ? "internal: result slab bound exceeded" : "internal: result slot bound exceeded";
-        ok = false;
-    }
-    if (ok) {
-        cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
-        cudaEventElapsedTime(&g.last_compute_ms, g.evk0, g.evk1);
-        g.last_algo_bytes = g.h_stats->algo_bytes;
-        R->n_containers = g.h_stats->dir_cursor;
-        R->slab_used = g.h_stats->slab_cursor;
+        ok = ok && cudaMemcpyAsync(R->pstats, g.d_stats, sizeof(OpStats), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+        cudaEventRecord(R->ev[3], g.stream);
+        // no synchronisation here: the counters are taken over by resolve() on first use
+        R->pending = true;
+        R->staging = pb.h;            // the pinned pair list must outlive its H2D copy
+        R->staging_bytes = pb.bytes;
+        pb.h = nullptr;
         R->parentA = A->h_ptr;
         R->parentB = B->h_ptr;
         R->portable_bytes = 0;
         R->mirrors_pending = np > 0;  // h_cnt / h_bytes / h_card: see ensure_mirrors()
-        g.last_out_portable = g.h_stats->out_portable;
-        if (np == 1) {  // a single result: its mirrors are the op's counters, no extra D2H
-            R->h_cnt[0] = (uint32_t)R->n_containers;
-            R->h_bytes[0] = R->slab_used;
-            R->mirrors_pending = false;
-        }
         R->lazy = (rules & RULES_LAZY) != 0 && !(rules & RULES_FLIP);
         for (size_t p = 0; p < np; p++) R->h_flags[p] = (A->h_flags[ia[p]] | B->h_flags[ib[p]]) & FLAG_COW;
+        g.last_op = R;
     }
-    pb.release();
+    pb.release();     // device buffers: stream-ordered reuse
     ib_.release();
     if (!ok) {
+        if (g.err.empty()) g.err = "batch op: enqueue failed";
         set_delete(R);
         return nullptr;
     }
@@ -1335,6 +1428,7 @@ int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, cons
     }
     if (ok) {
         memcpy(out, h_out, 8 * np);
+        g.last_op = nullptr;  // the rb200_last_* getters now describe this (synchronous) op
         cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
         cudaEventElapsedTime(&g.last_compute_ms, g.evk0, g.evk1);
     }
@@ -1405,6 +1499,7 @@ rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, s
         if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("or_many launch: ") + cudaGetErrorString(e); ok = false; }
     }
     if (ok) {
+        g.last_op = nullptr;  // the rb200_last_* getters now describe this (synchronous) op
         cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
         cudaEventElapsedTime(&g.last_compute_ms, g.evk0, g.evk1);
         const uint32_t nk = g.h_stats->nk;
@@ -1485,6 +1580,7 @@ rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n)
         if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("xor_many launch: ") + cudaGetErrorString(e); ok = false; }
     }
     if (ok) {
+        g.last_op = nullptr;  // the rb200_last_* getters now describe this (synchronous) op
         cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
         cudaEventElapsedTime(&g.last_compute_ms, g.evk0, g.evk1);
         const uint32_t live = (uint32_t)g.h_stats->dir_cursor;
@@ -1536,6 +1632,7 @@ int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out) {
 namespace {
 
 bool ensure_mirror(rb200_set *s) {
+    if (!resolve(s)) return false;
     if (s->m_dir) return true;
     s->m_dir = (uint8_t *)pin_alloc(s->L.total);
     s->m_slab = (uint8_t *)pin_alloc(s->slab_used);
@@ -1768,6 +1865,7 @@ rb200_download_stream_t *rb200_download_begin(const rb200_set_t *s, size_t chunk
 // defer: pack only; the caller owns the staging ring and enqueues the copies itself
 static rb200_download_stream *download_begin_impl(const rb200_set *s, size_t chunk_bitmaps, bool defer) {
     if (!ctx_init()) return nullptr;
+    if (!resolve(s)) return nullptr;
     const size_t nb = s->n_bitmaps;
     rb200_download_stream *st = new rb200_download_stream();
     st->nb = nb;
@@ -2416,6 +2514,7 @@ rb200_set_t *rb200_set_repair_after_lazy(const rb200_set_t *S) {
 }
 static rb200_set *convert_impl(const rb200_set *S, int mode) {
     if (!ctx_init()) return nullptr;
+    if (!resolve(S)) return nullptr;
     const uint64_t nc = S->n_containers;
     // mode 1 never grows a container by more than its 16-byte padding; mode 0 may expand runs
     const uint64_t bound = S->slab_used + 16 * nc + (mode == 0 ? nc * (uint64_t)BITSET_BYTES : 0) + 512;
@@ -2444,6 +2543,7 @@ static rb200_set *convert_impl(const rb200_set *S, int mode) {
 int rb200_set_to_uint32(const rb200_set_t *S, uint32_t **vals, uint64_t **off_out) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return -1;
+    if (!resolve(S)) return -1;
     const size_t nb = S->n_bitmaps;
     const uint64_t nc = S->n_containers;
     *vals = nullptr;
@@ -2512,6 +2612,7 @@ int rb200_set_serialize_frozen(const rb200_set_t *s, char **buf, uint64_t **off_
 }
 static int serialize_impl(const rb200_set *s, char **buf, uint64_t **off_out, uint64_t **len_out, bool frozen) {
     if (!ctx_init()) return -1;
+    if (!resolve(s)) return -1;
     if (reject_lazy(s, "serialize")) return -1;
     const size_t nb = s->n_bitmaps;
     *buf = nullptr;
@@ -3168,6 +3269,7 @@ HeapEl heap_pop(std::vector<HeapEl> &e, uint32_t &n) {  // pq_poll :84-95
 }
 // portable sizes (header + containers) of every bitmap of a set, lazy state included
 bool portable_sizes(const rb200_set *S, std::vector<uint32_t> &out) {
+    if (!resolve(S)) return false;
     const size_t nb = S->n_bitmaps;
     out.assign(nb, 0);
     if (!nb) return true;
@@ -3233,8 +3335,8 @@ rb200_set_t *rb200_or_many_heap(const rb200_set_t *S, const uint32_t *idx, size_
             R = batch_op_impl(OP_OR, a.set, b.set, &a.index, &b.index, 1, RULES_LAZY);
         if (a.temp) set_delete(a.set);
         if (b.temp) set_delete(b.set);
-        if (!R) { ok = false; break; }
-        heap_push(e, cnt, HeapEl{g.last_out_portable, true, R, 0});  // size measured by k_finalize_pairs
+        if (!R || !resolve(R)) { set_delete(R); ok = false; break; }
+        heap_push(e, cnt, HeapEl{R->out_portable, true, R, 0});  // size measured by k_finalize_pairs
     }
     if (!ok) {
         for (uint32_t i = 0; i < cnt; i++) if (e[i].temp) set_delete(e[i].set);

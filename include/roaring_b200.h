@@ -157,6 +157,11 @@ uint64_t rb200_set_payload_bytes(const rb200_set_t *s);     /* container_size_in
 rb200_set_t *rb200_batch_op(int op, const rb200_set_t *A, const rb200_set_t *B,
                             const uint32_t *ia, const uint32_t *ib, size_t npairs);
 
+/* Batch ops return as soon as their kernels are queued on the library stream; the op's counters
+ * (and a possible internal error) are collected when the result is first used.  This reads them:
+ * device time of the whole op / of its compute kernel (CUDA events), algorithmic bytes. */
+int rb200_set_op_stats(const rb200_set_t *s, float *device_ms, float *compute_ms, uint64_t *algorithmic_bytes);
+
 /* Same with flags (the results are always new bitmaps):
  *   RB200_INPLACE_RULES    type rules of the in-place twins (roaring_bitmap_or_inplace ...)
  *   RB200_LAZY_RULES       OR / XOR only: the lazy variants (roaring.h:932-977); the result set is
