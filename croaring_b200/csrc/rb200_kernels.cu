@@ -388,6 +388,7 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long acc_bytes = 0, acc_outb = 0;  // per-warp totals: one atomic each at the end
     for (uint32_t p = warp; p < npairs; p += nwarps) {
         const uint64_t i0 = item_off[p], i1 = item_off[p + 1];
         // pass 1: count surviving containers, cardinality and algorithmic bytes
@@ -422,8 +423,8 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
         unsigned long long base = 0;
         if (lane == 0) {
             base = atomicAdd(&st->dir_cursor, (unsigned long long)cnt);
-            atomicAdd(&st->algo_bytes, bytes);
-            atomicAdd(&st->out_portable, outb + portable_header_bytes(cnt, anyrun != 0));
+            acc_bytes += bytes;
+            acc_outb += outb + portable_header_bytes(cnt, anyrun != 0);
             out.bm_beg[p] = (uint32_t)base;
             out.bm_cnt[p] = cnt;
             out.bm_card[p] = card;
@@ -447,6 +448,10 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
             }
             done += __popc(m);
         }
+    }
+    if (lane == 0 && (acc_bytes | acc_outb)) {
+        atomicAdd(&st->algo_bytes, acc_bytes);
+        atomicAdd(&st->out_portable, acc_outb);
     }
 }
 
@@ -680,7 +685,9 @@ void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W,
 void launch_finalize_pairs(const SetView &A, const SetView &B, Items it, const uint64_t *item_off,
                            uint32_t npairs, SetOut out, OpStats *st, cudaStream_t s) {
     if (!npairs) return;
-    const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * 16);
+    // ~4 pairs per warp on big batches: the two per-warp counter atomics amortise, the per-pair
+    // directory allocation stays one atomic per pair
+    const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * 8);
     k_finalize_pairs<<<g, 128, 0, s>>>(A, B, it, item_off, npairs, out, st);
     g_launches++;
 }
