@@ -36,4 +36,4 @@ timeout 900 compute-sanitizer --tool memcheck python -c "import __graft_entry__ 
 timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/racecheck.log 2>&1
 fi
 cat gpurun_out/pytest_gpu.log | tail -2; tail -1 gpurun_out/smoke.log; head -c 400 gpurun_out/bench.json; echo; tail -3 gpurun_out/bench.err; head -c 300 gpurun_out/bench_ref.json; echo
-tail -2 gpurun_out/extras_*.err
+tail -qn 2 gpurun_out/extras_*.err
