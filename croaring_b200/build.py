@@ -37,7 +37,21 @@ def needs_build():
     return _newest(deps) > os.path.getmtime(LIB)
 
 
+WORKGEN_LIB = os.path.join(HERE, "libworkgen.so")
+
+
+def build_workgen(force=False):
+    """Host-only workload generators (plain C + pthreads; bench / test input builders)."""
+    src = os.path.join(CSRC, "workgen.c")
+    if not force and os.path.exists(WORKGEN_LIB) and os.path.getmtime(WORKGEN_LIB) >= os.path.getmtime(src):
+        return WORKGEN_LIB
+    subprocess.check_call([os.environ.get("CC", "gcc"), "-O3", "-fPIC", "-std=gnu11", "-shared",
+                           "-fvisibility=hidden", "-o", WORKGEN_LIB, src, "-lm", "-lpthread"])
+    return WORKGEN_LIB
+
+
 def build(force=False, verbose=False):
+    build_workgen(force)
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -367,7 +367,9 @@ static __device__ __noinline__ void acc_apply_runs(uint32_t *acc, const uint8_t 
         const uint32_t i = base + lane;
         const bool valid = i < n;
         const uint32_t r = valid ? __ldg(runs + i) : 0u;
-        const uint32_t lo = r & 0xffffu, hi = lo + (r >> 16);
+        // (hi is clamped: a run ending past 65535 can only come from a caller-built host bitmap that
+        //  breaks the reference's own invariants; it must not write outside the accumulator)
+        const uint32_t lo = r & 0xffffu, hi = min(lo + (r >> 16), 65535u);
         acc_apply_ranges<MODE, ATOMIC_INTERIOR>(acc, lo, hi, valid, lane);
     }
 }
@@ -384,7 +386,7 @@ static __device__ __noinline__ void acc_and_runs(uint32_t *acc, const uint8_t *s
         if (valid) {
             if (i > 0) {
                 const uint32_t r = __ldg(runs + i - 1);
-                lo = (int)((r & 0xffffu) + (r >> 16)) + 1;
+                lo = min((int)((r & 0xffffu) + (r >> 16)), 65535) + 1;
             }
             if (i < n) {
                 const uint32_t r = __ldg(runs + i);

@@ -23,6 +23,7 @@
 #include <functional>
 #include <stdio.h>
 #include <thread>
+#include <limits>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -571,7 +572,12 @@ int rb200_init(int device) {
 void rb200_set_stream(void *cuda_stream) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return;
-    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    if (next == g.stream) return;
+    // The device pools hand buffers back as soon as the work using them is ENQUEUED (stream-ordered
+    // reuse), which is only sound on one stream: drain the old stream before work moves to the new one.
+    cudaStreamSynchronize(g.stream);
+    g.stream = next;
 }
 
 void rb200_synchronize(void) {
@@ -1132,7 +1138,11 @@ static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens,
             g.err = std::string("deserialize: ") + cudaGetErrorString(e);
             ok = false;
         }
-        if (ok && g.h_stats->error) {
+        if (ok && g.h_stats->error == 4u) {
+            g.err = "malformed serialized bitmap: invalid container contents (a run ends past 65535, runs "
+                    "overlap or are out of order, or array values are not strictly increasing)";
+            ok = false;
+        } else if (ok && g.h_stats->error) {
             g.err = std::string(frozen ? "malformed frozen bitmap at index " : "malformed portable bitmap at index ") +
                     std::to_string((uint64_t)n - g.h_stats->nk);
             ok = false;
@@ -2739,6 +2749,13 @@ int rb200_batch_op_host(int op, const roaring_bitmap_t *const *a, const roaring_
 }
 
 // =================================================================== drop-in entry points
+// Entry points whose reference signature has no error channel (bool / void): a device failure is
+// reported on stderr (and aborts under RB200_STRICT=1) instead of passing for an answer.
+static void dropin_failed(const char *fn) {
+    fprintf(stderr, "libroaring_b200: %s failed: %s\n", fn, g.err.empty() ? "unknown error" : g.err.c_str());
+    const char *e = getenv("RB200_STRICT");
+    if (e && e[0] == '1') abort();
+}
 static roaring_bitmap_t *dropin_pair(int op, const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
     roaring_bitmap_t *out = nullptr;
     if (rb200_batch_op_host(op, &r1, &r2, 1, &out) != 0) return nullptr;
@@ -2781,14 +2798,14 @@ static void dropin_inplace(int op, roaring_bitmap_t *x1, const roaring_bitmap_t 
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     const roaring_bitmap_t *both[2] = {x1, x2};
     rb200_set *S = rb200_set_upload(both, 2);
-    if (!S) return;
+    if (!S) { dropin_failed("roaring_bitmap_*_inplace"); return; }
     rb200_set_bind_host(S, 1);
     const uint32_t ia = 0, ib = 1;
     rb200_set *R = batch_op_impl(op, S, S, &ia, &ib, 1, rules);
     roaring_bitmap_t *out = R ? rb200_set_download(R, 0) : nullptr;
     set_delete(R);
     set_delete(S);
-    if (!out) return;  // CUDA failure: x1 is left untouched, rb200_last_error() tells why
+    if (!out) { dropin_failed("roaring_bitmap_*_inplace"); return; }  // x1 is left untouched
     swap_into(x1, out);
 }
 static void swap_into(roaring_bitmap_t *x1, roaring_bitmap_t *out) {
@@ -2855,10 +2872,12 @@ uint64_t roaring_bitmap_xor_cardinality(const roaring_bitmap_t *r1, const roarin
 double roaring_bitmap_jaccard_index(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
     const uint64_t c1 = rb200_bitmap_get_cardinality(r1), c2 = rb200_bitmap_get_cardinality(r2);
     const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
+    if (inter == UINT64_MAX) return std::numeric_limits<double>::quiet_NaN();  // device failure: rb200_last_error()
     return (double)inter / (double)(c1 + c2 - inter);
 }
 bool roaring_bitmap_intersect(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
     const uint64_t inter = roaring_bitmap_and_cardinality(r1, r2);
+    if (inter == UINT64_MAX) dropin_failed("roaring_bitmap_intersect");
     return inter != 0 && inter != UINT64_MAX;
 }
 
@@ -2884,11 +2903,12 @@ static int dropin_relation(const roaring_bitmap_t *r1, const roaring_bitmap_t *r
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     const roaring_bitmap_t *both[2] = {r1, r2};
     rb200_set *S = rb200_set_upload(both, 2);
-    if (!S) return -1;
+    if (!S) { dropin_failed("roaring_bitmap_equals / is_subset / is_strict_subset"); return -1; }
     const uint32_t ia = 0, ib = 1;
     uint8_t out = 0;
     const int rc = rb200_batch_relations(S, S, &ia, &ib, 1, &out);
     set_delete(S);
+    if (rc != 0) dropin_failed("roaring_bitmap_equals / is_subset / is_strict_subset");
     return rc != 0 ? -1 : out;
 }
 bool roaring_bitmap_equals(const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
@@ -2917,7 +2937,10 @@ rb200_set_t *rb200_batch_flip(const rb200_set_t *S, const uint32_t *idx, size_t 
     std::vector<uint32_t> ia(n), ib(n, 0);
     for (size_t i = 0; i < n; i++) ia[i] = idx ? idx[i] : (uint32_t)i;
     std::vector<uint8_t> blob;
-    const bool noop = range_start >= range_end || range_start > (uint64_t)UINT32_MAX + 1;  // roaring.c:2292
+    // roaring.c:2292 (open range empty / start past the 32-bit universe) and :2303 (the CLOSED
+    // range, after the reference's truncation of both ends to 32 bits, is empty): plain copy
+    const bool noop = range_start >= range_end || range_start > (uint64_t)UINT32_MAX + 1 ||
+                      (uint32_t)range_start > (uint32_t)(range_end - 1);
     if (noop) {  // copy: symmetric difference with the empty bitmap
         const uint32_t hdr[2] = {SERIAL_COOKIE_NO_RUN, 0};
         blob.assign((const uint8_t *)hdr, (const uint8_t *)hdr + 8);
@@ -2967,7 +2990,9 @@ roaring_bitmap_t *roaring_bitmap_flip(const roaring_bitmap_t *r1, uint64_t range
 }
 void roaring_bitmap_flip_inplace(roaring_bitmap_t *r1, uint64_t range_start, uint64_t range_end) {
     if (range_start >= range_end || range_start > (uint64_t)UINT32_MAX + 1) return;  // roaring.c:2353
+    if ((uint32_t)range_start > (uint32_t)(range_end - 1)) return;                    // roaring.c:2364
     roaring_bitmap_t *out = roaring_bitmap_flip(r1, range_start, range_end);
+    if (!out) dropin_failed("roaring_bitmap_flip_inplace");
     if (out) {
         std::lock_guard<std::recursive_mutex> lk(g.mu);
         swap_into(r1, out);
@@ -3215,12 +3240,13 @@ void roaring_bitmap_repair_after_lazy(roaring_bitmap_t *r1) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     const roaring_bitmap_t *one[1] = {r1};
     rb200_set *S = rb200_set_upload(one, 1);
-    if (!S) return;
+    if (!S) { dropin_failed("roaring_bitmap_repair_after_lazy"); return; }
     rb200_set *R = rb200_set_repair_after_lazy(S);
     roaring_bitmap_t *out = R ? rb200_set_download(R, 0) : nullptr;
     set_delete(R);
     set_delete(S);
     if (out) swap_into(r1, out);
+    else dropin_failed("roaring_bitmap_repair_after_lazy");
 }
 
 // ---- roaring_bitmap_or_many_heap (src/roaring_priority_queue.c:200-250) ------------------------

@@ -991,8 +991,8 @@ k_deser_dir(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ roff,
 
 __global__ void __launch_bounds__(128)
 k_deser_copy(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ src_pos, uint64_t nc,
-             SetOut out, const OpStats *st) {
-    if (st->error) return;  // a malformed blob leaves directory entries unwritten: nothing to move
+             SetOut out, OpStats *st) {
+    if (st->error == 3u) return;  // a malformed blob leaves directory entries unwritten: nothing to move
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1005,17 +1005,32 @@ k_deser_copy(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ src_p
         warp_copy_unaligned(dst, src, n, lane);
         const uint32_t pad = round16(n) - n;
         if ((uint32_t)lane < pad) dst[n + lane] = 0;
-        if (t == T_RUN) {  // run_container_cardinality (run.c:1077)
+        // Container CONTENTS of an untrusted blob (the device-side counterpart of the payload checks of
+        // roaring_bitmap_internal_validate, src/containers/run.c:693-713, array.c:469-487): the
+        // kernels rasterise runs and index by array values without further checks, so a run that
+        // ends past 65535 or unsorted data must never reach them.
+        bool bad = false;
+        if (t == T_RUN) {  // run_container_cardinality (run.c:1077) + bounds / order of the runs
             uint32_t card = 0;
-            for (uint32_t k = lane; k < len; k += 32) card += ld_u16(src + 4 * k + 2) + 1u;
+            bad = len == 0;
+            for (uint32_t k = lane; k < len; k += 32) {
+                const uint32_t s0 = ld_u16(src + 4 * k), l0 = ld_u16(src + 4 * k + 2);
+                card += l0 + 1u;
+                if (s0 + l0 > 65535u) bad = true;
+                if (k > 0 && s0 <= ld_u16(src + 4 * k - 4) + ld_u16(src + 4 * k - 2)) bad = true;
+            }
             card = __reduce_add_sync(FULLMASK, card);
             if (lane == 0) out.c_card[c] = card;
+        } else if (t == T_ARRAY) {  // strictly increasing values
+            for (uint32_t k = lane + 1; k < len; k += 32)
+                if (ld_u16(src + 2 * k) <= ld_u16(src + 2 * k - 2)) bad = true;
         }
+        if (__any_sync(FULLMASK, bad) && lane == 0) atomicCAS(&st->error, 0u, 4u);
     }
 }
 
 __global__ void k_deser_bitmap_cards(SetOut out, uint32_t nb, const OpStats *st) {
-    if (st->error) return;
+    if (st->error == 3u) return;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;

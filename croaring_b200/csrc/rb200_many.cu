@@ -262,7 +262,7 @@ __device__ __forceinline__ void many_accumulate(ManySmem &sm, const SetView &S, 
                 atomicOr(sm.acc + cur_w, cur_m);
             } else if (kind[k] == 2) {  // one run
                 const uint32_t r = q[k].x;
-                const uint32_t s0 = r & 0xffffu, e0 = s0 + (r >> 16);
+                const uint32_t s0 = r & 0xffffu, e0 = min(s0 + (r >> 16), 65535u);
                 const uint32_t ws = s0 >> 5, we = e0 >> 5;
                 const uint32_t m_lo = ~0u << (s0 & 31), m_hi = ~0u >> (31 - (e0 & 31));
                 if (ws == we) {
@@ -554,7 +554,7 @@ k_xor_many(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
                 } else {
                     const uint32_t *runs = reinterpret_cast<const uint32_t *>(p);
                     for (uint32_t i = tid; i < l2; i += OM_THREADS) {
-                        const uint32_t r = __ldg(runs + i), s0 = r & 0xffffu, e0 = s0 + (r >> 16);
+                        const uint32_t r = __ldg(runs + i), s0 = r & 0xffffu, e0 = min(s0 + (r >> 16), 65535u);
                         const uint32_t ws = s0 >> 5, we = e0 >> 5;
                         const uint32_t m_lo = ~0u << (s0 & 31), m_hi = ~0u >> (31 - (e0 & 31));
                         if (ws == we) {

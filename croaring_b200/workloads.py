@@ -1,10 +1,104 @@
-"""Synthetic workload generators of BASELINE.json configs[2..4], numpy only.
+"""Synthetic workload generators of BASELINE.json configs[2..4].
 
 They emit portable-serialized bitmaps directly (the format of
 /root/reference/src/roaring_array.c:469-531), so neither the reference nor the oracle is needed
-to build inputs; parity tests feed the same bytes to both sides.
+to build inputs; parity tests feed the same bytes to both sides.  The full-size generators are
+plain C + pthreads (croaring_b200/csrc/workgen.c -> libworkgen.so; the PCG32 definition of the
+survey); the numpy helpers below build small hand-made cases for tests.
 """
+import ctypes as C
+import os
+
 import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_WG = None
+
+
+def _wg():
+    global _WG
+    if _WG is None:
+        path = os.path.join(_HERE, "libworkgen.so")
+        if not os.path.exists(path):
+            from . import build as _b
+            _b.build_workgen()
+        L = C.CDLL(path)
+        L.rb200_workgen_zipf.restype = C.c_int
+        L.rb200_workgen_zipf.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int,
+                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rb200_workgen_dense.restype = C.c_int
+        L.rb200_workgen_dense.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        L.rb200_workgen_free.restype = None
+        L.rb200_workgen_free.argtypes = [C.c_void_p, C.c_uint32]
+        _WG = L
+    return _WG
+
+
+def _threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class BlobArena:
+    """n portable blobs owned by C memory: `ptrs` / `lens` are ctypes arrays that go straight
+    into rb200_set_upload_serialized (and the reference's deserializer) without a Python copy."""
+
+    def __init__(self, n):
+        self.n = n
+        self.ptrs = (C.c_void_p * n)()
+        self.lens = (C.c_size_t * n)()
+        self.cards = np.zeros(n, dtype=np.uint64)
+
+    def __len__(self):
+        return self.n
+
+    def blob(self, i) -> bytes:
+        return C.string_at(self.ptrs[i], self.lens[i])
+
+    def blobs(self):
+        return [self.blob(i) for i in range(self.n)]
+
+    def total_bytes(self):
+        return int(sum(self.lens))
+
+    def free(self):
+        if self.n and _WG is not None:
+            _WG.rb200_workgen_free(self.ptrs, self.n)
+        self.n = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def zipf_universe(n_values, density):
+    """U = min(2^32, ceil(n / d)) (d = 0.001 is clamped by the 32-bit universe:
+    effective d_min = 10^7 / 2^32 ~ 0.00233)."""
+    return int(min(2 ** 32, -(-int(n_values) * 1000000 // int(round(density * 1000000)))))
+
+
+def zipf_arena(nb, universe, n_values=None, b0=0, density_draw=False, run_optimize=True, threads=None):
+    """Bitmaps b0..b0+nb-1 of the survey's Zipf family (see csrc/workgen.c) as a BlobArena.
+    n_values: one int (same cardinality for all) or None with density_draw (config 5)."""
+    A = BlobArena(nb)
+    rc = _wg().rb200_workgen_zipf(b0, nb, int(universe), None, int(n_values or 0), 1 if density_draw else 0,
+                                  1 if run_optimize else 0, threads or _threads(), A.ptrs, A.lens,
+                                  A.cards.ctypes.data)
+    if rc != 0:
+        raise MemoryError("rb200_workgen_zipf failed")
+    return A
+
+
+def dense_arena(nb, n_keys=16, i0=0, threads=None):
+    """Config 4: bitmaps i0..i0+nb-1, universe n_keys * 2^16, density 0.5."""
+    A = BlobArena(nb)
+    if _wg().rb200_workgen_dense(i0, nb, n_keys, threads or _threads(), A.ptrs, A.lens) != 0:
+        raise MemoryError("rb200_workgen_dense failed")
+    return A
 
 SERIAL_COOKIE_NO_RUN = 12346
 SERIAL_COOKIE = 12347
@@ -88,91 +182,10 @@ def values_to_blob(vals):
     return serialize_containers(keys.tolist(), conts)
 
 
-# ------------------------------------------------------------------------------------------
-# Zipfian many-way-union inputs (BASELINE.json configs[2] and [4]).
-#
-# SURVEY.md defines bitmap b as "draw v = floor(U^u) - 1, u ~ U(0,1], until n distinct values":
-# P(v) ∝ 1/(v+1) (Zipf s=1).  Drawing ~n*ln(U) samples per bitmap is far too slow for a bench
-# that must finish in minutes, so we generate the Poissonised form of the same process: value v
-# is present independently with probability 1 - exp(-c/(v+1)), c chosen so that the expected
-# cardinality is n.  Per 2^16-value container the inclusion density is (nearly) constant, so a
-# container is filled either by thresholding random bits (density >= 1/16, quantised to 1/16)
-# or by geometric gap sampling (sparse).  Low keys saturate (full containers -> exercises the
-# or_many full-container state machine), high keys are sparse arrays.
-def _zipf_key_density(n_keys, n_values):
-    mid = (np.arange(n_keys, dtype=np.float64) * 65536.0 + 32768.0)
-    lo, hi = 1e-3, 1e12
-    for _ in range(200):
-        c = np.sqrt(lo * hi)
-        tot = (1.0 - np.exp(-c / mid)).sum() * 65536.0
-        if tot > n_values:
-            hi = c
-        else:
-            lo = c
-    return 1.0 - np.exp(-np.sqrt(lo * hi) / mid)
-
-
-def _random_words(rng, n_words, sixteenths):
-    """n_words u64 with each bit set with probability sixteenths/16 (1..16)."""
-    if sixteenths >= 16:
-        return np.full(n_words, np.uint64(0xFFFFFFFFFFFFFFFF))
-    r = rng.integers(0, 2 ** 63, size=(4, n_words), dtype=np.int64).view(np.uint64)
-    r = r ^ (rng.integers(0, 2, size=(4, n_words), dtype=np.int64).view(np.uint64) << np.uint64(63))
-    acc = np.zeros(n_words, dtype=np.uint64)          # probability 0
-    for k in range(4):                                 # binary expansion, LSB first
-        acc = (acc | r[k]) if (sixteenths >> k) & 1 else (acc & r[k])
-    return acc
-
-
-def zipf_bitmap_blob(rng, n_values, density, run_optimize_full=True):
-    """One portable bitmap with ~n_values Zipf-distributed values over universe n_values/density
-    (clamped to 2^32).  Saturated containers are emitted as the full run [0,65535]."""
-    universe = min(2 ** 32, int(np.ceil(n_values / density)))
-    n_keys = (universe + 65535) // 65536
-    dens = _zipf_key_density(n_keys, n_values)
-    keys, conts = [], []
-    dense = np.flatnonzero(dens >= 1.0 / 16)
-    for k in dense:
-        q = int(min(16, max(1, round(dens[k] * 16))))
-        if q >= 16 and run_optimize_full:
-            conts.append(("r", np.array([[0, 65535]], dtype=np.uint16)))
-        else:
-            w = _random_words(rng, 1024, q)
-            card = int(np.unpackbits(w.view(np.uint8)).sum())
-            if card <= 4096:
-                bits = np.unpackbits(w.view(np.uint8), bitorder="little")
-                conts.append(("a", np.flatnonzero(bits).astype(np.uint16)))
-            else:
-                conts.append(("b", w))
-        keys.append(int(k))
-    # sparse tail: geometric gaps over the concatenated remaining universe, piecewise by key
-    sparse = np.flatnonzero(dens < 1.0 / 16)
-    if len(sparse):
-        # one gap stream per block of keys with similar density keeps this vectorised
-        for blk in np.array_split(sparse, max(1, len(sparse) // 64)):
-            if len(blk) == 0:
-                continue
-            d = float(dens[blk].mean())
-            span = len(blk) * 65536
-            m = int(span * d * 1.3 + 64)
-            pos = np.cumsum(rng.geometric(d, size=m)) - 1
-            pos = pos[pos < span]
-            kk = pos >> 16
-            low = (pos & 0xFFFF).astype(np.uint16)
-            ks, starts = np.unique(kk, return_index=True)
-            ends = np.append(starts[1:], len(pos))
-            for kidx, s, e in zip(ks, starts, ends):
-                if e - s > 4096:                      # cannot happen for d < 1/16 (mean 4096) but be safe
-                    bits = np.zeros(65536, dtype=np.uint8)
-                    bits[low[s:e]] = 1
-                    conts.append(("b", np.packbits(bits, bitorder="little").view(np.uint64)))
-                else:
-                    conts.append(("a", low[s:e]))
-                keys.append(int(blk[int(kidx)]))
-    order = np.argsort(keys, kind="stable")
-    return serialize_containers([keys[i] for i in order], [conts[i] for i in order])
-
-
 def zipf_blobs(n_bitmaps, n_values, density, seed=0):
-    return [zipf_bitmap_blob(np.random.default_rng(seed * 100003 + b), n_values, density)
-            for b in range(n_bitmaps)]
+    """n_bitmaps Zipf bitmaps of n_values values each at the given density as a list of bytes
+    (small test sizes; `seed` offsets the PCG32 stream index)."""
+    A = zipf_arena(n_bitmaps, zipf_universe(n_values, density), n_values, b0=1000 * seed)
+    out = A.blobs()
+    A.free()
+    return out

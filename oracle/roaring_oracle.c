@@ -1102,7 +1102,9 @@ size_t oracle_flip(const uint8_t *a, size_t na, uint64_t range_start, uint64_t r
                    size_t cap) {
     obm_t x, ans;
     if (!bm_parse(&x, a, na)) return (size_t)-1;
-    if (range_start >= range_end || range_start > (uint64_t)0xFFFFFFFFu + 1) { /* :2292-2294 */
+    /* :2292-2294, and flip_closed's own guard on the truncated 32-bit ends (:2303-2305) */
+    if (range_start >= range_end || range_start > (uint64_t)0xFFFFFFFFu + 1 ||
+        (uint32_t)range_start > (uint32_t)(range_end - 1)) {
         size_t r0 = bm_serialize(&x, out, cap);
         bm_free(&x);
         return r0;

@@ -90,6 +90,26 @@ def test_device_deserialize_rejects_malformed(rb, R):
         with pytest.raises(rb.RB200Error) as ei:
             rb.DeviceSet.from_serialized(good[:2] + [blob] + good[4:])
         assert "malformed portable bitmap at index 2" in str(ei.value), (name, str(ei.value))
+    # container CONTENTS are checked too (a run ending past 65535 would be rasterised
+    # outside the warp's accumulator): run overflow, overlapping runs, unsorted array values
+    content_cases = {}
+    rb_ = bytearray(runblob)
+    struct.pack_into("<HH", rb_, hdr + 2, 65000, 1000)            # first run: 65000 + 1000 > 65535
+    content_cases["run ends past 65535"] = bytes(rb_)
+    rb_ = bytearray(runblob)
+    if struct.unpack_from("<H", rb_, hdr)[0] >= 2:
+        s0, l0 = struct.unpack_from("<HH", rb_, hdr + 2)
+        struct.pack_into("<HH", rb_, hdr + 6, s0 + l0, 0)        # second run starts inside the first
+        content_cases["runs overlap"] = bytes(rb_)
+    r = R.from_values(np.array([5, 9, 13, 70000, 70001], dtype=np.uint32), run_optimize=False)
+    ab = bytearray(R.serialize(r))
+    R.free(r)
+    ab[8 + 8 * 2 + 8 * 0:8 + 16 + 2] = struct.pack("<H", 9)      # values 9, 9, 13: not strictly increasing
+    content_cases["array values not increasing"] = bytes(ab)
+    for name, blob in content_cases.items():
+        with pytest.raises(rb.RB200Error) as ei:
+            rb.DeviceSet.from_serialized(good[:2] + [blob] + good[4:])
+        assert "invalid container contents" in str(ei.value), (name, str(ei.value))
     # the library keeps working afterwards
     assert rb.DeviceSet.from_serialized(good).serialize_all() == good
 

@@ -111,7 +111,9 @@ def test_oracle_heap_vs_reference_realdata(O, R, ds):
 
 FLIP_RANGES = [(0, 1), (5, 6), (5, 7), (0, 65536), (0, 65537), (65535, 65537), (100, 70000), (65536, 131072),
                (1 << 16, (5 << 16) + 17), (3, 3), (9, 4), (0, 1 << 32), ((1 << 32) - 1, 1 << 32), ((1 << 32) - 70000, 1 << 32),
-               (123456, 654321), (2 << 16, (2 << 16) + 4097), ((1 << 32) + 1, (1 << 32) + 5)]
+               (123456, 654321), (2 << 16, (2 << 16) + 4097), ((1 << 32) + 1, (1 << 32) + 5),
+               # range_end past 2^32: the reference truncates both ends to 32 bits, the closed range is then empty
+               (10, (1 << 32) + 5), (100000, (1 << 32) + 5), (1 << 32, (1 << 32) + 7)]
 
 
 @pytest.mark.parametrize("seed", [17, 18])
