@@ -74,7 +74,7 @@ def lib():
     sig("rb200_last_compute_ms", C.c_float)
     sig("rb200_last_download_bytes", C.c_uint64)
     sig("rb200_set_upload", _P, C.POINTER(_P), C.c_size_t)
-    sig("rb200_set_upload_serialized", _P, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t)
+    sig("rb200_set_upload_serialized", _P, _P, _P, C.c_size_t)
     sig("rb200_set_free", None, _P)
     sig("rb200_set_bind_host", C.c_int, _P, C.c_int)
     sig("rb200_set_count", C.c_size_t, _P)
@@ -109,7 +109,7 @@ def lib():
     sig("rb200_serialized_free", None, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     sig("rb200_set_serialize_frozen", C.c_int, _P, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)),
         C.POINTER(C.POINTER(C.c_uint64)))
-    sig("rb200_set_upload_frozen", _P, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t)
+    sig("rb200_set_upload_frozen", _P, _P, _P, C.c_size_t)
     sig("rb200_download_begin", _P, _P, C.c_size_t)
     sig("rb200_download_chunk_capacity", C.c_size_t, _P)
     sig("rb200_download_next", C.c_size_t, _P, C.POINTER(_P))
@@ -120,6 +120,23 @@ def lib():
     sig("rb200_download_wait", C.c_int)
     sig("rb200_batch_op_host", C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_size_t,
         C.POINTER(_P))
+    sig("rb200_comm_unique_id", C.c_int, C.c_char_p)
+    sig("rb200_comm_init_rank", _P, C.c_char_p, C.c_int, C.c_int)
+    sig("rb200_comm_adopt", _P, _P, C.c_int, C.c_int)
+    sig("rb200_comm_size", C.c_int, _P)
+    sig("rb200_comm_rank", C.c_int, _P)
+    sig("rb200_comm_destroy", None, _P)
+    sig("rb200_comm_allreduce_u64", C.c_int, _P, _P, C.c_size_t)
+    sig("rb200_set_add_cardinality_device", C.c_int, _P, _P)
+    sig("rb200_plan_key_ranges", C.c_int, _P, _P, C.c_size_t, C.c_int, _P, _P, _P)
+    sig("rb200_blob_slice_keys", C.c_int, C.c_char_p, C.c_size_t, C.c_uint32, C.c_uint32,
+        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
+    sig("rb200_blobs_concat", C.c_int, _P, _P, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
+    sig("rb200_blob_free", None, C.c_void_p)
+    sig("rb200_set_upload_serialized_keyrange", _P, _P, _P, C.c_size_t, C.c_uint32, C.c_uint32)
+    sig("rb200_or_many_sharded", _P, _P, _P, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P,
+        _P, C.POINTER(C.c_uint64))
+    sig("rb200_last_collective_ms", C.c_float)
     _lib = L
     return L
 
@@ -336,8 +353,83 @@ def download_wait():
 
 
 def _blob_args(blobs):
+    """(char* array, size_t array, n) of a list of bytes or of a workloads.BlobArena (no copy)."""
+    if hasattr(blobs, "ptrs"):
+        return blobs.ptrs, blobs.lens, len(blobs)
     n = len(blobs)
     return (C.c_char_p * n)(*blobs), (C.c_size_t * n)(*[len(b) for b in blobs]), n
+
+
+class Comm:
+    """rb200_comm_t: the NCCL communicator of a multi-GPU job (one process per GPU), plain C ABI.
+    Comm.create(rank, world, bcast) bootstraps it: rank 0 draws the NCCL unique id and
+    `bcast(bytes_or_None) -> bytes` carries it to the other ranks (any out-of-band channel, e.g.
+    torch.distributed.broadcast_object_list)."""
+
+    def __init__(self, ptr):
+        if not ptr:
+            raise RB200Error(last_error() or "null communicator")
+        self.ptr = ptr
+
+    @classmethod
+    def create(cls, rank, world, bcast=None):
+        if world == 1:
+            return cls(lib().rb200_comm_init_rank(b"\0" * 128, 1, 0))
+        buf = C.create_string_buffer(128)
+        ident = None
+        if rank == 0:
+            if lib().rb200_comm_unique_id(buf) != 0:
+                raise RB200Error(last_error())
+            ident = buf.raw
+        ident = bcast(ident)
+        return cls(lib().rb200_comm_init_rank(ident, world, rank))
+
+    @property
+    def size(self):
+        return int(lib().rb200_comm_size(self.ptr))
+
+    @property
+    def rank(self):
+        return int(lib().rb200_comm_rank(self.ptr))
+
+    def allreduce_u64(self, device_ptr, count=1):
+        if lib().rb200_comm_allreduce_u64(self.ptr, _P(device_ptr), count) != 0:
+            raise RB200Error(last_error())
+
+    def destroy(self):
+        if self.ptr:
+            lib().rb200_comm_destroy(self.ptr)
+        self.ptr = None
+
+
+def plan_key_ranges(blobs, world):
+    """rb200_plan_key_ranges: ([(lo, hi)] * world balanced by container bytes, (first, last) live key)."""
+    pa, la, n = _blob_args(blobs)
+    lo = (C.c_uint32 * world)()
+    hi = (C.c_uint32 * world)()
+    span = (C.c_uint32 * 2)()
+    if lib().rb200_plan_key_ranges(pa, la, n, world, lo, hi, span) != 0:
+        raise RB200Error(last_error())
+    return [(int(lo[g]), int(hi[g])) for g in range(world)], (int(span[0]), int(span[1]))
+
+
+def blob_slice_keys(blob: bytes, key_lo, key_hi) -> bytes:
+    out, ln = C.c_void_p(), C.c_size_t()
+    if lib().rb200_blob_slice_keys(blob, len(blob), key_lo, key_hi, C.byref(out), C.byref(ln)) != 0:
+        raise RB200Error(last_error())
+    b = C.string_at(out.value, ln.value)
+    lib().rb200_blob_free(out)
+    return b
+
+
+def blobs_concat(blobs) -> bytes:
+    pa, la, n = _blob_args(blobs)
+    out, ln = C.c_void_p(), C.c_size_t()
+    if lib().rb200_blobs_concat(pa, la, n, C.byref(out), C.byref(ln)) != 0:
+        raise RB200Error(last_error())
+    b = C.string_at(out.value, ln.value)
+    lib().rb200_blob_free(out)
+    return b
 
 
 def r64_batch_op(op, a_blobs, b_blobs, ia, ib):
@@ -392,11 +484,14 @@ class DeviceSet:
         return cls(lib().rb200_set_upload(arr, len(bitmaps)))
 
     @classmethod
-    def from_serialized(cls, blobs):
-        n = len(blobs)
-        arr = (C.c_char_p * n)(*blobs)
-        lens = (C.c_size_t * n)(*[len(b) for b in blobs])
-        return cls(lib().rb200_set_upload_serialized(arr, lens, n))
+    def from_serialized(cls, blobs, key_lo=None, key_hi=None):
+        """blobs: list of bytes or a workloads.BlobArena.  key_lo / key_hi: keep only the containers
+        of that key range (what one rank of a key-sharded union uploads)."""
+        arr, lens, n = _blob_args(blobs)
+        if key_lo is None and key_hi is None:
+            return cls(lib().rb200_set_upload_serialized(arr, lens, n))
+        return cls(lib().rb200_set_upload_serialized_keyrange(arr, lens, n, key_lo or 0,
+                                                              65535 if key_hi is None else key_hi))
 
     @classmethod
     def from_frozen(cls, blobs):
@@ -504,6 +599,25 @@ class DeviceSet:
             assert card_per_key.dtype == np.uint32 and card_per_key.size == 65536
         p = lib().rb200_or_many_keyrange(self.ptr, ip, n, key_lo, key_hi, cp)
         return DeviceSet(p)
+
+    def or_many_sharded(self, comm, key_lo, key_hi, span, idx=None):
+        """rb200_or_many_sharded: (this rank's part as a DeviceSet, uint32 per-key cardinalities of
+        the span summed over the ranks, cardinality of the whole union)."""
+        if idx is None:
+            ip, n = None, len(self)
+        else:
+            idx = _u32(idx)
+            ip, n = idx.ctypes.data, idx.size
+        cards = np.zeros(max(0, span[1] - span[0] + 1), dtype=np.uint32)
+        tot = C.c_uint64(0)
+        p = lib().rb200_or_many_sharded(self.ptr, ip, n, key_lo, key_hi, span[0], span[1], comm.ptr,
+                                        cards.ctypes.data, C.byref(tot))
+        return DeviceSet(p), cards, int(tot.value)
+
+    def add_cardinality_device(self, device_ptr):
+        """*device_ptr (u64 in device memory) += sum of the cardinalities of the set's bitmaps."""
+        if lib().rb200_set_add_cardinality_device(self.ptr, _P(device_ptr)) != 0:
+            raise RB200Error(last_error())
 
     def xor_many(self, idx=None):
         if idx is None:

@@ -117,6 +117,7 @@ void launch_finalize_pairs(const SetView &A, const SetView &B, Items it, const u
                            uint32_t npairs, SetOut out, OpStats *st, cudaStream_t s);
 void launch_finalize_cards(Items it, const uint64_t *item_off, uint32_t npairs, uint64_t *out,
                            cudaStream_t s);
+void launch_sum_cardinalities(const uint64_t *bm_card, uint32_t n, uint64_t *d_acc, cudaStream_t s);
 void launch_set_cardinalities(const SetView &S, uint32_t n_bitmaps, uint64_t *out, cudaStream_t s);
 
 // packing for download: measure+scan (off/beg have n+1 entries), then copy

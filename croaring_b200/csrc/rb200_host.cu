@@ -35,6 +35,7 @@
 #pragma GCC visibility pop
 #include "rb200_common.h"
 #include "rb200_device.cuh"
+#include "rb200_internal.h"
 
 using namespace rb200;
 
@@ -103,7 +104,6 @@ struct Ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
-    std::string err;
     OpStats *d_stats = nullptr;
     OpStats *h_stats = nullptr;  // pinned
     uint32_t *d_flags = nullptr;   // 65536 key flags (or_many)
@@ -120,13 +120,15 @@ struct Ctx {
     std::vector<cudaEvent_t> evpool;  // timing events recycled between batch ops (under alloc_mu)
     struct rb200_set *last_op = nullptr;  // result of the most recent batch op (counters may be pending)
 } g;
+// rb200_last_error() is per calling thread: concurrent callers do not read each other's failures
+thread_local std::string t_err;
 std::map<uint8_t *, size_t> g_serialized_sizes;  // pinned blobs handed out by rb200_set_serialize
 
 #define CK(call)                                                                    \
     do {                                                                            \
         cudaError_t e_ = (call);                                                    \
         if (e_ != cudaSuccess) {                                                    \
-            g.err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+            t_err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
             return false;                                                           \
         }                                                                           \
     } while (0)
@@ -144,7 +146,7 @@ bool ctx_init(int device = -1) {
     if (g.inited) return true;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        g.err = "no CUDA device visible: libroaring_b200 has no CPU fallback";
+        t_err = "no CUDA device visible: libroaring_b200 has no CPU fallback";
         return false;
     }
     if (device >= 0) CK(cudaSetDevice(device));
@@ -188,7 +190,7 @@ void *dev_alloc(size_t n) {
         g.dpool.clear();
         e = cudaMalloc(&p, b);
         if (e != cudaSuccess) {
-            g.err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+            t_err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
             return nullptr;
         }
     }
@@ -221,7 +223,7 @@ void *pin_alloc(size_t n) {
     cudaError_t e = cudaHostAlloc(&p, b, cudaHostAllocDefault);
     if (moved) pthread_setaffinity_np(pthread_self(), sizeof(saved), &saved);
     if (e != cudaSuccess) {
-        g.err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
+        t_err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e);
         return nullptr;
     }
     return p;
@@ -366,21 +368,21 @@ void ev_put(cudaEvent_t e) {
 }
 
 // Wait for the op that produced `cs` (if it is still in flight) and take over its counters.
-// false: the op failed (g.err says why); the set must not be used.
+// false: the op failed (t_err says why); the set must not be used.
 bool resolve(const rb200_set *cs) {
     rb200_set *s = const_cast<rb200_set *>(cs);
     if (!s->pending) {
-        if (s->failed && g.err.empty()) g.err = "the operation that produced this set failed";
+        if (s->failed && t_err.empty()) t_err = "the operation that produced this set failed";
         return !s->failed;
     }
     s->pending = false;
     cudaError_t e = cudaEventSynchronize(s->ev[3]);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
-        g.err = std::string("batch op: ") + cudaGetErrorString(e);
+        t_err = std::string("batch op: ") + cudaGetErrorString(e);
         s->failed = true;
     } else if (s->pstats->error) {
-        g.err = s->pstats->error == 2 ? "internal: result slab bound exceeded" : "internal: result slot bound exceeded";
+        t_err = s->pstats->error == 2 ? "internal: result slab bound exceeded" : "internal: result slot bound exceeded";
         s->failed = true;
     } else {
         cudaEventElapsedTime(&s->ms, s->ev[0], s->ev[3]);
@@ -553,7 +555,7 @@ inline uint32_t host_container_card(const void *c, uint8_t type) {
 // =================================================================== C ABI: helpers
 extern "C" {
 
-const char *rb200_last_error(void) { return g.err.c_str(); }
+const char *rb200_last_error(void) { return t_err.c_str(); }
 uint64_t rb200_kernel_launches(void) { return g_launches; }
 static void settle_last_op() {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
@@ -992,7 +994,7 @@ rb200_set *upload_impl(const PackSrc &src) {
     pin_free(chunk[0], CH);
     pin_free(chunk[1], CH);
     if (!ok) {
-        if (g.err.empty()) g.err = "upload failed";
+        if (t_err.empty()) t_err = "upload failed";
         set_delete(s);
         return nullptr;
     }
@@ -1027,7 +1029,7 @@ rb200_set_t *rb200_set_upload_frozen(const char *const *bufs, const size_t *lens
 }
 static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens, size_t n, bool frozen) {
     if (!ctx_init()) return nullptr;
-    if (n > 0xffffffffull) { g.err = "too many bitmaps"; return nullptr; }
+    if (n > 0xffffffffull) { t_err = "too many bitmaps"; return nullptr; }
     // pass 1 (host): container count of every blob from its cookie; staging offsets
     uint64_t nc = 0, raw_total = 0, slab_total = 0;
     std::vector<uint32_t> cnt(n);
@@ -1045,7 +1047,7 @@ static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens,
             else ok = false;
         }
         if (!ok || size > 65536 || 4ull * size > lens[i]) {
-            g.err = std::string(frozen ? "malformed frozen bitmap at index " : "malformed portable bitmap at index ") + std::to_string(i);
+            t_err = std::string(frozen ? "malformed frozen bitmap at index " : "malformed portable bitmap at index ") + std::to_string(i);
             return nullptr;
         }
         cnt[i] = size;
@@ -1135,15 +1137,15 @@ static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens,
         ok = ok && stats_fetch();
         cudaError_t e = cudaStreamSynchronize(g.stream);
         if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
-            g.err = std::string("deserialize: ") + cudaGetErrorString(e);
+            t_err = std::string("deserialize: ") + cudaGetErrorString(e);
             ok = false;
         }
         if (ok && g.h_stats->error == 4u) {
-            g.err = "malformed serialized bitmap: invalid container contents (a run ends past 65535, runs "
+            t_err = "malformed serialized bitmap: invalid container contents (a run ends past 65535, runs "
                     "overlap or are out of order, or array values are not strictly increasing)";
             ok = false;
         } else if (ok && g.h_stats->error) {
-            g.err = std::string(frozen ? "malformed frozen bitmap at index " : "malformed portable bitmap at index ") +
+            t_err = std::string(frozen ? "malformed frozen bitmap at index " : "malformed portable bitmap at index ") +
                     std::to_string((uint64_t)n - g.h_stats->nk);
             ok = false;
         }
@@ -1159,7 +1161,7 @@ static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens,
     dev_free(d_raw, raw_total ? raw_total : 16);
     dev_free(d_src, 8 * (nc ? nc : 1));
     if (!ok) {
-        if (g.err.empty()) g.err = "upload_serialized failed";
+        if (t_err.empty()) t_err = "upload_serialized failed";
         set_delete(s);
         return nullptr;
     }
@@ -1171,7 +1173,7 @@ static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens,
 // are then rebuilt from the caller's own memory instead of crossing PCIe a second time.
 int rb200_set_bind_host(rb200_set_t *s, int enable) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
-    if (enable && !s->h_ptr_all) { g.err = "bind_host: set was not uploaded from host bitmaps"; return -1; }
+    if (enable && !s->h_ptr_all) { t_err = "bind_host: set was not uploaded from host bitmaps"; return -1; }
     s->h_ptr = enable ? s->h_ptr_all : nullptr;
     return 0;
 }
@@ -1227,7 +1229,7 @@ bool ensure_mirrors(const rb200_set *cs) {
         }
         s->mirrors_pending = false;
     } else {
-        g.err = "fetching result directory failed";
+        t_err = "fetching result directory failed";
     }
     pin_free(h, bytes);
     return ok;
@@ -1286,7 +1288,7 @@ struct PairBuf {
         for (size_t p = 0; p < np; p++) {
             const uint32_t a = ia[p], b = ib[p];
             if (a >= A->n_bitmaps || b >= B->n_bitmaps) {
-                g.err = "pair index out of range";
+                t_err = "pair index out of range";
                 return false;
             }
             hia[p] = a;
@@ -1326,23 +1328,23 @@ bool stats_fetch() {
 
 bool reject_lazy(const rb200_set *s, const char *what) {
     if (!s->lazy) return false;
-    g.err = std::string(what) + ": the set is in a lazy state, call rb200_set_repair_after_lazy first";
+    t_err = std::string(what) + ": the set is in a lazy state, call rb200_set_repair_after_lazy first";
     return true;
 }
 
 rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const uint32_t *ia,
                          const uint32_t *ib, size_t np, int rules = 0) {
     if (!ctx_init()) return nullptr;
-    if (op < 0 || op > 3) { g.err = "bad op"; return nullptr; }
+    if (op < 0 || op > 3) { t_err = "bad op"; return nullptr; }
     if (rules & RULES_LAZY) {
-        if (op != OP_OR && op != OP_XOR) { g.err = "lazy rules exist for OR and XOR only"; return nullptr; }
-        if (op == OP_XOR && (rules & (RULES_CONV | RULES_NOFULL))) { g.err = "bad lazy flags for XOR"; return nullptr; }
-        if ((rules & RULES_FLIP) && op != OP_XOR) { g.err = "bad flags"; return nullptr; }
+        if (op != OP_OR && op != OP_XOR) { t_err = "lazy rules exist for OR and XOR only"; return nullptr; }
+        if (op == OP_XOR && (rules & (RULES_CONV | RULES_NOFULL))) { t_err = "bad lazy flags for XOR"; return nullptr; }
+        if ((rules & RULES_FLIP) && op != OP_XOR) { t_err = "bad flags"; return nullptr; }
     } else {
-        if (rules & ~RULES_INPLACE) { g.err = "bad flags"; return nullptr; }
+        if (rules & ~RULES_INPLACE) { t_err = "bad flags"; return nullptr; }
         if (reject_lazy(A, "batch op") || reject_lazy(B, "batch op")) return nullptr;
     }
-    if (np > 0xffffffffull) { g.err = "too many pairs"; return nullptr; }
+    if (np > 0xffffffffull) { t_err = "too many pairs"; return nullptr; }
     PairBuf pb;
     ItemsBuf ib_;
     rb200_set *R = nullptr;
@@ -1385,7 +1387,7 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
     pb.release();     // device buffers: stream-ordered reuse
     ib_.release();
     if (!ok) {
-        if (g.err.empty()) g.err = "batch op: enqueue failed";
+        if (t_err.empty()) t_err = "batch op: enqueue failed";
         set_delete(R);
         return nullptr;
     }
@@ -1433,8 +1435,8 @@ int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, cons
         cudaEventRecord(g.ev1, g.stream);
         ok = ok && cudaMemcpyAsync(h_out, d_out, 8 * np, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
         cudaError_t e = cudaStreamSynchronize(g.stream);
-        if (e != cudaSuccess) { g.err = std::string("and_cardinality: ") + cudaGetErrorString(e); ok = false; }
-        if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("and_cardinality launch: ") + cudaGetErrorString(e); ok = false; }
+        if (e != cudaSuccess) { t_err = std::string("and_cardinality: ") + cudaGetErrorString(e); ok = false; }
+        if (ok && (e = cudaGetLastError()) != cudaSuccess) { t_err = std::string("and_cardinality launch: ") + cudaGetErrorString(e); ok = false; }
     }
     if (ok) {
         memcpy(out, h_out, 8 * np);
@@ -1449,18 +1451,35 @@ int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, cons
     return ok ? 0 : -1;
 }
 
-rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, size_t n,
-                                    uint32_t key_lo, uint32_t key_hi, uint32_t *card_per_key) {
+// Sharded form: after k_or_many the per-key cardinalities of [span_lo, span_hi] are all-reduced
+// across the communicator ON THE DEVICE (one ncclAllReduce on the library stream), then that
+// span alone (4 * K bytes) is read back.
+struct ShardArgs {
+    rb200_comm *comm;
+    uint32_t span_lo, span_hi;
+    uint32_t *card_span;   // host, span_hi - span_lo + 1 entries (may be null)
+    uint64_t *total_card;  // host (may be null)
+};
+static float g_last_collective_ms = 0.f;
+
+static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t n, uint32_t key_lo,
+                               uint32_t key_hi, uint32_t *card_per_key, const ShardArgs *sh) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return nullptr;
     if (key_hi > 65535) key_hi = 65535;
+    uint32_t span_n = 0;
+    if (sh) {
+        if (sh->span_hi > 65535 || sh->span_lo > sh->span_hi) { t_err = "or_many_sharded: bad key span"; return nullptr; }
+        span_n = sh->span_hi - sh->span_lo + 1;
+    }
+    const bool want_ck = card_per_key != nullptr || sh != nullptr;
     if (reject_lazy(S, "or_many")) return nullptr;
     if (!ensure_mirrors(S)) return nullptr;
     if (idx == nullptr) n = S->n_bitmaps;
     uint64_t tot = 0;
     for (size_t i = 0; i < n; i++) {
         const uint32_t b = idx ? idx[i] : (uint32_t)i;
-        if (b >= S->n_bitmaps) { g.err = "or_many: index out of range"; return nullptr; }
+        if (b >= S->n_bitmaps) { t_err = "or_many: index out of range"; return nullptr; }
         tot += S->h_cnt[b];
     }
     uint64_t maxk = key_lo <= key_hi ? (uint64_t)key_hi - key_lo + 1 : 0;
@@ -1479,14 +1498,16 @@ rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, s
         }
     }
     uint32_t *h_ck = nullptr;
-    if (ok && card_per_key) { h_ck = (uint32_t *)pin_alloc(65536 * 4); ok = h_ck != nullptr; }
+    cudaEvent_t evc0 = nullptr, evc1 = nullptr;
+    if (ok && want_ck) { h_ck = (uint32_t *)pin_alloc(65536 * 4); ok = h_ck != nullptr; }
+    if (ok && sh) { evc0 = ev_get(); evc1 = ev_get(); ok = evc0 && evc1; }
     if (ok) {
         cudaEventRecord(g.ev0, g.stream);
         ok = stats_reset();
         const SetView vs = S->view();
         launch_many_mark(vs, d_idx, (uint32_t)n, key_lo, key_hi, g.d_flags, g.stream);
         launch_many_compact(g.d_flags, g.d_keys, g.d_stats, g.stream);
-        if (card_per_key) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
+        if (want_ck) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
         cudaEventRecord(g.evk0, g.stream);
         // few keys x many bitmaps: split every key over several CTAs (partial unions merged in a
         // global scratch accumulator); the estimate of the key count is the largest directory
@@ -1497,16 +1518,23 @@ rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, s
         slices = std::min<uint32_t>(slices, (uint32_t)(n / 32));
         if (slices < 1) slices = 1;
         launch_or_many(vs, d_idx, (uint32_t)n, g.d_keys, slices, g.d_many_acc, g.d_many_tickets,
-                       MANY_SCRATCH_KEYS, R->out(), card_per_key ? g.d_cardkey : nullptr, g.d_stats,
+                       MANY_SCRATCH_KEYS, R->out(), want_ck ? g.d_cardkey : nullptr, g.d_stats,
                        g.sms, g.stream);
         cudaEventRecord(g.evk1, g.stream);
+        if (sh) {  // the ONE collective of the path: per-key cardinalities, summed over the ranks, on the device
+            cudaEventRecord(evc0, g.stream);
+            ok = ok && comm_allreduce_sum(sh->comm, g.d_cardkey + sh->span_lo, span_n, false, g.stream, t_err);
+            cudaEventRecord(evc1, g.stream);
+        }
         cudaEventRecord(g.ev1, g.stream);
         ok = ok && stats_fetch();
         if (card_per_key)
             ok = ok && cudaMemcpyAsync(h_ck, g.d_cardkey, 65536 * 4, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
+        else if (sh)
+            ok = ok && cudaMemcpyAsync(h_ck, g.d_cardkey + sh->span_lo, 4ull * span_n, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
         cudaError_t e = cudaStreamSynchronize(g.stream);
-        if (e != cudaSuccess) { g.err = std::string("or_many: ") + cudaGetErrorString(e); ok = false; }
-        if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("or_many launch: ") + cudaGetErrorString(e); ok = false; }
+        if (e != cudaSuccess) { t_err = std::string("or_many: ") + cudaGetErrorString(e); ok = false; }
+        if (ok && (e = cudaGetLastError()) != cudaSuccess) { t_err = std::string("or_many launch: ") + cudaGetErrorString(e); ok = false; }
     }
     if (ok) {
         g.last_op = nullptr;  // the rb200_last_* getters now describe this (synchronous) op
@@ -1523,6 +1551,14 @@ rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, s
         R->h_flags[0] = fl & FLAG_COW;
         if (card_per_key)
             for (int k = 0; k < 65536; k++) card_per_key[k] += h_ck[k];
+        if (sh) {
+            const uint32_t *span = card_per_key ? h_ck + sh->span_lo : h_ck;
+            uint64_t tot = 0;
+            for (uint32_t k = 0; k < span_n; k++) tot += span[k];
+            if (sh->card_span) memcpy(sh->card_span, span, 4ull * span_n);
+            if (sh->total_card) *sh->total_card = tot;
+            cudaEventElapsedTime(&g_last_collective_ms, evc0, evc1);
+        }
         // algorithmic bytes: all input containers in range + outputs; the
         // output term is added by the caller-visible stat only when the set is downloaded,
         // here we account inputs exactly from the host mirrors when the whole key space is used.
@@ -1533,15 +1569,51 @@ rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, s
     dev_free(d_idx, 4 * n);
     pin_free(h_idx, 4 * n);
     pin_free(h_ck, 65536 * 4);
+    ev_put(evc0);
+    ev_put(evc1);
     if (!ok) {
+        if (t_err.empty()) t_err = "or_many failed";
         set_delete(R);
         return nullptr;
     }
     return R;
 }
 
+rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, size_t n,
+                                    uint32_t key_lo, uint32_t key_hi, uint32_t *card_per_key) {
+    return or_many_impl(S, idx, n, key_lo, key_hi, card_per_key, nullptr);
+}
+
 rb200_set_t *rb200_or_many(const rb200_set_t *S, const uint32_t *idx, size_t n) {
-    return rb200_or_many_keyrange(S, idx, n, 0, 65535, nullptr);
+    return or_many_impl(S, idx, n, 0, 65535, nullptr, nullptr);
+}
+
+// Key-sharded roaring_bitmap_or_many: this rank reduces the keys [key_lo, key_hi]
+// of its resident set (which normally holds only those keys, rb200_set_upload_serialized_keyrange),
+// then the ranks exchange ONE all-reduce(sum) of the per-key result cardinalities over the key
+// span [span_lo, span_hi] every rank agreed on (rb200_plan_key_ranges).
+rb200_set_t *rb200_or_many_sharded(const rb200_set_t *S, const uint32_t *idx, size_t n, uint32_t key_lo,
+                                   uint32_t key_hi, uint32_t span_lo, uint32_t span_hi, rb200_comm_t *comm,
+                                   uint32_t *card_span, uint64_t *total_card) {
+    ShardArgs sh{comm, span_lo, span_hi, card_span, total_card};
+    return or_many_impl(S, idx, n, key_lo, key_hi, nullptr, &sh);
+}
+float rb200_last_collective_ms(void) { return g_last_collective_ms; }
+
+// *d_acc (device, u64) += sum of the cardinalities of every bitmap of the set, on the library stream
+// (a checksum that stays on the device until the caller reduces / reads it).
+int rb200_set_add_cardinality_device(const rb200_set_t *s, uint64_t *d_acc) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    if (s->failed) { t_err = "the operation that produced this set failed"; return -1; }
+    launch_sum_cardinalities((const uint64_t *)(s->d_dir + s->L.o_bcard), s->n_bitmaps, d_acc, g.stream);
+    return 0;
+}
+// in-place all-reduce(sum) of `count` u64 words in device memory on the library stream
+int rb200_comm_allreduce_u64(rb200_comm_t *comm, uint64_t *d_buf, size_t count) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!ctx_init()) return -1;
+    return comm_allreduce_sum(comm, d_buf, count, true, g.stream, t_err) ? 0 : -1;
 }
 
 // roaring_bitmap_xor_many (src/roaring.c:795-809) over S[idx[0..n)] (idx == NULL: all, in order).
@@ -1554,7 +1626,7 @@ rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n)
     uint64_t tot = 0;
     for (size_t i = 0; i < n; i++) {
         const uint32_t b = idx ? idx[i] : (uint32_t)i;
-        if (b >= S->n_bitmaps) { g.err = "xor_many: index out of range"; return nullptr; }
+        if (b >= S->n_bitmaps) { t_err = "xor_many: index out of range"; return nullptr; }
         tot += S->h_cnt[b];
     }
     const uint64_t maxk = std::min<uint64_t>(65536, tot);
@@ -1586,8 +1658,8 @@ rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n)
         cudaEventRecord(g.ev1, g.stream);
         ok = ok && stats_fetch();
         cudaError_t e = cudaStreamSynchronize(g.stream);
-        if (e != cudaSuccess) { g.err = std::string("xor_many: ") + cudaGetErrorString(e); ok = false; }
-        if (ok && (e = cudaGetLastError()) != cudaSuccess) { g.err = std::string("xor_many launch: ") + cudaGetErrorString(e); ok = false; }
+        if (e != cudaSuccess) { t_err = std::string("xor_many: ") + cudaGetErrorString(e); ok = false; }
+        if (ok && (e = cudaGetLastError()) != cudaSuccess) { t_err = std::string("xor_many launch: ") + cudaGetErrorString(e); ok = false; }
     }
     if (ok) {
         g.last_op = nullptr;  // the rb200_last_* getters now describe this (synchronous) op
@@ -1631,7 +1703,7 @@ int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out) {
     bool ok = cudaMemcpyAsync(h, s->d_dir + s->L.o_bcard, 8 * nb, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(g.stream) == cudaSuccess;
     if (ok) memcpy(out, h, 8 * nb);
-    else g.err = "set_cardinalities: copy failed";
+    else t_err = "set_cardinalities: copy failed";
     pin_free(h, 8 * nb);
     return ok ? 0 : -1;
 }
@@ -1651,7 +1723,7 @@ bool ensure_mirror(rb200_set *s) {
     if (s->slab_used)
         ok = ok && cudaMemcpyAsync(s->m_slab, s->d_slab, s->slab_used, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
     ok = ok && cudaStreamSynchronize(g.stream) == cudaSuccess;
-    if (!ok) g.err = "download: copy failed";
+    if (!ok) t_err = "download: copy failed";
     g.last_download_bytes = s->L.total + s->slab_used;
     return ok;
 }
@@ -1809,7 +1881,10 @@ unsigned host_workers() {
     if (!T) {
         const char *e = getenv("RB200_HOST_THREADS");
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        T = e ? (unsigned)atoi(e) : std::min(24u, std::max(1u, hw / 2));
+        // several ranks on one node (torchrun exports LOCAL_WORLD_SIZE) share the host cores
+        const char *lw = getenv("LOCAL_WORLD_SIZE");
+        const unsigned local_world = lw && atoi(lw) > 0 ? (unsigned)atoi(lw) : 1u;
+        T = e ? (unsigned)atoi(e) : std::min(24u, std::max(2u, hw / (2 * local_world)));
         if (T > 256) T = 256;
         if (T < 1) T = 1;
     }
@@ -1935,7 +2010,7 @@ static rb200_download_stream *download_begin_impl(const rb200_set *s, size_t chu
     dev_free(d_beg, 8 * (nb + 1));
     dev_free(d_cnt, 4 * nb);
     if (!ok) {
-        if (g.err.empty()) g.err = "download_begin failed";
+        if (t_err.empty()) t_err = "download_begin failed";
         stream_free(st);
         return nullptr;
     }
@@ -1955,7 +2030,7 @@ size_t rb200_download_next(rb200_download_stream_t *st, roaring_bitmap_t **out) 
     if (st->next_build >= st->chunk_end.size()) return 0;
     const size_t k = st->next_build;
     const size_t p0 = k ? st->chunk_end[k - 1] : 0, p1 = st->chunk_end[k];
-    if (cudaEventSynchronize(st->ev[k & 1]) != cudaSuccess) { g.err = "download_next: copy failed"; return (size_t)-1; }
+    if (cudaEventSynchronize(st->ev[k & 1]) != cudaSuccess) { t_err = "download_next: copy failed"; return (size_t)-1; }
     const uint8_t *buf = st->hbuf[k & 1];
     const uint64_t bias = st->h_ob[p0];
     const size_t n = p1 - p0;
@@ -1986,7 +2061,7 @@ size_t rb200_download_next(rb200_download_stream_t *st, roaring_bitmap_t **out) 
     if (!stream_enqueue(st)) failed = 1;  // refill the buffer we just drained
     if (failed) {
         for (size_t i = 0; i < n; i++) { bitmap_free_host(out[i]); out[i] = nullptr; }
-        g.err = "download_next: host allocation or copy failed";
+        t_err = "download_next: host allocation or copy failed";
         return (size_t)-1;
     }
     return n;
@@ -2056,7 +2131,7 @@ int rb200_download_foreach(const rb200_set_t *s, rb200_visit_fn fn, void *ctx) {
                 st->nb, st->chunk_end.size(), st->total_bytes / 1e6, t_pack, t_wait, t_build, ms_since(t_begin));
     stream_free(st);
     if (failed) {
-        if (g.err.empty()) g.err = "download_foreach: host allocation or copy failed";
+        if (t_err.empty()) t_err = "download_foreach: host allocation or copy failed";
         return -1;
     }
     return 0;
@@ -2161,7 +2236,7 @@ int rb200_download_foreach_many(const rb200_set_t *const *sets, size_t nsets, rb
     for (auto st : sts) if (st) stream_free(st);
     g.last_download_bytes = total;
     if (!ok || failed) {
-        if (g.err.empty()) g.err = "download_foreach_many: host allocation or copy failed";
+        if (t_err.empty()) t_err = "download_foreach_many: host allocation or copy failed";
         return -1;
     }
     return 0;
@@ -2309,7 +2384,7 @@ int rb200_download_foreach_async(const rb200_set_t *s, rb200_visit_fn fn, void *
     j->ctx = ctx;
     if (cudaEventCreateWithFlags(&j->ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventRecord(j->ready, g.stream) != cudaSuccess) {
-        g.err = "download_foreach_async: event failed";
+        t_err = "download_foreach_async: event failed";
         stream_free(j->st);
         delete j;
         return -1;
@@ -2344,7 +2419,7 @@ int rb200_download_wait(void) {
     dk.unlock();
     if (failed) {
         std::lock_guard<std::recursive_mutex> lk(g.mu);
-        g.err = why.empty() ? "asynchronous download failed" : why;
+        t_err = why.empty() ? "asynchronous download failed" : why;
         return -1;
     }
     return 0;
@@ -2360,7 +2435,7 @@ int rb200_visit_sum_cardinality(size_t index, roaring_bitmap_t *bm, void *ctx) {
 roaring_bitmap_t *rb200_set_download(const rb200_set_t *cs, size_t i) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     rb200_set *s = const_cast<rb200_set *>(cs);
-    if (i >= s->n_bitmaps) { g.err = "download: index out of range"; return nullptr; }
+    if (i >= s->n_bitmaps) { t_err = "download: index out of range"; return nullptr; }
     if (!ensure_mirror(s)) return nullptr;
     return build_bitmap(s, i);
 }
@@ -2478,13 +2553,13 @@ int rb200_set_download_all(const rb200_set_t *cs, roaring_bitmap_t **out) {
         if (cudaStreamSynchronize(g.stream) != cudaSuccess) failed = 1;
         if (failed) {
             for (size_t i = 0; i < nb; i++) { bitmap_free_host(out[i]); out[i] = nullptr; }
-            g.err = "download: host allocation or copy failed";
+            t_err = "download: host allocation or copy failed";
             ok = false;
         }
         g.last_download_bytes = P->L.total + P->slab_used;
     } else {
         cudaStreamSynchronize(g.stream);
-        if (g.err.empty()) g.err = "download: packing failed";
+        if (t_err.empty()) t_err = "download: packing failed";
     }
     if (trace)
         fprintf(stderr, "[rb200] download_all nb=%zu bytes=%.1f MB: measure+scan %.2f ms, alloc+enqueue %.2f ms, "
@@ -2535,7 +2610,7 @@ static rb200_set *convert_impl(const rb200_set *S, int mode) {
     ok = ok && stats_fetch();
     cudaError_t e = cudaStreamSynchronize(g.stream);
     if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
-        g.err = std::string("run_optimize: ") + cudaGetErrorString(e);
+        t_err = std::string("run_optimize: ") + cudaGetErrorString(e);
         ok = false;
     }
     if (!ok) { set_delete(R); return nullptr; }
@@ -2596,7 +2671,7 @@ int rb200_set_to_uint32(const rb200_set_t *S, uint32_t **vals, uint64_t **off_ou
     pin_free(h_off, 8 * (nb + 1));
     if (!ok) {
         pin_free(h_vals, 4 * total);
-        if (g.err.empty()) g.err = "set_to_uint32 failed";
+        if (t_err.empty()) t_err = "set_to_uint32 failed";
         return -1;
     }
     *vals = h_vals;
@@ -2682,7 +2757,7 @@ static int serialize_impl(const rb200_set *s, char **buf, uint64_t **off_out, ui
         free(*off_out);
         free(*len_out);
         *off_out = *len_out = nullptr;
-        if (g.err.empty()) g.err = "set_serialize failed";
+        if (t_err.empty()) t_err = "set_serialize failed";
         return -1;
     }
     *buf = (char *)h_blob;
@@ -2748,11 +2823,35 @@ int rb200_batch_op_host(int op, const roaring_bitmap_t *const *a, const roaring_
     return rc;
 }
 
+}  // extern "C"
+namespace rb200 {
+void set_error(const std::string &msg) { t_err = msg; }
+void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
+    if (n == 0) return;
+    unsigned T = host_workers();
+    if (T <= 1 || n < 2) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    if ((size_t)T > n) T = (unsigned)n;
+    std::atomic<size_t> next(0);
+    std::function<void()> work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            fn(i);
+        }
+    };
+    pool().run(work, T);
+}
+}  // namespace rb200
+extern "C" {
+
 // =================================================================== drop-in entry points
 // Entry points whose reference signature has no error channel (bool / void): a device failure is
 // reported on stderr (and aborts under RB200_STRICT=1) instead of passing for an answer.
 static void dropin_failed(const char *fn) {
-    fprintf(stderr, "libroaring_b200: %s failed: %s\n", fn, g.err.empty() ? "unknown error" : g.err.c_str());
+    fprintf(stderr, "libroaring_b200: %s failed: %s\n", fn, t_err.empty() ? "unknown error" : t_err.c_str());
     const char *e = getenv("RB200_STRICT");
     if (e && e[0] == '1') abort();
 }
@@ -3080,12 +3179,12 @@ bool plan_r64(int op, const char *const *a, const size_t *alen, size_t na, const
     std::vector<const char *> ptrs;
     std::vector<size_t> lens;
     for (size_t i = 0; i < na; i++) {
-        if (!parse_r64(a[i], alen[i], A[i])) { g.err = "malformed 64-bit portable bitmap (left) at index " + std::to_string(i); return false; }
+        if (!parse_r64(a[i], alen[i], A[i])) { t_err = "malformed 64-bit portable bitmap (left) at index " + std::to_string(i); return false; }
         baseA[i] = ptrs.size();
         for (auto &x : A[i]) { ptrs.push_back(x.ptr); lens.push_back(x.len); }
     }
     for (size_t i = 0; i < nb; i++) {
-        if (!parse_r64(b[i], blen[i], B[i])) { g.err = "malformed 64-bit portable bitmap (right) at index " + std::to_string(i); return false; }
+        if (!parse_r64(b[i], blen[i], B[i])) { t_err = "malformed 64-bit portable bitmap (right) at index " + std::to_string(i); return false; }
         baseB[i] = ptrs.size();
         for (auto &x : B[i]) { ptrs.push_back(x.ptr); lens.push_back(x.len); }
     }
@@ -3095,7 +3194,7 @@ bool plan_r64(int op, const char *const *a, const size_t *alen, size_t na, const
     lens.push_back(8);
     P.first.assign(1, 0);
     for (size_t p = 0; p < np; p++) {
-        if (ia[p] >= na || ib[p] >= nb) { g.err = "pair index out of range"; return false; }
+        if (ia[p] >= na || ib[p] >= nb) { t_err = "pair index out of range"; return false; }
         const auto &x = A[ia[p]], &y = B[ib[p]];
         size_t i = 0, j = 0;
         while (i < x.size() || j < y.size()) {
@@ -3126,7 +3225,7 @@ int rb200_r64_batch_op_serialized(int op, const char *const *a, const size_t *al
                                   const uint32_t *ib, size_t np, char **out, uint64_t **off_out, uint64_t **len_out) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!ctx_init()) return -1;
-    if (op < 0 || op > 3) { g.err = "bad op"; return -1; }
+    if (op < 0 || op > 3) { t_err = "bad op"; return -1; }
     *out = nullptr;
     *off_out = *len_out = nullptr;
     R64Plan P;
@@ -3179,7 +3278,7 @@ int rb200_r64_batch_op_serialized(int op, const char *const *a, const size_t *al
     if (!dst) {
         free(off);
         free(len);
-        g.err = "r64 batch op: host allocation failed";
+        t_err = "r64 batch op: host allocation failed";
         return -1;
     }
     *out = (char *)dst;
@@ -3313,7 +3412,7 @@ bool portable_sizes(const rb200_set *S, std::vector<uint32_t> &out) {
     dev_free(dex, 4 * nb);
     dev_free(dhr, 4 * nb);
     pin_free(h, 4 * nb);
-    if (!ok && g.err.empty()) g.err = "portable_sizes failed";
+    if (!ok && t_err.empty()) t_err = "portable_sizes failed";
     return ok;
 }
 }  // namespace
@@ -3324,7 +3423,7 @@ rb200_set_t *rb200_or_many_heap(const rb200_set_t *S, const uint32_t *idx, size_
     if (reject_lazy(S, "or_many_heap")) return nullptr;
     if (idx == nullptr) n = S->n_bitmaps;
     for (size_t i = 0; i < n; i++)
-        if (idx && idx[i] >= S->n_bitmaps) { g.err = "or_many_heap: index out of range"; return nullptr; }
+        if (idx && idx[i] >= S->n_bitmaps) { t_err = "or_many_heap: index out of range"; return nullptr; }
     if (n == 0) return rb200_or_many(S, idx, 0);
     if (n == 1) {  // roaring_bitmap_copy: union with an empty bitmap = pass-through of every container
         roaring_bitmap_t *e = bitmap_alloc(0);

@@ -484,6 +484,14 @@ __global__ void k_set_cardinalities(SetView S, uint32_t n, uint64_t *__restrict_
     }
 }
 
+// *acc += sum of bm_card[0..n) (device-resident checksum of a result set)
+__global__ void k_sum_cards(const uint64_t *__restrict__ bm_card, uint32_t n, unsigned long long *acc) {
+    unsigned long long v = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v += bm_card[i];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(acc, v);
+}
+
 // ------------------------------------------------------------------------------ or_many
 __global__ void k_many_mark(SetView S, const uint32_t *__restrict__ idx, uint32_t n,
                             uint32_t key_lo, uint32_t key_hi, uint32_t *__restrict__ flags) {
@@ -700,6 +708,12 @@ void launch_finalize_cards(Items it, const uint64_t *item_off, uint32_t npairs, 
     g_launches++;
 }
 
+void launch_sum_cardinalities(const uint64_t *bm_card, uint32_t n, uint64_t *d_acc, cudaStream_t s) {
+    if (!n) return;
+    const uint32_t blocks = (n + 255) / 256 < 592u ? (n + 255) / 256 : 592u;
+    k_sum_cards<<<blocks, 256, 0, s>>>(bm_card, n, (unsigned long long *)d_acc);
+    g_launches++;
+}
 void launch_set_cardinalities(const SetView &S, uint32_t n, uint64_t *out, cudaStream_t s) {
     if (!n) return;
     const uint32_t g = blocks_for_warps(n, 4, sm_count() * 16);

@@ -10,7 +10,8 @@
  *
  * The reference has no Zipf generator; the definition below is SURVEY.md §8(d)'s:
  *   PCG32 (the generator of /root/reference/benchmarks/random.h:18-30), stream of bitmap b:
- *   state = 0x853c49e6748fea9b ^ b, inc = 0xda3e39cb94b95bdb.  One draw r -> u = (r + 1) / 2^32 in
+ *   state = 0x853c49e6748fea9b ^ b, inc = 0xda3e39cb94b95bdb, first output discarded (it does not
+ *   depend on the low bits of the state, i.e. on b).  One draw r -> u = (r + 1) / 2^32 in
  *   (0, 1]; v = floor(U^u) - 1 clipped to [0, U)  (P(v) ~ 1/(v+1): Zipf s = 1 by inverse CDF).
  *   Draw until the bitmap holds n distinct values.  With `density_draw` (config 5) the FIRST draw of
  *   the stream picks the bitmap's density log-uniformly: d = 0.001 * 300^u, n = max(1, round(d*U)).
@@ -52,19 +53,6 @@ static uint64_t pcg32_jump(uint64_t state, uint64_t inc, uint64_t delta) {
 }
 
 /* ---------------------------------------------------------------- words -> portable bytes */
-typedef struct { uint8_t *p; size_t len, cap; } buf_t;
-
-static int buf_reserve(buf_t *b, size_t extra) {
-    if (b->len + extra <= b->cap) return 1;
-    size_t nc = b->cap ? b->cap : 4096;
-    while (nc < b->len + extra) nc *= 2;
-    uint8_t *np = (uint8_t *)realloc(b->p, nc);
-    if (!np) return 0;
-    b->p = np;
-    b->cap = nc;
-    return 1;
-}
-
 /* One bitmap from its membership bitset `bits` (universe rounded up to whole 2^16 chunks).
  * Returns a malloc'd portable blob.  run_optimize: apply convert_run_optimize's size rule. */
 static uint8_t *emit_portable(const uint64_t *bits, uint32_t n_keys, int run_optimize, size_t *len_out) {
@@ -197,6 +185,8 @@ static void *zipf_worker(void *arg) {
         if (i >= J->nb || J->failed) break;
         const uint32_t b = J->b0 + i;
         pcg32_t g = {0x853c49e6748fea9bULL ^ (uint64_t)b, 0xda3e39cb94b95bdbULL};
+        (void)pcg32_next(&g); /* the output function drops the low 27 state bits: without this
+                                 warm-up step every stream b < 2^27 would start with the same draw */
         uint64_t want = J->n_values ? J->n_values[i] : J->n_fixed;
         if (J->density_draw) {
             const double u0 = ((double)pcg32_next(&g) + 1.0) * (1.0 / 4294967296.0);

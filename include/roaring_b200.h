@@ -224,6 +224,54 @@ rb200_set_t *rb200_set_repair_after_lazy(const rb200_set_t *S);
 rb200_set_t *rb200_or_many_keyrange(const rb200_set_t *S, const uint32_t *idx, size_t n,
                                     uint32_t key_lo, uint32_t key_hi, uint32_t *card_per_key);
 
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  Pairwise batches shard by PAIR (every rank
+ * runs its own slice of the pair list, no data-path collective).  The many-way union shards the
+ * HIGH-16 KEY SPACE: contiguous key ranges balanced by input bytes, rank g holds only the
+ * containers of range g of every input, reduces them alone, and the ranks exchange ONE
+ * ncclAllReduce(sum) of the per-key result cardinalities, uint32[K], K = keys of the span, on the
+ * device.  The full result is the concatenation of the per-rank results in rank order.
+ * libnccl is resolved at run time (dlopen), only when a communicator of more than one rank is made.
+ * ------------------------------------------------------------------------------------- */
+#define RB200_COMM_ID_BYTES 128
+typedef struct rb200_comm rb200_comm_t;
+/* rank 0: a fresh NCCL unique id (ncclGetUniqueId) to hand to every rank by any out-of-band means */
+int rb200_comm_unique_id(char *id128);
+/* every rank: ncclCommInitRank on the library's current device (nranks == 1: no NCCL at all) */
+rb200_comm_t *rb200_comm_init_rank(const char *id128, int nranks, int rank);
+/* or wrap an ncclComm_t the application already owns (not destroyed by rb200_comm_destroy) */
+rb200_comm_t *rb200_comm_adopt(void *nccl_comm, int nranks, int rank);
+int rb200_comm_size(const rb200_comm_t *c);
+int rb200_comm_rank(const rb200_comm_t *c);
+void rb200_comm_destroy(rb200_comm_t *c);
+/* in-place all-reduce(sum) of `count` u64 words of DEVICE memory on the library stream */
+int rb200_comm_allreduce_u64(rb200_comm_t *comm, uint64_t *d_buf, size_t count);
+/* *d_acc (device u64) += sum of the cardinalities of every bitmap of the set, on the library stream */
+int rb200_set_add_cardinality_device(const rb200_set_t *s, uint64_t *d_acc);
+
+/* Host-side planning over portable-serialized inputs (no CUDA involved): nranks contiguous key
+ * ranges [key_lo[g], key_hi[g]] covering 0..65535, balanced by container bytes per key;
+ * span[0..1] = first / last key present in any input.  0 on success. */
+int rb200_plan_key_ranges(const char *const *bufs, const size_t *lens, size_t n, int nranks,
+                          uint32_t *key_lo, uint32_t *key_hi, uint32_t *span);
+/* the bitmap restricted to keys [key_lo, key_hi] / the concatenation of bitmaps on disjoint
+ * increasing key ranges, as new portable blobs (release with rb200_blob_free) */
+int rb200_blob_slice_keys(const char *buf, size_t len, uint32_t key_lo, uint32_t key_hi, char **out, size_t *outlen);
+int rb200_blobs_concat(const char *const *bufs, const size_t *lens, size_t n, char **out, size_t *outlen);
+void rb200_blob_free(char *blob);
+/* resident set holding only the containers with key in [key_lo, key_hi] of every input */
+rb200_set_t *rb200_set_upload_serialized_keyrange(const char *const *bufs, const size_t *lens, size_t n,
+                                                  uint32_t key_lo, uint32_t key_hi);
+/* This rank's part of roaring_bitmap_or_many over S[idx[0..n)] (keys [key_lo, key_hi]) + the ONE
+ * collective: per-key result cardinalities of [span_lo, span_hi] summed over the communicator on
+ * the device; card_span (host, span_hi - span_lo + 1 entries) and *total_card (cardinality of the
+ * whole union) are optional outputs, identical on every rank. */
+rb200_set_t *rb200_or_many_sharded(const rb200_set_t *S, const uint32_t *idx, size_t n, uint32_t key_lo,
+                                   uint32_t key_hi, uint32_t span_lo, uint32_t span_hi, rb200_comm_t *comm,
+                                   uint32_t *card_span, uint64_t *total_card);
+/* device time (ms) of the all-reduce of the last rb200_or_many_sharded call (CUDA events) */
+float rb200_last_collective_ms(void);
+
 /* Per-bitmap cardinalities of a set (host array of rb200_set_count entries); 0 on success. */
 int rb200_set_cardinalities(const rb200_set_t *s, uint64_t *out);
 

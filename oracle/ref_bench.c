@@ -5,8 +5,8 @@
  * The timed loops are the reference's own microbenchmark loops
  * (/root/reference/microbenchmarks/bench.cpp:85-96 SuccessiveIntersection, :196-207
  * SuccessiveUnion, :226-236 TotalUnion): result bitmaps are created, their cardinality read,
- * and freed inside the timed region.  Pairs are split statically over `nthreads` pthreads
- * (the library itself is single-threaded; BASELINE.md §3 "Cores").
+ * and freed inside the timed region.  The library itself is single-threaded; the N-thread figure
+ * hands the independent pairs out dynamically to a persistent pthread pool (BASELINE.md §3 "Cores").
  *
  * Prototypes are declared by hand (opaque pointers) so this file compiles anywhere the
  * prebuilt libroaring_ref.so is present.
@@ -28,6 +28,8 @@ extern roaring_bitmap_t *roaring_bitmap_xor(const roaring_bitmap_t *, const roar
 extern roaring_bitmap_t *roaring_bitmap_andnot(const roaring_bitmap_t *, const roaring_bitmap_t *);
 extern uint64_t roaring_bitmap_and_cardinality(const roaring_bitmap_t *, const roaring_bitmap_t *);
 extern roaring_bitmap_t *roaring_bitmap_or_many(size_t, const roaring_bitmap_t **);
+extern size_t roaring_bitmap_portable_size_in_bytes(const roaring_bitmap_t *r);
+extern size_t roaring_bitmap_portable_serialize(const roaring_bitmap_t *r, char *buf);
 extern int croaring_hardware_support(void);
 
 static double now_s(void) {
@@ -36,42 +38,131 @@ static double now_s(void) {
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
+/* ---- persistent worker pool, dynamic chunks ------------------------------------------------
+ * The N-thread throughput figure of SURVEY.md 8(d): the independent pairs are handed out in
+ * chunks of CHUNK pairs from one atomic counter (all-pairs lists are triangular: a static split
+ * would be unbalanced), to threads that live for the whole process (no pthread_create inside the
+ * timed region). */
+#define CHUNK 16
 typedef struct {
-    int op; /* 0 and, 1 or, 2 xor, 3 andnot, 4 and_cardinality */
+    int op; /* 0 and, 1 or, 2 xor, 3 andnot, 4 and_cardinality, 5 deserialize */
     roaring_bitmap_t **bms;
     const uint32_t *ia, *ib;
-    size_t lo, hi;
+    const char *const *bufs;
+    const size_t *lens;
+    size_t n;
+    volatile size_t next;
     uint64_t sum;
+    int failed;
 } job_t;
 
-static void *worker(void *arg) {
-    job_t *j = (job_t *)arg;
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t cv, done;
+    pthread_t *th;
+    int nth;        /* threads created */
+    int want;       /* helpers taking part in the current job */
+    int started, running;
+    uint64_t gen;
+    job_t *job;
+} P = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, 0, 0, NULL};
+
+static void run_job(job_t *j) {
     uint64_t s = 0;
-    for (size_t p = j->lo; p < j->hi; p++) {
-        const roaring_bitmap_t *a = j->bms[j->ia[p]], *b = j->bms[j->ib[p]];
-        if (j->op == 4) {
-            s += roaring_bitmap_and_cardinality(a, b);
-            continue;
+    for (;;) {
+        const size_t p0 = __sync_fetch_and_add(&j->next, (size_t)CHUNK);
+        if (p0 >= j->n) break;
+        const size_t p1 = p0 + CHUNK < j->n ? p0 + CHUNK : j->n;
+        for (size_t p = p0; p < p1; p++) {
+            if (j->op == 5) {
+                j->bms[p] = roaring_bitmap_portable_deserialize_safe(j->bufs[p], j->lens[p]);
+                if (!j->bms[p]) j->failed = 1;
+                continue;
+            }
+            const roaring_bitmap_t *a = j->bms[j->ia[p]], *b = j->bms[j->ib[p]];
+            if (j->op == 4) {
+                s += roaring_bitmap_and_cardinality(a, b);
+                continue;
+            }
+            roaring_bitmap_t *r = j->op == 0   ? roaring_bitmap_and(a, b)
+                                  : j->op == 1 ? roaring_bitmap_or(a, b)
+                                  : j->op == 2 ? roaring_bitmap_xor(a, b)
+                                               : roaring_bitmap_andnot(a, b);
+            s += roaring_bitmap_get_cardinality(r);
+            roaring_bitmap_free(r);
         }
-        roaring_bitmap_t *r = j->op == 0   ? roaring_bitmap_and(a, b)
-                              : j->op == 1 ? roaring_bitmap_or(a, b)
-                              : j->op == 2 ? roaring_bitmap_xor(a, b)
-                                           : roaring_bitmap_andnot(a, b);
-        s += roaring_bitmap_get_cardinality(r);
-        roaring_bitmap_free(r);
     }
-    j->sum = s;
+    __sync_fetch_and_add(&j->sum, s);
+}
+
+static void *pool_loop(void *arg) {
+    (void)arg;
+    uint64_t seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&P.mu);
+        while (!(P.gen != seen && P.job && P.started < P.want)) pthread_cond_wait(&P.cv, &P.mu);
+        seen = P.gen;
+        P.started++;
+        P.running++;
+        job_t *j = P.job;
+        pthread_mutex_unlock(&P.mu);
+        run_job(j);
+        pthread_mutex_lock(&P.mu);
+        P.running--;
+        if (P.started == P.want && P.running == 0) pthread_cond_broadcast(&P.done);
+        pthread_mutex_unlock(&P.mu);
+    }
     return NULL;
 }
 
-/* Deserialize n bitmaps once; returns an opaque handle (array of pointers). */
-void *refbench_load(size_t n, const char *const *bufs, const size_t *lens) {
-    roaring_bitmap_t **bms = (roaring_bitmap_t **)calloc(n ? n : 1, sizeof(*bms));
-    for (size_t i = 0; i < n; i++) {
-        bms[i] = roaring_bitmap_portable_deserialize_safe(bufs[i], lens[i]);
-        if (!bms[i]) return NULL;
+/* run j on nthreads threads (the caller is one of them) */
+static void pool_run(job_t *j, int nthreads) {
+    if (nthreads <= 1) { run_job(j); return; }
+    pthread_mutex_lock(&P.mu);
+    if (P.nth < nthreads - 1) {
+        P.th = (pthread_t *)realloc(P.th, sizeof(pthread_t) * (size_t)(nthreads - 1));
+        while (P.nth < nthreads - 1) {
+            if (pthread_create(&P.th[P.nth], NULL, pool_loop, NULL) != 0) break;
+            P.nth++;
+        }
     }
+    P.job = j;
+    P.want = nthreads - 1 < P.nth ? nthreads - 1 : P.nth;
+    P.started = P.running = 0;
+    P.gen++;
+    pthread_cond_broadcast(&P.cv);
+    pthread_mutex_unlock(&P.mu);
+    run_job(j);
+    pthread_mutex_lock(&P.mu);
+    while (!(P.started == P.want && P.running == 0)) pthread_cond_wait(&P.done, &P.mu);
+    P.job = NULL;
+    pthread_mutex_unlock(&P.mu);
+}
+
+/* Start the pool's threads ahead of the first timed pass. */
+void refbench_warm_pool(int nthreads) {
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.op = 4;
+    pool_run(&j, nthreads);
+}
+
+/* Deserialize n bitmaps once (nthreads threads); returns an opaque handle (array of pointers). */
+void *refbench_load_mt(size_t n, const char *const *bufs, const size_t *lens, int nthreads) {
+    roaring_bitmap_t **bms = (roaring_bitmap_t **)calloc(n ? n : 1, sizeof(*bms));
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.op = 5;
+    j.bms = bms;
+    j.bufs = bufs;
+    j.lens = lens;
+    j.n = n;
+    pool_run(&j, nthreads);
+    if (j.failed) return NULL;
     return bms;
+}
+void *refbench_load(size_t n, const char *const *bufs, const size_t *lens) {
+    return refbench_load_mt(n, bufs, lens, 1);
 }
 
 void refbench_unload(void *h, size_t n) {
@@ -83,31 +174,18 @@ void refbench_unload(void *h, size_t n) {
 /* One timed pass over the pair list with nthreads threads; returns seconds, *sumcard = checksum. */
 double refbench_pairs(void *h, int op, const uint32_t *ia, const uint32_t *ib, size_t npairs,
                       int nthreads, uint64_t *sumcard) {
-    roaring_bitmap_t **bms = (roaring_bitmap_t **)h;
+    job_t j;
+    memset(&j, 0, sizeof(j));
+    j.op = op;
+    j.bms = (roaring_bitmap_t **)h;
+    j.ia = ia;
+    j.ib = ib;
+    j.n = npairs;
     if (nthreads < 1) nthreads = 1;
-    job_t *jobs = (job_t *)calloc((size_t)nthreads, sizeof(job_t));
-    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
-    for (int t = 0; t < nthreads; t++) {
-        jobs[t].op = op;
-        jobs[t].bms = bms;
-        jobs[t].ia = ia;
-        jobs[t].ib = ib;
-        jobs[t].lo = npairs * (size_t)t / (size_t)nthreads;
-        jobs[t].hi = npairs * (size_t)(t + 1) / (size_t)nthreads;
-    }
     const double t0 = now_s();
-    if (nthreads == 1) {
-        worker(&jobs[0]);
-    } else {
-        for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, worker, &jobs[t]);
-        for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
-    }
+    pool_run(&j, nthreads);
     const double dt = now_s() - t0;
-    uint64_t s = 0;
-    for (int t = 0; t < nthreads; t++) s += jobs[t].sum;
-    if (sumcard) *sumcard = s;
-    free(jobs);
-    free(th);
+    if (sumcard) *sumcard = j.sum;
     return dt;
 }
 
@@ -131,3 +209,23 @@ double refbench_or_many(void *h, const uint32_t *idx, size_t n, int reps, uint64
 
 /* bit 0: AVX2, bit 1: AVX-512 (src/isadetection.c:291-345) */
 int refbench_hardware_support(void) { return croaring_hardware_support(); }
+
+/* One roaring_bitmap_or_many over bms[idx[0..n)] whose RESULT is returned as portable bytes
+ * (malloc'd, release with refbench_free) for byte-level parity checks; returns the seconds of the
+ * or_many call alone. */
+double refbench_or_many_bytes(void *h, const uint32_t *idx, size_t n, char **out, size_t *outlen, uint64_t *card) {
+    roaring_bitmap_t **bms = (roaring_bitmap_t **)h;
+    const roaring_bitmap_t **xs = (const roaring_bitmap_t **)calloc(n ? n : 1, sizeof(*xs));
+    for (size_t i = 0; i < n; i++) xs[i] = bms[idx ? idx[i] : i];
+    const double t0 = now_s();
+    roaring_bitmap_t *o = roaring_bitmap_or_many(n, xs);
+    const double dt = now_s() - t0;
+    if (card) *card = roaring_bitmap_get_cardinality(o);
+    const size_t sz = roaring_bitmap_portable_size_in_bytes(o);
+    *out = (char *)malloc(sz ? sz : 1);
+    *outlen = roaring_bitmap_portable_serialize(o, *out);
+    roaring_bitmap_free(o);
+    free(xs);
+    return dt;
+}
+void refbench_free(char *p) { free(p); }

@@ -27,16 +27,45 @@ class RefBench:
         L.refbench_or_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                        C.POINTER(C.c_uint64)]
         L.refbench_hardware_support.restype = C.c_int
+        L.refbench_load_mt.restype = C.c_void_p
+        L.refbench_load_mt.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        L.refbench_warm_pool.restype = None
+        L.refbench_warm_pool.argtypes = [C.c_int]
+        L.refbench_or_many_bytes.restype = C.c_double
+        L.refbench_or_many_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+        L.refbench_free.restype = None
+        L.refbench_free.argtypes = [C.c_void_p]
         self.L = L
 
-    def load(self, blobs):
+    def load(self, blobs, nthreads=1):
+        """blobs: list of bytes or a croaring_b200.workloads.BlobArena (pointers used in place)."""
         n = len(blobs)
-        arr = (C.c_char_p * n)(*blobs)
-        lens = (C.c_size_t * n)(*[len(b) for b in blobs])
-        h = self.L.refbench_load(n, arr, lens)
+        if hasattr(blobs, "ptrs"):
+            arr, lens = blobs.ptrs, blobs.lens
+        else:
+            arr = (C.c_char_p * n)(*blobs)
+            lens = (C.c_size_t * n)(*[len(b) for b in blobs])
+        h = self.L.refbench_load_mt(n, arr, lens, int(nthreads))
         if not h:
             raise ValueError("reference refused an input")
         return h, n
+
+    def warm_pool(self, nthreads):
+        self.L.refbench_warm_pool(int(nthreads))
+
+    def or_many_bytes(self, handle, idx=None):
+        """(seconds of the or_many call, portable bytes of its result, cardinality)."""
+        if idx is None:
+            ip, n = None, handle[1]
+        else:
+            idx = np.ascontiguousarray(idx, dtype=np.uint32)
+            ip, n = idx.ctypes.data, idx.size
+        out, ln, c = C.c_void_p(), C.c_size_t(), C.c_uint64()
+        dt = self.L.refbench_or_many_bytes(handle[0], ip, n, C.byref(out), C.byref(ln), C.byref(c))
+        b = C.string_at(out.value, ln.value)
+        self.L.refbench_free(out)
+        return float(dt), b, int(c.value)
 
     def unload(self, handle):
         self.L.refbench_unload(handle[0], handle[1])

@@ -31,8 +31,7 @@ def test_or_many_config2_scale_properties(rb):
     inter = S.and_cardinality(R1, ia, np.zeros(200, np.uint32))
     assert (inter == cards).all()                      # every input is a subset of the union
     # key-sharded evaluation concatenates to the same bytes
-    idxs = [sh.BlobIndex(b) for b in blobs]
-    ranges = sh.plan_key_ranges(sh.key_byte_histogram(idxs), 4)
+    ranges, _span = sh.plan_key_ranges(blobs, 4)
     parts, tot = [], np.zeros(65536, dtype=np.int64)
     for lo, hi in ranges:
         cpk = np.zeros(65536, dtype=np.uint32)

@@ -15,23 +15,25 @@ pytestmark = pytest.mark.gpu
 def test_sharded_or_many_matches_reference(rb, R, world):
     blobs = rb.load_realdata("weather_sept_85")[:50] + synth_blobs(R, 31, 50, key_space=30, max_keys=14) \
         + zipf_blobs(12, 300000, 0.1, seed=3)
-    idx = [sh.BlobIndex(b) for b in blobs]
-    ranges = sh.plan_key_ranges(sh.key_byte_histogram(idx), world)
-    total = np.zeros(65536, dtype=np.int64)
+    ranges, span = sh.plan_key_ranges(blobs, world)
+    one = rb.Comm.create(0, 1)          # a 1-rank communicator: rb200_or_many_sharded issues no collective
+    total = np.zeros(span[1] - span[0] + 1, dtype=np.int64)
     shards = []
     for rank in range(world):
         lo, hi = ranges[rank]
-        mine = [sh.slice_blob_by_keys(ix, lo, hi) for ix in idx]
-        S = rb.DeviceSet.from_serialized(mine)
-        cpk = np.zeros(65536, dtype=np.uint32)
-        r = S.or_many(key_lo=lo, key_hi=hi, card_per_key=cpk)
-        total += cpk                                   # what the NCCL all-reduce(sum) computes
-        shards.append(r.download(0).serialize())
+        S = rb.DeviceSet.from_serialized(blobs, lo, hi)          # host slicing in C + streamed upload
+        part, cards, tot = S.or_many_sharded(one, lo, hi, span)
+        assert tot == int(cards.astype(np.int64).sum())
+        total += cards                                           # what the NCCL all-reduce(sum) computes
+        shards.append(part.serialize_all()[0])
+    one.destroy()
     exp = R.many_bytes("or_many", blobs)
     assert sh.concat_blobs(shards) == exp
     e = R.deserialize(exp)
     assert int(total.sum()) == R.card(e)
     R.free(e)
+    ekeys, ecards = sh.blob_key_cards(exp)
+    assert np.array_equal(total[ekeys.astype(np.int64) - span[0]], ecards)
 
 
 def test_keyrange_on_unsliced_inputs(rb, R):
@@ -43,8 +45,7 @@ def test_keyrange_on_unsliced_inputs(rb, R):
         cpk = np.zeros(65536, dtype=np.uint32)
         got = S.or_many(key_lo=lo, key_hi=hi, card_per_key=cpk).download(0).serialize()
         assert got == sh.slice_blob_by_keys(exp, lo, hi)
-        ix = sh.BlobIndex(got)
-        assert int(cpk.sum()) == int(ix.cards.sum())
+        assert int(cpk.sum()) == int(sh.blob_key_cards(got)[1].sum())
 
 
 def test_zipf_or_many_saturation(rb, R, O):

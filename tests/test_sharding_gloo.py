@@ -1,6 +1,8 @@
-"""CPU tests (-m "not gpu") of the N>1 path: key-range planning, host slicing / concatenation of
-portable bitmaps, and the world_size-2 gloo run of the sharded many-way OR (the per-rank
-reduction is played by the oracle here; on GPU ranks it is DeviceSet.or_many)."""
+"""CPU tests (-m "not gpu") of the N>1 path: the host C entry points for key-range planning,
+slicing and concatenation of portable bitmaps (rb200_plan_key_ranges / rb200_blob_slice_keys /
+rb200_blobs_concat — no CUDA involved), and the world_size-2 gloo run of the sharded many-way OR
+protocol (the per-rank reduction is played by the oracle here and the all-reduce of the uint32[K]
+per-key cardinalities by gloo; on GPU ranks they are rb200_or_many_sharded + NCCL)."""
 import os
 import socket
 import sys
@@ -10,44 +12,53 @@ import pytest
 
 import croaring_b200.datasets as dsm
 from croaring_b200 import sharding as sh
+from croaring_b200 import workloads as wl
 from helpers import synth_blobs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_blob_index_roundtrip(R):
+def test_slice_concat_roundtrip(R):
     blobs = dsm.load_realdata("wikileaks-noquotes")[:30] + dsm.load_realdata("weather_sept_85")[:5] \
         + synth_blobs(R, 3, 30)
     for b in blobs:
-        ix = sh.BlobIndex(b)
-        mv = memoryview(b)
-        pay = [mv[int(s):int(s + z)] for s, z in zip(ix.starts, ix.sizes)]
-        assert sh.build_blob(ix.keys, ix.cards, ix.isrun, pay) == b
         # slicing into 3 key ranges and concatenating gives the bitmap back
         parts = [sh.slice_blob_by_keys(b, lo, hi) for lo, hi in ((0, 2), (3, 40), (41, 65535))]
         assert sh.concat_blobs(parts) == b
-        for p in parts:                       # every slice is a valid bitmap for the reference
-            r = R.deserialize(p)
+        assert sh.slice_blob_by_keys(b, 0, 65535) == b
+        for p, (lo, hi) in zip(parts, ((0, 2), (3, 40), (41, 65535))):
+            r = R.deserialize(p)                 # every slice is a valid bitmap for the reference
             assert R.validate(r)[0]
+            vals = R.to_array(r)
+            assert len(vals) == 0 or (int(vals[0]) >> 16 >= lo and int(vals[-1]) >> 16 <= hi)
             R.free(r)
+    with pytest.raises(Exception):
+        sh.concat_blobs([blobs[0], blobs[0]])    # overlapping key ranges are refused
 
 
 def test_plan_key_ranges_balanced_and_covering():
-    rng = np.random.default_rng(0)
+    A = wl.zipf_arena(24, 60 * 65536, None, density_draw=True)       # Zipf: bytes concentrate in low keys
+    blobs = A.blobs()
+    A.free()
     hist = np.zeros(65536, dtype=np.int64)
-    hist[:1526] = (rng.pareto(1.0, 1526) * 1e5).astype(np.int64) + 1     # Zipf-ish head
-    for world in (1, 2, 4, 8):
-        rs = sh.plan_key_ranges(hist, world)
+    for b in blobs:
+        keys, _ = sh.blob_key_cards(b)
+        for k in keys:
+            hist[k] += len(sh.slice_blob_by_keys(b, int(k), int(k)))  # header + payload of that key
+    for world in (1, 2, 3, 4, 8):
+        rs, span = sh.plan_key_ranges(blobs, world)
+        assert span == (0, 59)
         assert rs[0][0] == 0 and rs[-1][1] == 65535
         for (a, b), (c, d) in zip(rs, rs[1:]):
             assert b + 1 == c and a <= b and c <= d
         loads = [hist[a:b + 1].sum() for a, b in rs]
-        assert max(loads) <= hist.sum() / world + hist.max() + 1
+        assert max(loads) <= hist.sum() / world + hist.max() + 1, (world, loads)
 
 
 def _worker(rank, world, port, seed, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
     import torch.distributed as dist
     from oracle.oraclebind import oracle
     from oracle.refbind import ref
@@ -57,21 +68,23 @@ def _worker(rank, world, port, seed, q):
     O, R = oracle(), ref()
     blobs = dsm.load_realdata("census1881")[:40] + synth_blobs(R, seed, 40, key_space=24, max_keys=12)
 
-    def engine(shard_blobs, lo, hi):
-        out = O.many_bytes("or_many", shard_blobs)
-        ix = sh.BlobIndex(out)
-        cpk = np.zeros(65536, dtype=np.uint32)
-        cpk[ix.keys.astype(np.int64)] = ix.cards
-        assert len(ix.keys) == 0 or (ix.keys.min() >= lo and ix.keys.max() <= hi)
-        return out, cpk
+    def allreduce(a):
+        t = torch.from_numpy(a.astype(np.int64))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.numpy().astype(np.uint32)
 
-    full, cards, (lo, hi) = sh.or_many_sharded(blobs, rank, world, engine, dist=dist)
+    part, cards, (ranges, span) = sh.or_many_sharded_host(
+        blobs, rank, world, lambda mine, lo, hi: O.many_bytes("or_many", mine), allreduce)
     exp = O.many_bytes("or_many", blobs)
-    total = O.cardinality(exp)
-    ok = int(cards.sum()) == total                      # every rank knows the total after the all-reduce
+    ok = int(cards.astype(np.int64).sum()) == O.cardinality(exp)   # every rank knows the total after the all-reduce
+    ekeys, ecards = sh.blob_key_cards(exp)
+    ok = ok and len(cards) == span[1] - span[0] + 1 and np.array_equal(cards[ekeys.astype(np.int64) - span[0]], ecards)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(part, parts, dst=0)
     if rank == 0:
+        full = sh.concat_blobs(parts)
         ok = ok and full == exp and R.many_bytes("or_many", blobs) == exp
-    q.put((rank, ok, lo, hi))
+    q.put((rank, bool(ok), ranges[rank][0], ranges[rank][1]))
     dist.destroy_process_group()
 
 

@@ -20,6 +20,7 @@ def pcg32(state, inc):
 
 def zipf_values(b, U, n, density_draw=False):
     g = pcg32(0x853c49e6748fea9b ^ b, 0xda3e39cb94b95bdb)
+    next(g)                                      # warm-up step (see csrc/workgen.c)
     if density_draw:
         u0 = (next(g) + 1) / 4294967296.0
         n = max(1, int(round(0.001 * math.pow(300.0, u0) * U)))
