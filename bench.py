@@ -311,8 +311,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rb.init(local_rank)
-    stream = torch.cuda.current_stream()
+    # ONE explicit stream for everything that is timed: torch's current stream, the library's stream
+    # (rb200_set_stream) and the CUDA events that bracket the steps.  (The legacy default stream
+    # would not do: its handle is 0, which rb200_set_stream reads as "use the library's own stream".)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     rb.set_stream(stream.cuda_stream)
+    assert stream.cuda_stream != 0
 
     def bcast(obj):
         box = [obj]
@@ -387,13 +392,18 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize()
             tot_ms += e0.elapsed_time(e1)
-            for r in res:
+            for k, r in enumerate(res):
                 if collect:
                     ms, cms, ab = r.op_stats()
                     stats["algo_bytes"] += ab
                     stats["kernel_ms"] += cms
                     stats["device_ms"] += ms
                     stats["launches"] += 1
+                    name = f"{DATASETS[k // len(OPS)]}/{OPS[k % len(OPS)]}"
+                    pl = stats.setdefault("per_launch", {}).setdefault(name, [0.0, 0.0, 0])
+                    pl[0] += cms
+                    pl[1] += ms
+                    pl[2] += ab
                 r.free()
             if collect:
                 stats["checksum"] = int(d_chk.item())
@@ -745,6 +755,9 @@ def main():
                 "kernel_ms_per_launch": stats["kernel_ms"] / max(stats["launches"], 1),
                 "launches_timed": stats["launches"],
                 "step_ms_in_batch_ops": stats["device_ms"] / max(args.steps, 1),
+                "per_launch": {k: {"kernel_ms": v[0] / args.steps, "op_ms": v[1] / args.steps,
+                                   "gbs": v[2] / max(v[0], 1e-9) / 1e6}
+                               for k, v in stats.get("per_launch", {}).items()},
                 "note": "rank 0's launches; inputs (0.2-8.7 MB per dataset) are L2-resident within a step by "
                         "reuse, results stream to HBM; traffic = ncu dram bytes per launch at N = 1"}
 

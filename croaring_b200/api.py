@@ -120,6 +120,13 @@ def lib():
     sig("rb200_download_wait", C.c_int)
     sig("rb200_batch_op_host", C.c_int, C.c_int, C.POINTER(_P), C.POINTER(_P), C.c_size_t,
         C.POINTER(_P))
+    sig("rb200_r64_batch_op", C.c_int, C.c_int, _P, _P, C.c_size_t, _P)
+    sig("rb200_r64_batch_and_cardinality", C.c_int, _P, _P, C.c_size_t, _P)
+    for op in ("and", "or", "xor", "andnot"):
+        sig(f"roaring64_bitmap_{op}", _P, _P, _P)
+        sig(f"roaring64_bitmap_{op}_cardinality", C.c_uint64, _P, _P)
+    sig("roaring64_bitmap_jaccard_index", C.c_double, _P, _P)
+    sig("roaring64_bitmap_intersect", C.c_bool, _P, _P)
     sig("rb200_comm_unique_id", C.c_int, C.c_char_p)
     sig("rb200_comm_init_rank", _P, C.c_char_p, C.c_int, C.c_int)
     sig("rb200_comm_adopt", _P, _P, C.c_int, C.c_int)
@@ -456,6 +463,16 @@ def r64_and_cardinality(a_blobs, b_blobs, ia, ib):
                                                         ia.size, out.ctypes.data) != 0:
         raise RB200Error(last_error())
     return out
+
+
+def r64_batch_op_inmemory(op, a_ptrs, b_ptrs):
+    """rb200_r64_batch_op on in-memory roaring64_bitmap_t* (raw pointers of the host application's
+    CRoaring, which must be loaded RTLD_GLOBAL in this process): list of result pointers."""
+    n = len(a_ptrs)
+    pa, pb, out = (_P * n)(*a_ptrs), (_P * n)(*b_ptrs), (_P * n)()
+    if lib().rb200_r64_batch_op(OPS[op] if isinstance(op, str) else op, pa, pb, n, out) != 0:
+        raise RB200Error(last_error())
+    return [out[i] for i in range(n)]
 
 
 def batch_op_host(op, a, b):

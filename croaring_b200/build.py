@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libroaring_b200.so")
-SOURCES = ["rb200_kernels.cu", "rb200_many.cu", "rb200_convert.cu", "rb200_host.cu", "rb200_shard.cu"]
+SOURCES = ["rb200_kernels.cu", "rb200_many.cu", "rb200_many2.cu", "rb200_convert.cu", "rb200_host.cu", "rb200_shard.cu"]
 HEADERS = ["rb200_common.h", "rb200_device.cuh", "rb200_internal.h", os.path.join("..", "..", "include", "roaring_b200.h")]
 
 NVCC_FLAGS = [

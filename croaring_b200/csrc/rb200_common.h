@@ -27,6 +27,9 @@ constexpr int K_COPY_A = 2;   // pass-through of an unmatched container of the l
 constexpr int K_COPY_B = 3;
 
 // c_src encoding: container index in the left parent, or SRC_B | index in the right parent
+// SRC_SHARED (uploaded sets only): the host container was a SHARED (copy-on-write) wrapper — the
+// in-place twins then take the FUNCTIONAL cell for it (src/roaring.c:840, 1085-1088, 1235, 1376)
+constexpr uint32_t SRC_SHARED = 0xfffffffeu;
 constexpr uint32_t SRC_NONE = 0xffffffffu, SRC_B = 0x80000000u;   // pass-through of an unmatched container of the right bitmap
 
 // c_card of a BITSET container produced by a lazy op: the reference leaves its cardinality field
@@ -100,6 +103,23 @@ struct OpStats {
     unsigned long long out_portable;  // sum over result bitmaps of roaring_bitmap_portable_size_in_bytes
     unsigned int error;               // 0 = ok; 1 = slot overflow; 2 = slab overflow; 3 = malformed blob
     unsigned int nk;                  // or_many: number of distinct keys
+    unsigned int units;               // or_many: number of (key, slice) work units
+};
+
+// Key-major index of one many-way union (rb200_many2.cu): built per call on the device.
+struct Many2Index {
+    uint32_t *key_count;    // [65536] participants per key            (zero on entry)
+    uint32_t *key_units16;  // [65536] their stored bytes / 16         (zero on entry)
+    uint32_t *key_fill;     // [65536] fill cursors                    (zero on entry)
+    uint32_t *key_start;    // [65536] first index entry of the key
+    uint16_t *keys;         // [nk] live keys, increasing
+    uint32_t *key_slices;   // [nk] work units of the key
+    uint32_t *key_scratch;  // [nk] scratch slot of a split key
+    uint32_t *unit_first;   // [nk] first work unit of the key
+    uint32_t *unit_ki;      // [max_units] work unit -> live key index
+    uint32_t *e_pos;        // [entries] input position of the participant
+    uint32_t *e_cont;       // [entries] its container
+    uint8_t *e_tf;          // [entries] type | full-run / full-bitset flags
 };
 
 // --- launch wrappers (rb200_kernels.cu); every wrapper bumps g_launches -----------------
@@ -136,6 +156,11 @@ void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uin
                     uint32_t want_slices, uint32_t *scratch_acc, uint32_t *scratch_tickets,
                     uint32_t scratch_keys, SetOut out, uint32_t *card_per_key /*65536 or null*/,
                     OpStats *st, int sms, cudaStream_t s);
+
+void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
+                     const Many2Index &ix, uint32_t max_units, uint32_t *scratch, uint32_t *tickets,
+                     uint32_t scratch_slots, SetOut out, uint32_t *card_per_key, OpStats *st, int sms,
+                     cudaStream_t s, cudaEvent_t ev_kernel_start);
 
 void launch_pack_scan(const uint64_t *bytes, const uint32_t *cnts, uint32_t n, uint64_t *off,
                       uint64_t *beg, cudaStream_t s);

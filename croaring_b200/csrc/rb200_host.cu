@@ -51,6 +51,7 @@ struct shared_container_t { void *container; uint8_t typecode; uint32_t counter;
 constexpr uint8_t FLAG_COW = 1, FLAG_FROZEN = 2;  // roaring_types.h:46-49
 constexpr uint32_t SERIAL_COOKIE_NO_RUN = 12346, SERIAL_COOKIE = 12347;  // roaring_array.h:35-40
 constexpr int32_t NO_OFFSET_THRESHOLD = 4;
+constexpr uint32_t M2_SCRATCH_SLOTS = 2048, M2_SCRATCH_WORDS = 2 * ACC_WORDS + 32;  // rb200_many2.cu split keys
 constexpr uint32_t MANY_SCRATCH_KEYS = 4096;  // keys that may be split over several CTAs in or_many
 
 // ------------------------------------------------------------------ host allocation hooks
@@ -110,6 +111,9 @@ struct Ctx {
     uint16_t *d_keys = nullptr;    // 65536 compacted keys
     uint32_t *d_cardkey = nullptr; // 65536 per-key cardinalities
     uint32_t *d_many_acc = nullptr, *d_many_tickets = nullptr;  // split-key scratch (kept zeroed)
+    // second-generation or_many (rb200_many2.cu): per-key tables + split-key scratch (kept zeroed)
+    uint32_t *d_m2_tables = nullptr;   // 7 x 65536 u32: count | units16 | fill | start | slices | scratch | unit_first
+    uint32_t *d_m2_scratch = nullptr, *d_m2_tickets = nullptr;
     int sms = 148;
     std::multimap<size_t, void *> dpool, hpool;
     std::mutex alloc_mu;  // dpool / hpool are also used by the background downloader thread
@@ -166,6 +170,11 @@ bool ctx_init(int device = -1) {
     CK(cudaMalloc(&g.d_many_tickets, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
     CK(cudaMemset(g.d_many_acc, 0, (size_t)MANY_SCRATCH_KEYS * BITSET_BYTES));
     CK(cudaMemset(g.d_many_tickets, 0, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
+    CK(cudaMalloc(&g.d_m2_tables, 7 * 65536 * sizeof(uint32_t)));
+    CK(cudaMalloc(&g.d_m2_scratch, (size_t)M2_SCRATCH_SLOTS * M2_SCRATCH_WORDS * sizeof(uint32_t)));
+    CK(cudaMalloc(&g.d_m2_tickets, M2_SCRATCH_SLOTS * sizeof(uint32_t)));
+    CK(cudaMemset(g.d_m2_scratch, 0, (size_t)M2_SCRATCH_SLOTS * M2_SCRATCH_WORDS * sizeof(uint32_t)));
+    CK(cudaMemset(g.d_m2_tickets, 0, M2_SCRATCH_SLOTS * sizeof(uint32_t)));
     CK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, g.device));
     g_halloc.look();  // resolve the host allocator once, before any worker thread exists
     g.inited = true;
@@ -929,8 +938,10 @@ rb200_set *upload_impl(const PackSrc &src) {
                 uint32_t card, len;
                 const uint8_t *p;
                 uint16_t key;
+                bool was_shared = false;
                 if (ra) {
                     t = ra->typecodes[i];
+                    was_shared = t == T_SHARED;
                     const void *c = unwrap_shared(ra->containers[i], t);
                     key = ra->keys[i];
                     card = host_container_card(c, t);
@@ -974,7 +985,7 @@ rb200_set *upload_impl(const PackSrc &src) {
                 c_card[ci] = card;
                 c_len[ci] = len;
                 c_off[ci] = off;
-                c_src[ci] = SRC_NONE;
+                c_src[ci] = was_shared ? SRC_SHARED : SRC_NONE;
                 if (s->h_ptr_all) (*s->h_ptr_all)[ci] = p;
                 off += sb16;
                 bcard += card & CARD_MASK;
@@ -1501,7 +1512,38 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
     cudaEvent_t evc0 = nullptr, evc1 = nullptr;
     if (ok && want_ck) { h_ck = (uint32_t *)pin_alloc(65536 * 4); ok = h_ck != nullptr; }
     if (ok && sh) { evc0 = ev_get(); evc1 = ev_get(); ok = evc0 && evc1; }
-    if (ok) {
+    static const bool use_v1 = []() { const char *e = getenv("RB200_OR_MANY"); return e && !strcmp(e, "v1"); }();
+    // index of the second-generation kernel: entries + work-unit table from the device pool
+    uint64_t tot_kib = 0;
+    for (size_t i = 0; i < n; i++) tot_kib += (S->h_bytes[idx ? idx[i] : i] >> 10) + 1;
+    const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>(tot, std::min<uint64_t>(65536, tot) + tot_kib / 32 + 1));
+    const size_t e_bytes = al256(4 * tot) * 2 + al256(tot) + al256(4 * max_units);
+    uint8_t *d_index = nullptr;
+    if (ok && !use_v1) { d_index = (uint8_t *)dev_alloc(e_bytes); ok = d_index != nullptr; }
+    if (ok && !use_v1) {
+        cudaEventRecord(g.ev0, g.stream);
+        ok = stats_reset();
+        const SetView vs = S->view();
+        Many2Index ix;
+        ix.key_count = g.d_m2_tables;
+        ix.key_units16 = g.d_m2_tables + 65536;
+        ix.key_fill = g.d_m2_tables + 2 * 65536;
+        ix.key_start = g.d_m2_tables + 3 * 65536;
+        ix.key_slices = g.d_m2_tables + 4 * 65536;
+        ix.key_scratch = g.d_m2_tables + 5 * 65536;
+        ix.unit_first = g.d_m2_tables + 6 * 65536;
+        ix.keys = g.d_keys;
+        ix.e_pos = (uint32_t *)d_index;
+        ix.e_cont = (uint32_t *)(d_index + al256(4 * tot));
+        ix.e_tf = d_index + 2 * al256(4 * tot);
+        ix.unit_ki = (uint32_t *)(d_index + 2 * al256(4 * tot) + al256(tot));
+        cudaMemsetAsync(g.d_m2_tables, 0, 3 * 65536 * sizeof(uint32_t), g.stream);
+        if (want_ck) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
+        launch_or_many2(vs, d_idx, (uint32_t)n, key_lo, key_hi, ix, (uint32_t)std::min<uint64_t>(max_units, 0xffffffffu),
+                        g.d_m2_scratch, g.d_m2_tickets, M2_SCRATCH_SLOTS, R->out(), want_ck ? g.d_cardkey : nullptr,
+                        g.d_stats, g.sms, g.stream, g.evk0);
+    }
+    if (ok && use_v1) {
         cudaEventRecord(g.ev0, g.stream);
         ok = stats_reset();
         const SetView vs = S->view();
@@ -1520,6 +1562,8 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         launch_or_many(vs, d_idx, (uint32_t)n, g.d_keys, slices, g.d_many_acc, g.d_many_tickets,
                        MANY_SCRATCH_KEYS, R->out(), want_ck ? g.d_cardkey : nullptr, g.d_stats,
                        g.sms, g.stream);
+    }
+    if (ok) {
         cudaEventRecord(g.evk1, g.stream);
         if (sh) {  // the ONE collective of the path: per-key cardinalities, summed over the ranks, on the device
             cudaEventRecord(evc0, g.stream);
@@ -1567,6 +1611,7 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         g.last_algo_bytes = inb;
     }
     dev_free(d_idx, 4 * n);
+    dev_free(d_index, e_bytes);
     pin_free(h_idx, 4 * n);
     pin_free(h_ck, 65536 * 4);
     ev_put(evc0);
@@ -3305,6 +3350,138 @@ int rb200_r64_batch_and_cardinality_serialized(const char *const *a, const size_
         out[p] = s;
     }
     return 0;
+}
+
+// ---- in-memory roaring64_bitmap_t (include/roaring/roaring64.h:423-522; src/roaring64.c:1332-1895)
+// The 64-bit bitmap is an ART of (high-48 key -> container) owned by the reference library; its
+// layout is private to that library (src/art/art.c), so the binding goes through the two format
+// functions the reference exports for exactly this purpose: the operands are written with the
+// HOST APPLICATION's roaring64_bitmap_portable_serialize (resolved with dlsym in the running
+// process — the reference must be loaded, or nobody could have built a roaring64_bitmap_t), the
+// container grid runs on the device (rb200_r64_batch_op_serialized), and the result bytes become
+// a roaring64_bitmap_t again through roaring64_bitmap_portable_deserialize_safe.  Results are
+// byte-identical to the reference's (tests/test_gpu_r64.py).
+namespace {
+struct R64Api {
+    size_t (*size)(const roaring64_bitmap_t *) = nullptr;
+    size_t (*ser)(const roaring64_bitmap_t *, char *) = nullptr;
+    roaring64_bitmap_t *(*deser)(const char *, size_t) = nullptr;
+    uint64_t (*card)(const roaring64_bitmap_t *) = nullptr;
+    bool ok() {
+        if (size && ser && deser && card) return true;   // looked up lazily: the host library may load later
+        size = (decltype(size))dlsym(RTLD_DEFAULT, "roaring64_bitmap_portable_size_in_bytes");
+        ser = (decltype(ser))dlsym(RTLD_DEFAULT, "roaring64_bitmap_portable_serialize");
+        deser = (decltype(deser))dlsym(RTLD_DEFAULT, "roaring64_bitmap_portable_deserialize_safe");
+        card = (decltype(card))dlsym(RTLD_DEFAULT, "roaring64_bitmap_get_cardinality");
+        if (size && ser && deser && card) return true;
+        t_err = "roaring64: the host CRoaring library (roaring64_bitmap_portable_serialize / _deserialize_safe) "
+                "is not loaded in this process";
+        return false;
+    }
+} g_r64;
+
+// serialize n distinct in-memory bitmaps (in parallel) into owned buffers
+bool r64_serialize_all(const roaring64_bitmap_t *const *bms, size_t n, std::vector<std::vector<char>> &bufs) {
+    bufs.resize(n);
+    std::atomic<bool> ok(true);
+    rb200::parallel_for(n, [&](size_t i) {
+        const size_t sz = g_r64.size(bms[i]);
+        bufs[i].resize(sz ? sz : 1);
+        if (g_r64.ser(bms[i], bufs[i].data()) != sz) ok = false;
+    });
+    if (!ok) t_err = "roaring64: serialization of an operand failed";
+    return ok;
+}
+}  // namespace
+
+// out[k] = roaring64_bitmap_{and,or,xor,andnot}(a[k], b[k]) for npairs in-memory 64-bit bitmaps of the
+// host application's CRoaring; out[k] is a fresh roaring64_bitmap_t the caller frees with
+// roaring64_bitmap_free.  0 on success.
+int rb200_r64_batch_op(int op, const roaring64_bitmap_t *const *a, const roaring64_bitmap_t *const *b,
+                       size_t npairs, roaring64_bitmap_t **out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!g_r64.ok()) return -1;
+    if (npairs == 0) return 0;
+    std::vector<std::vector<char>> sa, sb;
+    if (!r64_serialize_all(a, npairs, sa) || !r64_serialize_all(b, npairs, sb)) return -1;
+    std::vector<const char *> pa(npairs), pb(npairs);
+    std::vector<size_t> la(npairs), lb(npairs);
+    std::vector<uint32_t> ia(npairs), ib(npairs);
+    for (size_t k = 0; k < npairs; k++) {
+        pa[k] = sa[k].data(); la[k] = g_r64.size(a[k]);
+        pb[k] = sb[k].data(); lb[k] = g_r64.size(b[k]);
+        ia[k] = ib[k] = (uint32_t)k;
+    }
+    char *blob = nullptr;
+    uint64_t *off = nullptr, *len = nullptr;
+    if (rb200_r64_batch_op_serialized(op, pa.data(), la.data(), npairs, pb.data(), lb.data(), npairs, ia.data(),
+                                      ib.data(), npairs, &blob, &off, &len) != 0)
+        return -1;
+    std::atomic<bool> ok(true);
+    rb200::parallel_for(npairs, [&](size_t k) {
+        out[k] = g_r64.deser(blob + off[k], (size_t)len[k]);
+        if (!out[k]) ok = false;
+    });
+    rb200_serialized_free(blob, off, len);
+    if (!ok) { t_err = "roaring64: the host library refused a result blob"; return -1; }
+    return 0;
+}
+
+int rb200_r64_batch_and_cardinality(const roaring64_bitmap_t *const *a, const roaring64_bitmap_t *const *b,
+                                    size_t npairs, uint64_t *out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!g_r64.ok()) return -1;
+    if (npairs == 0) return 0;
+    std::vector<std::vector<char>> sa, sb;
+    if (!r64_serialize_all(a, npairs, sa) || !r64_serialize_all(b, npairs, sb)) return -1;
+    std::vector<const char *> pa(npairs), pb(npairs);
+    std::vector<size_t> la(npairs), lb(npairs);
+    std::vector<uint32_t> ia(npairs), ib(npairs);
+    for (size_t k = 0; k < npairs; k++) {
+        pa[k] = sa[k].data(); la[k] = g_r64.size(a[k]);
+        pb[k] = sb[k].data(); lb[k] = g_r64.size(b[k]);
+        ia[k] = ib[k] = (uint32_t)k;
+    }
+    return rb200_r64_batch_and_cardinality_serialized(pa.data(), la.data(), npairs, pb.data(), lb.data(), npairs,
+                                                      ia.data(), ib.data(), npairs, out);
+}
+
+// drop-in symbols, include/roaring/roaring64.h:423-522
+static roaring64_bitmap_t *r64_dropin(int op, const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) {
+    roaring64_bitmap_t *out = nullptr;
+    return rb200_r64_batch_op(op, &r1, &r2, 1, &out) == 0 ? out : nullptr;
+}
+roaring64_bitmap_t *roaring64_bitmap_and(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) { return r64_dropin(OP_AND, r1, r2); }
+roaring64_bitmap_t *roaring64_bitmap_or(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) { return r64_dropin(OP_OR, r1, r2); }
+roaring64_bitmap_t *roaring64_bitmap_xor(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) { return r64_dropin(OP_XOR, r1, r2); }
+roaring64_bitmap_t *roaring64_bitmap_andnot(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) { return r64_dropin(OP_ANDNOT, r1, r2); }
+uint64_t roaring64_bitmap_and_cardinality(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) {
+    uint64_t c = UINT64_MAX;
+    if (rb200_r64_batch_and_cardinality(&r1, &r2, 1, &c) != 0) return UINT64_MAX;
+    return c;
+}
+// roaring64.c:1411-1437, 1600-1622...: inclusion-exclusion on and_cardinality
+uint64_t roaring64_bitmap_or_cardinality(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) {
+    const uint64_t i = roaring64_bitmap_and_cardinality(r1, r2);
+    return i == UINT64_MAX ? i : g_r64.card(r1) + g_r64.card(r2) - i;
+}
+uint64_t roaring64_bitmap_xor_cardinality(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) {
+    const uint64_t i = roaring64_bitmap_and_cardinality(r1, r2);
+    return i == UINT64_MAX ? i : g_r64.card(r1) + g_r64.card(r2) - 2 * i;
+}
+uint64_t roaring64_bitmap_andnot_cardinality(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) {
+    const uint64_t i = roaring64_bitmap_and_cardinality(r1, r2);
+    return i == UINT64_MAX ? i : g_r64.card(r1) - i;
+}
+double roaring64_bitmap_jaccard_index(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) {
+    const uint64_t i = roaring64_bitmap_and_cardinality(r1, r2);
+    if (i == UINT64_MAX) return std::numeric_limits<double>::quiet_NaN();
+    return (double)i / (double)(g_r64.card(r1) + g_r64.card(r2) - i);
+}
+bool roaring64_bitmap_intersect(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2) {
+    const uint64_t i = roaring64_bitmap_and_cardinality(r1, r2);
+    if (i == UINT64_MAX) dropin_failed("roaring64_bitmap_intersect");
+    return i != 0 && i != UINT64_MAX;
 }
 
 // ---- public lazy API (include/roaring/roaring.h:932-977) ------------------------------------

@@ -285,10 +285,15 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
             } else if (kind == K_COMPUTE) {
                 const uint32_t ca = it.ca[item], cb = it.cb[item];
                 const uint32_t rawA = A.c_card[ca];
+                // in-place twins: a SHARED left container takes the functional cell (roaring.c:1085-1088);
+                // the lazy in-place twins work on a writable copy instead (roaring.c:2636)
+                int cell_rules = rules;
+                if ((rules & (RULES_INPLACE | RULES_LAZY)) == RULES_INPLACE && A.c_src[ca] == SRC_SHARED)
+                    cell_rules &= ~RULES_INPLACE;
                 cell_compute<OP, LAZY>(acc, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
                              B.payload + B.c_off[cb], rawA & CARD_MASK, B.c_card[cb] & CARD_MASK,
                              A.c_len[ca], B.c_len[cb], slab + off, cap, lane, otype, ocard, olen,
-                             &st->error, rules, (rawA & CARD_UNKNOWN) != 0);
+                             &st->error, cell_rules, (rawA & CARD_UNKNOWN) != 0);
             } else {
                 const SetView &S = (kind == K_COPY_A) ? A : B;
                 const uint32_t c = (kind == K_COPY_A) ? it.ca[item] : it.cb[item];

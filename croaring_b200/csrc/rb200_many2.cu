@@ -1,0 +1,497 @@
+// rb200_many2.cu — N-way union (roaring_bitmap_or_many, src/roaring.c:775-790), second generation:
+// a key-major index built once per call, then one streaming pass over the payloads.
+//
+//   k_many2_count   histogram of the participating containers per high-16 key (+ their bytes)
+//   k_many2_scan    exclusive scan -> per-key segment of the index, list of live keys, and the
+//                   work units: a key whose participants weigh more than SLICE_BYTES is split
+//                   into several units (slices of its participant list) merged through a global
+//                   scratch accumulator
+//   k_many2_fill    index entries {input position, container, type|flags}, grouped by key
+//                   (order inside a key is arbitrary: nothing below needs it)
+//   k_or_many2      work unit = (key, slice): bitset participants are ORed in registers (every
+//                   thread owns 32 bytes of the 8 KiB, four containers in flight), arrays and runs
+//                   are rasterised into a shared accumulator by one warp each; the last slice of
+//                   a key counts, picks the reference's result type and re-encodes.
+//
+// The reference folds the inputs left to right with lazy cells (roaring_bitmap_lazy_or :2509-2598,
+// roaring_bitmap_lazy_or_inplace :2600-2682, container_lazy_or / container_lazy_ior
+// include/roaring/containers/containers.h:1113-1215, 1333-1442) and repairs once (:2845).  The
+// VALUE is order free; the result TYPE depends on the order only through a few order statistics
+// of the participants' metadata, which are computed by reductions instead of a sequential replay:
+//     first / second participant (smallest input positions), whether they are x[0], x[1] (their
+//     combine is the non-in-place container_lazy_or, roaring.c:2535-2550: no "is full" shortcut),
+//     F = the first in-place step that brings a full run (containers.h:1394-1399: the accumulator
+//         becomes the full RUN and later inputs are skipped, roaring.c:2621),
+//     L = the last in-place step before F whose input is a bitset: container_lazy_ior B,B computes
+//         the cardinality and turns a saturated accumulator into the full run (:1342-1352) — so a
+//         saturated union ends as RUN iff the union of the inputs up to and including L is
+//         already full.  Inputs after L (arrays / runs only) go to a second accumulator, which
+//         makes that test a popcount instead of a second pass over the payloads.
+#include <stdlib.h>
+
+#include "rb200_device.cuh"
+
+namespace rb200 {
+
+constexpr int M2_THREADS = 256;
+constexpr int M2_STAGE = 256;                    // index entries staged per round
+constexpr uint32_t M2_SLICE_BYTES = 384u << 10;  // payload bytes per work unit before a key is split
+constexpr uint32_t M2_MAX_SLICES = 64;
+constexpr uint32_t TF_FULL_RUN = 16, TF_FULL_BITSET = 32;
+constexpr uint32_t POS_NONE = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t entry_tf(const SetView &S, uint32_t c) {
+    const uint32_t t = S.c_type[c], l = S.c_len[c], cd = S.c_card[c] & CARD_MASK;
+    uint32_t f = t;
+    if (t == T_RUN && l == 1 && cd == 65536) f |= TF_FULL_RUN;
+    if (t == T_BITSET && cd == 65536) f |= TF_FULL_BITSET;
+    return f;
+}
+
+// ------------------------------------------------------------------------------ index
+__global__ void __launch_bounds__(128)
+k_many2_count(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
+              Many2Index ix) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < n; i += nwarps) {
+        const uint32_t b = idx ? idx[i] : i;
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        for (uint32_t c = lane; c < nc; c += 32) {
+            const uint32_t k = S.c_key[c0 + c];
+            if (k < key_lo || k > key_hi) continue;
+            atomicAdd(ix.key_count + k, 1u);
+            atomicAdd(ix.key_units16 + k, round16(stored_bytes(S.c_type[c0 + c], S.c_len[c0 + c])) >> 4);
+        }
+    }
+}
+
+// single CTA, 1024 threads, 64 keys per thread
+__global__ void __launch_bounds__(1024)
+k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t want_parallel, SetOut out,
+             OpStats *st) {
+    __shared__ uint32_t s_a[32], s_b[32], s_c[32], s_d[32];
+    __shared__ uint32_t s_split;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // pass 1: entries, live keys and total weight
+    uint32_t cnt = 0, live = 0, w16 = 0;
+    for (int k = 0; k < 64; k++) {
+        const uint32_t c = ix.key_count[tid * 64 + k];
+        cnt += c;
+        live += c ? 1u : 0u;
+        w16 += ix.key_units16[tid * 64 + k] >> 6;   // KiB, to stay inside 32 bits
+    }
+    uint32_t icnt = warp_incl_scan(cnt, lane), ilive = warp_incl_scan(live, lane), iw = warp_incl_scan(w16, lane);
+    if (lane == 31) { s_a[wid] = icnt; s_b[wid] = ilive; s_c[wid] = iw; }
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t a = s_a[lane], b = s_b[lane], c = s_c[lane];
+        const uint32_t sa = warp_incl_scan(a, lane), sb = warp_incl_scan(b, lane), sc = warp_incl_scan(c, lane);
+        s_a[lane] = sa - a;
+        s_b[lane] = sb - b;
+        s_c[lane] = sc;
+        if (lane == 31) {
+            st->nk = sb;
+            // few heavy keys: split them so that the grid has ~want_parallel units
+            const uint32_t total_kib = sc;
+            uint32_t slice_kib = M2_SLICE_BYTES >> 10;
+            if (want_parallel && total_kib / slice_kib < want_parallel) {
+                slice_kib = total_kib / want_parallel;
+                if (slice_kib < 32) slice_kib = 32;
+            }
+            s_split = slice_kib;
+        }
+    }
+    __syncthreads();
+    const uint32_t slice_kib = s_split;
+    uint32_t e = s_a[wid] + icnt - cnt, ki = s_b[wid] + ilive - live;
+    // pass 2: per key start / live index / slices
+    uint32_t units = 0, nsplit = 0;
+    for (int k = 0; k < 64; k++) {
+        const uint32_t key = tid * 64 + k, c = ix.key_count[key];
+        ix.key_start[key] = e;
+        e += c;
+        if (c) {
+            const uint32_t kib = ix.key_units16[key] >> 6;
+            uint32_t s = (kib + slice_kib - 1) / slice_kib;
+            const uint32_t by_cnt = (c + 3) >> 2;
+            if (s > by_cnt) s = by_cnt;
+            if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
+            if (s < 1) s = 1;
+            units += s;
+            nsplit += s > 1 ? 1u : 0u;
+        }
+    }
+    uint32_t iu = warp_incl_scan(units, lane), is = warp_incl_scan(nsplit, lane);
+    __syncthreads();
+    if (lane == 31) { s_a[wid] = iu; s_d[wid] = is; }
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t a = s_a[lane], d = s_d[lane];
+        const uint32_t sa = warp_incl_scan(a, lane), sd = warp_incl_scan(d, lane);
+        s_a[lane] = sa - a;
+        s_d[lane] = sd - d;
+    }
+    __syncthreads();
+    uint32_t u = s_a[wid] + iu - units, sp = s_d[wid] + is - nsplit;
+    for (int k = 0; k < 64; k++) {
+        const uint32_t key = tid * 64 + k, c = ix.key_count[key];
+        if (!c) continue;
+        const uint32_t kib = ix.key_units16[key] >> 6;
+        uint32_t s = (kib + slice_kib - 1) / slice_kib;
+        const uint32_t by_cnt = (c + 3) >> 2;
+        if (s > by_cnt) s = by_cnt;
+        if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
+        if (s < 1) s = 1;
+        uint32_t slot = POS_NONE;
+        if (s > 1) {
+            // a split key needs a scratch slot and room in the unit table; else it stays whole
+            // (the unit numbering below must not depend on this decision: units were reserved)
+            if (sp < scratch_slots && u + s <= max_units) slot = sp;
+            sp++;
+        }
+        ix.keys[ki] = (uint16_t)key;
+        ix.key_slices[ki] = slot == POS_NONE ? 1u : s;
+        ix.key_scratch[ki] = slot;
+        ix.unit_first[ki] = u;
+        // reserved-but-unused units of an unsplit heavy key are marked idle
+        for (uint32_t q = 0; q < s && u + q < max_units; q++)
+            ix.unit_ki[u + q] = (slot == POS_NONE && q > 0) ? POS_NONE : ki;
+        u += s;
+        ki++;
+    }
+    __syncthreads();
+    if (tid == 1023) {
+        st->units = u < max_units ? u : max_units;
+        out.bm_beg[0] = 0;
+        out.bm_cnt[0] = st->nk;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_many2_fill(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
+             Many2Index ix) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < n; i += nwarps) {
+        const uint32_t b = idx ? idx[i] : i;
+        const uint32_t c0 = S.bm_beg[b], nc = S.bm_cnt[b];
+        for (uint32_t c = lane; c < nc; c += 32) {
+            const uint32_t k = S.c_key[c0 + c];
+            if (k < key_lo || k > key_hi) continue;
+            const uint32_t slot = ix.key_start[k] + atomicAdd(ix.key_fill + k, 1u);
+            ix.e_pos[slot] = i;
+            ix.e_cont[slot] = c0 + c;
+            ix.e_tf[slot] = (uint8_t)entry_tf(S, c0 + c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ reduction
+struct Many2Smem {
+    uint32_t acc[ACC_WORDS];    // union of the inputs up to L (or of all of them when L is not needed)
+    uint32_t acc2[ACC_WORDS];   // union of the inputs after L
+    unsigned long long s_off[M2_STAGE];
+    uint32_t s_len[M2_STAGE];
+    uint32_t s_pos[M2_STAGE];
+    uint8_t s_tf[M2_STAGE];
+    uint32_t bs_list[M2_STAGE];  // staged entries that are bitsets / that are arrays or runs
+    uint32_t ar_list[M2_STAGE];
+    unsigned long long red64[M2_THREADS / 32];
+    uint32_t red32[M2_THREADS / 32][2];
+    uint32_t nbs, nar, unit, flag;
+    unsigned long long first, second;
+    uint32_t F, L, any_ib;
+};
+
+// min over the block of a u64 (all threads get the result); two barriers
+__device__ __forceinline__ unsigned long long block_min64(Many2Smem &sm, unsigned long long v) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(FULLMASK, v, d);
+        v = o < v ? o : v;
+    }
+    __syncthreads();
+    if (lane == 0) sm.red64[wid] = v;
+    __syncthreads();
+    unsigned long long r = sm.red64[0];
+#pragma unroll
+    for (int w = 1; w < M2_THREADS / 32; w++) r = sm.red64[w] < r ? sm.red64[w] : r;
+    return r;
+}
+
+__global__ void __launch_bounds__(M2_THREADS, 4)
+k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch, uint32_t *__restrict__ tickets,
+           SetOut out, uint32_t *__restrict__ card_per_key, OpStats *st) {
+    __shared__ __align__(16) Many2Smem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nunits = st->units;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm.unit = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
+        __syncthreads();
+        const uint32_t unit = sm.unit;
+        if (unit >= nunits) break;
+        const uint32_t ki = ix.unit_ki[unit];
+        if (ki == POS_NONE) continue;   // reserved for a key that could not be split
+        const uint32_t key = ix.keys[ki], ns = ix.key_slices[ki], sl = unit - ix.unit_first[ki];
+        const uint32_t e0 = ix.key_start[key], m = ix.key_count[key];
+
+        // ---- order statistics of the fold (metadata only, the whole participant list) -----------
+        // packed (position << 8 | type flags): the two smallest positions
+        unsigned long long m1 = ~0ull, m2 = ~0ull;
+        for (uint32_t e = tid; e < m; e += M2_THREADS) {
+            const unsigned long long v = ((unsigned long long)ix.e_pos[e0 + e] << 8) | ix.e_tf[e0 + e];
+            if (v < m1) { m2 = m1; m1 = v; }
+            else if (v < m2) m2 = v;
+        }
+        const unsigned long long first = block_min64(sm, m1);
+        const unsigned long long second = block_min64(sm, m1 == first ? m2 : m1);
+        const uint32_t pos1 = (uint32_t)(first >> 8), tf1 = (uint32_t)(first & 0xff);
+        const uint32_t pos2 = (uint32_t)(second >> 8), tf2 = (uint32_t)(second & 0xff);
+        const int t1 = tf1 & 15, t2 = tf2 & 15;
+        bool run_full = (tf1 & TF_FULL_RUN) != 0;
+        bool decided = (tf1 & (TF_FULL_RUN | TF_FULL_BITSET)) != 0;
+        bool first_full_bitset = (tf1 & TF_FULL_BITSET) != 0;
+        const bool non_inplace = m >= 2 && pos1 == 0 && pos2 == 1;   // roaring.c:2535-2550
+        uint32_t inplace_from = pos1;      // in-place steps: positions > inplace_from
+        if (non_inplace) {
+            first_full_bitset = false;
+            if (t1 != T_BITSET && t2 != T_BITSET) run_full = (tf2 & TF_FULL_RUN) != 0;   // c1 -> bitset, lazy_ior(B, c2)
+            else run_full = ((tf2 | tf1) & TF_FULL_RUN) != 0;                            // container_lazy_or copies a full run
+            decided = run_full;
+            inplace_from = pos2;
+        }
+        uint32_t L = POS_NONE;             // POS_NONE: no prefix test needed, everything goes to acc
+        bool any_ib = false;
+        if (m >= 2 && !decided) {
+            // F: first in-place step with a full run; L: last in-place bitset step before F
+            unsigned long long f = ~0ull;
+            for (uint32_t e = tid; e < m; e += M2_THREADS) {
+                const uint32_t p = ix.e_pos[e0 + e];
+                if (p > inplace_from && (ix.e_tf[e0 + e] & TF_FULL_RUN)) f = p < f ? p : f;
+            }
+            f = block_min64(sm, f);
+            if (f != ~0ull) run_full = true;
+            const uint32_t F = f == ~0ull ? POS_NONE : (uint32_t)f;
+            unsigned long long l = ~0ull;  // max as min of the complement
+            for (uint32_t e = tid; e < m; e += M2_THREADS) {
+                const uint32_t p = ix.e_pos[e0 + e];
+                if (p > inplace_from && p < F && (ix.e_tf[e0 + e] & 15) == T_BITSET) {
+                    const unsigned long long c = ~(unsigned long long)p;
+                    l = c < l ? c : l;
+                }
+            }
+            l = block_min64(sm, l);
+            if (l != ~0ull) {
+                any_ib = true;
+                if (!run_full) L = (uint32_t)(~l);
+            }
+        }
+
+        // ---- accumulate this unit's slice of the participants ---------------------------------
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < ACC_WORDS / 4; i += M2_THREADS) {
+            reinterpret_cast<uint4 *>(sm.acc)[i] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4 *>(sm.acc2)[i] = make_uint4(0, 0, 0, 0);
+        }
+        const uint32_t per = (m + ns - 1) / ns;
+        const uint32_t s_lo = min(sl * per, m), s_hi = min(s_lo + per, m);
+        uint32_t anyfull = 0, anyfull_pre = 0;   // bit flags, merged over the block at the end
+        for (uint32_t base = s_lo; base < s_hi; base += M2_STAGE) {
+            __syncthreads();
+            if (tid == 0) { sm.nbs = 0; sm.nar = 0; }
+            __syncthreads();
+            const uint32_t e = base + tid;
+            if (tid < M2_STAGE && e < s_hi) {
+                const uint32_t c = ix.e_cont[e0 + e], tf = ix.e_tf[e0 + e], p = ix.e_pos[e0 + e];
+                sm.s_off[tid] = S.c_off[c];
+                sm.s_len[tid] = S.c_len[c];
+                sm.s_pos[tid] = p;
+                sm.s_tf[tid] = (uint8_t)tf;
+                if (tf & (TF_FULL_RUN | TF_FULL_BITSET)) {
+                    anyfull = 1;
+                    if (L != POS_NONE && p <= L) anyfull_pre = 1;
+                }
+                if ((tf & 15) == T_BITSET) sm.bs_list[atomicAdd(&sm.nbs, 1u)] = tid;
+                else if (!(tf & TF_FULL_RUN)) sm.ar_list[atomicAdd(&sm.nar, 1u)] = tid;
+            }
+            __syncthreads();
+            // bitsets: registers, four containers in flight per thread (all of them are <= L)
+            const uint32_t nbs = sm.nbs;
+            for (uint32_t j = 0; j < nbs; j += 4) {
+                uint4 qa[4], qb[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (j + k < nbs) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(S.payload + sm.s_off[sm.bs_list[j + k]]);
+                        qa[k] = __ldg(src + tid);
+                        qb[k] = __ldg(src + tid + M2_THREADS);
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (j + k < nbs) {
+                        r0.x |= qa[k].x; r0.y |= qa[k].y; r0.z |= qa[k].z; r0.w |= qa[k].w;
+                        r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
+                    }
+            }
+            // arrays and runs: one warp per container, shared-memory atomics
+            const uint32_t nar = sm.nar;
+            for (uint32_t j = wid; j < nar; j += M2_THREADS / 32) {
+                const uint32_t q = sm.ar_list[j];
+                uint32_t *dst = (L != POS_NONE && sm.s_pos[q] > L) ? sm.acc2 : sm.acc;
+                const uint8_t *p = S.payload + sm.s_off[q];
+                if ((sm.s_tf[q] & 15) == T_ARRAY) acc_apply_array<0>(dst, p, sm.s_len[q], lane);
+                else acc_apply_runs<0, true>(dst, p, sm.s_len[q], lane);
+            }
+        }
+        __syncthreads();
+        anyfull = __syncthreads_or(anyfull);
+        anyfull_pre = __syncthreads_or(anyfull_pre);
+        // registers -> shared accumulator
+        {
+            uint4 *a4 = reinterpret_cast<uint4 *>(sm.acc);
+            uint4 a = a4[tid], b = a4[tid + M2_THREADS];
+            a.x |= r0.x; a.y |= r0.y; a.z |= r0.z; a.w |= r0.w;
+            b.x |= r1.x; b.y |= r1.y; b.z |= r1.z; b.w |= r1.w;
+            a4[tid] = a;
+            a4[tid + M2_THREADS] = b;
+        }
+        __syncthreads();
+
+        if (ns > 1) {
+            // ---- split key: publish the partial unions, the last slice finalises --------------
+            uint32_t *g = scratch + (size_t)ix.key_scratch[ki] * (2 * ACC_WORDS + 32);
+            for (int w = tid; w < ACC_WORDS; w += M2_THREADS) {
+                const uint32_t v = sm.acc[w], v2 = sm.acc2[w];
+                if (v) atomicOr(g + w, v);
+                if (v2) atomicOr(g + ACC_WORDS + w, v2);
+            }
+            if (tid == 0 && (anyfull | anyfull_pre)) atomicOr(g + 2 * ACC_WORDS, (anyfull ? 1u : 0u) | (anyfull_pre ? 2u : 0u));
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) sm.flag = (atomicAdd(tickets + ix.key_scratch[ki], 1u) == ns - 1) ? 1u : 0u;
+            __syncthreads();
+            if (!sm.flag) continue;
+            __threadfence();
+            for (int w = tid; w < ACC_WORDS; w += M2_THREADS) {
+                sm.acc[w] = __ldcg(g + w);
+                sm.acc2[w] = __ldcg(g + ACC_WORDS + w);
+                g[w] = 0;   // leave the scratch clean for the next call
+                g[ACC_WORDS + w] = 0;
+            }
+            const uint32_t fl = __ldcg(g + 2 * ACC_WORDS);
+            anyfull = fl & 1u;
+            anyfull_pre = fl & 2u;
+            __syncthreads();
+            if (tid == 0) { g[2 * ACC_WORDS] = 0; tickets[ix.key_scratch[ki]] = 0; }
+        }
+
+        // ---- count: cardinality of the prefix union, then of the whole union (+ run starts) -----
+        int cpre = 0;
+        if (L != POS_NONE)
+            for (int w = tid; w < ACC_WORDS; w += M2_THREADS) cpre += __popc(sm.acc[w]);
+        __syncthreads();
+        for (int w = tid; w < ACC_WORDS; w += M2_THREADS) {
+            uint32_t x = sm.acc[w] | sm.acc2[w];
+            if (anyfull) x = ~0u;   // a full container took part (full runs are not rasterised)
+            sm.acc[w] = x;
+        }
+        __syncthreads();
+        int c = 0, r = 0;
+        for (int w = tid; w < ACC_WORDS; w += M2_THREADS) {
+            const uint32_t x = sm.acc[w];
+            const uint32_t prev = w ? (sm.acc[w - 1] >> 31) : 0u;
+            c += __popc(x);
+            r += __popc(x & ~((x << 1) | prev));
+        }
+        c = __reduce_add_sync(FULLMASK, c);
+        r = __reduce_add_sync(FULLMASK, r);
+        cpre = __reduce_add_sync(FULLMASK, cpre);
+        if (lane == 0) { sm.red32[wid][0] = (uint32_t)c; sm.red32[wid][1] = (uint32_t)r; sm.red64[wid] = (unsigned long long)cpre; }
+        __syncthreads();
+        int card = 0, nruns = 0, card_pre = 0;
+        for (int w = 0; w < M2_THREADS / 32; w++) {
+            card += (int)sm.red32[w][0];
+            nruns += (int)sm.red32[w][1];
+            card_pre += (int)sm.red64[w];
+        }
+
+        // ---- result type (every thread computes the same value) ------------------------------
+        int otype;
+        if (m == 1) {
+            // one input carries the key: clone, then container_repair_after_lazy
+            // (containers.h:344-371); n == 1 is a plain copy (roaring.c:780-782)
+            if (n == 1) otype = t1;
+            else if (t1 == T_RUN) otype = rule_eff(card, nruns);
+            else if (t1 == T_ARRAY) otype = T_ARRAY;
+            else otype = rule_ab(card);
+        } else if (run_full) {
+            otype = T_RUN;
+        } else if (card == 65536 && any_ib && !first_full_bitset) {
+            // saturated with in-place bitset steps: full run iff the union up to L was already full
+            otype = (anyfull_pre || card_pre == 65536) ? T_RUN : T_BITSET;
+        } else {
+            otype = rule_ab(card);
+        }
+
+        // ---- emit ----------------------------------------------------------------------------
+        const uint64_t off = (uint64_t)ki * BITSET_BYTES;
+        uint8_t *dst = out.payload + off;
+        uint32_t olen;
+        if (otype == T_BITSET) {
+            olen = 1024;
+            for (int i = tid; i < ACC_WORDS / 4; i += M2_THREADS)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(sm.acc)[i];
+        } else if (otype == T_ARRAY) {
+            olen = (uint32_t)card;
+            if (wid == 0) acc_emit_array(sm.acc, reinterpret_cast<uint16_t *>(dst), lane);
+        } else {
+            olen = (uint32_t)nruns;
+            if (wid == 0) acc_emit_runs(sm.acc, reinterpret_cast<uint16_t *>(dst), lane);
+        }
+        if (tid == 0) {
+            out.c_key[ki] = (uint16_t)key;
+            out.c_type[ki] = (uint8_t)otype;
+            out.c_card[ki] = (uint32_t)card;
+            out.c_len[ki] = olen;
+            out.c_off[ki] = off;
+            out.c_src[ki] = SRC_NONE;
+            if (card_per_key) card_per_key[key] = (uint32_t)card;
+        }
+    }
+}
+
+// total cardinality of the one-bitmap result
+__global__ void k_many2_sum_cards(const uint32_t *__restrict__ c_card, const OpStats *st, uint64_t *__restrict__ out) {
+    __shared__ unsigned long long s[32];
+    const uint32_t n = st->nk;
+    unsigned long long v = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) v += c_card[i];
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += s[i];
+        out[0] = t;
+    }
+}
+
+void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
+                     const Many2Index &ix, uint32_t max_units, uint32_t *scratch, uint32_t *tickets,
+                     uint32_t scratch_slots, SetOut out, uint32_t *card_per_key, OpStats *st, int sms,
+                     cudaStream_t s, cudaEvent_t ev_kernel_start) {
+    const uint32_t gw = (uint32_t)sms * 8;
+    k_many2_count<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+    k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * 8, out, st);
+    k_many2_fill<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+    if (ev_kernel_start) cudaEventRecord(ev_kernel_start, s);
+    k_or_many2<<<sms * 4, M2_THREADS, 0, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
+    k_many2_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
+    g_launches += 5;
+}
+
+}  // namespace rb200

@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #define WG_API __attribute__((visibility("default")))
 
@@ -180,6 +181,16 @@ static void *zipf_worker(void *arg) {
     uint64_t *bits = (uint64_t *)calloc((size_t)n_keys * 1024, 8);
     if (!bits) { J->failed = 1; return NULL; }
     const double log2U = log2((double)U);
+    /* batch buffers of the partitioned path (universes whose bitset exceeds ~16 MiB) */
+    const uint64_t BATCH = 1u << 22;
+    const uint32_t nbuckets = (uint32_t)((U + (1u << 21) - 1) >> 21);
+    uint32_t *batch = NULL, *sorted = NULL, *hist = NULL;
+    if (U > (1ULL << 27)) {
+        batch = (uint32_t *)malloc(4 * BATCH);
+        sorted = (uint32_t *)malloc(4 * BATCH);
+        hist = (uint32_t *)malloc(4 * ((size_t)nbuckets + 2));
+        if (!batch || !sorted || !hist) { free(batch); free(sorted); free(hist); batch = sorted = hist = NULL; }
+    }
     for (;;) {
         const uint32_t i = __sync_fetch_and_add(&J->next, 1u);
         if (i >= J->nb || J->failed) break;
@@ -196,6 +207,33 @@ static void *zipf_worker(void *arg) {
         }
         if (want > U) want = U;
         uint64_t have = 0;
+        /* Large universes: the membership bitset (up to 512 MiB) does not fit any cache, so draws are
+         * consumed in batches that are first partitioned by their high bits (2^21-value ranges =
+         * 256 KiB of bitset each) and then applied range by range.  A batch never holds more draws
+         * than distinct values still missing, so no draw past the stopping point of the sequential
+         * definition is ever consumed and the resulting set is the same. */
+        while (batch && want - have >= 65536) {
+            uint64_t B = want - have;
+            if (B > BATCH) B = BATCH;
+            memset(hist, 0, sizeof(uint32_t) * (nbuckets + 1));
+            for (uint64_t i = 0; i < B; i++) {
+                const double u = ((double)pcg32_next(&g) + 1.0) * (1.0 / 4294967296.0);
+                double x = floor(exp2(u * log2U)) - 1.0;
+                if (x < 0.0) x = 0.0;
+                uint64_t v = (uint64_t)x;
+                if (v >= U) v = U - 1;
+                batch[i] = (uint32_t)v;
+                hist[(v >> 21) + 1]++;
+            }
+            for (uint32_t k = 0; k < nbuckets; k++) hist[k + 1] += hist[k];
+            for (uint64_t i = 0; i < B; i++) sorted[hist[batch[i] >> 21]++] = batch[i];
+            for (uint64_t i = 0; i < B; i++) {
+                const uint64_t v = sorted[i];
+                uint64_t *w = bits + (v >> 6);
+                const uint64_t m = 1ULL << (v & 63);
+                if (!(*w & m)) { *w |= m; have++; }
+            }
+        }
         while (have < want) {
             const double u = ((double)pcg32_next(&g) + 1.0) * (1.0 / 4294967296.0);
             double x = floor(exp2(u * log2U)) - 1.0;
@@ -215,6 +253,9 @@ static void *zipf_worker(void *arg) {
         memset(bits, 0, (size_t)n_keys * 8192);
     }
     free(bits);
+    free(batch);
+    free(sorted);
+    free(hist);
     return NULL;
 }
 
@@ -233,9 +274,13 @@ WG_API int rb200_workgen_zipf(uint32_t b0, uint32_t nb, uint64_t universe, const
     for (uint32_t i = 0; i < nb; i++) { blobs[i] = NULL; lens[i] = 0; }
     if (threads < 1) threads = 1;
     if ((uint32_t)threads > nb) threads = (int)nb;
-    /* every worker owns a membership bitset of the whole universe: bound the total to ~24 GiB */
-    const uint64_t per = ((universe + 65535) >> 16) * 8192ULL;
-    const uint64_t cap = (24ULL << 30) / (per ? per : 1);
+    /* every worker owns a membership bitset of the whole universe (+ 32 MiB of batch buffers):
+     * bound the total to a quarter of the physical memory, within [4, 96] GiB */
+    const uint64_t per = ((universe + 65535) >> 16) * 8192ULL + (40ULL << 20);
+    uint64_t budget = (uint64_t)sysconf(_SC_PHYS_PAGES) * (uint64_t)sysconf(_SC_PAGE_SIZE) / 4;
+    if (budget < (4ULL << 30)) budget = 4ULL << 30;
+    if (budget > (96ULL << 30)) budget = 96ULL << 30;
+    const uint64_t cap = budget / per;
     if ((uint64_t)threads > cap) threads = (int)(cap ? cap : 1);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
     int started = 0;

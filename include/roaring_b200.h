@@ -193,8 +193,8 @@ rb200_set_t *rb200_batch_flip(const rb200_set_t *S, const uint32_t *idx, size_t 
 /* 64-bit bitmaps (src/roaring64.c) through their portable format: result[k] =
  * roaring64_bitmap_{and,or,xor,andnot}(a[ia[k]], b[ib[k]]) — the same container grid per
  * high-32 bucket.  *out (pinned, owned by the library; blob k at *out + (*off)[k], (*len)[k]
- * bytes) is released with rb200_serialized_free.  The in-memory roaring64_bitmap_t (ART) is not
- * bound: bytes in, bytes out. */
+ * bytes) is released with rb200_serialized_free.  Bytes in, bytes out; the in-memory form is
+ * rb200_r64_batch_op below. */
 int rb200_r64_batch_op_serialized(int op, const char *const *a, const size_t *alen, size_t na,
                                   const char *const *b, const size_t *blen, size_t nb,
                                   const uint32_t *ia, const uint32_t *ib, size_t npairs, char **out,
@@ -203,6 +203,30 @@ int rb200_r64_batch_and_cardinality_serialized(const char *const *a, const size_
                                                const char *const *b, const size_t *blen, size_t nb,
                                                const uint32_t *ia, const uint32_t *ib, size_t npairs,
                                                uint64_t *out);
+
+/* In-memory 64-bit bitmaps of the HOST APPLICATION's CRoaring (the ART inside roaring64_bitmap_t is
+ * private to that library): operands and results cross through its own
+ * roaring64_bitmap_portable_serialize / _deserialize_safe, resolved in the running process.
+ * out[k] = a[k] op b[k]; the caller frees out[k] with roaring64_bitmap_free.  0 on success. */
+#ifndef ROARING64_H
+typedef struct roaring64_bitmap_s roaring64_bitmap_t;
+#endif
+int rb200_r64_batch_op(int op, const roaring64_bitmap_t *const *a, const roaring64_bitmap_t *const *b,
+                       size_t npairs, roaring64_bitmap_t **out);
+int rb200_r64_batch_and_cardinality(const roaring64_bitmap_t *const *a, const roaring64_bitmap_t *const *b,
+                                    size_t npairs, uint64_t *out);
+/* Drop-in symbols of the 64-bit hot path, include/roaring/roaring64.h:423-522
+ * (src/roaring64.c:1332, 1375, 1541, 1663, 1809 and the cardinality family). */
+roaring64_bitmap_t *roaring64_bitmap_and(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+roaring64_bitmap_t *roaring64_bitmap_or(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+roaring64_bitmap_t *roaring64_bitmap_xor(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+roaring64_bitmap_t *roaring64_bitmap_andnot(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+uint64_t roaring64_bitmap_and_cardinality(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+uint64_t roaring64_bitmap_or_cardinality(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+uint64_t roaring64_bitmap_xor_cardinality(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+uint64_t roaring64_bitmap_andnot_cardinality(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+double roaring64_bitmap_jaccard_index(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
+bool roaring64_bitmap_intersect(const roaring64_bitmap_t *r1, const roaring64_bitmap_t *r2);
 
 /* roaring_bitmap_or_many over S[idx[0..n)] (idx == NULL: all bitmaps in order).
  * Returns a device-resident set holding ONE bitmap. */

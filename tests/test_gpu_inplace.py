@@ -45,3 +45,39 @@ def test_inplace_or_full_rules(rb, R):
         assert res[k].serialize() == R.op_inplace_bytes("or", a, b), k
         assert fun[k].serialize() == R.op_bytes("or", a, b), k
     assert res[0].serialize() != fun[0].serialize()       # run vs bitset
+
+
+def test_inplace_with_shared_left_containers(rb, R):
+    """COW bitmaps: after roaring_bitmap_copy of a copy-on-write bitmap every
+    container is a SHARED wrapper; the reference's in-place twins then take the FUNCTIONAL cell for
+    a shared left container (src/roaring.c:840, 1085-1088, 1235, 1376) — observable in the
+    saturating bitset | bitset cell (BITSET, not the full RUN of container_ior)."""
+    even = np.arange(0, 65536, 2, dtype=np.uint32)
+    odd = np.arange(1, 65536, 2, dtype=np.uint32)
+    mk = lambda v, ro: R.serialize(R.from_values(v, run_optimize=ro))
+    extra = synth_blobs(R, 91, 12, key_space=5, max_keys=6, profiles=["full", "nearfull", "halves", "dense", "bitset", "array"])
+    lefts = [mk(np.concatenate([even, even + (1 << 16)]), False)] + extra[:6]
+    rights = [mk(np.concatenate([odd, odd + (1 << 16)]), False)] + extra[6:]
+    seen_diff = False
+    for a, b in zip(lefts, rights):
+        for op in OPS:
+            outs = []
+            for who in ("ref", "ours"):
+                x = R.deserialize(a)
+                R.L.roaring_bitmap_set_copy_on_write(x, True)
+                y = R.L.roaring_bitmap_copy(x)             # x and y now share every container
+                rhs = R.deserialize(b)
+                if who == "ref":
+                    getattr(R.L, f"roaring_bitmap_{op}_inplace")(y, rhs)
+                else:
+                    getattr(rb.lib(), f"roaring_bitmap_{op}_inplace")(y, rhs)   # OUR symbol on THEIR object
+                ok, why = R.validate(y)
+                assert ok, (who, op, why)
+                outs.append(R.serialize(y))
+                assert R.serialize(x) == a                # the sharing sibling is untouched
+                for z in (x, y, rhs):
+                    R.free(z)                             # the reference tears down what we swapped in
+            assert outs[0] == outs[1], op
+            if op == "or" and outs[0] != R.op_inplace_bytes("or", a, b):
+                seen_diff = True                          # shared left: functional cell, differs from plain in-place
+    assert seen_diff

@@ -93,14 +93,19 @@ def test_device_deserialize_rejects_malformed(rb, R):
     # container CONTENTS are checked too (a run ending past 65535 would be rasterised
     # outside the warp's accumulator): run overflow, overlapping runs, unsorted array values
     content_cases = {}
-    rb_ = bytearray(runblob)
-    struct.pack_into("<HH", rb_, hdr + 2, 65000, 1000)            # first run: 65000 + 1000 > 65535
+    vals = np.concatenate([np.arange(0, 100), np.arange(200, 300), np.arange(70000, 80000)]).astype(np.uint32)
+    r = R.from_values(vals, run_optimize=True)
+    rblob = R.serialize(r)                                         # 2 run containers: {2 runs}, {1 run}
+    R.free(r)
+    assert struct.unpack_from("<I", rblob, 0)[0] == (12347 | (1 << 16))
+    rhdr = 4 + 1 + 4 * 2                                           # cookie, run flags, key-card pairs (no offsets: n < 4)
+    assert struct.unpack_from("<HHHHH", rblob, rhdr) == (2, 0, 99, 200, 99)
+    rb_ = bytearray(rblob)
+    struct.pack_into("<HH", rb_, rhdr + 6, 65000, 1000)            # second run: 65000 + 1000 > 65535
     content_cases["run ends past 65535"] = bytes(rb_)
-    rb_ = bytearray(runblob)
-    if struct.unpack_from("<H", rb_, hdr)[0] >= 2:
-        s0, l0 = struct.unpack_from("<HH", rb_, hdr + 2)
-        struct.pack_into("<HH", rb_, hdr + 6, s0 + l0, 0)        # second run starts inside the first
-        content_cases["runs overlap"] = bytes(rb_)
+    rb_ = bytearray(rblob)
+    struct.pack_into("<HH", rb_, rhdr + 6, 99, 50)                 # second run starts inside the first
+    content_cases["runs overlap"] = bytes(rb_)
     r = R.from_values(np.array([5, 9, 13, 70000, 70001], dtype=np.uint32), run_optimize=False)
     ab = bytearray(R.serialize(r))
     R.free(r)

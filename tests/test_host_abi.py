@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_exports_match_header():
     hdr = open(os.path.join(ROOT, "include", "roaring_b200.h")).read()
-    declared = set(re.findall(r"\b((?:roaring_bitmap|rb200)_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b((?:roaring_bitmap|roaring64_bitmap|rb200)_[a-z0-9_]+)\s*\(", hdr))
     out = subprocess.check_output(["nm", "-D", "--defined-only", rb.api.LIB_PATH], text=True)
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     missing = declared - exported

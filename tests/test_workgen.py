@@ -35,7 +35,8 @@ def zipf_values(b, U, n, density_draw=False):
 
 
 def test_zipf_matches_definition_and_reference(R):
-    for (U, n, dd, ro) in [(300000, 20000, False, True), (1 << 20, 3000, False, True),
+    # ((1 << 28) + 12345: large universes take the batched / partitioned path of the generator)
+    for (U, n, dd, ro) in [(300000, 20000, False, True), (1 << 20, 3000, False, True), ((1 << 28) + 12345, 150000, False, True),
                            (200000, None, True, True), (300000, 20000, False, False)]:
         A = wl.zipf_arena(3, U, n, b0=5, density_draw=dd, run_optimize=ro, threads=2)
         for i in range(3):
