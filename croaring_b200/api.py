@@ -12,7 +12,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libroaring_b200.so")
+# RB200_LIB: load an experimental build instead (tuning runs, tools/time_ops.py); the product is
+# always the in-tree libroaring_b200.so
+LIB_PATH = os.environ.get("RB200_LIB") or os.path.join(_HERE, "libroaring_b200.so")
 
 AND, OR, XOR, ANDNOT = 0, 1, 2, 3
 OPS = {"and": AND, "or": OR, "xor": XOR, "andnot": ANDNOT}

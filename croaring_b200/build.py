@@ -50,28 +50,34 @@ def build_workgen(force=False):
     return WORKGEN_LIB
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: an experimental variant (-DNAME=VALUE ...) written to another .so (tuning
+    runs load it through RB200_LIB); the default build is the product."""
     build_workgen(force)
-    if not force and not needs_build():
+    lib = out or LIB
+    if not force and not out and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
+    tag = "" if not out else "." + os.path.basename(out).replace(".so", "")
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        o = os.path.join(CSRC, s.replace(".cu", tag + ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
         objs.append(o)
-    cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs + \
+    cmd = [nvcc, "-shared", "-cudart", "static", "-o", lib] + objs + \
           ["-Xlinker", "-Bsymbolic", "-ldl", "-lpthread"]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(LIB)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs,
+                out=os.path.abspath(outs[0]) if outs else None))

@@ -120,9 +120,16 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
 
 // ------------------------------------------------------------------------------ grid cells
 // Evaluate one matched cell on the warp's accumulator and write the result payload.
+#ifndef RB200_MERGE_LIMIT
+#define RB200_MERGE_LIMIT 2048   // array x array unions up to this many staged values take the merge path
+#endif
+#ifndef RB200_RANK_SCATTER
+#define RB200_RANK_SCATTER 1     // larger ones: accumulator + rank-scatter emission (0: find-first-set emission)
+#endif
+
 template <int OP, bool LAZY>
 __device__ __forceinline__ void
-cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
+cell_compute(uint32_t *acc, uint16_t *pre, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
              uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
              int lane, int &otype, uint32_t &ocard, uint32_t &olen, unsigned int *err,
              int rules, bool unkA) {
@@ -181,13 +188,51 @@ cell_compute(uint32_t *acc, int tA, int tB, const uint8_t *pa, const uint8_t *pb
     // (lazy rules: only unions / xors of at most ARRAY_LAZY_LOWERBOUND values stay arrays)
     const bool lazy_eager = lazy && OP == OP_XOR && inplace_rules;  // container_lazy_ixor A,A is eager
     if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY &&
-        ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= 2048u &&
+        ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= (uint32_t)RB200_MERGE_LIMIT &&
         (!lazy || lazy_eager || (cA + cB <= 1024u && !(rules & RULES_CONV)))) {
         if (round16(2 * (cA + cB)) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
         const uint32_t n = (op == OP_OR) ? merge_arrays<false>(acc, pa, cA, pb, cB, out, lane)
                                          : merge_arrays<true>(acc, pa, cA, pb, cB, out, lane);
         otype = n ? T_ARRAY : 0;  // cA + cB <= 4096 -> array (mixed_union.c:162-176, mixed_xor.c:196-205)
         ocard = olen = n;
+        return;
+    }
+
+    // ---- larger array x array unions / symmetric differences: accumulator + rank-scatter -------
+    if (RB200_RANK_SCATTER && !lazy && (op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY) {
+        const uint16_t *a16 = reinterpret_cast<const uint16_t *>(pa), *b16 = reinterpret_cast<const uint16_t *>(pb);
+        const uint32_t vlo = min((uint32_t)a16[0], (uint32_t)b16[0]);
+        const uint32_t vhi = max((uint32_t)a16[cA - 1], (uint32_t)b16[cB - 1]);
+        const int s0 = (int)(vlo >> 12), s1 = (int)(vhi >> 12) + 1;   // stripes of 4096 values that can hold a bit
+        acc_zero_span(acc, lane, s0, s1);
+        __syncwarp();
+        acc_apply_array<0>(acc, pa, cA, lane);
+        __syncwarp();
+        if (op == OP_OR) acc_apply_array<0>(acc, pb, cB, lane);
+        else acc_apply_array<1>(acc, pb, cB, lane);
+        __syncwarp();
+        const int card = acc_prefix_span(acc, pre, lane, s0, s1);
+        __syncwarp();
+        if (card == 0) { otype = 0; ocard = olen = 0; return; }
+        const int t = decide_type(op, tA, tB, cA, cB, lA, lB, card, 0);   // array x array: never a run
+        if (stored_bytes(t, t == T_BITSET ? 1024u : (uint32_t)card) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
+        if (t == T_BITSET) {
+            // stripes outside the span were not zeroed: complete the accumulator before the copy
+            acc_zero_span(acc, lane, 0, s0);
+            acc_zero_span(acc, lane, s1, 16);
+            __syncwarp();
+            acc_store_bitset(acc, out, lane);
+        } else if (op == OP_OR) {
+            rank_store_array<false>(acc, pre, pa, cA, reinterpret_cast<uint16_t *>(out), lane);
+            rank_store_array<false>(acc, pre, pb, cB, reinterpret_cast<uint16_t *>(out), lane);
+        } else {
+            rank_store_array<true>(acc, pre, pa, cA, reinterpret_cast<uint16_t *>(out), lane);
+            rank_store_array<true>(acc, pre, pb, cB, reinterpret_cast<uint16_t *>(out), lane);
+        }
+        __syncwarp();
+        otype = t;
+        ocard = (uint32_t)card;
+        olen = t == T_BITSET ? 1024u : (uint32_t)card;
         return;
     }
 
@@ -260,8 +305,10 @@ __global__ void __launch_bounds__(128)
 k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 uint64_t slab_cap, OpStats *st, int rules) {
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
+    __shared__ __align__(16) uint16_t s_pre[4][512];   // rank-scatter prefix table (rb200_device.cuh)
     const int lane = threadIdx.x & 31;
     uint32_t *acc = s_acc[threadIdx.x >> 5];
+    uint16_t *pre = s_pre[threadIdx.x >> 5];
     // dynamic scheduling: a ticket is TICKET consecutive items; the next ticket is requested
     // before the current one is processed so its latency hides behind the work.
     // (small batches: tickets of 1 so that every warp of the grid gets work at once)
@@ -290,7 +337,7 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 int cell_rules = rules;
                 if ((rules & (RULES_INPLACE | RULES_LAZY)) == RULES_INPLACE && A.c_src[ca] == SRC_SHARED)
                     cell_rules &= ~RULES_INPLACE;
-                cell_compute<OP, LAZY>(acc, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
+                cell_compute<OP, LAZY>(acc, pre, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
                              B.payload + B.c_off[cb], rawA & CARD_MASK, B.c_card[cb] & CARD_MASK,
                              A.c_len[ca], B.c_len[cb], slab + off, cap, lane, otype, ocard, olen,
                              &st->error, cell_rules, (rawA & CARD_UNKNOWN) != 0);
