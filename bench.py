@@ -28,7 +28,6 @@ import argparse
 import ctypes as C
 import hashlib
 import json
-import mmap
 import os
 import subprocess
 import sys
@@ -230,48 +229,6 @@ def run_reference(args, rank, world):
     emit(line)
 
 
-# ------------------------------------------------------------------------------- shared blobs
-class MappedBlobs:
-    """Blobs written by several ranks into /dev/shm files, mapped read-only: `ptrs` / `lens` go
-    straight into the C ABI (same duck type as workloads.BlobArena)."""
-
-    def __init__(self, paths_and_lens):
-        self.maps, ptrs, lens = [], [], []
-        for path, ln in paths_and_lens:
-            f = open(path, "rb")
-            size = os.fstat(f.fileno()).st_size
-            m = mmap.mmap(f.fileno(), size, prot=mmap.PROT_READ) if size else None
-            f.close()
-            self.maps.append(m)
-            base = C.addressof(C.c_char.from_buffer_copy(b"\0")) if m is None else \
-                np.frombuffer(m, dtype=np.uint8).ctypes.data
-            off = 0
-            for x in ln:
-                ptrs.append(base + off)
-                lens.append(int(x))
-                off += (int(x) + 15) & ~15
-        self.n = len(ptrs)
-        self.ptrs = (C.c_void_p * self.n)(*ptrs)
-        self.lens = (C.c_size_t * self.n)(*lens)
-
-    def __len__(self):
-        return self.n
-
-    def total_bytes(self):
-        return int(sum(self.lens))
-
-
-def write_arena(path, arena):
-    with open(path, "wb") as f:
-        for i in range(len(arena)):
-            ln = int(arena.lens[i])
-            f.write(C.string_at(arena.ptrs[i], ln))
-            pad = ((ln + 15) & ~15) - ln
-            if pad:
-                f.write(b"\0" * pad)
-    return [int(x) for x in arena.lens]
-
-
 # ------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -346,7 +303,7 @@ def main():
 
     peak, peak_src = peak_gbs()
     T_host = host_threads()
-    gen_threads = max(1, T_host // world)
+    gen_threads = max(2, wl._threads() // world)   # workload generator threads of this rank
 
     # ---- inputs: portable-serialized fixtures -> device-resident sets (outside the timed region)
     blobs = {ds: rb.load_realdata(ds) for ds in DATASETS}
@@ -595,7 +552,8 @@ def main():
         for d in ZIPF_DENSITIES:
             U = wl.zipf_universe(args.zipf_values, d)
             t0 = time.perf_counter()
-            A = wl.zipf_arena(args.zipf_bitmaps, U, args.zipf_values, threads=gen_threads)
+            A = wl.cached_arena(f"zipf_{args.zipf_bitmaps}x{args.zipf_values}_U{U}",
+                                lambda: wl.zipf_arena(args.zipf_bitmaps, U, args.zipf_values, threads=gen_threads))
             t_gen = time.perf_counter() - t0
             t0 = time.perf_counter()
             S = rb.DeviceSet.from_serialized(A)
@@ -650,18 +608,23 @@ def main():
     # ---- configs[4]: 10^8-universe, 1000-bitmap OR, key ranges over the run's N GPUs + NCCL all-reduce
     if "or_many_sharded" in extras:
         NB, U = args.sharded_bitmaps, 10 ** 8
-        lo, hi = NB * rank // world, NB * (rank + 1) // world
+        # the 1000 bitmaps are generated in 8 fixed blocks shared through /dev/shm: rank r builds (or
+        # finds, from an earlier run on this box) blocks r, r + N, ...; every rank then maps all of
+        # them, because it needs its key range of EVERY bitmap
+        NBLK = 8 if NB % 8 == 0 else 1
+        per = NB // NBLK
+        cdir = os.environ.get("RB200_WL_CACHE", "/dev/shm/rb200_wl_cache") or tmpdir
         t0 = time.perf_counter()
-        A = wl.zipf_arena(hi - lo, U, None, b0=lo, density_draw=True, threads=gen_threads)
-        if world > 1:                                     # every rank needs its key range of EVERY bitmap
-            os.makedirs(tmpdir, exist_ok=True)
-            my_lens = write_arena(os.path.join(tmpdir, f"zipf_{rank}.bin"), A)
-            A.free()
-            all_lens = [None] * world
-            dist.all_gather_object(all_lens, my_lens)
-            allb = MappedBlobs([(os.path.join(tmpdir, f"zipf_{r}.bin"), all_lens[r]) for r in range(world)])
-        else:
-            allb = A
+        for blk in range(rank, NBLK, world):
+            wl.cached_arena(f"zipf5_U{U}_b{blk * per}_n{per}",
+                            lambda blk=blk: wl.zipf_arena(per, U, None, b0=blk * per, density_draw=True,
+                                                          threads=gen_threads), cache_dir=cdir).free()
+        barrier()
+        parts = []
+        for blk in range(NBLK):
+            with open(os.path.join(cdir, f"zipf5_U{U}_b{blk * per}_n{per}.json")) as f:
+                parts.append((os.path.join(cdir, f"zipf5_U{U}_b{blk * per}_n{per}.bin"), json.load(f)["lens"]))
+        allb = wl.MappedArena(parts)
         t_gen = time.perf_counter() - t0
         ranges, span = rb.api.plan_key_ranges(allb, world)
         klo, khi = ranges[rank]
@@ -724,14 +687,7 @@ def main():
                                        "sample": "the whole 1000-way call once (1 thread: single-threaded API)"}
         extras["or_many_sharded"] = rec
         barrier()
-        if world > 1:
-            del allb
-            try:
-                os.remove(os.path.join(tmpdir, f"zipf_{rank}.bin"))
-            except OSError:
-                pass
-        else:
-            A.free()
+        del allb
         log(f"or_many_sharded: {d_ms:.3f} ms/call ({k_ms:.3f} kernel, {c_ms:.3f} nccl), parity {rec.get('parity')}")
 
     if rank != 0:
@@ -801,10 +757,6 @@ def main():
     comm.destroy()
     if world > 1:
         dist.destroy_process_group()
-    try:
-        os.rmdir(tmpdir)
-    except OSError:
-        pass
 
 
 if __name__ == "__main__":

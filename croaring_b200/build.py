@@ -46,7 +46,7 @@ def build_workgen(force=False):
     if not force and os.path.exists(WORKGEN_LIB) and os.path.getmtime(WORKGEN_LIB) >= os.path.getmtime(src):
         return WORKGEN_LIB
     subprocess.check_call([os.environ.get("CC", "gcc"), "-O3", "-fPIC", "-std=gnu11", "-shared",
-                           "-fvisibility=hidden", "-o", WORKGEN_LIB, src, "-lm", "-lpthread"])
+                           "-fvisibility=hidden", "-ffp-contract=off", "-o", WORKGEN_LIB, src, "-lm", "-lpthread"])
     return WORKGEN_LIB
 
 

@@ -12,19 +12,23 @@
  *   PCG32 (the generator of /root/reference/benchmarks/random.h:18-30), stream of bitmap b:
  *   state = 0x853c49e6748fea9b ^ b, inc = 0xda3e39cb94b95bdb, first output discarded (it does not
  *   depend on the low bits of the state, i.e. on b).  One draw r -> u = (r + 1) / 2^32 in
- *   (0, 1]; v = floor(U^u) - 1 clipped to [0, U)  (P(v) ~ 1/(v+1): Zipf s = 1 by inverse CDF).
+ *   (0, 1]; v = floor(U^u) - 1 clipped to [0, U)  (P(v) ~ 1/(v+1): Zipf s = 1 by inverse CDF; U^u by
+ *   the fixed double-precision recipe of zipf_value() below).
  *   Draw until the bitmap holds n distinct values.  With `density_draw` (config 5) the FIRST draw of
  *   the stream picks the bitmap's density log-uniformly: d = 0.001 * 300^u, n = max(1, round(d*U)).
  *   Config 4 (dense): bitmap i over universe 2^20, value j present iff draw number i*2^20 + j of the
  *   default pcg32_global stream (random.h:18-19) is odd — the single sequential stream of the
  *   survey's definition, reached in parallel with the LCG jump-ahead.
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+
+#include <sys/mman.h>
 
 #define WG_API __attribute__((visibility("default")))
 
@@ -36,6 +40,34 @@ static inline uint32_t pcg32_next(pcg32_t *g) {
     const uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u);
     const uint32_t rot = (uint32_t)(old >> 59u);
     return (xs >> rot) | (xs << ((0u - rot) & 31u));
+}
+
+/* v = floor(U^u) - 1 clipped to [0, U), u = (r + 1) / 2^32, with U^u = 2^(u * log2 U) evaluated by
+ * a fixed recipe in IEEE double arithmetic (no libm call per draw — the generator is bound by this
+ * line): 2^x = 2^floor(x) * T[j] * P(t), j = floor(256 * frac(x)), t = ln2 * (frac(x) - j/256) < 0.0028,
+ * P = Taylor polynomial of e^t to degree 4 (relative error < 2e-15), T[j] = pow(2, j/256) tabulated
+ * once.  tests/test_workgen.py restates the same recipe operation by operation. */
+static double g_T256[257];
+static void zipf_tables(void) {
+    static volatile int done = 0;
+    if (done) return;
+    for (int j = 0; j <= 256; j++) g_T256[j] = pow(2.0, (double)j / 256.0);
+    __sync_synchronize();
+    done = 1;
+}
+static inline uint64_t zipf_value(uint32_t r, double log2U, uint64_t U) {
+    const double u = ((double)r + 1.0) * (1.0 / 4294967296.0);
+    const double x = u * log2U;
+    const int xi = (int)x;                        /* x >= 0: truncation is floor */
+    const double f = x - (double)xi;
+    const int j = (int)(f * 256.0);
+    const double t = (f - (double)j * (1.0 / 256.0)) * 0.6931471805599453;
+    const double p = 1.0 + t * (1.0 + t * (0.5 + t * ((1.0 / 6.0) + t * (1.0 / 24.0))));
+    const double y = g_T256[j] * p * (double)(1ULL << xi);
+    uint64_t q = (uint64_t)y;                     /* floor(y), y >= 1 */
+    q = q ? q - 1 : 0;
+    if (q >= U) q = U - 1;
+    return q;
 }
 
 /* state after `delta` steps (the usual O(log delta) LCG jump) */
@@ -178,8 +210,14 @@ static void *zipf_worker(void *arg) {
     zipf_job_t *J = (zipf_job_t *)arg;
     const uint64_t U = J->universe;
     const uint32_t n_keys = (uint32_t)((U + 65535) >> 16);
-    uint64_t *bits = (uint64_t *)calloc((size_t)n_keys * 1024, 8);
+    /* the membership bitset: 2 MiB aligned + MADV_HUGEPAGE (128 workers first-touching 512 MiB each in
+     * 4 KiB pages serialise on the address-space lock) */
+    uint64_t *bits = NULL;
+    const size_t bits_bytes = ((size_t)n_keys * 8192 + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    if (posix_memalign((void **)&bits, 2u << 20, bits_bytes) != 0) bits = NULL;
     if (!bits) { J->failed = 1; return NULL; }
+    if (getenv("RB200_WG_THP")) madvise(bits, bits_bytes, MADV_HUGEPAGE);
+    memset(bits, 0, bits_bytes);
     const double log2U = log2((double)U);
     /* batch buffers of the partitioned path (universes whose bitset exceeds ~16 MiB) */
     const uint64_t BATCH = 1u << 22;
@@ -217,11 +255,7 @@ static void *zipf_worker(void *arg) {
             if (B > BATCH) B = BATCH;
             memset(hist, 0, sizeof(uint32_t) * (nbuckets + 1));
             for (uint64_t i = 0; i < B; i++) {
-                const double u = ((double)pcg32_next(&g) + 1.0) * (1.0 / 4294967296.0);
-                double x = floor(exp2(u * log2U)) - 1.0;
-                if (x < 0.0) x = 0.0;
-                uint64_t v = (uint64_t)x;
-                if (v >= U) v = U - 1;
+                const uint64_t v = zipf_value(pcg32_next(&g), log2U, U);
                 batch[i] = (uint32_t)v;
                 hist[(v >> 21) + 1]++;
             }
@@ -235,11 +269,7 @@ static void *zipf_worker(void *arg) {
             }
         }
         while (have < want) {
-            const double u = ((double)pcg32_next(&g) + 1.0) * (1.0 / 4294967296.0);
-            double x = floor(exp2(u * log2U)) - 1.0;
-            if (x < 0.0) x = 0.0;
-            uint64_t v = (uint64_t)x;
-            if (v >= U) v = U - 1;
+            const uint64_t v = zipf_value(pcg32_next(&g), log2U, U);
             uint64_t *w = bits + (v >> 6);
             const uint64_t m = 1ULL << (v & 63);
             if (!(*w & m)) { *w |= m; have++; }
@@ -266,6 +296,7 @@ WG_API int rb200_workgen_zipf(uint32_t b0, uint32_t nb, uint64_t universe, const
                               uint64_t n_fixed, int density_draw, int run_optimize, int threads,
                               uint8_t **blobs, size_t *lens, uint64_t *cards) {
     if (universe == 0 || universe > (1ULL << 32)) return -1;
+    zipf_tables();
     zipf_job_t J;
     memset(&J, 0, sizeof(J));
     J.b0 = b0; J.nb = nb; J.universe = universe; J.n_values = n_values; J.n_fixed = n_fixed;

@@ -28,10 +28,27 @@ def zipf_values(b, U, n, density_draw=False):
     seen = set()
     l2 = math.log2(U)
     while len(seen) < n:
-        u = (next(g) + 1) / 4294967296.0
-        v = int(max(0.0, math.floor(2.0 ** (u * l2)) - 1.0))
-        seen.add(min(v, U - 1))
+        seen.add(zipf_value(next(g), l2, U))
     return np.array(sorted(seen), dtype=np.uint32)
+
+
+T256 = [math.pow(2.0, j / 256.0) for j in range(257)]
+
+
+def zipf_value(r, log2u, U):
+    """csrc/workgen.c zipf_value(), operation by operation (IEEE doubles, no fused multiply-add)."""
+    u = (float(r) + 1.0) * (1.0 / 4294967296.0)
+    x = u * log2u
+    xi = math.floor(x)
+    f = x - xi
+    fj = math.floor(f * 256.0)
+    t = (f - fj * (1.0 / 256.0)) * 0.6931471805599453
+    p = 1.0 + t * (1.0 + t * (0.5 + t * ((1.0 / 6.0) + t * (1.0 / 24.0))))
+    y = T256[int(fj)] * p * float(1 << int(xi))
+    v = math.floor(y) - 1.0
+    if v < 0.0:
+        v = 0.0
+    return min(int(v), U - 1)
 
 
 def test_zipf_matches_definition_and_reference(R):

@@ -50,6 +50,22 @@ def main():
             if op in ("and", "or", "xor"):
                 tot_k += float(np.median(ks))
                 tot_o += float(np.median(os_))
+        # the literal 199-successive-pairs call: host enqueue time vs device time of one call
+        sa, sb = np.arange(len(blobs) - 1, dtype=np.uint32), np.arange(1, len(blobs), dtype=np.uint32)
+        import time
+        host_us, dev_ms = [], []
+        for rep in range(30):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = S.batch("or", S, sa, sb)
+            t1 = time.perf_counter()
+            ms, cms, ab = r.op_stats()
+            r.free()
+            if rep >= 5:
+                host_us.append((t1 - t0) * 1e6)
+                dev_ms.append(ms)
+        out["ops"][f"{ds}/successive_or"] = {"host_enqueue_us": round(float(np.median(host_us)), 1),
+                                             "device_us": round(float(np.median(dev_ms)) * 1e3, 1)}
         S.free()
     out["step_kernel_ms"] = round(tot_k, 4)
     out["step_op_ms"] = round(tot_o, 4)
