@@ -70,6 +70,9 @@ struct SetOut {
     uint32_t *bm_beg;
     uint32_t *bm_cnt;
     uint64_t *bm_card;  // per result bitmap: total cardinality
+    uint64_t *bm_bytes;   // per result bitmap: stored payload bytes (16-byte rounded slots)
+    uint64_t *bm_ebytes;  // per result bitmap: sum of round16(max(stored, min(8192, 2 * card))) — the
+                          // quantity that bounds what a later op on it can produce (see PairBuf::build)
     uint16_t *c_key;
     uint8_t *c_type;
     uint32_t *c_card;
@@ -88,6 +91,8 @@ struct Items {
     uint32_t *cb;        // container index in B (K_COMPUTE, K_COPY_B)
     uint64_t *slot_off;  // byte offset of the output slot in the result slab
     uint32_t *slot_cap;  // bytes reserved (upper bound on the result payload, 16-B multiple)
+    uint8_t *cls;        // code-path class of the item (CLS_*), CLS_NONE for holes
+    uint32_t *order;     // item ids sorted by class (null: tickets walk the items in place)
     uint8_t *otype;      // result container type (0 = dropped)
     uint32_t *ocard;     // result cardinality
     uint32_t *olen;      // result length (array values / runs)
@@ -104,7 +109,25 @@ struct OpStats {
     unsigned int error;               // 0 = ok; 1 = slot overflow; 2 = slab overflow; 3 = malformed blob
     unsigned int nk;                  // or_many: number of distinct keys
     unsigned int units;               // or_many: number of (key, slice) work units
+    unsigned int cls_count[8];        // pairwise ops: live work items per code-path class
+    unsigned int cls_cursor[8];       //               fill cursors of k_order_items
 };
+
+// Code-path classes of the pairwise work items.  k_compute_items is one large kernel (a code path
+// per cell family); when the warps of an SM run different families at the same time it is bound
+// by INSTRUCTION FETCH (ncu, profiles/r2: no_instruction stalls 6.3 per issued instruction), so
+// the tickets are handed out class by class: at any time almost every resident warp executes the
+// same few hundred instructions.  Heavy classes first (tail balance).
+constexpr int CLS_BB = 0;        // bitset x bitset
+constexpr int CLS_BA = 1;        // bitset x array (either side)
+constexpr int CLS_BR = 2;        // bitset x run
+constexpr int CLS_AA_ACC = 3;    // array x array through the accumulator (large unions / xors)
+constexpr int CLS_RUN_ACC = 4;   // run cells through the accumulator
+constexpr int CLS_AA = 5;        // array x array: filter / merge path
+constexpr int CLS_RUN_IV = 6;    // run cells by interval sweep
+constexpr int CLS_COPY = 7;      // pass-through
+constexpr int CLS_NONE = 0xff;
+constexpr int N_CLS = 8;
 
 // Key-major index of one many-way union (rb200_many2.cu): built per call on the device.
 struct Many2Index {
@@ -128,6 +151,7 @@ extern unsigned long long g_launches;
 void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, const uint32_t *ib,
                        const uint64_t *item_off, uint32_t npairs, int op, bool card_only, int rules,
                        Items it, OpStats *st, cudaStream_t s);
+void launch_order_items(Items it, uint64_t W, OpStats *st, cudaStream_t s);
 void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
                           uint8_t *slab, uint64_t slab_cap, OpStats *st, int rules,
                           cudaStream_t s);

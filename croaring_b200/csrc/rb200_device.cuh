@@ -125,6 +125,14 @@ __host__ __device__ __forceinline__ uint32_t portable_bytes(int t, uint32_t len)
     return t == T_BITSET ? (uint32_t)BITSET_BYTES : (t == T_ARRAY ? 2u * len : 2u + 4u * len);
 }
 
+// "Effective bytes" of a container: what it can contribute to the result of a later op on it — its
+// stored size, or the size of its values as an array / bitset if that is larger (a run of 4 bytes
+// can hold 65536 values).  Summed per bitmap it bounds the result slab of a batch (PairBuf::build).
+__host__ __device__ __forceinline__ uint32_t effective_bytes(int t, uint32_t len, uint32_t card) {
+    const uint32_t st = stored_bytes(t, len), byc = card > (uint32_t)MAX_ARRAY ? (uint32_t)BITSET_BYTES : 2u * card;
+    return round16(st > byc ? st : byc);
+}
+
 // Upper bound (bytes, multiple of 16) of the stored result of a COMPUTE cell.
 __host__ __device__ inline uint32_t slot_bound(int op, int tA, int tB, uint32_t cA, uint32_t cB,
                                                uint32_t lA, uint32_t lB) {
@@ -159,6 +167,11 @@ __host__ __device__ inline uint32_t slot_bound(int op, int tA, int tB, uint32_t 
         }
         if (b > FULLB) b = FULLB;
     }
+    // Whatever the cell: a non-lazy result is an array (2 * card), a bitset, or a run container that
+    // was chosen because it is no larger than either — so min(8192, 2 * card_max) bounds it too.
+    const uint32_t cmax = op == OP_AND ? cmin : (op == OP_ANDNOT ? cA : cA + cB);
+    const uint32_t g = cmax > (uint32_t)MAX_ARRAY ? FULLB : 2 * cmax;
+    if (g < b) b = g;
     return round16(b);
 }
 

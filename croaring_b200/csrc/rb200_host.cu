@@ -140,10 +140,14 @@ std::map<uint8_t *, size_t> g_serialized_sizes;  // pinned blobs handed out by r
 bool stats_reset();
 bool stats_fetch();
 
+// size classes of the device / pinned pools: 8 per octave (<= 12.5 % slack; the power-of-two
+// classes of round 1 could double a multi-GB result slab)
 size_t bucket(size_t n) {
     size_t b = 512;
     while (b < n) b <<= 1;
-    return b;
+    if (b <= 4096) return b;
+    const size_t step = b >> 4;            // b/2 < n <= b: classes b/2 + k * b/16
+    return (b >> 1) + ((n - (b >> 1) + step - 1) / step) * step;
 }
 
 bool ctx_init(int device = -1) {
@@ -249,12 +253,14 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Directory arrays carved out of one block (device and, mirrored, pinned host).
 struct DirLayout {
-    size_t o_beg, o_cnt, o_bcard, o_key, o_type, o_card, o_len, o_off, o_src, total;
+    size_t o_beg, o_cnt, o_bcard, o_bbytes, o_bebytes, o_key, o_type, o_card, o_len, o_off, o_src, total;
     void compute(size_t nb, size_t nc) {
         size_t o = 0;
         o_beg = o; o += al256(4 * nb);
-        o_cnt = o; o += al256(4 * nb);
+        o_cnt = o; o += al256(4 * nb);        // [cnt | bcard | bbytes | bebytes] are fetched with ONE copy
         o_bcard = o; o += al256(8 * nb);
+        o_bbytes = o; o += al256(8 * nb);
+        o_bebytes = o; o += al256(8 * nb);
         o_off = o; o += al256(8 * nc);
         o_card = o; o += al256(4 * nc);
         o_len = o; o += al256(4 * nc);
@@ -296,6 +302,7 @@ struct rb200_set {
     // the inputs instead of crossing PCIe again
     std::shared_ptr<std::vector<const void *>> h_ptr_all, h_ptr, parentA, parentB;  // h_ptr: bound (opt-in)
     std::vector<uint64_t> h_bytes;  // host mirror: upper bound of stored payload bytes per bitmap
+    std::vector<uint64_t> h_ebytes; // host mirror: upper bound of the "effective bytes" (rb200_device.cuh) per bitmap
     std::vector<uint8_t> h_flags;   // per bitmap: COW flag to propagate
     // lazily downloaded host mirror (pinned)
     uint8_t *m_dir = nullptr, *m_slab = nullptr;
@@ -318,6 +325,8 @@ struct rb200_set {
         v.bm_beg = (uint32_t *)(d_dir + L.o_beg);
         v.bm_cnt = (uint32_t *)(d_dir + L.o_cnt);
         v.bm_card = (uint64_t *)(d_dir + L.o_bcard);
+        v.bm_bytes = (uint64_t *)(d_dir + L.o_bbytes);
+        v.bm_ebytes = (uint64_t *)(d_dir + L.o_bebytes);
         v.c_key = (uint16_t *)(d_dir + L.o_key);
         v.c_type = (uint8_t *)(d_dir + L.o_type);
         v.c_card = (uint32_t *)(d_dir + L.o_card);
@@ -347,6 +356,7 @@ rb200_set *set_new(uint32_t nb, uint64_t dir_cap, uint64_t slab_cap) {
     }
     s->h_cnt.assign(nb, 0);
     s->h_bytes.assign(nb, 0);
+    s->h_ebytes.assign(nb, 0);
     s->h_flags.assign(nb, 0);
     return s;
 }
@@ -403,6 +413,7 @@ bool resolve(const rb200_set *cs) {
         if (s->n_bitmaps == 1) {  // a single result: its mirrors are the op's counters, no extra D2H
             s->h_cnt[0] = (uint32_t)s->n_containers;
             s->h_bytes[0] = s->slab_used;
+            s->h_ebytes[0] = std::max<uint64_t>(s->slab_used, s->n_containers * (uint64_t)BITSET_BYTES);
             s->mirrors_pending = false;
         }
     }
@@ -932,7 +943,7 @@ rb200_set *upload_impl(const PackSrc &src) {
             bm_cnt[b] = (uint32_t)size;
             s->h_cnt[b] = (uint32_t)size;
             s->h_flags[b] = ra ? (ra->flags & FLAG_COW) : 0;
-            uint64_t bcard = 0, bbytes = 0;
+            uint64_t bcard = 0, bbytes = 0, bebytes = 0;
             for (int32_t i = 0; i < size; i++, ci++) {
                 uint8_t t;
                 uint32_t card, len;
@@ -990,10 +1001,12 @@ rb200_set *upload_impl(const PackSrc &src) {
                 off += sb16;
                 bcard += card & CARD_MASK;
                 bbytes += sb16;
+                bebytes += effective_bytes(t, len, card & CARD_MASK);
                 s->portable_bytes += portable_bytes(t, len);
             }
             bm_card[b] = bcard;
             s->h_bytes[b] = bbytes;
+            s->h_ebytes[b] = bebytes;
         }
         if (ok) ok = flush();
         if (ok && cudaMemcpyAsync(s->d_dir, hd, s->L.total, cudaMemcpyHostToDevice, g.stream) != cudaSuccess)
@@ -1092,6 +1105,7 @@ static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens,
             h_bc[n + i] = cnt[i];
             s->h_cnt[i] = cnt[i];
             s->h_bytes[i] = lens[i] + 16ull * cnt[i];
+            s->h_ebytes[i] = (uint64_t)cnt[i] * BITSET_BYTES + lens[i];   // replaced by the device's figures (ensure_mirrors)
             const uint64_t hdr = ((cnt[i] && (((uint8_t)bufs[i][0] | ((uint8_t)bufs[i][1] << 8)) == SERIAL_COOKIE))
                                      ? 4 + (cnt[i] + 7) / 8 + (cnt[i] < (uint32_t)NO_OFFSET_THRESHOLD ? 4ull : 8ull) * cnt[i]
                                      : 8 + 8ull * cnt[i]);
@@ -1163,6 +1177,7 @@ static rb200_set *upload_blobs_impl(const char *const *bufs, const size_t *lens,
     } else {
         cudaStreamSynchronize(g.stream);
     }
+    if (ok) s->mirrors_pending = n > 0;   // exact per-bitmap bytes / effective bytes: k_deser_bitmap_cards wrote them
     for (int k = 0; k < 2; k++) if (cev[k]) cudaEventDestroy(cev[k]);
     pin_free(chunk[0], CH);
     pin_free(chunk[1], CH);
@@ -1223,7 +1238,8 @@ bool ensure_mirrors(const rb200_set *cs) {
     if (!resolve(cs)) return false;
     if (!s->mirrors_pending) return true;
     const size_t nb = s->n_bitmaps;
-    const size_t bytes = (s->L.o_bcard - s->L.o_cnt) + 8 * nb;
+    // one copy: [cnt | bcard | bbytes | bebytes], all written by the kernel that produced the set
+    const size_t bytes = (s->L.o_bebytes - s->L.o_cnt) + 8 * nb;
     uint8_t *h = (uint8_t *)pin_alloc(bytes);
     if (!h) return false;
     bool ok = cudaMemcpyAsync(h, s->d_dir + s->L.o_cnt, bytes, cudaMemcpyDeviceToHost, g.stream) == cudaSuccess &&
@@ -1231,12 +1247,13 @@ bool ensure_mirrors(const rb200_set *cs) {
     if (ok) {
         const uint32_t *cnt = (const uint32_t *)h;
         const uint64_t *card = (const uint64_t *)(h + (s->L.o_bcard - s->L.o_cnt));
+        const uint64_t *bb = (const uint64_t *)(h + (s->L.o_bbytes - s->L.o_cnt));
+        const uint64_t *be = (const uint64_t *)(h + (s->L.o_bebytes - s->L.o_cnt));
         s->h_card.assign(card, card + nb);
         for (size_t p = 0; p < nb; p++) {
             s->h_cnt[p] = cnt[p];
-            s->h_bytes[p] = (uint64_t)cnt[p] * BITSET_BYTES;  // upper bound: every container <= 8 KiB
-            if (s->lazy)  // ... except runs left unconverted by lazy unions (<= 128 KiB each)
-                s->h_bytes[p] = std::min<uint64_t>((uint64_t)cnt[p] * 16 * BITSET_BYTES, s->slab_used);
+            s->h_bytes[p] = bb[p];    // exact stored bytes (16-byte rounded slots) of this bitmap
+            s->h_ebytes[p] = be[p];   // what a later op on it can produce at most (see PairBuf::build)
         }
         s->mirrors_pending = false;
     } else {
@@ -1250,9 +1267,12 @@ struct ItemsBuf {
     uint8_t *block = nullptr;
     size_t bytes = 0;
     Items it;
-    bool alloc(uint64_t W) {
+    // order_min: batches with at least that many item slots get the class-ordered ticket list
+    bool alloc(uint64_t W, bool with_order = false) {
         size_t o = 0;
         const size_t o_off = o; o += al256(8 * W);
+        const size_t o_order = o; if (with_order) o += al256(4 * W);
+        const size_t o_cls = o; if (with_order) o += al256(W);
         const size_t o_ca = o; o += al256(4 * W);
         const size_t o_cb = o; o += al256(4 * W);
         const size_t o_cap = o; o += al256(4 * W);
@@ -1265,6 +1285,8 @@ struct ItemsBuf {
         block = (uint8_t *)dev_alloc(bytes);
         if (!block) return false;
         it.slot_off = (uint64_t *)(block + o_off);
+        it.order = with_order ? (uint32_t *)(block + o_order) : nullptr;
+        it.cls = with_order ? block + o_cls : nullptr;
         it.ca = (uint32_t *)(block + o_ca);
         it.cb = (uint32_t *)(block + o_cb);
         it.slot_cap = (uint32_t *)(block + o_cap);
@@ -1285,8 +1307,9 @@ struct PairBuf {
     uint32_t *d_ia = nullptr, *d_ib = nullptr;
     uint64_t *d_off = nullptr;
     uint64_t W = 0, slab_bound = 0;
+    // op: OP_* of the batch (OP_AND also for the cardinality-only sweeps, which need no slab)
     bool build(const rb200_set *A, const rb200_set *B, const uint32_t *ia, const uint32_t *ib,
-               size_t np, bool and_like, bool lazy = false) {
+               size_t np, int op, bool lazy = false) {
         if (!ensure_mirrors(A) || !ensure_mirrors(B)) return false;
         const size_t o_off = 0, o_ia = al256(8 * (np + 1)), o_ib = o_ia + al256(4 * np);
         bytes = o_ib + al256(4 * np);
@@ -1307,11 +1330,23 @@ struct PairBuf {
             off[p] = w;
             const uint32_t na = A->h_cnt[a], nb = B->h_cnt[b];
             w += (uint64_t)na + nb;
-            // upper bound of the result slab: pass-through bytes + 8 KiB per possible match
-            const uint64_t m = na < nb ? na : nb;
-            sb += (and_like ? 0 : A->h_bytes[a] + B->h_bytes[b]) + m * (uint64_t)BITSET_BYTES + 512;
-            // lazy array x run unions stay runs: up to 4 bytes per input value / run on top
-            if (lazy) sb += 2 * (A->h_bytes[a] + B->h_bytes[b]);
+            // Upper bound of the result slab of this pair, from the per-bitmap "effective bytes" E
+            // (sum over containers of max(stored, min(8192, 2 * card)), 16-byte rounded): every
+            // result container — computed or passed through — is an array, a bitset or a run no
+            // larger than either, so it fits min(8192, 2 * card_result); card_result <= cA + cB
+            // (OR, XOR), <= min(cA, cB) (AND), <= cA (ANDNOT).  slot_bound() obeys the same limits.
+            const uint64_t EA = A->h_ebytes[a], EB = B->h_ebytes[b];
+            if (lazy) {
+                // lazy array x run unions stay runs (4 bytes per input value / run), flips add 8 KiB per key
+                const uint64_t m = na < nb ? na : nb;
+                sb += 3 * (EA + EB) + m * (uint64_t)BITSET_BYTES + 512;
+            } else if (op == OP_AND) {
+                sb += (EA < EB ? EA : EB) + 64;
+            } else if (op == OP_ANDNOT) {
+                sb += EA + 64;
+            } else {
+                sb += EA + EB + 64;
+            }
         }
         off[np] = w;
         W = w;
@@ -1359,8 +1394,10 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
     PairBuf pb;
     ItemsBuf ib_;
     rb200_set *R = nullptr;
-    bool ok = pb.build(A, B, ia, ib, np, op == OP_AND, (rules & RULES_LAZY) != 0);
-    if (ok) ok = ib_.alloc(pb.W);
+    bool ok = pb.build(A, B, ia, ib, np, op, (rules & RULES_LAZY) != 0);
+    // class-ordered tickets pay one more small kernel: only for batches that fill the GPU
+    static const uint64_t order_min = []() { const char *e = getenv("RB200_ORDER_MIN"); return e ? (uint64_t)atoll(e) : 16384ull; }();
+    if (ok) ok = ib_.alloc(pb.W, pb.W >= order_min);
     if (ok) {
         R = set_new((uint32_t)np, pb.W, pb.slab_bound);
         ok = R != nullptr;
@@ -1376,6 +1413,7 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         const SetView va = A->view(), vb = B->view();
         launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, rules, ib_.it,
                           g.d_stats, g.stream);
+        launch_order_items(ib_.it, pb.W, g.d_stats, g.stream);
         cudaEventRecord(R->ev[1], g.stream);
         launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, g.stream);
         cudaEventRecord(R->ev[2], g.stream);
@@ -1430,7 +1468,7 @@ int rb200_batch_and_cardinality(const rb200_set_t *A, const rb200_set_t *B, cons
     PairBuf pb;
     ItemsBuf ib_;
     uint64_t *d_out = nullptr, *h_out = nullptr;
-    bool ok = pb.build(A, B, ia, ib, np, true);
+    bool ok = pb.build(A, B, ia, ib, np, OP_AND);
     if (ok) ok = ib_.alloc(pb.W);
     if (ok) { d_out = (uint64_t *)dev_alloc(8 * np); h_out = (uint64_t *)pin_alloc(8 * np); ok = d_out && h_out; }
     if (ok) {
@@ -1589,6 +1627,7 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         R->slab_used = (uint64_t)nk * BITSET_BYTES;
         R->h_cnt[0] = nk;
         R->h_bytes[0] = (uint64_t)nk * BITSET_BYTES;
+        R->h_ebytes[0] = (uint64_t)nk * BITSET_BYTES;
         uint8_t fl = 0;
         // roaring_bitmap_lazy_or propagates COW from the inputs (roaring.c:2523)
         for (size_t i = 0; i < n; i++) fl |= S->h_flags[idx ? idx[i] : i];
@@ -1715,6 +1754,7 @@ rb200_set_t *rb200_xor_many(const rb200_set_t *S, const uint32_t *idx, size_t n)
         R->slab_used = (uint64_t)g.h_stats->nk * BITSET_BYTES;
         R->h_cnt[0] = live;
         R->h_bytes[0] = (uint64_t)live * BITSET_BYTES;
+        R->h_ebytes[0] = (uint64_t)live * BITSET_BYTES;
         uint8_t fl = 0;
         for (size_t i = 0; i < n; i++) fl |= S->h_flags[idx ? idx[i] : i];
         R->h_flags[0] = fl & FLAG_COW;
@@ -2664,7 +2704,10 @@ static rb200_set *convert_impl(const rb200_set *S, int mode) {
     R->h_flags = S->h_flags;
     if (!ensure_mirrors(S)) { set_delete(R); return nullptr; }
     R->h_cnt = S->h_cnt;
-    for (size_t b = 0; b < R->n_bitmaps; b++) R->h_bytes[b] = (uint64_t)R->h_cnt[b] * BITSET_BYTES;
+    for (size_t b = 0; b < R->n_bitmaps; b++) {
+        R->h_bytes[b] = (uint64_t)R->h_cnt[b] * BITSET_BYTES;
+        R->h_ebytes[b] = std::max<uint64_t>(R->h_bytes[b], S->h_ebytes[b]);
+    }
     return R;
 }
 

@@ -45,6 +45,25 @@ __device__ __forceinline__ uint32_t upper_bound_u16(const uint16_t *a, uint32_t 
     return lo;
 }
 
+#ifndef RB200_MERGE_LIMIT
+#define RB200_MERGE_LIMIT 2048   // array x array unions up to this many staged values take the merge path
+#endif
+#ifndef RB200_RANK_SCATTER
+#define RB200_RANK_SCATTER 1     // larger ones: accumulator + rank-scatter emission (0: find-first-set emission)
+#endif
+
+// code-path class of a matched cell (see rb200_common.h CLS_*); mirrors the branches of cell_compute
+__device__ __forceinline__ int cell_class(int op, int tA, int tB, uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB) {
+    const bool bA = tA == T_BITSET, bB = tB == T_BITSET;
+    if (bA && bB) return CLS_BB;
+    if (bA || bB) return (bA ? tB : tA) == T_ARRAY ? CLS_BA : CLS_BR;
+    if (tA == T_ARRAY && tB == T_ARRAY) {
+        if (op == OP_AND || op == OP_ANDNOT) return CLS_AA;
+        return ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= (uint32_t)RB200_MERGE_LIMIT ? CLS_AA : CLS_AA_ACC;
+    }
+    return (tA == T_RUN ? lA : cA) + (tB == T_RUN ? lB : cB) <= 512u ? CLS_RUN_IV : CLS_RUN_ACC;
+}
+
 // ------------------------------------------------------------------------------ planner
 __global__ void __launch_bounds__(128)
 k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
@@ -61,7 +80,7 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
         const uint32_t tot = na + nb;
         for (uint32_t t0 = 0; t0 < tot; t0 += 32) {
             const uint32_t t = t0 + lane;
-            int kind = K_HOLE;
+            int kind = K_HOLE, cls = CLS_NONE;
             uint32_t ca = 0, cb = 0, cap = 0, pos = 0, key = 0;
             if (t < tot) {
                 if (t < na) {
@@ -78,9 +97,11 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
                             cap = (rules & RULES_LAZY)
                                       ? slot_bound_lazy(A.c_type[ca], B.c_type[cb], cA, cB, A.c_len[ca], B.c_len[cb])
                                       : slot_bound(op, A.c_type[ca], B.c_type[cb], cA, cB, A.c_len[ca], B.c_len[cb]);
+                            cls = cell_class(op, A.c_type[ca], B.c_type[cb], cA, cB, A.c_len[ca], B.c_len[cb]);
                         }
                     } else if (op != OP_AND && !card_only) {
                         kind = K_COPY_A;
+                        cls = CLS_COPY;
                         cap = round16(stored_bytes(A.c_type[ca], A.c_len[ca]));
                     }
                 } else {
@@ -92,6 +113,7 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
                     pos = j + ub;
                     if (!matched && (op == OP_OR || op == OP_XOR) && !card_only) {
                         kind = K_COPY_B;
+                        cls = CLS_COPY;
                         cap = round16(stored_bytes(B.c_type[cb], B.c_len[cb]));
                     }
                 }
@@ -110,23 +132,50 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
                 it.cb[idx] = cb;
                 it.slot_off[idx] = slab_base + incl - cap;
                 it.slot_cap[idx] = cap;
+                if (it.cls) it.cls[idx] = (uint8_t)cls;
                 it.otype[idx] = 0;
                 it.ocard[idx] = 0;
                 it.olen[idx] = 0;
             }
+            if (it.cls) {   // live items per class (one atomic per class present in this stripe)
+#pragma unroll
+                for (int c = 0; c < N_CLS; c++) {
+                    const unsigned m = __ballot_sync(FULLMASK, cls == c);
+                    if (m && lane == 0) atomicAdd(&st->cls_count[c], (unsigned)__popc(m));
+                }
+            }
+        }
+    }
+}
+
+// item ids grouped by class: order[prefix(class) + k]; warp-aggregated cursors
+__global__ void __launch_bounds__(256)
+k_order_items(Items it, uint64_t W, OpStats *st) {
+    const int lane = threadIdx.x & 31;
+    uint32_t pre[N_CLS];
+    uint32_t run = 0;
+#pragma unroll
+    for (int c = 0; c < N_CLS; c++) { pre[c] = run; run += st->cls_count[c]; }
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = warp * 32; base < W; base += nwarps * 32) {
+        const uint64_t i = base + lane;
+        const int c = i < W ? (int)it.cls[i] : CLS_NONE;
+#pragma unroll
+        for (int cc = 0; cc < N_CLS; cc++) {
+            const unsigned m = __ballot_sync(FULLMASK, c == cc);
+            if (!m) continue;
+            const int leader = __ffs(m) - 1;
+            uint32_t b = 0;
+            if (lane == leader) b = atomicAdd(&st->cls_cursor[cc], (unsigned)__popc(m));
+            b = __shfl_sync(FULLMASK, b, leader);
+            if (c == cc) it.order[pre[cc] + b + __popc(m & lanemask_lt())] = (uint32_t)i;
         }
     }
 }
 
 // ------------------------------------------------------------------------------ grid cells
 // Evaluate one matched cell on the warp's accumulator and write the result payload.
-#ifndef RB200_MERGE_LIMIT
-#define RB200_MERGE_LIMIT 2048   // array x array unions up to this many staged values take the merge path
-#endif
-#ifndef RB200_RANK_SCATTER
-#define RB200_RANK_SCATTER 1     // larger ones: accumulator + rank-scatter emission (0: find-first-set emission)
-#endif
-
 template <int OP, bool LAZY>
 __device__ __forceinline__ void
 cell_compute(uint32_t *acc, uint16_t *pre, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
@@ -153,7 +202,8 @@ cell_compute(uint32_t *acc, uint16_t *pre, int tA, int tB, const uint8_t *pa, co
         const uint8_t *po = arrA ? pb : pa;
         const uint32_t lo = arrA ? lB : lA;
         uint32_t n;
-        if (2 * narr > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
+        // (the filter writes only the values it keeps: at most min(cA, cB) of them)
+        if (2 * min(cA, cB) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
         if (to == T_BITSET && narr < 192) {  // few probes: test the bits where they are
             n = filter_array<false, true>(parr, narr, reinterpret_cast<const uint32_t *>(po),
                                           reinterpret_cast<uint16_t *>(out), lane);
@@ -312,6 +362,13 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
     // dynamic scheduling: a ticket is TICKET consecutive items; the next ticket is requested
     // before the current one is processed so its latency hides behind the work.
     // (small batches: tickets of 1 so that every warp of the grid gets work at once)
+    // with an order list (big batches) the tickets walk the live items class by class
+    if (it.order) {
+        unsigned long long live = 0;
+#pragma unroll
+        for (int c = 0; c < N_CLS; c++) live += st->cls_count[c];
+        W = live;
+    }
     const unsigned long long TICKET = (W >= 8ull * ((unsigned long long)gridDim.x * 4)) ? 4ull : 1ull;
     unsigned long long tk = 0;
     if (lane == 0) tk = atomicAdd(&st->work_counter, TICKET);
@@ -320,7 +377,8 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
         unsigned long long next = 0;
         if (lane == 0) next = atomicAdd(&st->work_counter, TICKET);
         const unsigned long long tend = tk + TICKET < W ? tk + TICKET : W;
-        for (unsigned long long item = tk; item < tend; item++) {
+        for (unsigned long long slot = tk; slot < tend; slot++) {
+            const unsigned long long item = it.order ? (unsigned long long)it.order[slot] : slot;
             const int kind = it.kind[item];
             if (kind == K_HOLE) continue;
             const uint64_t off = it.slot_off[item];
@@ -445,13 +503,17 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
         const uint64_t i0 = item_off[p], i1 = item_off[p + 1];
         // pass 1: count surviving containers, cardinality and algorithmic bytes
         uint32_t cnt = 0, anyrun = 0;
-        unsigned long long card = 0, bytes = 0, outb = 0;
+        unsigned long long card = 0, bytes = 0, outb = 0, sbytes = 0, ebytes = 0;
         for (uint64_t i = i0 + lane; i < i1; i += 32) {
             const int kind = it.kind[i];
             if (kind == K_HOLE) continue;
             const int ot = it.otype[i];
             const uint32_t osz = ot ? portable_bytes(ot, it.olen[i]) : 0u;
             outb += osz;
+            if (ot) {
+                sbytes += round16(stored_bytes(ot, it.olen[i]));
+                ebytes += effective_bytes(ot, it.olen[i], it.ocard[i] & CARD_MASK);
+            }
             anyrun |= (ot == T_RUN) ? 1u : 0u;
             if (kind == K_COMPUTE) {
                 const uint32_t ca = it.ca[i], cb = it.cb[i];
@@ -471,6 +533,8 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
             card += __shfl_xor_sync(FULLMASK, card, d);
             bytes += __shfl_xor_sync(FULLMASK, bytes, d);
             outb += __shfl_xor_sync(FULLMASK, outb, d);
+            sbytes += __shfl_xor_sync(FULLMASK, sbytes, d);
+            ebytes += __shfl_xor_sync(FULLMASK, ebytes, d);
         }
         unsigned long long base = 0;
         if (lane == 0) {
@@ -480,6 +544,8 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
             out.bm_beg[p] = (uint32_t)base;
             out.bm_cnt[p] = cnt;
             out.bm_card[p] = card;
+            out.bm_bytes[p] = sbytes;
+            out.bm_ebytes[p] = ebytes;
         }
         base = __shfl_sync(FULLMASK, base, 0);
         // pass 2: ordered compaction into the directory
@@ -711,6 +777,13 @@ void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, c
     if (!npairs) return;
     const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * 16);
     k_plan_pairs<<<g, 128, 0, s>>>(A, B, ia, ib, item_off, npairs, op, card_only, rules, it, st);
+    g_launches++;
+}
+
+void launch_order_items(Items it, uint64_t W, OpStats *st, cudaStream_t s) {
+    if (!W || !it.order) return;
+    const uint32_t g = blocks_for_warps((W + 31) / 32, 8, sm_count() * 8);
+    k_order_items<<<g, 256, 0, s>>>(it, W, st);
     g_launches++;
 }
 
@@ -1102,10 +1175,18 @@ __global__ void k_deser_bitmap_cards(SetOut out, uint32_t nb, const OpStats *st)
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t b = warp; b < nb; b += nwarps) {
         const uint32_t c0 = out.bm_beg[b], n = out.bm_cnt[b];
-        unsigned long long card = 0;
-        for (uint32_t i = lane; i < n; i += 32) card += out.c_card[c0 + i];
-        for (int d = 16; d > 0; d >>= 1) card += __shfl_xor_sync(FULLMASK, card, d);
-        if (lane == 0) out.bm_card[b] = card;
+        unsigned long long card = 0, sbytes = 0, ebytes = 0;
+        for (uint32_t i = lane; i < n; i += 32) {
+            card += out.c_card[c0 + i];
+            sbytes += round16(stored_bytes(out.c_type[c0 + i], out.c_len[c0 + i]));
+            ebytes += effective_bytes(out.c_type[c0 + i], out.c_len[c0 + i], out.c_card[c0 + i]);
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            card += __shfl_xor_sync(FULLMASK, card, d);
+            sbytes += __shfl_xor_sync(FULLMASK, sbytes, d);
+            ebytes += __shfl_xor_sync(FULLMASK, ebytes, d);
+        }
+        if (lane == 0) { out.bm_card[b] = card; out.bm_bytes[b] = sbytes; out.bm_ebytes[b] = ebytes; }
     }
 }
 
