@@ -906,6 +906,82 @@ interval_cell(uint32_t *acc, int op, int tA, int tB, const uint8_t *pa, const ui
     return true;
 }
 
+// ---------------------------------------------------------------- TMA bulk copies + mbarrier
+// Operand staging the Blackwell way: ONE elected thread issues cp.async.bulk (global -> shared,
+// whole containers, 16-byte granules) against an mbarrier; the bytes land asynchronously while the
+// other warps keep working on the previous batch, and nobody holds registers for loads in flight.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// wait for the phase with the given parity; a bounded spin: a lost transaction traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0;; spin++) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+// shared-memory twins of acc_apply_array / acc_apply_runs (operands staged by bulk copies)
+template <int MODE>
+__device__ __forceinline__ void acc_apply_array_s(uint32_t *acc, const uint8_t *src, uint32_t n, int lane) {
+    const uint4 *v4 = reinterpret_cast<const uint4 *>(src);
+    const uint32_t nvec = (n + 7) >> 3;
+    for (uint32_t i = lane; i < nvec; i += 32) {
+        const uint4 q = v4[i];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t left = n - i * 8;
+        uint32_t cur_w = (w[0] & 0xffffu) >> 5, cur_m = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+            const uint32_t wi = v >> 5, bit = 1u << (v & 31);
+            if (k == 0 || k < (int)left) {
+                if (wi != cur_w) {
+                    acc_atom<MODE>(acc + cur_w, cur_m);
+                    cur_w = wi;
+                    cur_m = bit;
+                } else {
+                    cur_m |= bit;
+                }
+            }
+        }
+        acc_atom<MODE>(acc + cur_w, cur_m);
+    }
+}
+template <int MODE, bool ATOMIC_INTERIOR>
+static __device__ __noinline__ void acc_apply_runs_s(uint32_t *acc, const uint8_t *src, uint32_t n, int lane) {
+    const uint32_t *runs = reinterpret_cast<const uint32_t *>(src);
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        const uint32_t r = valid ? runs[i] : 0u;
+        const uint32_t lo = r & 0xffffu, hi = min(lo + (r >> 16), 65535u);
+        acc_apply_ranges<MODE, ATOMIC_INTERIOR>(acc, lo, hi, valid, lane);
+    }
+}
+
 // 16-byte vector copy of a stored payload (pass-through containers)
 __device__ __forceinline__ void warp_copy16(uint8_t *dst, const uint8_t *src, uint32_t bytes,
                                             int lane) {

@@ -8,10 +8,13 @@
 //                   scratch accumulator
 //   k_many2_fill    index entries {input position, container, type|flags}, grouped by key
 //                   (order inside a key is arbitrary: nothing below needs it)
-//   k_or_many2      work unit = (key, slice): bitset participants are ORed in registers (every
-//                   thread owns 32 bytes of the 8 KiB, four containers in flight), arrays and runs
-//                   are rasterised into a shared accumulator by one warp each; the last slice of
-//                   a key counts, picks the reference's result type and re-encodes.
+//   k_or_many2      work unit = (key, slice): the participants' payloads are staged into shared
+//                   memory by TMA bulk copies (cp.async.bulk + one mbarrier per half of a 64 KiB
+//                   ping-pong buffer, issued by one thread, whole containers per copy), so the
+//                   loads of the next batch are in flight while the CTA consumes the current one:
+//                   bitsets are ORed into registers (every thread owns 32 bytes of the 8 KiB),
+//                   arrays and runs are rasterised into a shared accumulator by one warp each; the
+//                   last slice of a key counts, picks the reference's result type and re-encodes.
 //
 // The reference folds the inputs left to right with lazy cells (roaring_bitmap_lazy_or :2509-2598,
 // roaring_bitmap_lazy_or_inplace :2600-2682, container_lazy_or / container_lazy_ior
@@ -190,18 +193,24 @@ k_many2_fill(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t k
 }
 
 // ------------------------------------------------------------------------------ reduction
+constexpr uint32_t M2_HALF = 32u << 10;   // bytes of one staging half (two halves: ping / pong)
+constexpr uint32_t M2_HALF_ENTRIES = 128;  // participants staged per half at most
+
 struct Many2Smem {
+    uint8_t ring[2][M2_HALF];   // operand staging: filled by cp.async.bulk, one mbarrier per half
     uint32_t acc[ACC_WORDS];    // union of the inputs up to L (or of all of them when L is not needed)
     uint32_t acc2[ACC_WORDS];   // union of the inputs after L
+    uint64_t bar[2];            // mbarriers of the two halves
+    uint16_t h_bs[2][M2_HALF_ENTRIES], h_ar[2][M2_HALF_ENTRIES];   // staged bitsets / arrays+runs of a half (entry ids)
+    uint32_t h_soff[M2_STAGE];  // byte offset of a staged entry inside its half
+    uint32_t h_nbs[2], h_nar[2], h_big[2];
     unsigned long long s_off[M2_STAGE];
     uint32_t s_len[M2_STAGE];
     uint32_t s_pos[M2_STAGE];
     uint8_t s_tf[M2_STAGE];
-    uint32_t bs_list[M2_STAGE];  // staged entries that are bitsets / that are arrays or runs
-    uint32_t ar_list[M2_STAGE];
     unsigned long long red64[M2_THREADS / 32];
     uint32_t red32[M2_THREADS / 32][2];
-    uint32_t nbs, nar, unit, flag;
+    uint32_t unit, flag;
     unsigned long long first, second;
     uint32_t F, L, any_ib;
 };
@@ -222,12 +231,20 @@ __device__ __forceinline__ unsigned long long block_min64(Many2Smem &sm, unsigne
     return r;
 }
 
-__global__ void __launch_bounds__(M2_THREADS, 4)
+__global__ void __launch_bounds__(M2_THREADS, 2)
 k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch, uint32_t *__restrict__ tickets,
            SetOut out, uint32_t *__restrict__ card_per_key, OpStats *st) {
-    __shared__ __align__(16) Many2Smem sm;
+    extern __shared__ __align__(128) uint8_t m2_smem_raw[];
+    Many2Smem &sm = *reinterpret_cast<Many2Smem *>(m2_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nunits = st->units;
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        mbar_fence_init();
+    }
+    uint32_t ph0 = 0, ph1 = 0;   // phase parity of the two staging halves (every thread tracks both)
+    __syncthreads();
     for (;;) {
         __syncthreads();
         if (tid == 0) sm.unit = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
@@ -302,9 +319,8 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
         uint32_t anyfull = 0, anyfull_pre = 0;   // bit flags, merged over the block at the end
         for (uint32_t base = s_lo; base < s_hi; base += M2_STAGE) {
             __syncthreads();
-            if (tid == 0) { sm.nbs = 0; sm.nar = 0; }
-            __syncthreads();
             const uint32_t e = base + tid;
+            const uint32_t R = min((uint32_t)M2_STAGE, s_hi - base);   // entries of this round
             if (tid < M2_STAGE && e < s_hi) {
                 const uint32_t c = ix.e_cont[e0 + e], tf = ix.e_tf[e0 + e], p = ix.e_pos[e0 + e];
                 sm.s_off[tid] = S.c_off[c];
@@ -315,36 +331,92 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                     anyfull = 1;
                     if (L != POS_NONE && p <= L) anyfull_pre = 1;
                 }
-                if ((tf & 15) == T_BITSET) sm.bs_list[atomicAdd(&sm.nbs, 1u)] = tid;
-                else if (!(tf & TF_FULL_RUN)) sm.ar_list[atomicAdd(&sm.nar, 1u)] = tid;
             }
             __syncthreads();
-            // bitsets: registers, four containers in flight per thread (all of them are <= L)
-            const uint32_t nbs = sm.nbs;
-            for (uint32_t j = 0; j < nbs; j += 4) {
-                uint4 qa[4], qb[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (j + k < nbs) {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(S.payload + sm.s_off[sm.bs_list[j + k]]);
-                        qa[k] = __ldg(src + tid);
-                        qb[k] = __ldg(src + tid + M2_THREADS);
+            // ---- two-half pipeline: thread 0 packs the next entries of the round into a half and
+            // issues their bulk copies; everybody consumes the other half meanwhile
+            uint32_t next = 0;   // next entry of the round to stage (thread 0's cursor, kept uniform)
+            auto issue = [&](int h) {
+                // (executed by every thread so that `next` stays uniform; only thread 0 touches the
+                //  tables, the barrier and the copy engine)
+                uint32_t bytes = 0, nbs = 0, nar = 0, big = POS_NONE;
+                while (next < R && nbs + nar < M2_HALF_ENTRIES) {
+                    const uint32_t tf = sm.s_tf[next], t = tf & 15;
+                    const uint32_t sz = (tf & TF_FULL_RUN) ? 0u : round16(stored_bytes((int)t, sm.s_len[next]));
+                    if (sz > M2_HALF) {   // an oversized run container (unoptimised input): straight from global
+                        if (nbs + nar == 0 && big == POS_NONE) { big = next; next++; }
+                        break;
                     }
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (j + k < nbs) {
-                        r0.x |= qa[k].x; r0.y |= qa[k].y; r0.z |= qa[k].z; r0.w |= qa[k].w;
-                        r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
+                    if (bytes + sz > M2_HALF) break;
+                    if (tid == 0) {
+                        sm.h_soff[next] = bytes;
+                        if (sz) {
+                            if (t == T_BITSET) sm.h_bs[h][nbs] = (uint16_t)next;
+                            else sm.h_ar[h][nar] = (uint16_t)next;
+                        }
                     }
-            }
-            // arrays and runs: one warp per container, shared-memory atomics
-            const uint32_t nar = sm.nar;
-            for (uint32_t j = wid; j < nar; j += M2_THREADS / 32) {
-                const uint32_t q = sm.ar_list[j];
-                uint32_t *dst = (L != POS_NONE && sm.s_pos[q] > L) ? sm.acc2 : sm.acc;
-                const uint8_t *p = S.payload + sm.s_off[q];
-                if ((sm.s_tf[q] & 15) == T_ARRAY) acc_apply_array<0>(dst, p, sm.s_len[q], lane);
-                else acc_apply_runs<0, true>(dst, p, sm.s_len[q], lane);
+                    if (sz) { if (t == T_BITSET) nbs++; else nar++; }
+                    bytes += sz;
+                    next++;
+                }
+                if (tid == 0) {
+                    sm.h_nbs[h] = nbs;
+                    sm.h_nar[h] = nar;
+                    sm.h_big[h] = big;
+                    mbar_arrive_expect_tx(&sm.bar[h], bytes);
+                    for (uint32_t k = 0; k < nbs; k++) {
+                        const uint32_t q = sm.h_bs[h][k];
+                        bulk_copy_g2s(sm.ring[h] + sm.h_soff[q], S.payload + sm.s_off[q], BITSET_BYTES, &sm.bar[h]);
+                    }
+                    for (uint32_t k = 0; k < nar; k++) {
+                        const uint32_t q = sm.h_ar[h][k];
+                        bulk_copy_g2s(sm.ring[h] + sm.h_soff[q], S.payload + sm.s_off[q],
+                                      round16(stored_bytes(sm.s_tf[q] & 15, sm.s_len[q])), &sm.bar[h]);
+                    }
+                }
+            };
+            uint32_t staged = 0;      // halves issued and not yet consumed
+            issue(0);
+            staged++;
+            if (next < R) { issue(1); staged++; }
+            int h = 0;
+            while (staged) {
+                mbar_wait(&sm.bar[h], h ? ph1 : ph0);
+                if (h) ph1 ^= 1; else ph0 ^= 1;
+                // bitsets of the half: registers <- shared (all of them are <= L), two at a time
+                const uint32_t nbs = sm.h_nbs[h], nar = sm.h_nar[h];
+                for (uint32_t j = 0; j < nbs; j += 2) {
+                    const uint4 *s0 = reinterpret_cast<const uint4 *>(sm.ring[h] + sm.h_soff[sm.h_bs[h][j]]);
+                    const uint4 a0 = s0[tid], b0 = s0[tid + M2_THREADS];
+                    r0.x |= a0.x; r0.y |= a0.y; r0.z |= a0.z; r0.w |= a0.w;
+                    r1.x |= b0.x; r1.y |= b0.y; r1.z |= b0.z; r1.w |= b0.w;
+                    if (j + 1 < nbs) {
+                        const uint4 *s1 = reinterpret_cast<const uint4 *>(sm.ring[h] + sm.h_soff[sm.h_bs[h][j + 1]]);
+                        const uint4 a1 = s1[tid], b1 = s1[tid + M2_THREADS];
+                        r0.x |= a1.x; r0.y |= a1.y; r0.z |= a1.z; r0.w |= a1.w;
+                        r1.x |= b1.x; r1.y |= b1.y; r1.z |= b1.z; r1.w |= b1.w;
+                    }
+                }
+                // arrays and runs: one warp per container, shared-memory atomics on the accumulator
+                for (uint32_t j = wid; j < nar; j += M2_THREADS / 32) {
+                    const uint32_t q = sm.h_ar[h][j];
+                    uint32_t *dst = (L != POS_NONE && sm.s_pos[q] > L) ? sm.acc2 : sm.acc;
+                    const uint8_t *p = sm.ring[h] + sm.h_soff[q];
+                    if ((sm.s_tf[q] & 15) == T_ARRAY) acc_apply_array_s<0>(dst, p, sm.s_len[q], lane);
+                    else acc_apply_runs_s<0, true>(dst, p, sm.s_len[q], lane);
+                }
+                const uint32_t big = sm.h_big[h];
+                if (big != POS_NONE) {   // oversized run container: every warp takes a share, from global
+                    uint32_t *dst = (L != POS_NONE && sm.s_pos[big] > L) ? sm.acc2 : sm.acc;
+                    const uint32_t nr = sm.s_len[big], per_w = (nr + M2_THREADS / 32 - 1) / (M2_THREADS / 32);
+                    const uint32_t r_lo = min((uint32_t)wid * per_w, nr), r_hi = min(r_lo + per_w, nr);
+                    if (r_hi > r_lo)
+                        acc_apply_runs<0, true>(dst, S.payload + sm.s_off[big] + 4ull * r_lo, r_hi - r_lo, lane);
+                }
+                __syncthreads();   // the half is free again
+                staged--;
+                if (next < R) { issue(h); staged++; }
+                h ^= 1;
             }
         }
         __syncthreads();
@@ -489,7 +561,12 @@ void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t
     k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * 8, out, st);
     k_many2_fill<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
     if (ev_kernel_start) cudaEventRecord(ev_kernel_start, s);
-    k_or_many2<<<sms * 4, M2_THREADS, 0, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_or_many2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Many2Smem));
+        attr = true;
+    }
+    k_or_many2<<<sms * 2, M2_THREADS, sizeof(Many2Smem), s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
     k_many2_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
     g_launches += 5;
 }

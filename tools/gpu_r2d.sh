@@ -18,3 +18,6 @@ timeout 1500 python -m pytest tests -m gpu -x -q --timeout 900 2>&1 | tail -8 > 
 cat gpurun_out/pytest_gpu.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_compute_items -s 1 -c 1 \
    -f -o gpurun_out/prof_compute_r2b python tools/profile_target.py pairs 2 > gpurun_out/ncu_compute_r2b.out 2>&1
+for d in 0.3 0.03 0.003; do timeout 600 python tools/prof_many.py $d 3 2>&1 | tail -2; done > gpurun_out/many_tma.log 2>&1
+timeout 900 python tools/prof_many.py 0 3 1000 2>&1 | tail -2 >> gpurun_out/many_tma.log
+cat gpurun_out/many_tma.log
