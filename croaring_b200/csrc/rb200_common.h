@@ -141,9 +141,24 @@ struct Many2Index {
     uint32_t *unit_first;   // [nk] first work unit of the key
     uint32_t *unit_ki;      // [max_units] work unit -> live key index
     uint32_t *e_pos;        // [entries] input position of the participant
-    uint32_t *e_cont;       // [entries] its container
+    uint64_t *e_off;        // [entries] payload offset of its container in the slab
+    uint32_t *e_len;        // [entries] c_len of its container
     uint8_t *e_tf;          // [entries] type | full-run / full-bitset flags
 };
+
+// ---- single-pair fused path (rb200_fused.cu): packed input block (host-pinned -> device) and
+// output block (mapped pinned host memory the kernel writes directly)
+constexpr int FUSED_WARPS = 8;
+constexpr uint32_t FUSED_MAX_ITEMS = 512;          // containers of both operands together
+constexpr uint32_t FUSED_IN_BYTES = 1u << 20;      // packed operands must fit
+constexpr uint32_t FUSED_OUT_BYTES = 2u << 20;     // result slots must fit (else: the batched path)
+struct FusedHdr { uint32_t na, nb, o_key, o_type, o_shared, o_card, o_len, o_off, pad[8]; };   // 64 B; offsets from the block start
+struct FusedOutHdr { volatile uint32_t seq; uint32_t error, n_out, pad; };
+constexpr uint32_t FUSED_OUT_KEY = 64, FUSED_OUT_TYPE = FUSED_OUT_KEY + 2 * FUSED_MAX_ITEMS,
+                   FUSED_OUT_CARD = FUSED_OUT_TYPE + FUSED_MAX_ITEMS, FUSED_OUT_LEN = FUSED_OUT_CARD + 4 * FUSED_MAX_ITEMS,
+                   FUSED_OUT_OFF = FUSED_OUT_LEN + 4 * FUSED_MAX_ITEMS, FUSED_OUT_PAYLOAD = FUSED_OUT_OFF + 4 * FUSED_MAX_ITEMS;
+bool launch_pair_fused(int op, const uint8_t *d_in, uint8_t *out_mapped, uint32_t out_bytes, int rules, uint32_t seq,
+                       cudaStream_t s);
 
 // --- launch wrappers (rb200_kernels.cu); every wrapper bumps g_launches -----------------
 extern unsigned long long g_launches;
@@ -184,7 +199,7 @@ void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uin
 void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
                      const Many2Index &ix, uint32_t max_units, uint32_t *scratch, uint32_t *tickets,
                      uint32_t scratch_slots, SetOut out, uint32_t *card_per_key, OpStats *st, int sms,
-                     cudaStream_t s, cudaEvent_t ev_kernel_start);
+                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma);
 
 void launch_pack_scan(const uint64_t *bytes, const uint32_t *cnts, uint32_t n, uint64_t *off,
                       uint64_t *beg, cudaStream_t s);

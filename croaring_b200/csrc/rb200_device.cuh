@@ -333,6 +333,35 @@ __device__ __forceinline__ void acc_apply_array(uint32_t *acc, const uint8_t *sr
     }
 }
 
+// same with the first vector of every lane already loaded by the caller (several containers in flight)
+template <int MODE>
+__device__ __forceinline__ void acc_apply_array_first(uint32_t *acc, const uint8_t *src, uint32_t n, uint4 q,
+                                                      int lane) {
+    const uint4 *v4 = reinterpret_cast<const uint4 *>(src);
+    const uint32_t nvec = (n + 7) >> 3;
+    for (uint32_t i = lane; i < nvec; i += 32) {
+        if (i != (uint32_t)lane) q = __ldg(v4 + i);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const uint32_t left = n - i * 8;
+        uint32_t cur_w = (w[0] & 0xffffu) >> 5, cur_m = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+            const uint32_t wi = v >> 5, bit = 1u << (v & 31);
+            if (k == 0 || k < (int)left) {
+                if (wi != cur_w) {
+                    acc_atom<MODE>(acc + cur_w, cur_m);
+                    cur_w = wi;
+                    cur_m = bit;
+                } else {
+                    cur_m |= bit;
+                }
+            }
+        }
+        acc_atom<MODE>(acc + cur_w, cur_m);
+    }
+}
+
 // Warp-collective: every lane brings one closed range [lo,hi] (valid==false: none).
 // Boundary words use shared-memory atomics; interior words are owned by exactly one range
 // (ranges of one container never overlap) so they are plain stores; long interiors are

@@ -114,6 +114,9 @@ struct Ctx {
     // second-generation or_many (rb200_many2.cu): per-key tables + split-key scratch (kept zeroed)
     uint32_t *d_m2_tables = nullptr;   // 7 x 65536 u32: count | units16 | fill | start | slices | scratch | unit_first
     uint32_t *d_m2_scratch = nullptr, *d_m2_tickets = nullptr;
+    // single-pair fused path (rb200_fused.cu): packed operands (pinned + device), mapped result block
+    uint8_t *h_fused_in = nullptr, *d_fused_in = nullptr, *h_fused_out = nullptr, *d_fused_out = nullptr;
+    uint32_t fused_seq = 0;
     int sms = 148;
     std::multimap<size_t, void *> dpool, hpool;
     std::mutex alloc_mu;  // dpool / hpool are also used by the background downloader thread
@@ -179,6 +182,11 @@ bool ctx_init(int device = -1) {
     CK(cudaMalloc(&g.d_m2_tickets, M2_SCRATCH_SLOTS * sizeof(uint32_t)));
     CK(cudaMemset(g.d_m2_scratch, 0, (size_t)M2_SCRATCH_SLOTS * M2_SCRATCH_WORDS * sizeof(uint32_t)));
     CK(cudaMemset(g.d_m2_tickets, 0, M2_SCRATCH_SLOTS * sizeof(uint32_t)));
+    CK(cudaHostAlloc(&g.h_fused_in, FUSED_IN_BYTES, cudaHostAllocDefault));
+    CK(cudaMalloc(&g.d_fused_in, FUSED_IN_BYTES));
+    CK(cudaHostAlloc(&g.h_fused_out, FUSED_OUT_BYTES, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&g.d_fused_out, g.h_fused_out, 0));
+    memset(g.h_fused_out, 0, 64);
     CK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, g.device));
     g_halloc.look();  // resolve the host allocator once, before any worker thread exists
     g.inited = true;
@@ -1555,7 +1563,7 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
     uint64_t tot_kib = 0;
     for (size_t i = 0; i < n; i++) tot_kib += (S->h_bytes[idx ? idx[i] : i] >> 10) + 1;
     const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>(tot, std::min<uint64_t>(65536, tot) + tot_kib / 32 + 1));
-    const size_t e_bytes = al256(4 * tot) * 2 + al256(tot) + al256(4 * max_units);
+    const size_t e_bytes = al256(4 * tot) * 2 + al256(8 * tot) + al256(tot) + al256(4 * max_units);
     uint8_t *d_index = nullptr;
     if (ok && !use_v1) { d_index = (uint8_t *)dev_alloc(e_bytes); ok = d_index != nullptr; }
     if (ok && !use_v1) {
@@ -1571,15 +1579,20 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         ix.key_scratch = g.d_m2_tables + 5 * 65536;
         ix.unit_first = g.d_m2_tables + 6 * 65536;
         ix.keys = g.d_keys;
-        ix.e_pos = (uint32_t *)d_index;
-        ix.e_cont = (uint32_t *)(d_index + al256(4 * tot));
-        ix.e_tf = d_index + 2 * al256(4 * tot);
-        ix.unit_ki = (uint32_t *)(d_index + 2 * al256(4 * tot) + al256(tot));
+        ix.e_off = (uint64_t *)d_index;
+        ix.e_pos = (uint32_t *)(d_index + al256(8 * tot));
+        ix.e_len = (uint32_t *)(d_index + al256(8 * tot) + al256(4 * tot));
+        ix.e_tf = d_index + al256(8 * tot) + 2 * al256(4 * tot);
+        ix.unit_ki = (uint32_t *)(d_index + al256(8 * tot) + 2 * al256(4 * tot) + al256(tot));
+        // operand staging by TMA bulk copies pays off when the containers are mostly bitsets
+        // (RB200_OR_MANY_TMA=0/1 forces the choice)
+        static const int tma_env = []() { const char *e = getenv("RB200_OR_MANY_TMA"); return e ? atoi(e) : -1; }();
+        const bool use_tma = tma_env >= 0 ? tma_env != 0 : (tot > 0 && tot_kib / tot >= 4);
         cudaMemsetAsync(g.d_m2_tables, 0, 3 * 65536 * sizeof(uint32_t), g.stream);
         if (want_ck) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
         launch_or_many2(vs, d_idx, (uint32_t)n, key_lo, key_hi, ix, (uint32_t)std::min<uint64_t>(max_units, 0xffffffffu),
                         g.d_m2_scratch, g.d_m2_tickets, M2_SCRATCH_SLOTS, R->out(), want_ck ? g.d_cardkey : nullptr,
-                        g.d_stats, g.sms, g.stream, g.evk0);
+                        g.d_stats, g.sms, g.stream, g.evk0, use_tma);
     }
     if (ok && use_v1) {
         cudaEventRecord(g.ev0, g.stream);
@@ -2943,8 +2956,123 @@ static void dropin_failed(const char *fn) {
     const char *e = getenv("RB200_STRICT");
     if (e && e[0] == '1') abort();
 }
+// One small pair in ONE launch (rb200_fused.cu).  Returns 1: *out holds the result; 0: the pair
+// does not qualify (too many containers / bytes) — use the batched path; -1: failure (t_err).
+static int pair_fused(int op, const roaring_bitmap_t *r1, const roaring_bitmap_t *r2, int rules,
+                      roaring_bitmap_t **out) {
+    static const bool off = []() { const char *e = getenv("RB200_NO_FUSED"); return e && e[0] == '1'; }();
+    if (off || !ctx_init()) return off ? 0 : -1;
+    const roaring_array_t *ra[2] = {&r1->high_low_container, &r2->high_low_container};
+    const uint32_t na = (uint32_t)ra[0]->size, nb = (uint32_t)ra[1]->size, n = na + nb;
+    if (n > FUSED_MAX_ITEMS) return 0;
+    // layout of the packed block
+    FusedHdr hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.na = na;
+    hdr.nb = nb;
+    size_t o = sizeof(FusedHdr);
+    hdr.o_key = (uint32_t)o; o += (2 * (size_t)n + 15) & ~(size_t)15;
+    hdr.o_type = (uint32_t)o; o += ((size_t)n + 15) & ~(size_t)15;
+    hdr.o_shared = (uint32_t)o; o += ((size_t)n + 15) & ~(size_t)15;
+    hdr.o_card = (uint32_t)o; o += (4 * (size_t)n + 15) & ~(size_t)15;
+    hdr.o_len = (uint32_t)o; o += (4 * (size_t)n + 15) & ~(size_t)15;
+    hdr.o_off = (uint32_t)o; o += (4 * (size_t)n + 15) & ~(size_t)15;
+    uint8_t *h = g.h_fused_in;
+    uint16_t *c_key = (uint16_t *)(h + hdr.o_key);
+    uint8_t *c_type = h + hdr.o_type, *c_shared = h + hdr.o_shared;
+    uint32_t *c_card = (uint32_t *)(h + hdr.o_card), *c_len = (uint32_t *)(h + hdr.o_len), *c_off = (uint32_t *)(h + hdr.o_off);
+    uint64_t E[2] = {0, 0};
+    uint32_t ci = 0;
+    for (int side = 0; side < 2; side++) {
+        for (int32_t i = 0; i < ra[side]->size; i++, ci++) {
+            uint8_t t = ra[side]->typecodes[i];
+            const bool was_shared = t == T_SHARED;
+            const void *c = unwrap_shared(ra[side]->containers[i], t);
+            uint32_t card = host_container_card(c, t), len;
+            const uint8_t *p;
+            if (t == T_BITSET) {
+                len = 1024;
+                p = (const uint8_t *)((const bitset_container_t *)c)->words;
+                if (((const bitset_container_t *)c)->cardinality < 0) return 0;   // lazy state: batched path
+            } else if (t == T_ARRAY) {
+                len = card;
+                p = (const uint8_t *)((const array_container_t *)c)->array;
+            } else {
+                len = (uint32_t)((const run_container_t *)c)->n_runs;
+                p = (const uint8_t *)((const run_container_t *)c)->runs;
+            }
+            const uint32_t sb = stored_bytes(t, len), sb16 = round16(sb);
+            if (o + sb16 > FUSED_IN_BYTES) return 0;
+            memcpy(h + o, p, sb);
+            if (sb16 > sb) memset(h + o + sb, 0, sb16 - sb);
+            c_key[ci] = ra[side]->keys[i];
+            c_type[ci] = t;
+            c_shared[ci] = was_shared ? 1 : 0;
+            c_card[ci] = card;
+            c_len[ci] = len;
+            c_off[ci] = (uint32_t)o;
+            o += sb16;
+            E[side] += effective_bytes(t, len, card);
+        }
+    }
+    // the result slots must fit the mapped block (same bound as PairBuf::build)
+    const uint64_t need = FUSED_OUT_PAYLOAD + (op == OP_AND ? std::min(E[0], E[1]) : op == OP_ANDNOT ? E[0] : E[0] + E[1]);
+    if (need > FUSED_OUT_BYTES) return 0;
+    memcpy(h, &hdr, sizeof(hdr));
+    const uint32_t seq = ++g.fused_seq ? g.fused_seq : ++g.fused_seq;
+    FusedOutHdr *oh = (FusedOutHdr *)g.h_fused_out;
+    if (cudaMemcpyAsync(g.d_fused_in, h, o, cudaMemcpyHostToDevice, g.stream) != cudaSuccess ||
+        !launch_pair_fused(op, g.d_fused_in, g.d_fused_out, FUSED_OUT_BYTES, rules, seq, g.stream)) {
+        t_err = std::string("fused pair: ") + cudaGetErrorString(cudaGetLastError());
+        return -1;
+    }
+    // wait for the sequence word in mapped memory (the kernel writes it last, after a system fence);
+    // a short spin, then the ordinary stream synchronisation
+    bool seen = false;
+    for (int spin = 0; spin < 20000 && !seen; spin++) {
+        seen = oh->seq == seq;
+        if (!seen) __builtin_ia32_pause();
+    }
+    if (!seen) {
+        const cudaError_t e = cudaStreamSynchronize(g.stream);
+        if (e != cudaSuccess || oh->seq != seq) {
+            t_err = std::string("fused pair: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "result never arrived");
+            return -1;
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (oh->error == 2) return 0;   // slots did not fit after all: batched path
+    if (oh->error) { t_err = "fused pair: internal: result slot bound exceeded"; return -1; }
+    const uint32_t no = oh->n_out;
+    roaring_bitmap_t *r = bitmap_alloc((int32_t)no);
+    if (!r) { t_err = "out of host memory"; return -1; }
+    roaring_array_t *rr = &r->high_low_container;
+    rr->flags = (ra[0]->flags | ra[1]->flags) & FLAG_COW;   // roaring.c:738, 890
+    const uint8_t *ob = g.h_fused_out;
+    const uint16_t *o_key = (const uint16_t *)(ob + FUSED_OUT_KEY);
+    const uint8_t *o_type = ob + FUSED_OUT_TYPE;
+    const uint32_t *o_card = (const uint32_t *)(ob + FUSED_OUT_CARD), *o_len = (const uint32_t *)(ob + FUSED_OUT_LEN),
+                   *o_off = (const uint32_t *)(ob + FUSED_OUT_OFF);
+    for (uint32_t k = 0; k < no; k++) {
+        void *hc = container_from_payload(o_type[k], o_card[k], o_len[k], ob + o_off[k]);
+        if (!hc) { bitmap_free_host(r); t_err = "out of host memory"; return -1; }
+        rr->containers[k] = hc;
+        rr->keys[k] = o_key[k];
+        rr->typecodes[k] = o_type[k];
+        rr->size = (int32_t)k + 1;
+    }
+    *out = r;
+    return 1;
+}
+
 static roaring_bitmap_t *dropin_pair(int op, const roaring_bitmap_t *r1, const roaring_bitmap_t *r2) {
     roaring_bitmap_t *out = nullptr;
+    {
+        std::lock_guard<std::recursive_mutex> lk(g.mu);
+        const int f = pair_fused(op, r1, r2, 0, &out);
+        if (f == 1) return out;
+        if (f < 0) return nullptr;
+    }
     if (rb200_batch_op_host(op, &r1, &r2, 1, &out) != 0) return nullptr;
     return out;
 }
@@ -2983,6 +3111,12 @@ roaring_bitmap_t *roaring_bitmap_or_many(size_t number, const roaring_bitmap_t *
 static void swap_into(roaring_bitmap_t *x1, roaring_bitmap_t *out);
 static void dropin_inplace(int op, roaring_bitmap_t *x1, const roaring_bitmap_t *x2, int rules = RULES_INPLACE) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (rules == RULES_INPLACE) {   // (the lazy in-place twins take the batched path)
+        roaring_bitmap_t *fo = nullptr;
+        const int f = pair_fused(op, x1, x2, RULES_INPLACE, &fo);
+        if (f == 1) { swap_into(x1, fo); return; }
+        if (f < 0) { dropin_failed("roaring_bitmap_*_inplace"); return; }
+    }
     const roaring_bitmap_t *both[2] = {x1, x2};
     rb200_set *S = rb200_set_upload(both, 2);
     if (!S) { dropin_failed("roaring_bitmap_*_inplace"); return; }

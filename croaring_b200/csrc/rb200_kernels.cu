@@ -10,6 +10,7 @@
 //   k_or_many         CTA per key: N-way union (roaring.c:775-790, 2509-2682, 2845) with the
 //                     reference's full-container state machine (containers.h:1342-1404).
 #include "rb200_device.cuh"
+#include "rb200_cells.cuh"
 
 namespace rb200 {
 
@@ -45,13 +46,6 @@ __device__ __forceinline__ uint32_t upper_bound_u16(const uint16_t *a, uint32_t 
     return lo;
 }
 
-#ifndef RB200_MERGE_LIMIT
-#define RB200_MERGE_LIMIT 2048   // array x array unions up to this many staged values take the merge path
-#endif
-#ifndef RB200_RANK_SCATTER
-#define RB200_RANK_SCATTER 1     // larger ones: accumulator + rank-scatter emission (0: find-first-set emission)
-#endif
-
 // code-path class of a matched cell (see rb200_common.h CLS_*); mirrors the branches of cell_compute
 __device__ __forceinline__ int cell_class(int op, int tA, int tB, uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB) {
     const bool bA = tA == T_BITSET, bB = tB == T_BITSET;
@@ -69,9 +63,12 @@ __global__ void __launch_bounds__(128)
 k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
              const uint32_t *__restrict__ ib, const uint64_t *__restrict__ item_off,
              uint32_t npairs, int op, bool card_only, int rules, Items it, OpStats *st) {
+    __shared__ unsigned int s_cls[N_CLS];   // live items per class of this block (one global atomic per class at the end)
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (threadIdx.x < N_CLS) s_cls[threadIdx.x] = 0;
+    __syncthreads();
     for (uint32_t p = warp; p < npairs; p += nwarps) {
         const uint32_t a = ia[p], b = ib[p];
         const uint32_t a0 = A.bm_beg[a], na = A.bm_cnt[a];
@@ -137,221 +134,79 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
                 it.ocard[idx] = 0;
                 it.olen[idx] = 0;
             }
-            if (it.cls) {   // live items per class (one atomic per class present in this stripe)
+            if (it.cls) {   // live items per class
 #pragma unroll
                 for (int c = 0; c < N_CLS; c++) {
                     const unsigned m = __ballot_sync(FULLMASK, cls == c);
-                    if (m && lane == 0) atomicAdd(&st->cls_count[c], (unsigned)__popc(m));
+                    if (m && lane == 0) atomicAdd(&s_cls[c], (unsigned)__popc(m));
                 }
             }
         }
     }
+    __syncthreads();
+    if (it.cls && threadIdx.x < N_CLS && s_cls[threadIdx.x]) atomicAdd(&st->cls_count[threadIdx.x], s_cls[threadIdx.x]);
 }
 
-// item ids grouped by class: order[prefix(class) + k]; warp-aggregated cursors
+// item ids grouped by class: order[prefix(class) + k].  A block takes chunks of 2048 item slots
+// (256 per warp); per chunk ONE global atomic per class reserves the block's range, the ranks
+// inside come from ballots and an 8-warp scan in shared memory.
 __global__ void __launch_bounds__(256)
 k_order_items(Items it, uint64_t W, OpStats *st) {
-    const int lane = threadIdx.x & 31;
-    uint32_t pre[N_CLS];
-    uint32_t run = 0;
+    __shared__ uint32_t s_wcnt[8][N_CLS], s_base[N_CLS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t pre_l = 0;   // lane c (< N_CLS): first slot of class c in the order list
+    for (int c = 0; c < N_CLS; c++)
+        if (c < lane) pre_l += st->cls_count[c];
+    for (uint64_t chunk = (uint64_t)blockIdx.x * 2048; chunk < W; chunk += (uint64_t)gridDim.x * 2048) {
+        const uint64_t w0 = chunk + (uint64_t)wid * 256;
+        int cl[8];
+        uint32_t mycnt = 0;   // lane c: this warp's items of class c
 #pragma unroll
-    for (int c = 0; c < N_CLS; c++) { pre[c] = run; run += st->cls_count[c]; }
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t base = warp * 32; base < W; base += nwarps * 32) {
-        const uint64_t i = base + lane;
-        const int c = i < W ? (int)it.cls[i] : CLS_NONE;
+        for (int s8 = 0; s8 < 8; s8++) {
+            const uint64_t i = w0 + s8 * 32 + lane;
+            cl[s8] = i < W ? (int)it.cls[i] : CLS_NONE;
 #pragma unroll
-        for (int cc = 0; cc < N_CLS; cc++) {
-            const unsigned m = __ballot_sync(FULLMASK, c == cc);
-            if (!m) continue;
-            const int leader = __ffs(m) - 1;
-            uint32_t b = 0;
-            if (lane == leader) b = atomicAdd(&st->cls_cursor[cc], (unsigned)__popc(m));
-            b = __shfl_sync(FULLMASK, b, leader);
-            if (c == cc) it.order[pre[cc] + b + __popc(m & lanemask_lt())] = (uint32_t)i;
+            for (int cc = 0; cc < N_CLS; cc++) {
+                const unsigned m = __ballot_sync(FULLMASK, cl[s8] == cc);
+                if (lane == cc) mycnt += __popc(m);
+            }
         }
+        if (lane < N_CLS) s_wcnt[wid][lane] = mycnt;
+        __syncthreads();
+        if (wid == 0 && lane < N_CLS) {
+            uint32_t run = 0;
+            for (int w = 0; w < 8; w++) {
+                const uint32_t t = s_wcnt[w][lane];
+                s_wcnt[w][lane] = run;
+                run += t;
+            }
+            s_base[lane] = run ? atomicAdd(&st->cls_cursor[lane], run) : 0u;
+        }
+        __syncthreads();
+        uint32_t nxt = lane < N_CLS ? pre_l + s_base[lane] + s_wcnt[wid][lane] : 0u;   // lane c: next slot of class c
+#pragma unroll
+        for (int s8 = 0; s8 < 8; s8++) {
+            const uint64_t i = w0 + s8 * 32 + lane;
+#pragma unroll
+            for (int cc = 0; cc < N_CLS; cc++) {
+                const unsigned m = __ballot_sync(FULLMASK, cl[s8] == cc);
+                if (!m) continue;
+                const uint32_t b = __shfl_sync(FULLMASK, nxt, cc);
+                if (cl[s8] == cc) it.order[b + __popc(m & lanemask_lt())] = (uint32_t)i;
+                if (lane == cc) nxt += __popc(m);
+            }
+        }
+        __syncthreads();
     }
 }
 
-// ------------------------------------------------------------------------------ grid cells
-// Evaluate one matched cell on the warp's accumulator and write the result payload.
+// (the grid cells themselves — cell_compute — live in rb200_cells.cuh, shared with rb200_fused.cu)
+
+#ifndef RB200_CI_MINBLOCKS
+#define RB200_CI_MINBLOCKS 6   // resident CTAs per SM the register allocation is held to (6 = what the 36 KiB of shared memory allow)
+#endif
 template <int OP, bool LAZY>
-__device__ __forceinline__ void
-cell_compute(uint32_t *acc, uint16_t *pre, int tA, int tB, const uint8_t *pa, const uint8_t *pb,
-             uint32_t cA, uint32_t cB, uint32_t lA, uint32_t lB, uint8_t *out, uint32_t cap,
-             int lane, int &otype, uint32_t &ocard, uint32_t &olen, unsigned int *err,
-             int rules, bool unkA) {
-    // ---- run x run / array x run with few intervals: boundary sweep, no accumulator ---------
-    constexpr int op = OP;
-    const bool inplace_rules = (rules & RULES_INPLACE) != 0;
-    constexpr bool lazy = LAZY && (OP == OP_OR || OP == OP_XOR);
-    if (!lazy && (tA == T_RUN || tB == T_RUN) && tA != T_BITSET && tB != T_BITSET &&
-        (tA == T_RUN ? lA : cA) + (tB == T_RUN ? lB : cB) <= 512u) {
-        if (interval_cell(acc, op, tA, tB, pa, pb, cA, cB, lA, lB, out, cap, lane, otype, ocard, olen))
-            return;
-    }
-
-    // ---- result is always an array and one side is an array: filter, no re-encode --------
-    if (op == OP_AND && (tA == T_ARRAY || tB == T_ARRAY)) {
-        // filter the array side through the other side's bits
-        const bool arrA = (tA == T_ARRAY) && !(tB == T_ARRAY && cB < cA);  // filter the smaller
-        const uint8_t *parr = arrA ? pa : pb;
-        const uint32_t narr = arrA ? cA : cB;
-        const int to = arrA ? tB : tA;
-        const uint8_t *po = arrA ? pb : pa;
-        const uint32_t lo = arrA ? lB : lA;
-        uint32_t n;
-        // (the filter writes only the values it keeps: at most min(cA, cB) of them)
-        if (2 * min(cA, cB) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-        if (to == T_BITSET && narr < 192) {  // few probes: test the bits where they are
-            n = filter_array<false, true>(parr, narr, reinterpret_cast<const uint32_t *>(po),
-                                          reinterpret_cast<uint16_t *>(out), lane);
-        } else {
-            acc_load(acc, to, po, lo, lane);
-            n = filter_array<false, true>(parr, narr, acc, reinterpret_cast<uint16_t *>(out), lane);
-            __syncwarp();
-        }
-        otype = n ? T_ARRAY : 0;
-        ocard = olen = n;
-        return;
-    }
-    if (op == OP_ANDNOT && tA == T_ARRAY) {
-        uint32_t n;
-        if (2 * cA > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-        if (tB == T_BITSET && cA < 192) {
-            n = filter_array<true, true>(pa, cA, reinterpret_cast<const uint32_t *>(pb),
-                                         reinterpret_cast<uint16_t *>(out), lane);
-        } else {
-            acc_load(acc, tB, pb, lB, lane);
-            n = filter_array<true, true>(pa, cA, acc, reinterpret_cast<uint16_t *>(out), lane);
-            __syncwarp();
-        }
-        otype = n ? T_ARRAY : 0;
-        ocard = olen = n;
-        return;
-    }
-
-    // ---- array x array union / xor whose result is known to stay an array: warp merge path ---
-    // (measured on B200, weather_sept_85 all-pairs OR: staging limit 2032 values -> 1.41 ms,
-    //  1024 -> 1.50 ms, split merge up to 4064 -> 2.06 ms; the accumulator round trip wins above)
-    // (lazy rules: only unions / xors of at most ARRAY_LAZY_LOWERBOUND values stay arrays)
-    const bool lazy_eager = lazy && OP == OP_XOR && inplace_rules;  // container_lazy_ixor A,A is eager
-    if ((op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY &&
-        ((cA + 7) & ~7u) + ((cB + 7) & ~7u) <= (uint32_t)RB200_MERGE_LIMIT &&
-        (!lazy || lazy_eager || (cA + cB <= 1024u && !(rules & RULES_CONV)))) {
-        if (round16(2 * (cA + cB)) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-        const uint32_t n = (op == OP_OR) ? merge_arrays<false>(acc, pa, cA, pb, cB, out, lane)
-                                         : merge_arrays<true>(acc, pa, cA, pb, cB, out, lane);
-        otype = n ? T_ARRAY : 0;  // cA + cB <= 4096 -> array (mixed_union.c:162-176, mixed_xor.c:196-205)
-        ocard = olen = n;
-        return;
-    }
-
-    // ---- larger array x array unions / symmetric differences: accumulator + rank-scatter -------
-    if (RB200_RANK_SCATTER && !lazy && (op == OP_OR || op == OP_XOR) && tA == T_ARRAY && tB == T_ARRAY) {
-        const uint16_t *a16 = reinterpret_cast<const uint16_t *>(pa), *b16 = reinterpret_cast<const uint16_t *>(pb);
-        const uint32_t vlo = min((uint32_t)a16[0], (uint32_t)b16[0]);
-        const uint32_t vhi = max((uint32_t)a16[cA - 1], (uint32_t)b16[cB - 1]);
-        const int s0 = (int)(vlo >> 12), s1 = (int)(vhi >> 12) + 1;   // stripes of 4096 values that can hold a bit
-        acc_zero_span(acc, lane, s0, s1);
-        __syncwarp();
-        acc_apply_array<0>(acc, pa, cA, lane);
-        __syncwarp();
-        if (op == OP_OR) acc_apply_array<0>(acc, pb, cB, lane);
-        else acc_apply_array<1>(acc, pb, cB, lane);
-        __syncwarp();
-        const int card = acc_prefix_span(acc, pre, lane, s0, s1);
-        __syncwarp();
-        if (card == 0) { otype = 0; ocard = olen = 0; return; }
-        const int t = decide_type(op, tA, tB, cA, cB, lA, lB, card, 0);   // array x array: never a run
-        if (stored_bytes(t, t == T_BITSET ? 1024u : (uint32_t)card) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-        if (t == T_BITSET) {
-            // stripes outside the span were not zeroed: complete the accumulator before the copy
-            acc_zero_span(acc, lane, 0, s0);
-            acc_zero_span(acc, lane, s1, 16);
-            __syncwarp();
-            acc_store_bitset(acc, out, lane);
-        } else if (op == OP_OR) {
-            rank_store_array<false>(acc, pre, pa, cA, reinterpret_cast<uint16_t *>(out), lane);
-            rank_store_array<false>(acc, pre, pb, cB, reinterpret_cast<uint16_t *>(out), lane);
-        } else {
-            rank_store_array<true>(acc, pre, pa, cA, reinterpret_cast<uint16_t *>(out), lane);
-            rank_store_array<true>(acc, pre, pb, cB, reinterpret_cast<uint16_t *>(out), lane);
-        }
-        __syncwarp();
-        otype = t;
-        ocard = (uint32_t)card;
-        olen = t == T_BITSET ? 1024u : (uint32_t)card;
-        return;
-    }
-
-    // ---- general path: acc = A op B --------------------------------------------------------
-    int card = -1, nruns = 0;
-    if (tA == T_BITSET && tB == T_BITSET) {
-        switch (op) {
-            case OP_AND: card = acc_bitset_op_bitset<OP_AND>(acc, pa, pb, lane); break;
-            case OP_OR: card = acc_bitset_op_bitset<OP_OR>(acc, pa, pb, lane); break;
-            case OP_XOR: card = acc_bitset_op_bitset<OP_XOR>(acc, pa, pb, lane); break;
-            default: card = acc_bitset_op_bitset<OP_ANDNOT>(acc, pa, pb, lane); break;
-        }
-        __syncwarp();
-    } else {
-        acc_load(acc, tA, pa, lA, lane);
-        if (tB == T_BITSET) {
-            switch (op) {
-                case OP_AND: acc_op_bitset<OP_AND>(acc, pb, lane); break;
-                case OP_OR: acc_op_bitset<OP_OR>(acc, pb, lane); break;
-                case OP_XOR: acc_op_bitset<OP_XOR>(acc, pb, lane); break;
-                default: acc_op_bitset<OP_ANDNOT>(acc, pb, lane); break;
-            }
-        } else if (tB == T_ARRAY) {
-            switch (op) {
-                case OP_AND: acc_and_array(acc, pb, cB, lane); break;  // not reached (filter path)
-                case OP_OR: acc_apply_array<0>(acc, pb, cB, lane); break;
-                case OP_XOR: acc_apply_array<1>(acc, pb, cB, lane); break;
-                default: acc_apply_array<2>(acc, pb, cB, lane); break;
-            }
-        } else {
-            switch (op) {
-                case OP_AND: acc_and_runs(acc, pb, lB, lane); break;
-                case OP_OR: acc_apply_runs<0, false>(acc, pb, lB, lane); break;
-                case OP_XOR: acc_apply_runs<1, false>(acc, pb, lB, lane); break;
-                default: acc_apply_runs<2, false>(acc, pb, lB, lane); break;
-            }
-        }
-        __syncwarp();
-    }
-    const bool want_runs = lazy ? ((tA == T_RUN || tB == T_RUN) && tA != T_BITSET && tB != T_BITSET)
-                                : cell_needs_runs(op, tA, tB);
-    if (card < 0 || want_runs) acc_count(acc, lane, want_runs, card, nruns);
-    if (card == 0) { otype = 0; ocard = olen = 0; return; }
-    bool unknown = false;
-    int t = lazy ? decide_type_lazy(op, rules, tA, tB, cA, cB, lA, lB, unkA, card, nruns, unknown)
-                 : decide_type(op, tA, tB, cA, cB, lA, lB, card, nruns);
-    if (OP == OP_OR && inplace_rules && !lazy) {
-        // roaring_bitmap_or_inplace: a full left container is left untouched (roaring.c:1081-1083)
-        // and container_ior turns a saturated bitset|bitset into the full run (containers.h:1234-1242)
-        const bool a_full = is_full_run(tA, lA, cA) || (tA == T_BITSET && cA == 65536u);
-        if (a_full) t = tA;
-        else if (tA == T_BITSET && tB == T_BITSET && card == 65536) t = T_RUN;
-    }
-    if (t == T_RUN && !want_runs) {  // bitset OR full-run -> [0,65535]
-        nruns = 1;
-    }
-    const uint32_t len = (t == T_BITSET) ? 1024u : (t == T_ARRAY ? (uint32_t)card : (uint32_t)nruns);
-    if (stored_bytes(t, len) > cap) { if (lane == 0) atomicExch(err, 1u); otype = 0; return; }
-    if (t == T_BITSET) acc_store_bitset(acc, out, lane);
-    else if (t == T_ARRAY) acc_emit_array(acc, reinterpret_cast<uint16_t *>(out), lane);
-    else acc_emit_runs(acc, reinterpret_cast<uint16_t *>(out), lane);
-    __syncwarp();
-    otype = t;
-    ocard = (uint32_t)card | (unknown ? CARD_UNKNOWN : 0u);
-    olen = len;
-}
-
-template <int OP, bool LAZY>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RB200_CI_MINBLOCKS)
 k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 uint64_t slab_cap, OpStats *st, int rules) {
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
@@ -369,7 +224,8 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
         for (int c = 0; c < N_CLS; c++) live += st->cls_count[c];
         W = live;
     }
-    const unsigned long long TICKET = (W >= 8ull * ((unsigned long long)gridDim.x * 4)) ? 4ull : 1ull;
+    const unsigned long long TICKET = (W >= 32ull * ((unsigned long long)gridDim.x * 4)) ? 8ull
+                                      : (W >= 8ull * ((unsigned long long)gridDim.x * 4)) ? 4ull : 1ull;
     unsigned long long tk = 0;
     if (lane == 0) tk = atomicAdd(&st->work_counter, TICKET);
     tk = __shfl_sync(FULLMASK, tk, 0);
@@ -377,47 +233,83 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
         unsigned long long next = 0;
         if (lane == 0) next = atomicAdd(&st->work_counter, TICKET);
         const unsigned long long tend = tk + TICKET < W ? tk + TICKET : W;
-        for (unsigned long long slot = tk; slot < tend; slot++) {
-            const unsigned long long item = it.order ? (unsigned long long)it.order[slot] : slot;
-            const int kind = it.kind[item];
+        // ---- metadata of the whole ticket, fetched by its first lanes in parallel: the four
+        // dependent levels (order -> item -> container -> payload) cost one round trip per LEVEL and
+        // ticket instead of one per level and ITEM; the fields travel by shuffle
+        const unsigned long long myslot = tk + lane;
+        const bool mine = lane < (int)TICKET && myslot < tend;
+        unsigned long long m_item = 0, m_off = 0, m_pa = 0, m_pb = 0;
+        int m_kind = K_HOLE;
+        uint32_t m_cap = 0, m_types = 0, m_cA = 0, m_cB = 0, m_lA = 0, m_lB = 0, m_flags = 0;
+        if (mine) {
+            m_item = it.order ? (unsigned long long)it.order[myslot] : myslot;
+            m_kind = it.kind[m_item];
+            if (m_kind != K_HOLE) {
+                m_off = it.slot_off[m_item];
+                m_cap = it.slot_cap[m_item];
+                if (m_kind == K_COMPUTE) {
+                    const uint32_t ca = it.ca[m_item], cb = it.cb[m_item];
+                    m_types = (uint32_t)A.c_type[ca] | ((uint32_t)B.c_type[cb] << 8);
+                    m_cA = A.c_card[ca];
+                    m_cB = B.c_card[cb];
+                    m_lA = A.c_len[ca];
+                    m_lB = B.c_len[cb];
+                    m_pa = A.c_off[ca];
+                    m_pb = B.c_off[cb];
+                    if ((rules & (RULES_INPLACE | RULES_LAZY)) == RULES_INPLACE && A.c_src[ca] == SRC_SHARED) m_flags = 1;
+                } else {
+                    const SetView &S = (m_kind == K_COPY_A) ? A : B;
+                    const uint32_t c = (m_kind == K_COPY_A) ? it.ca[m_item] : it.cb[m_item];
+                    m_types = S.c_type[c];
+                    m_cA = S.c_card[c];
+                    m_lA = S.c_len[c];
+                    m_pa = S.c_off[c];
+                }
+            }
+        }
+        uint32_t r_otype = 0, r_ocard = 0, r_olen = 0;   // results of MY item (lane j keeps item j's)
+        const int nslots = (int)(tend - tk);
+        for (int j = 0; j < nslots; j++) {
+            const int kind = __shfl_sync(FULLMASK, m_kind, j);
             if (kind == K_HOLE) continue;
-            const uint64_t off = it.slot_off[item];
-            const uint32_t cap = it.slot_cap[item];
+            const uint64_t off = __shfl_sync(FULLMASK, m_off, j);
+            const uint32_t cap = __shfl_sync(FULLMASK, m_cap, j);
+            const uint32_t types = __shfl_sync(FULLMASK, m_types, j);
+            const uint32_t cA = __shfl_sync(FULLMASK, m_cA, j), lA = __shfl_sync(FULLMASK, m_lA, j);
+            const uint64_t pa = __shfl_sync(FULLMASK, m_pa, j);
             int otype = 0;
             uint32_t ocard = 0, olen = 0;
             if (off + cap > slab_cap) {
                 if (lane == 0) atomicExch(&st->error, 2u);
             } else if (kind == K_COMPUTE) {
-                const uint32_t ca = it.ca[item], cb = it.cb[item];
-                const uint32_t rawA = A.c_card[ca];
+                const uint32_t cB = __shfl_sync(FULLMASK, m_cB, j), lB = __shfl_sync(FULLMASK, m_lB, j);
+                const uint64_t pb = __shfl_sync(FULLMASK, m_pb, j);
                 // in-place twins: a SHARED left container takes the functional cell (roaring.c:1085-1088);
                 // the lazy in-place twins work on a writable copy instead (roaring.c:2636)
                 int cell_rules = rules;
-                if ((rules & (RULES_INPLACE | RULES_LAZY)) == RULES_INPLACE && A.c_src[ca] == SRC_SHARED)
-                    cell_rules &= ~RULES_INPLACE;
-                cell_compute<OP, LAZY>(acc, pre, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
-                             B.payload + B.c_off[cb], rawA & CARD_MASK, B.c_card[cb] & CARD_MASK,
-                             A.c_len[ca], B.c_len[cb], slab + off, cap, lane, otype, ocard, olen,
-                             &st->error, cell_rules, (rawA & CARD_UNKNOWN) != 0);
+                if (__shfl_sync(FULLMASK, m_flags, j)) cell_rules &= ~RULES_INPLACE;
+                cell_compute<OP, LAZY>(acc, pre, (int)(types & 0xff), (int)(types >> 8), A.payload + pa, B.payload + pb,
+                                       cA & CARD_MASK, cB & CARD_MASK, lA, lB, slab + off, cap, lane, otype, ocard,
+                                       olen, &st->error, cell_rules, (cA & CARD_UNKNOWN) != 0);
             } else {
                 const SetView &S = (kind == K_COPY_A) ? A : B;
-                const uint32_t c = (kind == K_COPY_A) ? it.ca[item] : it.cb[item];
-                otype = S.c_type[c];
-                ocard = S.c_card[c];
-                olen = S.c_len[c];
+                otype = (int)types;
+                ocard = cA;
+                olen = lA;
                 // roaring_bitmap_flip on an absent key: container_range_of_ones (containers.h:300-312)
                 // makes a one-value range an ARRAY; {start, 0} and {start} share their first 2 bytes
                 if (LAZY && (rules & RULES_FLIP) && kind == K_COPY_B && (ocard & CARD_MASK) == 1u) {
                     otype = T_ARRAY;
                     olen = 1;
                 }
-                warp_copy16(slab + off, S.payload + S.c_off[c], stored_bytes(otype, olen), lane);
+                warp_copy16(slab + off, S.payload + pa, stored_bytes(otype, olen), lane);
             }
-            if (lane == 0) {
-                it.otype[item] = (uint8_t)otype;
-                it.ocard[item] = ocard;
-                it.olen[item] = olen;
-            }
+            if (lane == j) { r_otype = (uint32_t)otype; r_ocard = ocard; r_olen = olen; }
+        }
+        if (mine && m_kind != K_HOLE) {
+            it.otype[m_item] = (uint8_t)r_otype;
+            it.ocard[m_item] = r_ocard;
+            it.olen[m_item] = r_olen;
         }
         tk = __shfl_sync(FULLMASK, next, 0);
     }
@@ -782,7 +674,8 @@ void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, c
 
 void launch_order_items(Items it, uint64_t W, OpStats *st, cudaStream_t s) {
     if (!W || !it.order) return;
-    const uint32_t g = blocks_for_warps((W + 31) / 32, 8, sm_count() * 8);
+    const uint64_t chunks = (W + 2047) / 2048;
+    const uint32_t g = (uint32_t)(chunks < (uint64_t)sm_count() * 8 ? chunks : (uint64_t)sm_count() * 8);
     k_order_items<<<g, 256, 0, s>>>(it, W, st);
     g_launches++;
 }

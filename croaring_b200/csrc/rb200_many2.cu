@@ -98,11 +98,10 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
             st->nk = sb;
             // few heavy keys: split them so that the grid has ~want_parallel units
             const uint32_t total_kib = sc;
-            uint32_t slice_kib = M2_SLICE_BYTES >> 10;
-            if (want_parallel && total_kib / slice_kib < want_parallel) {
-                slice_kib = total_kib / want_parallel;
-                if (slice_kib < 32) slice_kib = 32;
-            }
+            // a key is split only to fill the machine: every split costs a merge through global
+            // memory and a second look at the key's metadata.  Target ~want_parallel units overall.
+            uint32_t slice_kib = total_kib / (want_parallel ? want_parallel : 1);
+            if (slice_kib < 32) slice_kib = 32;
             s_split = slice_kib;
         }
     }
@@ -117,7 +116,7 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
         e += c;
         if (c) {
             const uint32_t kib = ix.key_units16[key] >> 6;
-            uint32_t s = (kib + slice_kib - 1) / slice_kib;
+            uint32_t s = (kib + slice_kib / 2) / slice_kib;   // to nearest: a key a little over one slice stays whole
             const uint32_t by_cnt = (c + 3) >> 2;
             if (s > by_cnt) s = by_cnt;
             if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
@@ -142,7 +141,7 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
         const uint32_t key = tid * 64 + k, c = ix.key_count[key];
         if (!c) continue;
         const uint32_t kib = ix.key_units16[key] >> 6;
-        uint32_t s = (kib + slice_kib - 1) / slice_kib;
+        uint32_t s = (kib + slice_kib / 2) / slice_kib;
         const uint32_t by_cnt = (c + 3) >> 2;
         if (s > by_cnt) s = by_cnt;
         if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
@@ -186,7 +185,8 @@ k_many2_fill(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t k
             if (k < key_lo || k > key_hi) continue;
             const uint32_t slot = ix.key_start[k] + atomicAdd(ix.key_fill + k, 1u);
             ix.e_pos[slot] = i;
-            ix.e_cont[slot] = c0 + c;
+            ix.e_off[slot] = S.c_off[c0 + c];
+            ix.e_len[slot] = S.c_len[c0 + c];
             ix.e_tf[slot] = (uint8_t)entry_tf(S, c0 + c);
         }
     }
@@ -197,13 +197,14 @@ constexpr uint32_t M2_HALF = 32u << 10;   // bytes of one staging half (two halv
 constexpr uint32_t M2_HALF_ENTRIES = 128;  // participants staged per half at most
 
 struct Many2Smem {
-    uint8_t ring[2][M2_HALF];   // operand staging: filled by cp.async.bulk, one mbarrier per half
     uint32_t acc[ACC_WORDS];    // union of the inputs up to L (or of all of them when L is not needed)
     uint32_t acc2[ACC_WORDS];   // union of the inputs after L
     uint64_t bar[2];            // mbarriers of the two halves
     uint16_t h_bs[2][M2_HALF_ENTRIES], h_ar[2][M2_HALF_ENTRIES];   // staged bitsets / arrays+runs of a half (entry ids)
     uint32_t h_soff[M2_STAGE];  // byte offset of a staged entry inside its half
     uint32_t h_nbs[2], h_nar[2], h_big[2];
+    uint16_t bs_list[M2_STAGE], ar_list[M2_STAGE];   // direct path: staged bitsets / arrays+runs of a round
+    uint32_t nbs, nar;
     unsigned long long s_off[M2_STAGE];
     uint32_t s_len[M2_STAGE];
     uint32_t s_pos[M2_STAGE];
@@ -231,14 +232,18 @@ __device__ __forceinline__ unsigned long long block_min64(Many2Smem &sm, unsigne
     return r;
 }
 
-__global__ void __launch_bounds__(M2_THREADS, 2)
+// TMA = true: operands staged by bulk copies (bitset-dominated inputs); false: direct global loads
+// (array-dominated inputs, where a bulk copy per small container costs more than it hides)
+template <bool TMA>
+__global__ void __launch_bounds__(M2_THREADS, TMA ? 2 : 3)
 k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch, uint32_t *__restrict__ tickets,
            SetOut out, uint32_t *__restrict__ card_per_key, OpStats *st) {
     extern __shared__ __align__(128) uint8_t m2_smem_raw[];
     Many2Smem &sm = *reinterpret_cast<Many2Smem *>(m2_smem_raw);
+    uint8_t(*ring)[M2_HALF] = reinterpret_cast<uint8_t(*)[M2_HALF]>(m2_smem_raw + ((sizeof(Many2Smem) + 127) & ~(size_t)127));
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t nunits = st->units;
-    if (tid == 0) {
+    if (TMA && tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
         mbar_fence_init();
@@ -321,18 +326,77 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
             __syncthreads();
             const uint32_t e = base + tid;
             const uint32_t R = min((uint32_t)M2_STAGE, s_hi - base);   // entries of this round
+            if (!TMA && tid == 0) { sm.nbs = 0; sm.nar = 0; }
+            if (!TMA) __syncthreads();
             if (tid < M2_STAGE && e < s_hi) {
-                const uint32_t c = ix.e_cont[e0 + e], tf = ix.e_tf[e0 + e], p = ix.e_pos[e0 + e];
-                sm.s_off[tid] = S.c_off[c];
-                sm.s_len[tid] = S.c_len[c];
+                const uint32_t tf = ix.e_tf[e0 + e], p = ix.e_pos[e0 + e];
+                sm.s_off[tid] = ix.e_off[e0 + e];
+                sm.s_len[tid] = ix.e_len[e0 + e];
                 sm.s_pos[tid] = p;
                 sm.s_tf[tid] = (uint8_t)tf;
                 if (tf & (TF_FULL_RUN | TF_FULL_BITSET)) {
                     anyfull = 1;
                     if (L != POS_NONE && p <= L) anyfull_pre = 1;
                 }
+                if (!TMA) {
+                    if ((tf & 15) == T_BITSET) sm.bs_list[atomicAdd(&sm.nbs, 1u)] = (uint16_t)tid;
+                    else if (!(tf & TF_FULL_RUN)) sm.ar_list[atomicAdd(&sm.nar, 1u)] = (uint16_t)tid;
+                }
             }
             __syncthreads();
+            if (!TMA) {
+                // bitsets: registers, four containers in flight per thread (all of them are <= L)
+                const uint32_t nbs = sm.nbs;
+                for (uint32_t j = 0; j < nbs; j += 4) {
+                    uint4 qa[4], qb[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (j + k < nbs) {
+                            const uint4 *src = reinterpret_cast<const uint4 *>(S.payload + sm.s_off[sm.bs_list[j + k]]);
+                            qa[k] = __ldg(src + tid);
+                            qb[k] = __ldg(src + tid + M2_THREADS);
+                        }
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (j + k < nbs) {
+                            r0.x |= qa[k].x; r0.y |= qa[k].y; r0.z |= qa[k].z; r0.w |= qa[k].w;
+                            r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
+                        }
+                }
+                // arrays and runs: a warp takes FOUR containers at a time and issues the first vector
+                // of each before touching the accumulator (small arrays are one vector per lane: the
+                // loads of four containers in flight instead of one)
+                const uint32_t nar = sm.nar;
+                for (uint32_t j = wid; j < nar; j += 4 * (M2_THREADS / 32)) {
+                    uint4 q[4];
+                    uint32_t qi[4], nn[4];
+                    const uint8_t *pp[4];
+                    uint32_t *dd[4];
+                    bool isarr[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t jj = j + k * (M2_THREADS / 32);
+                        nn[k] = 0;
+                        isarr[k] = false;
+                        if (jj < nar) {
+                            qi[k] = sm.ar_list[jj];
+                            pp[k] = S.payload + sm.s_off[qi[k]];
+                            nn[k] = sm.s_len[qi[k]];
+                            dd[k] = (L != POS_NONE && sm.s_pos[qi[k]] > L) ? sm.acc2 : sm.acc;
+                            isarr[k] = (sm.s_tf[qi[k]] & 15) == T_ARRAY;
+                            if (isarr[k] && (uint32_t)lane < ((nn[k] + 7) >> 3))
+                                q[k] = __ldg(reinterpret_cast<const uint4 *>(pp[k]) + lane);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (!nn[k]) continue;
+                        if (isarr[k]) acc_apply_array_first<0>(dd[k], pp[k], nn[k], q[k], lane);
+                        else acc_apply_runs<0, true>(dd[k], pp[k], nn[k], lane);
+                    }
+                }
+                continue;
+            }
             // ---- two-half pipeline: thread 0 packs the next entries of the round into a half and
             // issues their bulk copies; everybody consumes the other half meanwhile
             uint32_t next = 0;   // next entry of the round to stage (thread 0's cursor, kept uniform)
@@ -366,11 +430,11 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                     mbar_arrive_expect_tx(&sm.bar[h], bytes);
                     for (uint32_t k = 0; k < nbs; k++) {
                         const uint32_t q = sm.h_bs[h][k];
-                        bulk_copy_g2s(sm.ring[h] + sm.h_soff[q], S.payload + sm.s_off[q], BITSET_BYTES, &sm.bar[h]);
+                        bulk_copy_g2s(ring[h] + sm.h_soff[q], S.payload + sm.s_off[q], BITSET_BYTES, &sm.bar[h]);
                     }
                     for (uint32_t k = 0; k < nar; k++) {
                         const uint32_t q = sm.h_ar[h][k];
-                        bulk_copy_g2s(sm.ring[h] + sm.h_soff[q], S.payload + sm.s_off[q],
+                        bulk_copy_g2s(ring[h] + sm.h_soff[q], S.payload + sm.s_off[q],
                                       round16(stored_bytes(sm.s_tf[q] & 15, sm.s_len[q])), &sm.bar[h]);
                     }
                 }
@@ -386,12 +450,12 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                 // bitsets of the half: registers <- shared (all of them are <= L), two at a time
                 const uint32_t nbs = sm.h_nbs[h], nar = sm.h_nar[h];
                 for (uint32_t j = 0; j < nbs; j += 2) {
-                    const uint4 *s0 = reinterpret_cast<const uint4 *>(sm.ring[h] + sm.h_soff[sm.h_bs[h][j]]);
+                    const uint4 *s0 = reinterpret_cast<const uint4 *>(ring[h] + sm.h_soff[sm.h_bs[h][j]]);
                     const uint4 a0 = s0[tid], b0 = s0[tid + M2_THREADS];
                     r0.x |= a0.x; r0.y |= a0.y; r0.z |= a0.z; r0.w |= a0.w;
                     r1.x |= b0.x; r1.y |= b0.y; r1.z |= b0.z; r1.w |= b0.w;
                     if (j + 1 < nbs) {
-                        const uint4 *s1 = reinterpret_cast<const uint4 *>(sm.ring[h] + sm.h_soff[sm.h_bs[h][j + 1]]);
+                        const uint4 *s1 = reinterpret_cast<const uint4 *>(ring[h] + sm.h_soff[sm.h_bs[h][j + 1]]);
                         const uint4 a1 = s1[tid], b1 = s1[tid + M2_THREADS];
                         r0.x |= a1.x; r0.y |= a1.y; r0.z |= a1.z; r0.w |= a1.w;
                         r1.x |= b1.x; r1.y |= b1.y; r1.z |= b1.z; r1.w |= b1.w;
@@ -401,7 +465,7 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                 for (uint32_t j = wid; j < nar; j += M2_THREADS / 32) {
                     const uint32_t q = sm.h_ar[h][j];
                     uint32_t *dst = (L != POS_NONE && sm.s_pos[q] > L) ? sm.acc2 : sm.acc;
-                    const uint8_t *p = sm.ring[h] + sm.h_soff[q];
+                    const uint8_t *p = ring[h] + sm.h_soff[q];
                     if ((sm.s_tf[q] & 15) == T_ARRAY) acc_apply_array_s<0>(dst, p, sm.s_len[q], lane);
                     else acc_apply_runs_s<0, true>(dst, p, sm.s_len[q], lane);
                 }
@@ -555,18 +619,23 @@ __global__ void k_many2_sum_cards(const uint32_t *__restrict__ c_card, const OpS
 void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
                      const Many2Index &ix, uint32_t max_units, uint32_t *scratch, uint32_t *tickets,
                      uint32_t scratch_slots, SetOut out, uint32_t *card_per_key, OpStats *st, int sms,
-                     cudaStream_t s, cudaEvent_t ev_kernel_start) {
+                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma) {
     const uint32_t gw = (uint32_t)sms * 8;
     k_many2_count<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
-    k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * 8, out, st);
+    k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * (use_tma ? 4 : 6), out, st);
     k_many2_fill<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
     if (ev_kernel_start) cudaEventRecord(ev_kernel_start, s);
+    const size_t smem_direct = (sizeof(Many2Smem) + 127) & ~(size_t)127, smem_tma = smem_direct + 2 * M2_HALF;
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_or_many2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Many2Smem));
+        cudaFuncSetAttribute(k_or_many2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma);
+        cudaFuncSetAttribute(k_or_many2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_direct);
         attr = true;
     }
-    k_or_many2<<<sms * 2, M2_THREADS, sizeof(Many2Smem), s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
+    if (use_tma)
+        k_or_many2<true><<<sms * 2, M2_THREADS, smem_tma, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
+    else
+        k_or_many2<false><<<sms * 3, M2_THREADS, smem_direct, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
     k_many2_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
     g_launches += 5;
 }

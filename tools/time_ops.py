@@ -67,6 +67,18 @@ def main():
         out["ops"][f"{ds}/successive_or"] = {"host_enqueue_us": round(float(np.median(host_us)), 1),
                                              "device_us": round(float(np.median(dev_ms)) * 1e3, 1)}
         S.free()
+    # drop-in single-pair latency (census1881 csv0 AND / OR csv1 through the reference-named symbols)
+    import time as _t
+    blobs = rb.load_realdata("census1881")
+    a, b = rb.Bitmap.deserialize(blobs[0]), rb.Bitmap.deserialize(blobs[1])
+    for name, fn in (("and", lambda: a & b), ("or", lambda: a | b)):
+        ts = []
+        for rep in range(120):
+            t0 = _t.perf_counter()
+            r = fn()
+            ts.append(_t.perf_counter() - t0)
+            r.free()
+        out["ops"][f"dropin_{name}_us"] = round(float(np.median(ts[20:]) * 1e6), 1)
     out["step_kernel_ms"] = round(tot_k, 4)
     out["step_op_ms"] = round(tot_o, 4)
     print(json.dumps(out))
