@@ -10,7 +10,11 @@ namespace rb200 {
 #define RB200_MERGE_LIMIT 2048   // array x array unions up to this many staged values take the merge path
 #endif
 #ifndef RB200_RANK_SCATTER
-#define RB200_RANK_SCATTER 1     // larger ones: accumulator + rank-scatter emission (0: find-first-set emission)
+// larger ones: 1 = accumulator + rank-scatter emission (rb200_device.cuh), 0 = accumulator + ordered
+// find-first-set emission.  Measured on B200 with class-ordered tickets (profiles/r2): rank-scatter
+// executes 20 % fewer instructions but is 3 % SLOWER per step (4.81 vs 4.67 ms of kernel time: its
+// 2-byte scattered loads / stores wait on the memory pipe), so the default stays 0.
+#define RB200_RANK_SCATTER 0
 #endif
 
 // ------------------------------------------------------------------------------ grid cells

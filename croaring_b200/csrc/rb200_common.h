@@ -139,6 +139,8 @@ struct Many2Index {
     uint32_t *key_slices;   // [nk] work units of the key
     uint32_t *key_scratch;  // [nk] scratch slot of a split key
     uint32_t *unit_first;   // [nk] first work unit of the key
+    unsigned long long *fold_first, *fold_second;   // [nk] order statistics of the fold (k_many2_fold)
+    uint32_t *fold_F, *fold_L;                      // [nk]
     uint32_t *unit_ki;      // [max_units] work unit -> live key index
     uint32_t *e_pos;        // [entries] input position of the participant
     uint64_t *e_off;        // [entries] payload offset of its container in the slab
@@ -159,6 +161,9 @@ constexpr uint32_t FUSED_OUT_KEY = 64, FUSED_OUT_TYPE = FUSED_OUT_KEY + 2 * FUSE
                    FUSED_OUT_OFF = FUSED_OUT_LEN + 4 * FUSED_MAX_ITEMS, FUSED_OUT_PAYLOAD = FUSED_OUT_OFF + 4 * FUSED_MAX_ITEMS;
 bool launch_pair_fused(int op, const uint8_t *d_in, uint8_t *out_mapped, uint32_t out_bytes, int rules, uint32_t seq,
                        cudaStream_t s);
+void launch_pairs_fused(const SetView &A, const SetView &B, const uint32_t *ia, const uint32_t *ib, uint32_t npairs,
+                        int op, int rules, uint8_t *slab, uint64_t slab_cap, SetOut out, OpStats *st, int sms,
+                        cudaStream_t s);
 
 // --- launch wrappers (rb200_kernels.cu); every wrapper bumps g_launches -----------------
 extern unsigned long long g_launches;

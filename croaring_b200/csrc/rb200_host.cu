@@ -112,7 +112,7 @@ struct Ctx {
     uint32_t *d_cardkey = nullptr; // 65536 per-key cardinalities
     uint32_t *d_many_acc = nullptr, *d_many_tickets = nullptr;  // split-key scratch (kept zeroed)
     // second-generation or_many (rb200_many2.cu): per-key tables + split-key scratch (kept zeroed)
-    uint32_t *d_m2_tables = nullptr;   // 7 x 65536 u32: count | units16 | fill | start | slices | scratch | unit_first
+    uint32_t *d_m2_tables = nullptr;   // 13 x 65536 u32: count | units16 | fill | start | slices | scratch | unit_first | fold_first(2) | fold_second(2) | fold_F | fold_L
     uint32_t *d_m2_scratch = nullptr, *d_m2_tickets = nullptr;
     // single-pair fused path (rb200_fused.cu): packed operands (pinned + device), mapped result block
     uint8_t *h_fused_in = nullptr, *d_fused_in = nullptr, *h_fused_out = nullptr, *d_fused_out = nullptr;
@@ -177,7 +177,7 @@ bool ctx_init(int device = -1) {
     CK(cudaMalloc(&g.d_many_tickets, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
     CK(cudaMemset(g.d_many_acc, 0, (size_t)MANY_SCRATCH_KEYS * BITSET_BYTES));
     CK(cudaMemset(g.d_many_tickets, 0, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
-    CK(cudaMalloc(&g.d_m2_tables, 7 * 65536 * sizeof(uint32_t)));
+    CK(cudaMalloc(&g.d_m2_tables, 13 * 65536 * sizeof(uint32_t)));
     CK(cudaMalloc(&g.d_m2_scratch, (size_t)M2_SCRATCH_SLOTS * M2_SCRATCH_WORDS * sizeof(uint32_t)));
     CK(cudaMalloc(&g.d_m2_tickets, M2_SCRATCH_SLOTS * sizeof(uint32_t)));
     CK(cudaMemset(g.d_m2_scratch, 0, (size_t)M2_SCRATCH_SLOTS * M2_SCRATCH_WORDS * sizeof(uint32_t)));
@@ -1315,6 +1315,7 @@ struct PairBuf {
     uint32_t *d_ia = nullptr, *d_ib = nullptr;
     uint64_t *d_off = nullptr;
     uint64_t W = 0, slab_bound = 0;
+    uint32_t max_items = 0;   // largest na + nb of a pair (the single-launch path handles <= FUSED_MAX_ITEMS)
     // op: OP_* of the batch (OP_AND also for the cardinality-only sweeps, which need no slab)
     bool build(const rb200_set *A, const rb200_set *B, const uint32_t *ia, const uint32_t *ib,
                size_t np, int op, bool lazy = false) {
@@ -1338,6 +1339,7 @@ struct PairBuf {
             off[p] = w;
             const uint32_t na = A->h_cnt[a], nb = B->h_cnt[b];
             w += (uint64_t)na + nb;
+            if (na + nb > max_items) max_items = na + nb;
             // Upper bound of the result slab of this pair, from the per-bitmap "effective bytes" E
             // (sum over containers of max(stored, min(8192, 2 * card)), 16-byte rounded): every
             // result container — computed or passed through — is an array, a bitset or a run no
@@ -1405,7 +1407,10 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
     bool ok = pb.build(A, B, ia, ib, np, op, (rules & RULES_LAZY) != 0);
     // class-ordered tickets pay one more small kernel: only for batches that fill the GPU
     static const uint64_t order_min = []() { const char *e = getenv("RB200_ORDER_MIN"); return e ? (uint64_t)atoll(e) : 16384ull; }();
-    if (ok) ok = ib_.alloc(pb.W, pb.W >= order_min);
+    // small batches of small pairs: ONE launch, a CTA per pair (rb200_fused.cu)
+    static const uint64_t fused_max_pairs = []() { const char *e = getenv("RB200_FUSED_PAIRS"); return e ? (uint64_t)atoll(e) : 4096ull; }();
+    const bool fused = ok && !(rules & RULES_LAZY) && np <= fused_max_pairs && pb.max_items <= FUSED_MAX_ITEMS;
+    if (ok && !fused) ok = ib_.alloc(pb.W, pb.W >= order_min);
     if (ok) {
         R = set_new((uint32_t)np, pb.W, pb.slab_bound);
         ok = R != nullptr;
@@ -1419,13 +1424,20 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         cudaEventRecord(R->ev[0], g.stream);
         ok = stats_reset();
         const SetView va = A->view(), vb = B->view();
-        launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, rules, ib_.it,
-                          g.d_stats, g.stream);
-        launch_order_items(ib_.it, pb.W, g.d_stats, g.stream);
-        cudaEventRecord(R->ev[1], g.stream);
-        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, g.stream);
-        cudaEventRecord(R->ev[2], g.stream);
-        launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
+        if (fused) {
+            cudaEventRecord(R->ev[1], g.stream);
+            launch_pairs_fused(va, vb, pb.d_ia, pb.d_ib, (uint32_t)np, op, rules, R->d_slab, R->slab_cap, R->out(),
+                               g.d_stats, g.sms, g.stream);
+            cudaEventRecord(R->ev[2], g.stream);
+        } else {
+            launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, rules, ib_.it,
+                              g.d_stats, g.stream);
+            launch_order_items(ib_.it, pb.W, g.d_stats, g.stream);
+            cudaEventRecord(R->ev[1], g.stream);
+            launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, g.stream);
+            cudaEventRecord(R->ev[2], g.stream);
+            launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
+        }
         ok = ok && cudaMemcpyAsync(R->pstats, g.d_stats, sizeof(OpStats), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
         cudaEventRecord(R->ev[3], g.stream);
         // no synchronisation here: the counters are taken over by resolve() on first use
@@ -1578,6 +1590,10 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         ix.key_slices = g.d_m2_tables + 4 * 65536;
         ix.key_scratch = g.d_m2_tables + 5 * 65536;
         ix.unit_first = g.d_m2_tables + 6 * 65536;
+        ix.fold_first = (unsigned long long *)(g.d_m2_tables + 7 * 65536);
+        ix.fold_second = (unsigned long long *)(g.d_m2_tables + 9 * 65536);
+        ix.fold_F = g.d_m2_tables + 11 * 65536;
+        ix.fold_L = g.d_m2_tables + 12 * 65536;
         ix.keys = g.d_keys;
         ix.e_off = (uint64_t *)d_index;
         ix.e_pos = (uint32_t *)(d_index + al256(8 * tot));

@@ -224,8 +224,7 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
         for (int c = 0; c < N_CLS; c++) live += st->cls_count[c];
         W = live;
     }
-    const unsigned long long TICKET = (W >= 32ull * ((unsigned long long)gridDim.x * 4)) ? 8ull
-                                      : (W >= 8ull * ((unsigned long long)gridDim.x * 4)) ? 4ull : 1ull;
+    const unsigned long long TICKET = (W >= 8ull * ((unsigned long long)gridDim.x * 4)) ? 4ull : 1ull;
     unsigned long long tk = 0;
     if (lane == 0) tk = atomicAdd(&st->work_counter, TICKET);
     tk = __shfl_sync(FULLMASK, tk, 0);
@@ -233,83 +232,50 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
         unsigned long long next = 0;
         if (lane == 0) next = atomicAdd(&st->work_counter, TICKET);
         const unsigned long long tend = tk + TICKET < W ? tk + TICKET : W;
-        // ---- metadata of the whole ticket, fetched by its first lanes in parallel: the four
-        // dependent levels (order -> item -> container -> payload) cost one round trip per LEVEL and
-        // ticket instead of one per level and ITEM; the fields travel by shuffle
-        const unsigned long long myslot = tk + lane;
-        const bool mine = lane < (int)TICKET && myslot < tend;
-        unsigned long long m_item = 0, m_off = 0, m_pa = 0, m_pb = 0;
-        int m_kind = K_HOLE;
-        uint32_t m_cap = 0, m_types = 0, m_cA = 0, m_cB = 0, m_lA = 0, m_lB = 0, m_flags = 0;
-        if (mine) {
-            m_item = it.order ? (unsigned long long)it.order[myslot] : myslot;
-            m_kind = it.kind[m_item];
-            if (m_kind != K_HOLE) {
-                m_off = it.slot_off[m_item];
-                m_cap = it.slot_cap[m_item];
-                if (m_kind == K_COMPUTE) {
-                    const uint32_t ca = it.ca[m_item], cb = it.cb[m_item];
-                    m_types = (uint32_t)A.c_type[ca] | ((uint32_t)B.c_type[cb] << 8);
-                    m_cA = A.c_card[ca];
-                    m_cB = B.c_card[cb];
-                    m_lA = A.c_len[ca];
-                    m_lB = B.c_len[cb];
-                    m_pa = A.c_off[ca];
-                    m_pb = B.c_off[cb];
-                    if ((rules & (RULES_INPLACE | RULES_LAZY)) == RULES_INPLACE && A.c_src[ca] == SRC_SHARED) m_flags = 1;
-                } else {
-                    const SetView &S = (m_kind == K_COPY_A) ? A : B;
-                    const uint32_t c = (m_kind == K_COPY_A) ? it.ca[m_item] : it.cb[m_item];
-                    m_types = S.c_type[c];
-                    m_cA = S.c_card[c];
-                    m_lA = S.c_len[c];
-                    m_pa = S.c_off[c];
-                }
-            }
-        }
-        uint32_t r_otype = 0, r_ocard = 0, r_olen = 0;   // results of MY item (lane j keeps item j's)
-        const int nslots = (int)(tend - tk);
-        for (int j = 0; j < nslots; j++) {
-            const int kind = __shfl_sync(FULLMASK, m_kind, j);
+        // (tried in round 2: fetching the metadata of the whole ticket with its first lanes and passing
+        //  the fields by shuffle — 17 more live registers, spills at the 6-CTA register budget and
+        //  8-item tickets made every launch 15-60 % SLOWER; the per-item dependent loads stay)
+        for (unsigned long long slot = tk; slot < tend; slot++) {
+            const unsigned long long item = it.order ? (unsigned long long)it.order[slot] : slot;
+            const int kind = it.kind[item];
             if (kind == K_HOLE) continue;
-            const uint64_t off = __shfl_sync(FULLMASK, m_off, j);
-            const uint32_t cap = __shfl_sync(FULLMASK, m_cap, j);
-            const uint32_t types = __shfl_sync(FULLMASK, m_types, j);
-            const uint32_t cA = __shfl_sync(FULLMASK, m_cA, j), lA = __shfl_sync(FULLMASK, m_lA, j);
-            const uint64_t pa = __shfl_sync(FULLMASK, m_pa, j);
+            const uint64_t off = it.slot_off[item];
+            const uint32_t cap = it.slot_cap[item];
             int otype = 0;
             uint32_t ocard = 0, olen = 0;
             if (off + cap > slab_cap) {
                 if (lane == 0) atomicExch(&st->error, 2u);
             } else if (kind == K_COMPUTE) {
-                const uint32_t cB = __shfl_sync(FULLMASK, m_cB, j), lB = __shfl_sync(FULLMASK, m_lB, j);
-                const uint64_t pb = __shfl_sync(FULLMASK, m_pb, j);
+                const uint32_t ca = it.ca[item], cb = it.cb[item];
+                const uint32_t rawA = A.c_card[ca];
                 // in-place twins: a SHARED left container takes the functional cell (roaring.c:1085-1088);
                 // the lazy in-place twins work on a writable copy instead (roaring.c:2636)
                 int cell_rules = rules;
-                if (__shfl_sync(FULLMASK, m_flags, j)) cell_rules &= ~RULES_INPLACE;
-                cell_compute<OP, LAZY>(acc, pre, (int)(types & 0xff), (int)(types >> 8), A.payload + pa, B.payload + pb,
-                                       cA & CARD_MASK, cB & CARD_MASK, lA, lB, slab + off, cap, lane, otype, ocard,
-                                       olen, &st->error, cell_rules, (cA & CARD_UNKNOWN) != 0);
+                if ((rules & (RULES_INPLACE | RULES_LAZY)) == RULES_INPLACE && A.c_src[ca] == SRC_SHARED)
+                    cell_rules &= ~RULES_INPLACE;
+                cell_compute<OP, LAZY>(acc, pre, A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
+                             B.payload + B.c_off[cb], rawA & CARD_MASK, B.c_card[cb] & CARD_MASK,
+                             A.c_len[ca], B.c_len[cb], slab + off, cap, lane, otype, ocard, olen,
+                             &st->error, cell_rules, (rawA & CARD_UNKNOWN) != 0);
             } else {
                 const SetView &S = (kind == K_COPY_A) ? A : B;
-                otype = (int)types;
-                ocard = cA;
-                olen = lA;
+                const uint32_t c = (kind == K_COPY_A) ? it.ca[item] : it.cb[item];
+                otype = S.c_type[c];
+                ocard = S.c_card[c];
+                olen = S.c_len[c];
                 // roaring_bitmap_flip on an absent key: container_range_of_ones (containers.h:300-312)
                 // makes a one-value range an ARRAY; {start, 0} and {start} share their first 2 bytes
                 if (LAZY && (rules & RULES_FLIP) && kind == K_COPY_B && (ocard & CARD_MASK) == 1u) {
                     otype = T_ARRAY;
                     olen = 1;
                 }
-                warp_copy16(slab + off, S.payload + pa, stored_bytes(otype, olen), lane);
+                warp_copy16(slab + off, S.payload + S.c_off[c], stored_bytes(otype, olen), lane);
             }
-            if (lane == j) { r_otype = (uint32_t)otype; r_ocard = ocard; r_olen = olen; }
-        }
-        if (mine && m_kind != K_HOLE) {
-            it.otype[m_item] = (uint8_t)r_otype;
-            it.ocard[m_item] = r_ocard;
-            it.olen[m_item] = r_olen;
+            if (lane == 0) {
+                it.otype[item] = (uint8_t)otype;
+                it.ocard[item] = ocard;
+                it.olen[item] = olen;
+            }
         }
         tk = __shfl_sync(FULLMASK, next, 0);
     }

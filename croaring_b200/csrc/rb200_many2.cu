@@ -98,10 +98,13 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
             st->nk = sb;
             // few heavy keys: split them so that the grid has ~want_parallel units
             const uint32_t total_kib = sc;
-            // a key is split only to fill the machine: every split costs a merge through global
-            // memory and a second look at the key's metadata.  Target ~want_parallel units overall.
-            uint32_t slice_kib = total_kib / (want_parallel ? want_parallel : 1);
-            if (slice_kib < 32) slice_kib = 32;
+            // few heavy keys: split them so that the grid has ~want_parallel units (measured: units of
+            // ~384 KiB beat both finer and coarser ones at every density of config 3)
+            uint32_t slice_kib = M2_SLICE_BYTES >> 10;
+            if (want_parallel && total_kib / slice_kib < want_parallel) {
+                slice_kib = total_kib / want_parallel;
+                if (slice_kib < 32) slice_kib = 32;
+            }
             s_split = slice_kib;
         }
     }
@@ -116,7 +119,7 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
         e += c;
         if (c) {
             const uint32_t kib = ix.key_units16[key] >> 6;
-            uint32_t s = (kib + slice_kib / 2) / slice_kib;   // to nearest: a key a little over one slice stays whole
+            uint32_t s = (kib + slice_kib - 1) / slice_kib;
             const uint32_t by_cnt = (c + 3) >> 2;
             if (s > by_cnt) s = by_cnt;
             if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
@@ -141,7 +144,7 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
         const uint32_t key = tid * 64 + k, c = ix.key_count[key];
         if (!c) continue;
         const uint32_t kib = ix.key_units16[key] >> 6;
-        uint32_t s = (kib + slice_kib / 2) / slice_kib;
+        uint32_t s = (kib + slice_kib - 1) / slice_kib;
         const uint32_t by_cnt = (c + 3) >> 2;
         if (s > by_cnt) s = by_cnt;
         if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
@@ -192,6 +195,65 @@ k_many2_fill(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t k
     }
 }
 
+// Order statistics of the reference's fold, once per key (warp per live key): the main kernel's
+// work units (several per heavy key) only read the four words.
+//   fold_first / fold_second : (position << 8 | type flags) of the two earliest participants
+//   fold_F : first in-place step that brings a full run (POS_NONE: none)
+//   fold_L : last in-place bitset step before F (POS_NONE: none)
+__global__ void __launch_bounds__(128)
+k_many2_fold(Many2Index ix, const OpStats *st) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nk = st->nk;
+    for (uint32_t ki = warp; ki < nk; ki += nwarps) {
+        const uint32_t key = ix.keys[ki];
+        const uint32_t e0 = ix.key_start[key], m = ix.key_count[key];
+        unsigned long long m1 = ~0ull, m2 = ~0ull;
+        for (uint32_t e = lane; e < m; e += 32) {
+            const unsigned long long v = ((unsigned long long)ix.e_pos[e0 + e] << 8) | ix.e_tf[e0 + e];
+            if (v < m1) { m2 = m1; m1 = v; }
+            else if (v < m2) m2 = v;
+        }
+        unsigned long long first = m1;
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(FULLMASK, first, d); first = o < first ? o : first; }
+        unsigned long long second = m1 == first ? m2 : m1;
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(FULLMASK, second, d); second = o < second ? o : second; }
+        const uint32_t pos1 = (uint32_t)(first >> 8), tf1 = (uint32_t)(first & 0xff);
+        const uint32_t pos2 = (uint32_t)(second >> 8), tf2 = (uint32_t)(second & 0xff);
+        const int t1 = tf1 & 15, t2 = tf2 & 15;
+        bool decided = (tf1 & (TF_FULL_RUN | TF_FULL_BITSET)) != 0;
+        const bool non_inplace = m >= 2 && pos1 == 0 && pos2 == 1;   // roaring.c:2535-2550
+        uint32_t inplace_from = pos1;
+        if (non_inplace) {
+            decided = (t1 != T_BITSET && t2 != T_BITSET) ? (tf2 & TF_FULL_RUN) != 0 : ((tf2 | tf1) & TF_FULL_RUN) != 0;
+            inplace_from = pos2;
+        }
+        uint32_t F = POS_NONE, L = POS_NONE;
+        if (m >= 2 && !decided) {
+            uint32_t f = POS_NONE;
+            for (uint32_t e = lane; e < m; e += 32) {
+                const uint32_t p = ix.e_pos[e0 + e];
+                if (p > inplace_from && (ix.e_tf[e0 + e] & TF_FULL_RUN)) f = min(f, p);
+            }
+            F = __reduce_min_sync(FULLMASK, f);
+            uint32_t l = 0;   // position + 1, 0 = none
+            for (uint32_t e = lane; e < m; e += 32) {
+                const uint32_t p = ix.e_pos[e0 + e];
+                if (p > inplace_from && p < F && (ix.e_tf[e0 + e] & 15) == T_BITSET) l = max(l, p + 1);
+            }
+            l = __reduce_max_sync(FULLMASK, l);
+            if (l) L = l - 1;
+        }
+        if (lane == 0) {
+            ix.fold_first[ki] = first;
+            ix.fold_second[ki] = second;
+            ix.fold_F[ki] = F;
+            ix.fold_L[ki] = L;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ reduction
 constexpr uint32_t M2_HALF = 32u << 10;   // bytes of one staging half (two halves: ping / pong)
 constexpr uint32_t M2_HALF_ENTRIES = 128;  // participants staged per half at most
@@ -235,7 +297,7 @@ __device__ __forceinline__ unsigned long long block_min64(Many2Smem &sm, unsigne
 // TMA = true: operands staged by bulk copies (bitset-dominated inputs); false: direct global loads
 // (array-dominated inputs, where a bulk copy per small container costs more than it hides)
 template <bool TMA>
-__global__ void __launch_bounds__(M2_THREADS, TMA ? 2 : 3)
+__global__ void __launch_bounds__(M2_THREADS, TMA ? 2 : 4)
 k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch, uint32_t *__restrict__ tickets,
            SetOut out, uint32_t *__restrict__ card_per_key, OpStats *st) {
     extern __shared__ __align__(128) uint8_t m2_smem_raw[];
@@ -250,27 +312,21 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
     }
     uint32_t ph0 = 0, ph1 = 0;   // phase parity of the two staging halves (every thread tracks both)
     __syncthreads();
+    if (tid == 0) sm.unit = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
     for (;;) {
         __syncthreads();
-        if (tid == 0) sm.unit = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
-        __syncthreads();
         const uint32_t unit = sm.unit;
+        __syncthreads();
+        // the next ticket is drawn now: its latency hides behind this unit's work
+        if (tid == 0) sm.unit = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
         if (unit >= nunits) break;
         const uint32_t ki = ix.unit_ki[unit];
         if (ki == POS_NONE) continue;   // reserved for a key that could not be split
         const uint32_t key = ix.keys[ki], ns = ix.key_slices[ki], sl = unit - ix.unit_first[ki];
         const uint32_t e0 = ix.key_start[key], m = ix.key_count[key];
 
-        // ---- order statistics of the fold (metadata only, the whole participant list) -----------
-        // packed (position << 8 | type flags): the two smallest positions
-        unsigned long long m1 = ~0ull, m2 = ~0ull;
-        for (uint32_t e = tid; e < m; e += M2_THREADS) {
-            const unsigned long long v = ((unsigned long long)ix.e_pos[e0 + e] << 8) | ix.e_tf[e0 + e];
-            if (v < m1) { m2 = m1; m1 = v; }
-            else if (v < m2) m2 = v;
-        }
-        const unsigned long long first = block_min64(sm, m1);
-        const unsigned long long second = block_min64(sm, m1 == first ? m2 : m1);
+        // ---- order statistics of the fold: computed once per key by k_many2_fold ------------------
+        const unsigned long long first = ix.fold_first[ki], second = ix.fold_second[ki];
         const uint32_t pos1 = (uint32_t)(first >> 8), tf1 = (uint32_t)(first & 0xff);
         const uint32_t pos2 = (uint32_t)(second >> 8), tf2 = (uint32_t)(second & 0xff);
         const int t1 = tf1 & 15, t2 = tf2 & 15;
@@ -278,38 +334,20 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
         bool decided = (tf1 & (TF_FULL_RUN | TF_FULL_BITSET)) != 0;
         bool first_full_bitset = (tf1 & TF_FULL_BITSET) != 0;
         const bool non_inplace = m >= 2 && pos1 == 0 && pos2 == 1;   // roaring.c:2535-2550
-        uint32_t inplace_from = pos1;      // in-place steps: positions > inplace_from
         if (non_inplace) {
             first_full_bitset = false;
             if (t1 != T_BITSET && t2 != T_BITSET) run_full = (tf2 & TF_FULL_RUN) != 0;   // c1 -> bitset, lazy_ior(B, c2)
             else run_full = ((tf2 | tf1) & TF_FULL_RUN) != 0;                            // container_lazy_or copies a full run
             decided = run_full;
-            inplace_from = pos2;
         }
         uint32_t L = POS_NONE;             // POS_NONE: no prefix test needed, everything goes to acc
         bool any_ib = false;
         if (m >= 2 && !decided) {
-            // F: first in-place step with a full run; L: last in-place bitset step before F
-            unsigned long long f = ~0ull;
-            for (uint32_t e = tid; e < m; e += M2_THREADS) {
-                const uint32_t p = ix.e_pos[e0 + e];
-                if (p > inplace_from && (ix.e_tf[e0 + e] & TF_FULL_RUN)) f = p < f ? p : f;
-            }
-            f = block_min64(sm, f);
-            if (f != ~0ull) run_full = true;
-            const uint32_t F = f == ~0ull ? POS_NONE : (uint32_t)f;
-            unsigned long long l = ~0ull;  // max as min of the complement
-            for (uint32_t e = tid; e < m; e += M2_THREADS) {
-                const uint32_t p = ix.e_pos[e0 + e];
-                if (p > inplace_from && p < F && (ix.e_tf[e0 + e] & 15) == T_BITSET) {
-                    const unsigned long long c = ~(unsigned long long)p;
-                    l = c < l ? c : l;
-                }
-            }
-            l = block_min64(sm, l);
-            if (l != ~0ull) {
+            if (ix.fold_F[ki] != POS_NONE) run_full = true;
+            const uint32_t l = ix.fold_L[ki];
+            if (l != POS_NONE) {
                 any_ib = true;
-                if (!run_full) L = (uint32_t)(~l);
+                if (!run_full) L = l;
             }
         }
 
@@ -363,37 +401,14 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                             r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
                         }
                 }
-                // arrays and runs: a warp takes FOUR containers at a time and issues the first vector
-                // of each before touching the accumulator (small arrays are one vector per lane: the
-                // loads of four containers in flight instead of one)
+                // arrays and runs: one warp per container, shared-memory atomics on the accumulator
                 const uint32_t nar = sm.nar;
-                for (uint32_t j = wid; j < nar; j += 4 * (M2_THREADS / 32)) {
-                    uint4 q[4];
-                    uint32_t qi[4], nn[4];
-                    const uint8_t *pp[4];
-                    uint32_t *dd[4];
-                    bool isarr[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint32_t jj = j + k * (M2_THREADS / 32);
-                        nn[k] = 0;
-                        isarr[k] = false;
-                        if (jj < nar) {
-                            qi[k] = sm.ar_list[jj];
-                            pp[k] = S.payload + sm.s_off[qi[k]];
-                            nn[k] = sm.s_len[qi[k]];
-                            dd[k] = (L != POS_NONE && sm.s_pos[qi[k]] > L) ? sm.acc2 : sm.acc;
-                            isarr[k] = (sm.s_tf[qi[k]] & 15) == T_ARRAY;
-                            if (isarr[k] && (uint32_t)lane < ((nn[k] + 7) >> 3))
-                                q[k] = __ldg(reinterpret_cast<const uint4 *>(pp[k]) + lane);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if (!nn[k]) continue;
-                        if (isarr[k]) acc_apply_array_first<0>(dd[k], pp[k], nn[k], q[k], lane);
-                        else acc_apply_runs<0, true>(dd[k], pp[k], nn[k], lane);
-                    }
+                for (uint32_t j = wid; j < nar; j += M2_THREADS / 32) {
+                    const uint32_t q = sm.ar_list[j];
+                    uint32_t *dst = (L != POS_NONE && sm.s_pos[q] > L) ? sm.acc2 : sm.acc;
+                    const uint8_t *p = S.payload + sm.s_off[q];
+                    if ((sm.s_tf[q] & 15) == T_ARRAY) acc_apply_array<0>(dst, p, sm.s_len[q], lane);
+                    else acc_apply_runs<0, true>(dst, p, sm.s_len[q], lane);
                 }
                 continue;
             }
@@ -622,8 +637,9 @@ void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t
                      cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma) {
     const uint32_t gw = (uint32_t)sms * 8;
     k_many2_count<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
-    k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * (use_tma ? 4 : 6), out, st);
+    k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * 8, out, st);
     k_many2_fill<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+    k_many2_fold<<<gw, 128, 0, s>>>(ix, st);
     if (ev_kernel_start) cudaEventRecord(ev_kernel_start, s);
     const size_t smem_direct = (sizeof(Many2Smem) + 127) & ~(size_t)127, smem_tma = smem_direct + 2 * M2_HALF;
     static bool attr = false;
@@ -635,9 +651,9 @@ void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t
     if (use_tma)
         k_or_many2<true><<<sms * 2, M2_THREADS, smem_tma, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
     else
-        k_or_many2<false><<<sms * 3, M2_THREADS, smem_direct, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
+        k_or_many2<false><<<sms * 4, M2_THREADS, smem_direct, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
     k_many2_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
-    g_launches += 5;
+    g_launches += 6;
 }
 
 }  // namespace rb200
