@@ -131,8 +131,8 @@ constexpr int N_CLS = 8;
 
 // Key-major index of one many-way union (rb200_many2.cu): built per call on the device.
 struct Many2Index {
-    uint32_t *key_count;    // [65536] participants per key            (zero on entry)
-    uint32_t *key_units16;  // [65536] their stored bytes / 16         (zero on entry)
+    unsigned long long *key_cu;  // [65536] participants << 40 | stored bytes / 16   (zero on entry)
+    uint32_t *key_count;    // [65536] participants per key (decoded by k_many2_scan)
     uint32_t *key_fill;     // [65536] fill cursors                    (zero on entry)
     uint32_t *key_start;    // [65536] first index entry of the key
     uint16_t *keys;         // [nk] live keys, increasing
@@ -142,10 +142,7 @@ struct Many2Index {
     unsigned long long *fold_first, *fold_second;   // [nk] order statistics of the fold (k_many2_fold)
     uint32_t *fold_F, *fold_L;                      // [nk]
     uint32_t *unit_ki;      // [max_units] work unit -> live key index
-    uint32_t *e_pos;        // [entries] input position of the participant
-    uint64_t *e_off;        // [entries] payload offset of its container in the slab
-    uint32_t *e_len;        // [entries] c_len of its container
-    uint8_t *e_tf;          // [entries] type | full-run / full-bitset flags
+    uint4 *ent;             // [entries] {payload offset / 16, input position, c_len, type | full flags}
 };
 
 // ---- single-pair fused path (rb200_fused.cu): packed input block (host-pinned -> device) and

@@ -195,7 +195,7 @@ struct PairsSmem {
 };
 
 template <int OP>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, 1)
+__global__ void __launch_bounds__(FUSED_WARPS * 32, 2)
 k_pairs_fused(SetView A, SetView B, const uint32_t *__restrict__ ia, const uint32_t *__restrict__ ib,
               uint32_t npairs, int rules, uint8_t *slab, uint64_t slab_cap, SetOut out, OpStats *st) {
     extern __shared__ __align__(128) uint8_t fused_smem_raw[];

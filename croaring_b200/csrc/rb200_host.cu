@@ -112,7 +112,7 @@ struct Ctx {
     uint32_t *d_cardkey = nullptr; // 65536 per-key cardinalities
     uint32_t *d_many_acc = nullptr, *d_many_tickets = nullptr;  // split-key scratch (kept zeroed)
     // second-generation or_many (rb200_many2.cu): per-key tables + split-key scratch (kept zeroed)
-    uint32_t *d_m2_tables = nullptr;   // 13 x 65536 u32: count | units16 | fill | start | slices | scratch | unit_first | fold_first(2) | fold_second(2) | fold_F | fold_L
+    uint32_t *d_m2_tables = nullptr;   // 14 x 65536 u32: key_cu(2) | fill | count | units16 | fill | start | slices | scratch | unit_first | fold_first(2) | fold_second(2) | fold_F | fold_L
     uint32_t *d_m2_scratch = nullptr, *d_m2_tickets = nullptr;
     // single-pair fused path (rb200_fused.cu): packed operands (pinned + device), mapped result block
     uint8_t *h_fused_in = nullptr, *d_fused_in = nullptr, *h_fused_out = nullptr, *d_fused_out = nullptr;
@@ -177,7 +177,7 @@ bool ctx_init(int device = -1) {
     CK(cudaMalloc(&g.d_many_tickets, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
     CK(cudaMemset(g.d_many_acc, 0, (size_t)MANY_SCRATCH_KEYS * BITSET_BYTES));
     CK(cudaMemset(g.d_many_tickets, 0, MANY_SCRATCH_KEYS * sizeof(uint32_t)));
-    CK(cudaMalloc(&g.d_m2_tables, 13 * 65536 * sizeof(uint32_t)));
+    CK(cudaMalloc(&g.d_m2_tables, 14 * 65536 * sizeof(uint32_t)));
     CK(cudaMalloc(&g.d_m2_scratch, (size_t)M2_SCRATCH_SLOTS * M2_SCRATCH_WORDS * sizeof(uint32_t)));
     CK(cudaMalloc(&g.d_m2_tickets, M2_SCRATCH_SLOTS * sizeof(uint32_t)));
     CK(cudaMemset(g.d_m2_scratch, 0, (size_t)M2_SCRATCH_SLOTS * M2_SCRATCH_WORDS * sizeof(uint32_t)));
@@ -1570,12 +1570,14 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
     cudaEvent_t evc0 = nullptr, evc1 = nullptr;
     if (ok && want_ck) { h_ck = (uint32_t *)pin_alloc(65536 * 4); ok = h_ck != nullptr; }
     if (ok && sh) { evc0 = ev_get(); evc1 = ev_get(); ok = evc0 && evc1; }
-    static const bool use_v1 = []() { const char *e = getenv("RB200_OR_MANY"); return e && !strcmp(e, "v1"); }();
+    static const bool env_v1 = []() { const char *e = getenv("RB200_OR_MANY"); return e && !strcmp(e, "v1"); }();
+    // the index packs payload offsets / 16 into 32 bits and participants per key into 24
+    const bool use_v1 = env_v1 || S->slab_used >= (64ull << 30) || n >= (1u << 24);
     // index of the second-generation kernel: entries + work-unit table from the device pool
     uint64_t tot_kib = 0;
     for (size_t i = 0; i < n; i++) tot_kib += (S->h_bytes[idx ? idx[i] : i] >> 10) + 1;
     const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>(tot, std::min<uint64_t>(65536, tot) + tot_kib / 32 + 1));
-    const size_t e_bytes = al256(4 * tot) * 2 + al256(8 * tot) + al256(tot) + al256(4 * max_units);
+    const size_t e_bytes = al256(16 * tot) + al256(4 * max_units);
     uint8_t *d_index = nullptr;
     if (ok && !use_v1) { d_index = (uint8_t *)dev_alloc(e_bytes); ok = d_index != nullptr; }
     if (ok && !use_v1) {
@@ -1583,23 +1585,20 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         ok = stats_reset();
         const SetView vs = S->view();
         Many2Index ix;
-        ix.key_count = g.d_m2_tables;
-        ix.key_units16 = g.d_m2_tables + 65536;
-        ix.key_fill = g.d_m2_tables + 2 * 65536;
-        ix.key_start = g.d_m2_tables + 3 * 65536;
-        ix.key_slices = g.d_m2_tables + 4 * 65536;
-        ix.key_scratch = g.d_m2_tables + 5 * 65536;
-        ix.unit_first = g.d_m2_tables + 6 * 65536;
-        ix.fold_first = (unsigned long long *)(g.d_m2_tables + 7 * 65536);
-        ix.fold_second = (unsigned long long *)(g.d_m2_tables + 9 * 65536);
-        ix.fold_F = g.d_m2_tables + 11 * 65536;
-        ix.fold_L = g.d_m2_tables + 12 * 65536;
+        ix.key_cu = (unsigned long long *)g.d_m2_tables;          // [0, 2): zeroed per call
+        ix.key_fill = g.d_m2_tables + 2 * 65536;                  // [2, 3): zeroed per call
+        ix.key_count = g.d_m2_tables + 3 * 65536;
+        ix.key_start = g.d_m2_tables + 4 * 65536;
+        ix.key_slices = g.d_m2_tables + 5 * 65536;
+        ix.key_scratch = g.d_m2_tables + 6 * 65536;
+        ix.unit_first = g.d_m2_tables + 7 * 65536;
+        ix.fold_first = (unsigned long long *)(g.d_m2_tables + 8 * 65536);
+        ix.fold_second = (unsigned long long *)(g.d_m2_tables + 10 * 65536);
+        ix.fold_F = g.d_m2_tables + 12 * 65536;
+        ix.fold_L = g.d_m2_tables + 13 * 65536;
         ix.keys = g.d_keys;
-        ix.e_off = (uint64_t *)d_index;
-        ix.e_pos = (uint32_t *)(d_index + al256(8 * tot));
-        ix.e_len = (uint32_t *)(d_index + al256(8 * tot) + al256(4 * tot));
-        ix.e_tf = d_index + al256(8 * tot) + 2 * al256(4 * tot);
-        ix.unit_ki = (uint32_t *)(d_index + al256(8 * tot) + 2 * al256(4 * tot) + al256(tot));
+        ix.ent = (uint4 *)d_index;
+        ix.unit_ki = (uint32_t *)(d_index + al256(16 * tot));
         // operand staging by TMA bulk copies pays off when the containers are mostly bitsets
         // (RB200_OR_MANY_TMA=0/1 forces the choice)
         static const int tma_env = []() { const char *e = getenv("RB200_OR_MANY_TMA"); return e ? atoi(e) : -1; }();

@@ -64,8 +64,8 @@ k_many2_count(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t 
         for (uint32_t c = lane; c < nc; c += 32) {
             const uint32_t k = S.c_key[c0 + c];
             if (k < key_lo || k > key_hi) continue;
-            atomicAdd(ix.key_count + k, 1u);
-            atomicAdd(ix.key_units16 + k, round16(stored_bytes(S.c_type[c0 + c], S.c_len[c0 + c])) >> 4);
+            // one atomic per container: participants in the high 24 bits, stored bytes / 16 in the low 40
+            atomicAdd(ix.key_cu + k, (1ull << 40) | (unsigned long long)(round16(stored_bytes(S.c_type[c0 + c], S.c_len[c0 + c])) >> 4));
         }
     }
 }
@@ -80,10 +80,11 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
     // pass 1: entries, live keys and total weight
     uint32_t cnt = 0, live = 0, w16 = 0;
     for (int k = 0; k < 64; k++) {
-        const uint32_t c = ix.key_count[tid * 64 + k];
+        const unsigned long long cu = ix.key_cu[tid * 64 + k];
+        const uint32_t c = (uint32_t)(cu >> 40);
         cnt += c;
         live += c ? 1u : 0u;
-        w16 += ix.key_units16[tid * 64 + k] >> 6;   // KiB, to stay inside 32 bits
+        w16 += (uint32_t)((cu & ((1ull << 40) - 1)) >> 6);   // KiB, to stay inside 32 bits
     }
     uint32_t icnt = warp_incl_scan(cnt, lane), ilive = warp_incl_scan(live, lane), iw = warp_incl_scan(w16, lane);
     if (lane == 31) { s_a[wid] = icnt; s_b[wid] = ilive; s_c[wid] = iw; }
@@ -114,11 +115,14 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
     // pass 2: per key start / live index / slices
     uint32_t units = 0, nsplit = 0;
     for (int k = 0; k < 64; k++) {
-        const uint32_t key = tid * 64 + k, c = ix.key_count[key];
+        const uint32_t key = tid * 64 + k;
+        const unsigned long long cu = ix.key_cu[key];
+        const uint32_t c = (uint32_t)(cu >> 40);
         ix.key_start[key] = e;
+        ix.key_count[key] = c;
         e += c;
         if (c) {
-            const uint32_t kib = ix.key_units16[key] >> 6;
+            const uint32_t kib = (uint32_t)((cu & ((1ull << 40) - 1)) >> 6);
             uint32_t s = (kib + slice_kib - 1) / slice_kib;
             const uint32_t by_cnt = (c + 3) >> 2;
             if (s > by_cnt) s = by_cnt;
@@ -141,9 +145,11 @@ k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t
     __syncthreads();
     uint32_t u = s_a[wid] + iu - units, sp = s_d[wid] + is - nsplit;
     for (int k = 0; k < 64; k++) {
-        const uint32_t key = tid * 64 + k, c = ix.key_count[key];
+        const uint32_t key = tid * 64 + k;
+        const unsigned long long cu = ix.key_cu[key];
+        const uint32_t c = (uint32_t)(cu >> 40);
         if (!c) continue;
-        const uint32_t kib = ix.key_units16[key] >> 6;
+        const uint32_t kib = (uint32_t)((cu & ((1ull << 40) - 1)) >> 6);
         uint32_t s = (kib + slice_kib - 1) / slice_kib;
         const uint32_t by_cnt = (c + 3) >> 2;
         if (s > by_cnt) s = by_cnt;
@@ -187,10 +193,8 @@ k_many2_fill(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t k
             const uint32_t k = S.c_key[c0 + c];
             if (k < key_lo || k > key_hi) continue;
             const uint32_t slot = ix.key_start[k] + atomicAdd(ix.key_fill + k, 1u);
-            ix.e_pos[slot] = i;
-            ix.e_off[slot] = S.c_off[c0 + c];
-            ix.e_len[slot] = S.c_len[c0 + c];
-            ix.e_tf[slot] = (uint8_t)entry_tf(S, c0 + c);
+            // {payload offset / 16, input position, length, type flags}: ONE 16-byte store
+            ix.ent[slot] = make_uint4((uint32_t)(S.c_off[c0 + c] >> 4), i, S.c_len[c0 + c], entry_tf(S, c0 + c));
         }
     }
 }
@@ -211,7 +215,8 @@ k_many2_fold(Many2Index ix, const OpStats *st) {
         const uint32_t e0 = ix.key_start[key], m = ix.key_count[key];
         unsigned long long m1 = ~0ull, m2 = ~0ull;
         for (uint32_t e = lane; e < m; e += 32) {
-            const unsigned long long v = ((unsigned long long)ix.e_pos[e0 + e] << 8) | ix.e_tf[e0 + e];
+            const uint4 en = ix.ent[e0 + e];
+            const unsigned long long v = ((unsigned long long)en.y << 8) | en.w;
             if (v < m1) { m2 = m1; m1 = v; }
             else if (v < m2) m2 = v;
         }
@@ -233,14 +238,16 @@ k_many2_fold(Many2Index ix, const OpStats *st) {
         if (m >= 2 && !decided) {
             uint32_t f = POS_NONE;
             for (uint32_t e = lane; e < m; e += 32) {
-                const uint32_t p = ix.e_pos[e0 + e];
-                if (p > inplace_from && (ix.e_tf[e0 + e] & TF_FULL_RUN)) f = min(f, p);
+                const uint4 en = ix.ent[e0 + e];
+                const uint32_t p = en.y;
+                if (p > inplace_from && (en.w & TF_FULL_RUN)) f = min(f, p);
             }
             F = __reduce_min_sync(FULLMASK, f);
             uint32_t l = 0;   // position + 1, 0 = none
             for (uint32_t e = lane; e < m; e += 32) {
-                const uint32_t p = ix.e_pos[e0 + e];
-                if (p > inplace_from && p < F && (ix.e_tf[e0 + e] & 15) == T_BITSET) l = max(l, p + 1);
+                const uint4 en = ix.ent[e0 + e];
+                const uint32_t p = en.y;
+                if (p > inplace_from && p < F && (en.w & 15) == T_BITSET) l = max(l, p + 1);
             }
             l = __reduce_max_sync(FULLMASK, l);
             if (l) L = l - 1;
@@ -367,9 +374,10 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
             if (!TMA && tid == 0) { sm.nbs = 0; sm.nar = 0; }
             if (!TMA) __syncthreads();
             if (tid < M2_STAGE && e < s_hi) {
-                const uint32_t tf = ix.e_tf[e0 + e], p = ix.e_pos[e0 + e];
-                sm.s_off[tid] = ix.e_off[e0 + e];
-                sm.s_len[tid] = ix.e_len[e0 + e];
+                const uint4 en = ix.ent[e0 + e];
+                const uint32_t tf = en.w, p = en.y;
+                sm.s_off[tid] = (unsigned long long)en.x << 4;
+                sm.s_len[tid] = en.z;
                 sm.s_pos[tid] = p;
                 sm.s_tf[tid] = (uint8_t)tf;
                 if (tf & (TF_FULL_RUN | TF_FULL_BITSET)) {
