@@ -158,9 +158,7 @@ constexpr uint32_t FUSED_OUT_KEY = 64, FUSED_OUT_TYPE = FUSED_OUT_KEY + 2 * FUSE
                    FUSED_OUT_OFF = FUSED_OUT_LEN + 4 * FUSED_MAX_ITEMS, FUSED_OUT_PAYLOAD = FUSED_OUT_OFF + 4 * FUSED_MAX_ITEMS;
 bool launch_pair_fused(int op, const uint8_t *d_in, uint8_t *out_mapped, uint32_t out_bytes, int rules, uint32_t seq,
                        cudaStream_t s);
-void launch_pairs_fused(const SetView &A, const SetView &B, const uint32_t *ia, const uint32_t *ib, uint32_t npairs,
-                        int op, int rules, uint8_t *slab, uint64_t slab_cap, SetOut out, OpStats *st, int sms,
-                        cudaStream_t s);
+
 
 // --- launch wrappers (rb200_kernels.cu); every wrapper bumps g_launches -----------------
 extern unsigned long long g_launches;

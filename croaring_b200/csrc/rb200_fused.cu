@@ -176,218 +176,6 @@ k_pair_fused(const uint8_t *__restrict__ in, uint8_t *out, uint32_t out_bytes, i
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Small BATCHES over resident sets in one launch: a CTA per pair does plan -> cells -> finalize for
-// its pair (the three phases of the batched path need no grid-wide ordering: slots and directory
-// ranges come from two bump allocators).  For batches of up to a few thousand small pairs — the
-// literal "successive pairs" sweep of the reference's benchmark, 199 pairs per call — this replaces
-// three launches and two round trips through the work-item arrays in global memory.
-struct PairsSmem {
-    uint32_t acc[FUSED_WARPS][ACC_WORDS];
-    uint16_t pre[FUSED_WARPS][512];
-    uint16_t keys[FUSED_MAX_ITEMS];
-    uint32_t i_ca[FUSED_MAX_ITEMS], i_cb[FUSED_MAX_ITEMS];
-    uint32_t i_slot[FUSED_MAX_ITEMS], i_cap[FUSED_MAX_ITEMS], i_ocard[FUSED_MAX_ITEMS], i_olen[FUSED_MAX_ITEMS];
-    uint16_t i_key[FUSED_MAX_ITEMS];
-    uint8_t i_kind[FUSED_MAX_ITEMS], i_otype[FUSED_MAX_ITEMS];
-    unsigned long long slab_base, dir_base;
-    uint32_t err;
-};
-
-template <int OP>
-__global__ void __launch_bounds__(FUSED_WARPS * 32, 2)
-k_pairs_fused(SetView A, SetView B, const uint32_t *__restrict__ ia, const uint32_t *__restrict__ ib,
-              uint32_t npairs, int rules, uint8_t *slab, uint64_t slab_cap, SetOut out, OpStats *st) {
-    extern __shared__ __align__(128) uint8_t fused_smem_raw[];
-    PairsSmem &sm = *reinterpret_cast<PairsSmem *>(fused_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (uint32_t p = blockIdx.x; p < npairs; p += gridDim.x) {
-        __syncthreads();
-        const uint32_t a = ia[p], b = ib[p];
-        const uint32_t a0 = A.bm_beg[a], na = A.bm_cnt[a], b0 = B.bm_beg[b], nb = B.bm_cnt[b], n = na + nb;
-        for (uint32_t i = tid; i < n; i += blockDim.x) sm.keys[i] = i < na ? A.c_key[a0 + i] : B.c_key[b0 + i - na];
-        if (tid == 0) sm.err = 0;
-        __syncthreads();
-        // ---- plan
-        for (uint32_t t = tid; t < n; t += blockDim.x) {
-            int kind = K_HOLE;
-            uint32_t ca = 0, cb = 0, cap = 0, pos, key;
-            if (t < na) {
-                ca = a0 + t;
-                key = sm.keys[t];
-                const uint32_t lb = lb_u16(sm.keys + na, nb, key);
-                const bool matched = lb < nb && sm.keys[na + lb] == key;
-                pos = t + lb;
-                if (matched) {
-                    cb = b0 + lb;
-                    kind = K_COMPUTE;
-                    cap = slot_bound(OP, A.c_type[ca], B.c_type[cb], A.c_card[ca] & CARD_MASK, B.c_card[cb] & CARD_MASK,
-                                     A.c_len[ca], B.c_len[cb]);
-                } else if (OP != OP_AND) {
-                    kind = K_COPY_A;
-                    cap = round16(stored_bytes(A.c_type[ca], A.c_len[ca]));
-                }
-            } else {
-                const uint32_t j = t - na;
-                cb = b0 + j;
-                key = sm.keys[t];
-                uint32_t lo = 0, hi = na;
-                while (lo < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (sm.keys[mid] <= key) lo = mid + 1;
-                    else hi = mid;
-                }
-                const bool matched = lo > 0 && sm.keys[lo - 1] == key;
-                pos = j + lo;
-                if (!matched && (OP == OP_OR || OP == OP_XOR)) {
-                    kind = K_COPY_B;
-                    cap = round16(stored_bytes(B.c_type[cb], B.c_len[cb]));
-                }
-            }
-            sm.i_kind[pos] = (uint8_t)kind;
-            sm.i_ca[pos] = ca;
-            sm.i_cb[pos] = cb;
-            sm.i_key[pos] = (uint16_t)key;
-            sm.i_cap[pos] = cap;
-            sm.i_otype[pos] = 0;
-            sm.i_ocard[pos] = 0;
-            sm.i_olen[pos] = 0;
-        }
-        __syncthreads();
-        if (wid == 0) {   // slots of the pair: one bump allocation, offsets by scan
-            uint32_t run = 0;
-            for (uint32_t base = 0; base < n; base += 32) {
-                const uint32_t i = base + lane, c = i < n ? sm.i_cap[i] : 0u;
-                const uint32_t incl = warp_incl_scan(c, lane);
-                if (i < n) sm.i_slot[i] = run + incl - c;
-                run += __shfl_sync(FULLMASK, incl, 31);
-            }
-            if (lane == 0) {
-                sm.slab_base = run ? atomicAdd(&st->slab_cursor, (unsigned long long)run) : 0ull;
-                if (sm.slab_base + run > slab_cap) { sm.err = 2; atomicExch(&st->error, 2u); }
-            }
-        }
-        __syncthreads();
-        const unsigned long long sbase = sm.slab_base;
-        // ---- cells: one warp per item
-        if (!sm.err) {
-            for (uint32_t item = wid; item < n; item += FUSED_WARPS) {
-                const int kind = sm.i_kind[item];
-                if (kind == K_HOLE) continue;
-                int otype = 0;
-                uint32_t ocard = 0, olen = 0;
-                uint8_t *dst = slab + sbase + sm.i_slot[item];
-                if (kind == K_COMPUTE) {
-                    const uint32_t ca = sm.i_ca[item], cb = sm.i_cb[item];
-                    const uint32_t rawA = A.c_card[ca];
-                    int cell_rules = rules;
-                    if ((rules & RULES_INPLACE) && A.c_src[ca] == SRC_SHARED) cell_rules &= ~RULES_INPLACE;
-                    cell_compute<OP, false>(sm.acc[wid], sm.pre[wid], A.c_type[ca], B.c_type[cb], A.payload + A.c_off[ca],
-                                            B.payload + B.c_off[cb], rawA & CARD_MASK, B.c_card[cb] & CARD_MASK,
-                                            A.c_len[ca], B.c_len[cb], dst, sm.i_cap[item], lane, otype, ocard, olen,
-                                            &st->error, cell_rules, false);
-                } else {
-                    const SetView &S = kind == K_COPY_A ? A : B;
-                    const uint32_t c = kind == K_COPY_A ? sm.i_ca[item] : sm.i_cb[item];
-                    otype = S.c_type[c];
-                    ocard = S.c_card[c];
-                    olen = S.c_len[c];
-                    warp_copy16(dst, S.payload + S.c_off[c], stored_bytes(otype, olen), lane);
-                }
-                if (lane == 0) { sm.i_otype[item] = (uint8_t)otype; sm.i_ocard[item] = ocard; sm.i_olen[item] = olen; }
-            }
-        }
-        __syncthreads();
-        // ---- finalize (warp 0): counters, directory range, ordered compaction
-        if (wid == 0) {
-            uint32_t cnt = 0, anyrun = 0;
-            unsigned long long card = 0, bytes = 0, outb = 0, sbytes = 0, ebytes = 0;
-            for (uint32_t i = lane; i < n; i += 32) {
-                const int kind = sm.i_kind[i];
-                if (kind == K_HOLE) continue;
-                const int ot = sm.i_otype[i];
-                const uint32_t osz = ot ? portable_bytes(ot, sm.i_olen[i]) : 0u;
-                outb += osz;
-                if (ot) {
-                    sbytes += round16(stored_bytes(ot, sm.i_olen[i]));
-                    ebytes += effective_bytes(ot, sm.i_olen[i], sm.i_ocard[i] & CARD_MASK);
-                    anyrun |= ot == T_RUN ? 1u : 0u;
-                    cnt++;
-                    card += sm.i_ocard[i] & CARD_MASK;
-                }
-                if (kind == K_COMPUTE) {
-                    const uint32_t ca = sm.i_ca[i], cb = sm.i_cb[i];
-                    bytes += portable_bytes(A.c_type[ca], A.c_len[ca]) + portable_bytes(B.c_type[cb], B.c_len[cb]) + osz;
-                } else {
-                    bytes += 2ull * osz;
-                }
-            }
-            cnt = __reduce_add_sync(FULLMASK, cnt);
-            anyrun = __reduce_or_sync(FULLMASK, anyrun);
-            for (int d = 16; d > 0; d >>= 1) {
-                card += __shfl_xor_sync(FULLMASK, card, d);
-                bytes += __shfl_xor_sync(FULLMASK, bytes, d);
-                outb += __shfl_xor_sync(FULLMASK, outb, d);
-                sbytes += __shfl_xor_sync(FULLMASK, sbytes, d);
-                ebytes += __shfl_xor_sync(FULLMASK, ebytes, d);
-            }
-            unsigned long long dbase = 0;
-            if (lane == 0) {
-                dbase = atomicAdd(&st->dir_cursor, (unsigned long long)cnt);
-                atomicAdd(&st->algo_bytes, bytes);
-                const uint32_t hdr = anyrun ? 4u + ((cnt + 7u) >> 3) + (cnt < 4u ? 4u * cnt : 8u * cnt) : 8u + 8u * cnt;
-                atomicAdd(&st->out_portable, outb + hdr);
-                out.bm_beg[p] = (uint32_t)dbase;
-                out.bm_cnt[p] = cnt;
-                out.bm_card[p] = card;
-                out.bm_bytes[p] = sbytes;
-                out.bm_ebytes[p] = ebytes;
-            }
-            dbase = __shfl_sync(FULLMASK, dbase, 0);
-            uint32_t done = 0;
-            for (uint32_t base = 0; base < n; base += 32) {
-                const uint32_t i = base + lane;
-                const bool live = i < n && sm.i_kind[i] != K_HOLE && sm.i_otype[i] != 0;
-                const unsigned m = __ballot_sync(FULLMASK, live);
-                if (live) {
-                    const uint64_t o = dbase + done + __popc(m & lanemask_lt());
-                    out.c_key[o] = sm.i_key[i];
-                    out.c_type[o] = sm.i_otype[i];
-                    out.c_card[o] = sm.i_ocard[i];
-                    out.c_len[o] = sm.i_olen[i];
-                    out.c_off[o] = sbase + sm.i_slot[i];
-                    const int kd = sm.i_kind[i];
-                    out.c_src[o] = kd == K_COPY_A ? sm.i_ca[i] : (kd == K_COPY_B ? (SRC_B | sm.i_cb[i]) : SRC_NONE);
-                }
-                done += __popc(m);
-            }
-        }
-    }
-}
-
-void launch_pairs_fused(const SetView &A, const SetView &B, const uint32_t *ia, const uint32_t *ib, uint32_t npairs,
-                        int op, int rules, uint8_t *slab, uint64_t slab_cap, SetOut out, OpStats *st, int sms,
-                        cudaStream_t s) {
-    if (!npairs) return;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_pairs_fused<OP_AND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairsSmem));
-        cudaFuncSetAttribute(k_pairs_fused<OP_OR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairsSmem));
-        cudaFuncSetAttribute(k_pairs_fused<OP_XOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairsSmem));
-        cudaFuncSetAttribute(k_pairs_fused<OP_ANDNOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairsSmem));
-        attr = true;
-    }
-    const uint32_t g = npairs < (uint32_t)sms * 2 ? npairs : (uint32_t)sms * 2;
-    const size_t smem = sizeof(PairsSmem);
-    switch (op) {
-        case OP_AND: k_pairs_fused<OP_AND><<<g, FUSED_WARPS * 32, smem, s>>>(A, B, ia, ib, npairs, rules, slab, slab_cap, out, st); break;
-        case OP_OR: k_pairs_fused<OP_OR><<<g, FUSED_WARPS * 32, smem, s>>>(A, B, ia, ib, npairs, rules, slab, slab_cap, out, st); break;
-        case OP_XOR: k_pairs_fused<OP_XOR><<<g, FUSED_WARPS * 32, smem, s>>>(A, B, ia, ib, npairs, rules, slab, slab_cap, out, st); break;
-        default: k_pairs_fused<OP_ANDNOT><<<g, FUSED_WARPS * 32, smem, s>>>(A, B, ia, ib, npairs, rules, slab, slab_cap, out, st); break;
-    }
-    g_launches++;
-}
-
 bool launch_pair_fused(int op, const uint8_t *d_in, uint8_t *out_mapped, uint32_t out_bytes, int rules, uint32_t seq,
                        cudaStream_t s) {
     static bool attr = false;

@@ -1315,7 +1315,6 @@ struct PairBuf {
     uint32_t *d_ia = nullptr, *d_ib = nullptr;
     uint64_t *d_off = nullptr;
     uint64_t W = 0, slab_bound = 0;
-    uint32_t max_items = 0;   // largest na + nb of a pair (the single-launch path handles <= FUSED_MAX_ITEMS)
     // op: OP_* of the batch (OP_AND also for the cardinality-only sweeps, which need no slab)
     bool build(const rb200_set *A, const rb200_set *B, const uint32_t *ia, const uint32_t *ib,
                size_t np, int op, bool lazy = false) {
@@ -1339,7 +1338,6 @@ struct PairBuf {
             off[p] = w;
             const uint32_t na = A->h_cnt[a], nb = B->h_cnt[b];
             w += (uint64_t)na + nb;
-            if (na + nb > max_items) max_items = na + nb;
             // Upper bound of the result slab of this pair, from the per-bitmap "effective bytes" E
             // (sum over containers of max(stored, min(8192, 2 * card)), 16-byte rounded): every
             // result container — computed or passed through — is an array, a bitset or a run no
@@ -1407,10 +1405,10 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
     bool ok = pb.build(A, B, ia, ib, np, op, (rules & RULES_LAZY) != 0);
     // class-ordered tickets pay one more small kernel: only for batches that fill the GPU
     static const uint64_t order_min = []() { const char *e = getenv("RB200_ORDER_MIN"); return e ? (uint64_t)atoll(e) : 16384ull; }();
-    // small batches of small pairs: ONE launch, a CTA per pair (rb200_fused.cu)
-    static const uint64_t fused_max_pairs = []() { const char *e = getenv("RB200_FUSED_PAIRS"); return e ? (uint64_t)atoll(e) : 4096ull; }();
-    const bool fused = ok && !(rules & RULES_LAZY) && np <= fused_max_pairs && pb.max_items <= FUSED_MAX_ITEMS;
-    if (ok && !fused) ok = ib_.alloc(pb.W, pb.W >= order_min);
+    // (tried in round 2: ONE launch with a CTA per pair doing plan -> cells -> finalize for small batches —
+    //  the 199-pair successive sweep took 84-174 us of device time per call instead of 53-126 us: a
+    //  pair's cells serialise on its 8 warps while the three-kernel path spreads them over the GPU)
+    if (ok) ok = ib_.alloc(pb.W, pb.W >= order_min);
     if (ok) {
         R = set_new((uint32_t)np, pb.W, pb.slab_bound);
         ok = R != nullptr;
@@ -1424,20 +1422,13 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
         cudaEventRecord(R->ev[0], g.stream);
         ok = stats_reset();
         const SetView va = A->view(), vb = B->view();
-        if (fused) {
-            cudaEventRecord(R->ev[1], g.stream);
-            launch_pairs_fused(va, vb, pb.d_ia, pb.d_ib, (uint32_t)np, op, rules, R->d_slab, R->slab_cap, R->out(),
-                               g.d_stats, g.sms, g.stream);
-            cudaEventRecord(R->ev[2], g.stream);
-        } else {
-            launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, rules, ib_.it,
-                              g.d_stats, g.stream);
-            launch_order_items(ib_.it, pb.W, g.d_stats, g.stream);
-            cudaEventRecord(R->ev[1], g.stream);
-            launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, g.stream);
-            cudaEventRecord(R->ev[2], g.stream);
-            launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
-        }
+        launch_plan_pairs(va, vb, pb.d_ia, pb.d_ib, pb.d_off, (uint32_t)np, op, false, rules, ib_.it,
+                          g.d_stats, g.stream);
+        launch_order_items(ib_.it, pb.W, g.d_stats, g.stream);
+        cudaEventRecord(R->ev[1], g.stream);
+        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, g.stream);
+        cudaEventRecord(R->ev[2], g.stream);
+        launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
         ok = ok && cudaMemcpyAsync(R->pstats, g.d_stats, sizeof(OpStats), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;
         cudaEventRecord(R->ev[3], g.stream);
         // no synchronisation here: the counters are taken over by resolve() on first use
@@ -1602,7 +1593,7 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         // operand staging by TMA bulk copies pays off when the containers are mostly bitsets
         // (RB200_OR_MANY_TMA=0/1 forces the choice)
         static const int tma_env = []() { const char *e = getenv("RB200_OR_MANY_TMA"); return e ? atoi(e) : -1; }();
-        const bool use_tma = tma_env >= 0 ? tma_env != 0 : (tot > 0 && tot_kib / tot >= 4);
+        const bool use_tma = tma_env >= 0 ? tma_env != 0 : (tot > 0 && tot_kib / tot >= 7);   // measured: 6 KiB average (config 3, d = 0.1) is already faster direct
         cudaMemsetAsync(g.d_m2_tables, 0, 3 * 65536 * sizeof(uint32_t), g.stream);
         if (want_ck) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
         launch_or_many2(vs, d_idx, (uint32_t)n, key_lo, key_hi, ix, (uint32_t)std::min<uint64_t>(max_units, 0xffffffffu),
