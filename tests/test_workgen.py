@@ -91,3 +91,13 @@ def test_dense_is_the_global_pcg_stream(R):
         assert A.blob(i) == R.serialize(r), i
         R.free(r)
     A.free()
+
+
+def test_cached_arena_roundtrip(tmp_path):
+    """The /dev/shm memoisation of the generators returns the very bytes the generator emitted."""
+    build = lambda: wl.zipf_arena(4, 10 ** 6, None, b0=3, density_draw=True, threads=2)
+    a = wl.cached_arena("t", build, cache_dir=str(tmp_path))
+    first, cards = a.blobs(), [int(x) for x in a.cards]
+    b = wl.cached_arena("t", build, cache_dir=str(tmp_path))
+    assert type(b).__name__ == "MappedArena" and b.blobs() == first and [int(x) for x in b.cards] == cards
+    assert wl.cached_arena("t", build, cache_dir="").blobs() == first      # caching disabled: rebuilt, same bytes
