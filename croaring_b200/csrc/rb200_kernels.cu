@@ -217,12 +217,13 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
     // dynamic scheduling: a ticket is TICKET consecutive items; the next ticket is requested
     // before the current one is processed so its latency hides behind the work.
     // (small batches: tickets of 1 so that every warp of the grid gets work at once)
-    // with an order list (big batches) the tickets walk the live items class by class; the
-    // pass-through class (the last one) belongs to k_copy_items
+    // with an order list (big batches) the tickets walk the live items class by class
+    // (tried: a lean kernel of its own for the pass-through class — 40 registers, no accumulator —
+    //  launched behind this one: 4.78 vs 4.53 ms per step, the copies no longer overlap the cells)
     if (it.order) {
         unsigned long long live = 0;
 #pragma unroll
-        for (int c = 0; c < N_CLS - 1; c++) live += st->cls_count[c];
+        for (int c = 0; c < N_CLS; c++) live += st->cls_count[c];
         W = live;
     }
     const unsigned long long TICKET = (W >= 8ull * ((unsigned long long)gridDim.x * 4)) ? 4ull : 1ull;
@@ -279,49 +280,6 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
             }
         }
         tk = __shfl_sync(FULLMASK, next, 0);
-    }
-}
-
-// Pass-through containers of an ordered batch (class CLS_COPY): a lean kernel of its own — no
-// accumulator, 32 registers, 64 resident warps per SM hide the three dependent metadata loads that
-// dominate a 1-2 KiB copy (census1881 / wikileaks OR and XOR are 13 and 10 copies per pair against
-// 0.8 and 4.3 computed cells).
-__global__ void __launch_bounds__(256, 6)
-k_copy_items(SetView A, SetView B, Items it, uint8_t *slab, uint64_t slab_cap, OpStats *st, int rules) {
-    const int lane = threadIdx.x & 31;
-    unsigned long long first = 0;
-#pragma unroll
-    for (int c = 0; c < N_CLS - 1; c++) first += st->cls_count[c];
-    const unsigned long long n = st->cls_count[CLS_COPY];
-    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long w = warp; w < n; w += nwarps) {
-        const unsigned long long item = it.order[first + w];
-        const int kind = it.kind[item];
-        const uint64_t off = it.slot_off[item];
-        const uint32_t cap = it.slot_cap[item];
-        int otype = 0;
-        uint32_t ocard = 0, olen = 0;
-        if (off + cap > slab_cap) {
-            if (lane == 0) atomicExch(&st->error, 2u);
-        } else {
-            const SetView &S = (kind == K_COPY_A) ? A : B;
-            const uint32_t c = (kind == K_COPY_A) ? it.ca[item] : it.cb[item];
-            otype = S.c_type[c];
-            ocard = S.c_card[c];
-            olen = S.c_len[c];
-            // roaring_bitmap_flip on an absent key: container_range_of_ones (containers.h:300-312)
-            if ((rules & RULES_FLIP) && kind == K_COPY_B && (ocard & CARD_MASK) == 1u) {
-                otype = T_ARRAY;
-                olen = 1;
-            }
-            warp_copy16(slab + off, S.payload + S.c_off[c], stored_bytes(otype, olen), lane);
-        }
-        if (lane == 0) {
-            it.otype[item] = (uint8_t)otype;
-            it.ocard[item] = ocard;
-            it.olen[item] = olen;
-        }
     }
 }
 
@@ -708,10 +666,6 @@ void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t
         default: k_compute_items<OP_ANDNOT, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules); break;
     }
     g_launches++;
-    if (it.order && op != OP_AND) {   // (AND has no pass-through)
-        k_copy_items<<<sm_count() * 8, 256, 0, s>>>(A, B, it, slab, slab_cap, st, rules);
-        g_launches++;
-    }
 }
 
 void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W, OpStats *st,
