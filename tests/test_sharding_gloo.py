@@ -44,7 +44,7 @@ def test_plan_key_ranges_balanced_and_covering():
     for b in blobs:
         keys, _ = sh.blob_key_cards(b)
         for k in keys:
-            hist[k] += len(sh.slice_blob_by_keys(b, int(k), int(k)))  # header + payload of that key
+            hist[k] += len(sh.slice_blob_by_keys(b, int(k), int(k))) + 512  # header + payload of that key + the per-container weight
     for world in (1, 2, 3, 4, 8):
         rs, span = sh.plan_key_ranges(blobs, world)
         assert span == (0, 59)
