@@ -118,11 +118,13 @@ struct OpStats {
 // by INSTRUCTION FETCH (ncu, profiles/r2: no_instruction stalls 6.3 per issued instruction), so
 // the tickets are handed out class by class: at any time almost every resident warp executes the
 // same few hundred instructions.  Heavy classes first (tail balance).
-constexpr int CLS_BB = 0;        // bitset x bitset
-constexpr int CLS_BA = 1;        // bitset x array (either side)
-constexpr int CLS_BR = 2;        // bitset x run
-constexpr int CLS_AA_ACC = 3;    // array x array through the accumulator (large unions / xors)
-constexpr int CLS_RUN_ACC = 4;   // run cells through the accumulator
+// (measured with per-item clocks, tools/scale_probe.py: run cells through the accumulator cost
+//  100-450 k clocks each under load, 10-30x the average item — they go first)
+constexpr int CLS_RUN_ACC = 0;   // run cells through the accumulator
+constexpr int CLS_BR = 1;        // bitset x run
+constexpr int CLS_AA_ACC = 2;    // array x array through the accumulator (large unions / xors)
+constexpr int CLS_BA = 3;        // bitset x array (either side)
+constexpr int CLS_BB = 4;        // bitset x bitset
 constexpr int CLS_AA = 5;        // array x array: filter / merge path
 constexpr int CLS_RUN_IV = 6;    // run cells by interval sweep
 constexpr int CLS_COPY = 7;      // pass-through
@@ -199,7 +201,7 @@ void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uin
 void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
                      const Many2Index &ix, uint32_t max_units, uint32_t *scratch, uint32_t *tickets,
                      uint32_t scratch_slots, SetOut out, uint32_t *card_per_key, OpStats *st, int sms,
-                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma);
+                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma, bool window_index);
 
 void launch_pack_scan(const uint64_t *bytes, const uint32_t *cnts, uint32_t n, uint64_t *off,
                       uint64_t *beg, cudaStream_t s);

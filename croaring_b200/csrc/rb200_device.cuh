@@ -333,6 +333,28 @@ __device__ __forceinline__ void acc_apply_array(uint32_t *acc, const uint8_t *sr
     }
 }
 
+// one 16-byte vector (8 values, `left` of them valid, >= 1) of a sorted array into the accumulator
+template <int MODE>
+__device__ __forceinline__ void acc_apply_vec(uint32_t *acc, uint4 q, uint32_t left) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t cur_w = (w[0] & 0xffffu) >> 5, cur_m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+        const uint32_t wi = v >> 5, bit = 1u << (v & 31);
+        if (k == 0 || k < (int)left) {
+            if (wi != cur_w) {
+                acc_atom<MODE>(acc + cur_w, cur_m);
+                cur_w = wi;
+                cur_m = bit;
+            } else {
+                cur_m |= bit;
+            }
+        }
+    }
+    acc_atom<MODE>(acc + cur_w, cur_m);
+}
+
 // same with the first vector of every lane already loaded by the caller (several containers in flight)
 template <int MODE>
 __device__ __forceinline__ void acc_apply_array_first(uint32_t *acc, const uint8_t *src, uint32_t n, uint4 q,

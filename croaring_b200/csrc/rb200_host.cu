@@ -1563,7 +1563,7 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
     if (ok && sh) { evc0 = ev_get(); evc1 = ev_get(); ok = evc0 && evc1; }
     static const bool env_v1 = []() { const char *e = getenv("RB200_OR_MANY"); return e && !strcmp(e, "v1"); }();
     // the index packs payload offsets / 16 into 32 bits and participants per key into 24
-    const bool use_v1 = env_v1 || S->slab_used >= (64ull << 30) || n >= (1u << 24);
+    const bool use_v1 = env_v1 || S->slab_used >= (64ull << 30) || n >= (1u << 22);
     // index of the second-generation kernel: entries + work-unit table from the device pool
     uint64_t tot_kib = 0;
     for (size_t i = 0; i < n; i++) tot_kib += (S->h_bytes[idx ? idx[i] : i] >> 10) + 1;
@@ -1594,11 +1594,16 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         // (RB200_OR_MANY_TMA=0/1 forces the choice)
         static const int tma_env = []() { const char *e = getenv("RB200_OR_MANY_TMA"); return e ? atoi(e) : -1; }();
         const bool use_tma = tma_env >= 0 ? tma_env != 0 : (tot > 0 && tot_kib / tot >= 7);   // measured: 6 KiB average (config 3, d = 0.1) is already faster direct
+        // index build: key windows + shared-memory counting when the directories are long (a window
+        // costs one directory search per input), one L2 atomic per container otherwise
+        // (RB200_OR_MANY_INDEX=window / atomic forces the choice)
+        static const int win_env = []() { const char *e = getenv("RB200_OR_MANY_INDEX"); return !e ? -1 : !strcmp(e, "window") ? 1 : 0; }();
+        const bool window_index = win_env >= 0 ? win_env != 0 : (tot >= 64 * (uint64_t)n);
         cudaMemsetAsync(g.d_m2_tables, 0, 3 * 65536 * sizeof(uint32_t), g.stream);
         if (want_ck) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
         launch_or_many2(vs, d_idx, (uint32_t)n, key_lo, key_hi, ix, (uint32_t)std::min<uint64_t>(max_units, 0xffffffffu),
                         g.d_m2_scratch, g.d_m2_tickets, M2_SCRATCH_SLOTS, R->out(), want_ck ? g.d_cardkey : nullptr,
-                        g.d_stats, g.sms, g.stream, g.evk0, use_tma);
+                        g.d_stats, g.sms, g.stream, g.evk0, use_tma, window_index);
     }
     if (ok && use_v1) {
         cudaEventRecord(g.ev0, g.stream);

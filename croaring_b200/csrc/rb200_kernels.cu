@@ -205,6 +205,16 @@ k_order_items(Items it, uint64_t W, OpStats *st) {
 #ifndef RB200_CI_MINBLOCKS
 #define RB200_CI_MINBLOCKS 6   // resident CTAs per SM the register allocation is held to (6 = what the 36 KiB of shared memory allow)
 #endif
+#ifdef RB200_PROBE
+// tuning aid (variant builds only, never the product): slowest item / warp of the last launch
+__device__ unsigned long long g_probe[8];
+extern "C" __attribute__((visibility("default"))) void rb200_debug_probe(unsigned long long *out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_probe, sizeof(g_probe));
+    unsigned long long z[8] = {0, 0, ~0ull, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_probe, z, sizeof(z));
+}
+#endif
 template <int OP, bool LAZY>
 __global__ void __launch_bounds__(128, RB200_CI_MINBLOCKS)
 k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
@@ -220,27 +230,40 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
     // with an order list (big batches) the tickets walk the live items class by class
     // (tried: a lean kernel of its own for the pass-through class — 40 registers, no accumulator —
     //  launched behind this one: 4.78 vs 4.53 ms per step, the copies no longer overlap the cells)
+    // Ticket granularity (measured, tools/scale_probe.py): cells take ONE item per ticket — four
+    // consecutive heavy cells on one warp were the tail of every launch (weather OR at 1/8 of the
+    // pairs: 363 -> 218 us) — pass-through copies four (fewer atomics on the copy-heavy launches).
+    unsigned long long n_cells = W, T = W;      // no order list (small batches): tickets of one item
     if (it.order) {
         unsigned long long live = 0;
 #pragma unroll
         for (int c = 0; c < N_CLS; c++) live += st->cls_count[c];
         W = live;
+        n_cells = live - st->cls_count[CLS_COPY];
+        T = n_cells + (st->cls_count[CLS_COPY] + 3) / 4;
     }
-    const unsigned long long TICKET = (W >= 8ull * ((unsigned long long)gridDim.x * 4)) ? 4ull : 1ull;
     unsigned long long tk = 0;
-    if (lane == 0) tk = atomicAdd(&st->work_counter, TICKET);
+#ifdef RB200_PROBE
+    const long long probe_w0 = clock64();
+    unsigned long long probe_n = 0;
+#endif
+    if (lane == 0) tk = atomicAdd(&st->work_counter, 1ull);
     tk = __shfl_sync(FULLMASK, tk, 0);
-    while (tk < W) {
+    while (tk < T) {
         unsigned long long next = 0;
-        if (lane == 0) next = atomicAdd(&st->work_counter, TICKET);
-        const unsigned long long tend = tk + TICKET < W ? tk + TICKET : W;
+        if (lane == 0) next = atomicAdd(&st->work_counter, 1ull);
+        const unsigned long long t0 = tk < n_cells ? tk : n_cells + (tk - n_cells) * 4;
+        const unsigned long long tend = tk < n_cells ? tk + 1 : (t0 + 4 < W ? t0 + 4 : W);
         // (tried in round 2: fetching the metadata of the whole ticket with its first lanes and passing
         //  the fields by shuffle — 17 more live registers, spills at the 6-CTA register budget and
         //  8-item tickets made every launch 15-60 % SLOWER; the per-item dependent loads stay)
-        for (unsigned long long slot = tk; slot < tend; slot++) {
+        for (unsigned long long slot = t0; slot < tend; slot++) {
             const unsigned long long item = it.order ? (unsigned long long)it.order[slot] : slot;
             const int kind = it.kind[item];
             if (kind == K_HOLE) continue;
+#ifdef RB200_PROBE
+            const long long probe_t0 = clock64();
+#endif
             const uint64_t off = it.slot_off[item];
             const uint32_t cap = it.slot_cap[item];
             int otype = 0;
@@ -278,9 +301,33 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 it.ocard[item] = ocard;
                 it.olen[item] = olen;
             }
+#ifdef RB200_PROBE
+            if (lane == 0) {
+                const unsigned long long dt = (unsigned long long)(clock64() - probe_t0);
+                unsigned long long tag = (unsigned long long)kind << 28;
+                if (kind == K_COMPUTE) {
+                    const uint32_t ca = it.ca[item], cb = it.cb[item];
+                    tag |= (unsigned long long)A.c_type[ca] << 26 | (unsigned long long)B.c_type[cb] << 24 |
+                           (unsigned long long)((A.c_card[ca] & CARD_MASK) >> 5) << 12 | ((B.c_card[cb] & CARD_MASK) >> 5);
+                }
+                atomicMax(&g_probe[0], dt << 32 | tag);
+                atomicAdd(&g_probe[3], dt);
+                atomicAdd(&g_probe[4], 1ull);
+                atomicAdd(&g_probe[5 + (kind == K_COMPUTE ? 0 : 1)], dt);
+                probe_n++;
+            }
+#endif
         }
         tk = __shfl_sync(FULLMASK, next, 0);
     }
+#ifdef RB200_PROBE
+    if (lane == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - probe_w0);
+        atomicMax(&g_probe[1], dt << 32 | probe_n);
+        atomicMin(&g_probe[2], dt << 32 | probe_n);
+        atomicAdd(&g_probe[7], dt);
+    }
+#endif
 }
 
 // container_and_cardinality for one matched cell (containers.h:811-859)

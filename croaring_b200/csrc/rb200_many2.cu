@@ -32,6 +32,8 @@
 //         makes that test a popcount instead of a second pass over the payloads.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "rb200_device.cuh"
 
 namespace rb200 {
@@ -42,6 +44,10 @@ constexpr uint32_t M2_SLICE_BYTES = 384u << 10;  // payload bytes per work unit 
 constexpr uint32_t M2_MAX_SLICES = 64;
 constexpr uint32_t TF_FULL_RUN = 16, TF_FULL_BITSET = 32;
 constexpr uint32_t POS_NONE = 0xffffffffu;
+#ifndef RB200_M2_FLAT_VECS
+#define RB200_M2_FLAT_VECS 32
+#endif
+constexpr uint32_t M2_FLAT_VECS = RB200_M2_FLAT_VECS;   // arrays below this many 16-byte vectors go through the flat list
 
 __device__ __forceinline__ uint32_t entry_tf(const SetView &S, uint32_t c) {
     const uint32_t t = S.c_type[c], l = S.c_len[c], cd = S.c_card[c] & CARD_MASK;
@@ -70,113 +76,231 @@ k_many2_count(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t 
     }
 }
 
-// single CTA, 1024 threads, 64 keys per thread
+// key-window form of the index build (inputs with long directories): a CTA owns windows of 32
+// consecutive keys; thread t finds where window w starts in the (sorted) directory of bitmap t —
+// keys are distinct, so position <= key - first key: a galloping search from that bound, 1-3 probes
+// on dense directories — then a warp reads the <= 32 containers of (window, bitmap) in one
+// coalesced access and counts them with SHARED-memory atomics.  No global atomic anywhere
+// (the bitmap-major kernels above spend one L2 atomic per container: 1.7 + 3.3 ms on the 13 M
+// containers of config 3 at density 0.003; this form: see profiles/).
+constexpr int M2W_KEYS = 32, M2W_THREADS = 256;
+
+// live key span of the participants -> key_fill[0] = largest key, key_fill[1] = 65535 - smallest key
+__global__ void __launch_bounds__(256)
+k_many2_span(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t *__restrict__ span) {
+    uint32_t hi = 0, lo_c = 0;
+    bool any = false;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t b = idx ? idx[i] : i;
+        const uint32_t nc = S.bm_cnt[b];
+        if (!nc) continue;
+        const uint32_t c0 = S.bm_beg[b];
+        hi = max(hi, (uint32_t)S.c_key[c0 + nc - 1]);
+        lo_c = max(lo_c, 65535u - (uint32_t)S.c_key[c0]);
+        any = true;
+    }
+    hi = __reduce_max_sync(FULLMASK, hi);
+    lo_c = __reduce_max_sync(FULLMASK, lo_c);
+    if (__any_sync(FULLMASK, any) && (threadIdx.x & 31) == 0) {
+        atomicMax(span, hi);
+        atomicMax(span + 1, lo_c);
+    }
+}
+
+// first directory position of bitmap (c0, nc) whose key is >= k0
+__device__ __forceinline__ uint32_t window_lower_bound(const uint16_t *__restrict__ keys, uint32_t nc, uint32_t k0) {
+    const uint32_t kfirst = keys[0];
+    if (k0 <= kfirst) return 0;
+    uint32_t lo = 0, hi = min(nc, k0 - kfirst), w = 1;
+    while (lo < hi) {                      // gallop down from the bound
+        uint32_t p = hi > w ? hi - w : 0u;
+        if (p < lo) p = lo;
+        if (keys[p] < k0) { lo = p + 1; break; }
+        hi = p;
+        w <<= 1;
+    }
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < k0) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(M2W_THREADS)
+k_many2_window(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
+               Many2Index ix) {
+    __shared__ uint32_t s_cnt[M2W_KEYS], s_b16[M2W_KEYS], s_start[M2W_KEYS];
+    __shared__ uint32_t s_seg[M2W_THREADS], s_c0[M2W_THREADS], s_nc[M2W_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t span_hi = min(ix.key_fill[0], key_hi), span_lo = max(65535u - ix.key_fill[1], key_lo);
+    if (span_lo > span_hi) return;
+    const uint32_t w0 = span_lo / M2W_KEYS, w1 = span_hi / M2W_KEYS;
+    for (uint32_t w = w0 + blockIdx.x; w <= w1; w += gridDim.x) {
+        const uint32_t k0 = w * M2W_KEYS;
+        if (tid < M2W_KEYS) {
+            s_cnt[tid] = 0;
+            s_b16[tid] = 0;
+            if (FILL) s_start[tid] = ix.key_start[k0 + tid];
+        }
+        for (uint32_t base = 0; base < n; base += M2W_THREADS) {
+            __syncthreads();
+            {   // every thread: where the window starts in one bitmap's directory
+                const uint32_t i = base + tid;
+                uint32_t nc = 0, c0 = 0, seg = 0;
+                if (i < n) {
+                    const uint32_t b = idx ? idx[i] : i;
+                    nc = S.bm_cnt[b];
+                    c0 = S.bm_beg[b];
+                    if (nc) {
+                        if ((uint32_t)S.c_key[c0 + nc - 1] < k0) nc = 0;   // directory ends before the window
+                        else seg = window_lower_bound(S.c_key + c0, nc, k0);
+                    }
+                }
+                s_seg[tid] = seg;
+                s_c0[tid] = c0;
+                s_nc[tid] = nc;
+            }
+            __syncthreads();
+            const uint32_t m = min((uint32_t)M2W_THREADS, n - base);
+            for (uint32_t q = wid; q < m; q += M2W_THREADS / 32) {
+                const uint32_t nc = s_nc[q], p = s_seg[q] + lane;
+                if (p >= nc) continue;                     // (whole warp when the bitmap has nothing here)
+                const uint32_t c = s_c0[q] + p;
+                const uint32_t k = S.c_key[c];
+                if (k >= k0 + M2W_KEYS || k < key_lo || k > key_hi) continue;
+                const uint32_t t = S.c_type[c], l = S.c_len[c];
+                if (!FILL) {
+                    atomicAdd(&s_cnt[k - k0], 1u);
+                    atomicAdd(&s_b16[k - k0], round16(stored_bytes(t, l)) >> 4);
+                } else {
+                    const uint32_t cd = S.c_card[c] & CARD_MASK;
+                    uint32_t f = t;
+                    if (t == T_RUN && l == 1 && cd == 65536) f |= TF_FULL_RUN;
+                    if (t == T_BITSET && cd == 65536) f |= TF_FULL_BITSET;
+                    const uint32_t slot = s_start[k - k0] + atomicAdd(&s_cnt[k - k0], 1u);
+                    ix.ent[slot] = make_uint4((uint32_t)(S.c_off[c] >> 4), base + q, l, f);
+                }
+            }
+        }
+        __syncthreads();
+        if (!FILL && tid < M2W_KEYS && k0 + tid <= 65535u)
+            ix.key_cu[k0 + tid] = ((unsigned long long)s_cnt[tid] << 40) | s_b16[tid];
+        __syncthreads();
+    }
+}
+
+// single CTA, 1024 threads: tiles of 4096 keys, 4 consecutive keys per thread (coalesced), running carries
+__device__ __forceinline__ uint32_t key_units(unsigned long long cu, uint32_t slice_kib) {
+    const uint32_t c = (uint32_t)(cu >> 40);
+    if (!c) return 0;
+    const uint32_t kib = (uint32_t)((cu & ((1ull << 40) - 1)) >> 6);
+    uint32_t s = (kib + slice_kib - 1) / slice_kib;
+    const uint32_t by_cnt = (c + 3) >> 2;
+    if (s > by_cnt) s = by_cnt;
+    if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
+    if (s < 1) s = 1;
+    return s;
+}
+
 __global__ void __launch_bounds__(1024)
 k_many2_scan(Many2Index ix, uint32_t scratch_slots, uint32_t max_units, uint32_t want_parallel, SetOut out,
-             OpStats *st) {
-    __shared__ uint32_t s_a[32], s_b[32], s_c[32], s_d[32];
+             OpStats *st, int has_span) {
+    __shared__ uint32_t s_w[32][4];
+    __shared__ uint32_t s_carry[4];
     __shared__ uint32_t s_split;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // pass 1: entries, live keys and total weight
-    uint32_t cnt = 0, live = 0, w16 = 0;
-    for (int k = 0; k < 64; k++) {
-        const unsigned long long cu = ix.key_cu[tid * 64 + k];
-        const uint32_t c = (uint32_t)(cu >> 40);
-        cnt += c;
-        live += c ? 1u : 0u;
-        w16 += (uint32_t)((cu & ((1ull << 40) - 1)) >> 6);   // KiB, to stay inside 32 bits
+    const uint32_t ntiles = has_span ? (min(ix.key_fill[0], 65535u) >> 12) + 1 : 16u;
+    // pass 1: total weight -> slice size
+    uint32_t w16 = 0;
+    for (uint32_t t = 0; t < ntiles; t++) {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(ix.key_cu + t * 4096 + tid * 4);
+        const ulonglong2 a = p[0], b = p[1];
+        const unsigned long long M = (1ull << 40) - 1;
+        w16 += (uint32_t)((a.x & M) >> 6) + (uint32_t)((a.y & M) >> 6) + (uint32_t)((b.x & M) >> 6) + (uint32_t)((b.y & M) >> 6);   // KiB, to stay inside 32 bits
     }
-    uint32_t icnt = warp_incl_scan(cnt, lane), ilive = warp_incl_scan(live, lane), iw = warp_incl_scan(w16, lane);
-    if (lane == 31) { s_a[wid] = icnt; s_b[wid] = ilive; s_c[wid] = iw; }
+    w16 = __reduce_add_sync(FULLMASK, w16);
+    if (lane == 0) s_w[wid][0] = w16;
+    if (tid < 4) s_carry[tid] = 0;
     __syncthreads();
-    if (wid == 0) {
-        const uint32_t a = s_a[lane], b = s_b[lane], c = s_c[lane];
-        const uint32_t sa = warp_incl_scan(a, lane), sb = warp_incl_scan(b, lane), sc = warp_incl_scan(c, lane);
-        s_a[lane] = sa - a;
-        s_b[lane] = sb - b;
-        s_c[lane] = sc;
-        if (lane == 31) {
-            st->nk = sb;
-            // few heavy keys: split them so that the grid has ~want_parallel units
-            const uint32_t total_kib = sc;
-            // few heavy keys: split them so that the grid has ~want_parallel units (measured: units of
-            // ~384 KiB beat both finer and coarser ones at every density of config 3)
-            uint32_t slice_kib = M2_SLICE_BYTES >> 10;
-            if (want_parallel && total_kib / slice_kib < want_parallel) {
-                slice_kib = total_kib / want_parallel;
-                if (slice_kib < 32) slice_kib = 32;
-            }
-            s_split = slice_kib;
+    if (tid == 0) {
+        uint32_t total_kib = 0;
+        for (int i = 0; i < 32; i++) total_kib += s_w[i][0];
+        // few heavy keys: split them so that the grid has ~want_parallel units (measured: units of
+        // ~384 KiB beat both finer and coarser ones at every density of config 3)
+        uint32_t slice_kib = M2_SLICE_BYTES >> 10;
+        if (want_parallel && total_kib / slice_kib < want_parallel) {
+            slice_kib = total_kib / want_parallel;
+            if (slice_kib < 32) slice_kib = 32;
         }
+        s_split = slice_kib;
     }
     __syncthreads();
     const uint32_t slice_kib = s_split;
-    uint32_t e = s_a[wid] + icnt - cnt, ki = s_b[wid] + ilive - live;
-    // pass 2: per key start / live index / slices
-    uint32_t units = 0, nsplit = 0;
-    for (int k = 0; k < 64; k++) {
-        const uint32_t key = tid * 64 + k;
-        const unsigned long long cu = ix.key_cu[key];
-        const uint32_t c = (uint32_t)(cu >> 40);
-        ix.key_start[key] = e;
-        ix.key_count[key] = c;
-        e += c;
-        if (c) {
-            const uint32_t kib = (uint32_t)((cu & ((1ull << 40) - 1)) >> 6);
-            uint32_t s = (kib + slice_kib - 1) / slice_kib;
-            const uint32_t by_cnt = (c + 3) >> 2;
-            if (s > by_cnt) s = by_cnt;
-            if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
-            if (s < 1) s = 1;
-            units += s;
-            nsplit += s > 1 ? 1u : 0u;
+    // pass 2: per key start / live index / slices / units, tile by tile
+    for (uint32_t t = 0; t < 16; t++) {
+        const uint32_t key0 = t * 4096 + tid * 4;
+        if (t >= ntiles) {   // beyond the span: empty keys
+            *reinterpret_cast<uint4 *>(ix.key_count + key0) = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(ix.key_cu + key0);
+        const ulonglong2 a = p[0], b = p[1];
+        const unsigned long long cu[4] = {a.x, a.y, b.x, b.y};
+        uint32_t c[4], s[4];
+        uint32_t cnt = 0, live = 0, units = 0, nsplit = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            c[k] = (uint32_t)(cu[k] >> 40);
+            s[k] = key_units(cu[k], slice_kib);
+            cnt += c[k];
+            live += c[k] ? 1u : 0u;
+            units += s[k];
+            nsplit += s[k] > 1 ? 1u : 0u;
+        }
+        const uint32_t icnt = warp_incl_scan(cnt, lane), ilive = warp_incl_scan(live, lane),
+                       iu = warp_incl_scan(units, lane), is = warp_incl_scan(nsplit, lane);
+        __syncthreads();                       // s_w of the previous tile consumed
+        if (lane == 31) { s_w[wid][0] = icnt; s_w[wid][1] = ilive; s_w[wid][2] = iu; s_w[wid][3] = is; }
+        __syncthreads();
+        uint32_t e = s_carry[0] + icnt - cnt, ki = s_carry[1] + ilive - live, u = s_carry[2] + iu - units,
+                 sp = s_carry[3] + is - nsplit;
+        for (int w = 0; w < wid; w++) { e += s_w[w][0]; ki += s_w[w][1]; u += s_w[w][2]; sp += s_w[w][3]; }
+        __syncthreads();                       // carries read by everyone
+        if (tid == 1023) { s_carry[0] = e + cnt; s_carry[1] = ki + live; s_carry[2] = u + units; s_carry[3] = sp + nsplit; }
+        uint32_t st4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { st4[k] = e; e += c[k]; }
+        *reinterpret_cast<uint4 *>(ix.key_start + key0) = make_uint4(st4[0], st4[1], st4[2], st4[3]);
+        *reinterpret_cast<uint4 *>(ix.key_count + key0) = make_uint4(c[0], c[1], c[2], c[3]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!c[k]) continue;
+            uint32_t slot = POS_NONE;
+            if (s[k] > 1) {
+                // a split key needs a scratch slot and room in the unit table; else it stays whole
+                // (the unit numbering must not depend on this decision: units were reserved)
+                if (sp < scratch_slots && u + s[k] <= max_units) slot = sp;
+                sp++;
+            }
+            ix.keys[ki] = (uint16_t)(key0 + k);
+            ix.key_slices[ki] = slot == POS_NONE ? 1u : s[k];
+            ix.key_scratch[ki] = slot;
+            ix.unit_first[ki] = u;
+            // reserved-but-unused units of an unsplit heavy key are marked idle
+            for (uint32_t q = 0; q < s[k] && u + q < max_units; q++)
+                ix.unit_ki[u + q] = (slot == POS_NONE && q > 0) ? POS_NONE : ki;
+            u += s[k];
+            ki++;
         }
     }
-    uint32_t iu = warp_incl_scan(units, lane), is = warp_incl_scan(nsplit, lane);
     __syncthreads();
-    if (lane == 31) { s_a[wid] = iu; s_d[wid] = is; }
-    __syncthreads();
-    if (wid == 0) {
-        const uint32_t a = s_a[lane], d = s_d[lane];
-        const uint32_t sa = warp_incl_scan(a, lane), sd = warp_incl_scan(d, lane);
-        s_a[lane] = sa - a;
-        s_d[lane] = sd - d;
-    }
-    __syncthreads();
-    uint32_t u = s_a[wid] + iu - units, sp = s_d[wid] + is - nsplit;
-    for (int k = 0; k < 64; k++) {
-        const uint32_t key = tid * 64 + k;
-        const unsigned long long cu = ix.key_cu[key];
-        const uint32_t c = (uint32_t)(cu >> 40);
-        if (!c) continue;
-        const uint32_t kib = (uint32_t)((cu & ((1ull << 40) - 1)) >> 6);
-        uint32_t s = (kib + slice_kib - 1) / slice_kib;
-        const uint32_t by_cnt = (c + 3) >> 2;
-        if (s > by_cnt) s = by_cnt;
-        if (s > M2_MAX_SLICES) s = M2_MAX_SLICES;
-        if (s < 1) s = 1;
-        uint32_t slot = POS_NONE;
-        if (s > 1) {
-            // a split key needs a scratch slot and room in the unit table; else it stays whole
-            // (the unit numbering below must not depend on this decision: units were reserved)
-            if (sp < scratch_slots && u + s <= max_units) slot = sp;
-            sp++;
-        }
-        ix.keys[ki] = (uint16_t)key;
-        ix.key_slices[ki] = slot == POS_NONE ? 1u : s;
-        ix.key_scratch[ki] = slot;
-        ix.unit_first[ki] = u;
-        // reserved-but-unused units of an unsplit heavy key are marked idle
-        for (uint32_t q = 0; q < s && u + q < max_units; q++)
-            ix.unit_ki[u + q] = (slot == POS_NONE && q > 0) ? POS_NONE : ki;
-        u += s;
-        ki++;
-    }
-    __syncthreads();
-    if (tid == 1023) {
-        st->units = u < max_units ? u : max_units;
+    if (tid == 0) {
+        st->nk = s_carry[1];
+        st->units = s_carry[2] < max_units ? s_carry[2] : max_units;
         out.bm_beg[0] = 0;
-        out.bm_cnt[0] = st->nk;
+        out.bm_cnt[0] = s_carry[1];
     }
 }
 
@@ -272,8 +396,9 @@ struct Many2Smem {
     uint16_t h_bs[2][M2_HALF_ENTRIES], h_ar[2][M2_HALF_ENTRIES];   // staged bitsets / arrays+runs of a half (entry ids)
     uint32_t h_soff[M2_STAGE];  // byte offset of a staged entry inside its half
     uint32_t h_nbs[2], h_nar[2], h_big[2];
-    uint16_t bs_list[M2_STAGE], ar_list[M2_STAGE];   // direct path: staged bitsets / arrays+runs of a round
+    uint16_t bs_list[M2_STAGE], ar_list[M2_STAGE];   // direct path: staged bitsets / runs + larger arrays of a round
     uint32_t nbs, nar;
+    uint32_t s_vend[M2_STAGE];  // direct path: inclusive prefix of the 16-byte vectors of the staged ARRAYS (entry order)
     unsigned long long s_off[M2_STAGE];
     uint32_t s_len[M2_STAGE];
     uint32_t s_pos[M2_STAGE];
@@ -373,6 +498,7 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
             const uint32_t R = min((uint32_t)M2_STAGE, s_hi - base);   // entries of this round
             if (!TMA && tid == 0) { sm.nbs = 0; sm.nar = 0; }
             if (!TMA) __syncthreads();
+            uint32_t my_vec = 0;
             if (tid < M2_STAGE && e < s_hi) {
                 const uint4 en = ix.ent[e0 + e];
                 const uint32_t tf = en.w, p = en.y;
@@ -386,8 +512,17 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                 }
                 if (!TMA) {
                     if ((tf & 15) == T_BITSET) sm.bs_list[atomicAdd(&sm.nbs, 1u)] = (uint16_t)tid;
+                    else if ((tf & 15) == T_ARRAY && en.z < 8 * M2_FLAT_VECS) my_vec = (en.z + 7) >> 3;
                     else if (!(tf & TF_FULL_RUN)) sm.ar_list[atomicAdd(&sm.nar, 1u)] = (uint16_t)tid;
                 }
+            }
+            if (!TMA) {   // block scan of the array vectors (entry order)
+                const uint32_t inc = warp_incl_scan(my_vec, lane);
+                if (lane == 31) sm.red32[wid][0] = inc;
+                __syncthreads();
+                uint32_t pre = 0;
+                for (int w = 0; w < wid; w++) pre += sm.red32[w][0];
+                sm.s_vend[tid] = pre + inc;
             }
             __syncthreads();
             if (!TMA) {
@@ -409,7 +544,38 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                             r1.x |= qb[k].x; r1.y |= qb[k].y; r1.z |= qb[k].z; r1.w |= qb[k].w;
                         }
                 }
-                // arrays and runs: one warp per container, shared-memory atomics on the accumulator
+                // small arrays: the 16-byte vectors of ALL of them as one flat list, a thread per vector
+                // (two in flight): every lane loads whatever the container sizes are — a warp per
+                // container left 18 of 32 lanes idle on the ~110-value arrays of the sparse densities
+                // (config 3, d = 0.003: 3.62 -> 2.50 ms; arrays that fill a warp's 32 lanes anyway stay
+                //  on the warp path below: flat for all sizes cost 1.15 -> 1.28 ms at d = 0.03)
+                const uint32_t V = sm.s_vend[M2_STAGE - 1];
+                for (uint32_t x0 = tid; x0 < V; x0 += 2 * M2_THREADS) {
+                    uint4 qv[2];
+                    uint32_t left[2];
+                    uint32_t *dst[2];
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const uint32_t x = x0 + k * M2_THREADS;
+                        left[k] = 0;
+                        if (x < V) {
+                            uint32_t lo = 0, hi = R;   // first entry whose inclusive prefix exceeds x
+                            while (lo < hi) {
+                                const uint32_t mid = (lo + hi) >> 1;
+                                if (sm.s_vend[mid] > x) hi = mid;
+                                else lo = mid + 1;
+                            }
+                            const uint32_t n = sm.s_len[lo], i = x - (sm.s_vend[lo] - ((n + 7) >> 3));
+                            dst[k] = (L != POS_NONE && sm.s_pos[lo] > L) ? sm.acc2 : sm.acc;
+                            left[k] = n - i * 8;
+                            qv[k] = __ldg(reinterpret_cast<const uint4 *>(S.payload + sm.s_off[lo]) + i);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; k++)
+                        if (left[k]) acc_apply_vec<0>(dst[k], qv[k], left[k]);
+                }
+                // runs and larger arrays: one warp per container, shared-memory atomics on the accumulator
                 const uint32_t nar = sm.nar;
                 for (uint32_t j = wid; j < nar; j += M2_THREADS / 32) {
                     const uint32_t q = sm.ar_list[j];
@@ -642,11 +808,21 @@ __global__ void k_many2_sum_cards(const uint32_t *__restrict__ c_card, const OpS
 void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
                      const Many2Index &ix, uint32_t max_units, uint32_t *scratch, uint32_t *tickets,
                      uint32_t scratch_slots, SetOut out, uint32_t *card_per_key, OpStats *st, int sms,
-                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma) {
+                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma, bool window_index) {
     const uint32_t gw = (uint32_t)sms * 8;
-    k_many2_count<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
-    k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * 8, out, st);
-    k_many2_fill<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+    if (window_index) {
+        // long directories: key-window index build, shared-memory counting, no global atomics
+        const uint32_t gs = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 4));
+        k_many2_span<<<gs, 256, 0, s>>>(S, idx, n, ix.key_fill);
+        k_many2_window<false><<<sms * 6, M2W_THREADS, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+        k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * 8, out, st, 1);
+        k_many2_window<true><<<sms * 6, M2W_THREADS, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+        g_launches += 1;
+    } else {
+        k_many2_count<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+        k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * 8, out, st, 0);
+        k_many2_fill<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+    }
     k_many2_fold<<<gw, 128, 0, s>>>(ix, st);
     if (ev_kernel_start) cudaEventRecord(ev_kernel_start, s);
     const size_t smem_direct = (sizeof(Many2Smem) + 127) & ~(size_t)127, smem_tma = smem_direct + 2 * M2_HALF;
