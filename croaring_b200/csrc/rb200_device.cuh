@@ -305,11 +305,27 @@ __device__ __forceinline__ void acc_plain(uint32_t *p) {
 
 // acc op= {sorted u16 array}.  128-bit loads (8 values per lane); bits that fall in the same
 // 32-bit word are merged in registers before the shared-memory atomic.
+#ifndef RB200_APPLY_SPARSE_MAX
+#define RB200_APPLY_SPARSE_MAX 0   // arrays below this many values skip the merging (0 = always merge)
+#endif
 template <int MODE>
 __device__ __forceinline__ void acc_apply_array(uint32_t *acc, const uint8_t *src, uint32_t n,
                                                 int lane) {
     const uint4 *v4 = reinterpret_cast<const uint4 *>(src);
     const uint32_t nvec = (n + 7) >> 3;
+    if (n < (uint32_t)RB200_APPLY_SPARSE_MAX) {    // sparse: one atomic per value, no merging
+        for (uint32_t i = lane; i < nvec; i += 32) {
+            const uint4 q = __ldg(v4 + i);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t left = n - i * 8;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+                if (k < (int)left) acc_atom<MODE>(acc + (v >> 5), 1u << (v & 31));
+            }
+        }
+        return;
+    }
     for (uint32_t i = lane; i < nvec; i += 32) {
         const uint4 q = __ldg(v4 + i);
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -353,6 +369,16 @@ __device__ __forceinline__ void acc_apply_vec(uint32_t *acc, uint4 q, uint32_t l
         }
     }
     acc_atom<MODE>(acc + cur_w, cur_m);
+}
+
+// same for a SPARSE array (values rarely share a 32-bit word: merging them first costs more than it saves)
+__device__ __forceinline__ void acc_or_vec_sparse(uint32_t *acc, uint4 q, uint32_t left) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+        if (k < (int)left) atomicOr(acc + (v >> 5), 1u << (v & 31));
+    }
 }
 
 // same with the first vector of every lane already loaded by the caller (several containers in flight)

@@ -207,11 +207,11 @@ k_order_items(Items it, uint64_t W, OpStats *st) {
 #endif
 #ifdef RB200_PROBE
 // tuning aid (variant builds only, never the product): slowest item / warp of the last launch
-__device__ unsigned long long g_probe[8];
+__device__ unsigned long long g_probe[24];   // [8 + cls] clocks, [16 + cls] items of the class
 extern "C" __attribute__((visibility("default"))) void rb200_debug_probe(unsigned long long *out) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out, g_probe, sizeof(g_probe));
-    unsigned long long z[8] = {0, 0, ~0ull, 0, 0, 0, 0, 0};
+    unsigned long long z[24] = {0, 0, ~0ull};
     cudaMemcpyToSymbol(g_probe, z, sizeof(z));
 }
 #endif
@@ -314,6 +314,9 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
                 atomicAdd(&g_probe[3], dt);
                 atomicAdd(&g_probe[4], 1ull);
                 atomicAdd(&g_probe[5 + (kind == K_COMPUTE ? 0 : 1)], dt);
+                const int pc = it.cls[item] & 7;
+                atomicAdd(&g_probe[8 + pc], dt);
+                atomicAdd(&g_probe[16 + pc], 1ull);
                 probe_n++;
             }
 #endif

@@ -45,7 +45,10 @@ constexpr uint32_t M2_MAX_SLICES = 64;
 constexpr uint32_t TF_FULL_RUN = 16, TF_FULL_BITSET = 32;
 constexpr uint32_t POS_NONE = 0xffffffffu;
 #ifndef RB200_M2_FLAT_VECS
-#define RB200_M2_FLAT_VECS 32
+#define RB200_M2_FLAT_VECS 513
+#endif
+#ifndef RB200_M2_MERGE_MIN
+#define RB200_M2_MERGE_MIN 100000   // arrays of at least this many values merge same-word bits before the atomic
 #endif
 constexpr uint32_t M2_FLAT_VECS = RB200_M2_FLAT_VECS;   // arrays below this many 16-byte vectors go through the flat list
 
@@ -428,8 +431,11 @@ __device__ __forceinline__ unsigned long long block_min64(Many2Smem &sm, unsigne
 
 // TMA = true: operands staged by bulk copies (bitset-dominated inputs); false: direct global loads
 // (array-dominated inputs, where a bulk copy per small container costs more than it hides)
+#ifndef RB200_M2_MINB
+#define RB200_M2_MINB 4   // resident CTAs per SM of the direct path (register budget 64 at 4)
+#endif
 template <bool TMA>
-__global__ void __launch_bounds__(M2_THREADS, TMA ? 2 : 4)
+__global__ void __launch_bounds__(M2_THREADS, TMA ? 2 : RB200_M2_MINB)
 k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch, uint32_t *__restrict__ tickets,
            SetOut out, uint32_t *__restrict__ card_per_key, OpStats *st) {
     extern __shared__ __align__(128) uint8_t m2_smem_raw[];
@@ -550,30 +556,35 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                 // (config 3, d = 0.003: 3.62 -> 2.50 ms; arrays that fill a warp's 32 lanes anyway stay
                 //  on the warp path below: flat for all sizes cost 1.15 -> 1.28 ms at d = 0.03)
                 const uint32_t V = sm.s_vend[M2_STAGE - 1];
-                for (uint32_t x0 = tid; x0 < V; x0 += 2 * M2_THREADS) {
-                    uint4 qv[2];
-                    uint32_t left[2];
-                    uint32_t *dst[2];
+                for (uint32_t x0 = 4 * tid; x0 < V; x0 += 4 * M2_THREADS) {
+                    // four CONSECUTIVE vectors per thread: one search, then a linear walk; all four loads in flight
+                    uint32_t q = 0, hi = R;   // first entry whose inclusive prefix exceeds x0
+                    while (q < hi) {
+                        const uint32_t mid = (q + hi) >> 1;
+                        if (sm.s_vend[mid] > x0) hi = mid;
+                        else q = mid + 1;
+                    }
+                    uint4 qv[4];
+                    uint32_t left[4], ent[4];
 #pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        const uint32_t x = x0 + k * M2_THREADS;
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t x = x0 + k;
                         left[k] = 0;
                         if (x < V) {
-                            uint32_t lo = 0, hi = R;   // first entry whose inclusive prefix exceeds x
-                            while (lo < hi) {
-                                const uint32_t mid = (lo + hi) >> 1;
-                                if (sm.s_vend[mid] > x) hi = mid;
-                                else lo = mid + 1;
-                            }
-                            const uint32_t n = sm.s_len[lo], i = x - (sm.s_vend[lo] - ((n + 7) >> 3));
-                            dst[k] = (L != POS_NONE && sm.s_pos[lo] > L) ? sm.acc2 : sm.acc;
+                            while (sm.s_vend[q] <= x) q++;
+                            const uint32_t n = sm.s_len[q], i = x - (sm.s_vend[q] - ((n + 7) >> 3));
+                            ent[k] = q;
                             left[k] = n - i * 8;
-                            qv[k] = __ldg(reinterpret_cast<const uint4 *>(S.payload + sm.s_off[lo]) + i);
+                            qv[k] = __ldg(reinterpret_cast<const uint4 *>(S.payload + sm.s_off[q]) + i);
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < 2; k++)
-                        if (left[k]) acc_apply_vec<0>(dst[k], qv[k], left[k]);
+                    for (int k = 0; k < 4; k++)
+                        if (left[k]) {
+                            uint32_t *dst = (L != POS_NONE && sm.s_pos[ent[k]] > L) ? sm.acc2 : sm.acc;
+                            if (sm.s_len[ent[k]] < (uint32_t)RB200_M2_MERGE_MIN) acc_or_vec_sparse(dst, qv[k], left[k]);
+                            else acc_apply_vec<0>(dst, qv[k], left[k]);
+                        }
                 }
                 // runs and larger arrays: one warp per container, shared-memory atomics on the accumulator
                 const uint32_t nar = sm.nar;
@@ -835,7 +846,7 @@ void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t
     if (use_tma)
         k_or_many2<true><<<sms * 2, M2_THREADS, smem_tma, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
     else
-        k_or_many2<false><<<sms * 4, M2_THREADS, smem_direct, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
+        k_or_many2<false><<<sms * RB200_M2_MINB, M2_THREADS, smem_direct, s>>>(S, ix, n, scratch, tickets, out, card_per_key, st);
     k_many2_sum_cards<<<1, 1024, 0, s>>>(out.c_card, st, out.bm_card);
     g_launches += 6;
 }

@@ -32,7 +32,7 @@ def main():
     rb.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     probe = getattr(rb.lib(), "rb200_debug_probe", None) if hasattr(rb.lib(), "rb200_debug_probe") else None
-    buf = (ctypes.c_ulonglong * 8)()
+    buf = (ctypes.c_ulonglong * 24)()
     for ds in a.datasets.split(","):
         blobs = rb.load_realdata(ds)
         S = rb.DeviceSet.from_serialized(blobs)
@@ -70,6 +70,9 @@ def main():
                     cell["cell_clk_sum"] = pr[5]
                     cell["copy_clk_sum"] = pr[6]
                     cell["warp_clk_sum"] = pr[7]
+                    names = ["RUN_ACC", "BR", "AA_ACC", "BA", "BB", "AA", "RUN_IV", "COPY"]
+                    cell["classes"] = {names[c]: {"items": pr[16 + c], "avg_clk": round(pr[8 + c] / max(pr[16 + c], 1)),
+                                                  "share": round(pr[8 + c] / max(pr[3], 1), 3)} for c in range(8) if pr[16 + c]}
                 row[f"s{st}"] = cell
             print(json.dumps(row), flush=True)
         S.free()
