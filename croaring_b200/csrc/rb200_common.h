@@ -170,7 +170,7 @@ void launch_plan_pairs(const SetView &A, const SetView &B, const uint32_t *ia, c
                        Items it, OpStats *st, cudaStream_t s);
 void launch_order_items(Items it, uint64_t W, OpStats *st, cudaStream_t s);
 void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
-                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int rules,
+                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int rules, int copy_ticket,
                           cudaStream_t s);
 void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W, OpStats *st,
                        cudaStream_t s);

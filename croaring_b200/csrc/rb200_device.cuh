@@ -306,7 +306,8 @@ __device__ __forceinline__ void acc_plain(uint32_t *p) {
 // acc op= {sorted u16 array}.  128-bit loads (8 values per lane); bits that fall in the same
 // 32-bit word are merged in registers before the shared-memory atomic.
 #ifndef RB200_APPLY_SPARSE_MAX
-#define RB200_APPLY_SPARSE_MAX 0   // arrays below this many values skip the merging (0 = always merge)
+#define RB200_APPLY_SPARSE_MAX 4097   // arrays below this many values set their bits one atomic per value (measured: merging same-word
+                                      // bits in registers first costs more instructions than it saves atomics: 4.31 -> 4.16 ms per step)
 #endif
 template <int MODE>
 __device__ __forceinline__ void acc_apply_array(uint32_t *acc, const uint8_t *src, uint32_t n,
@@ -1029,22 +1030,11 @@ __device__ __forceinline__ void acc_apply_array_s(uint32_t *acc, const uint8_t *
         const uint4 q = v4[i];
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
         const uint32_t left = n - i * 8;
-        uint32_t cur_w = (w[0] & 0xffffu) >> 5, cur_m = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const uint32_t v = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
-            const uint32_t wi = v >> 5, bit = 1u << (v & 31);
-            if (k == 0 || k < (int)left) {
-                if (wi != cur_w) {
-                    acc_atom<MODE>(acc + cur_w, cur_m);
-                    cur_w = wi;
-                    cur_m = bit;
-                } else {
-                    cur_m |= bit;
-                }
-            }
+            if (k < (int)left) acc_atom<MODE>(acc + (v >> 5), 1u << (v & 31));
         }
-        acc_atom<MODE>(acc + cur_w, cur_m);
     }
 }
 template <int MODE, bool ATOMIC_INTERIOR>

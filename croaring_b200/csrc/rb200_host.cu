@@ -1426,7 +1426,15 @@ rb200_set *batch_op_impl(int op, const rb200_set *A, const rb200_set *B, const u
                           g.d_stats, g.stream);
         launch_order_items(ib_.it, pb.W, g.d_stats, g.stream);
         cudaEventRecord(R->ev[1], g.stream);
-        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, g.stream);
+        // pass-through tickets: one item per lane, fewer lanes when the operands' containers are big
+        // (32 x 8 KiB on one warp would be the tail of the launch)
+        const uint64_t n_cont = A->n_containers + B->n_containers;
+        const uint64_t avg_b = n_cont ? (A->slab_used + B->slab_used) / n_cont : 4096;
+        // (measured on the real-data suite, kernel ms per OR+XOR step at 4 / 8 / 16 / 32 items: 3.09 / 3.06 /
+        //  3.07 / 3.11; 1 item: 3.57 — RB200_COPY_TICKET overrides)
+        static const int ct_env = []() { const char *e = getenv("RB200_COPY_TICKET"); return e ? std::min(32, std::max(1, atoi(e))) : 0; }();
+        const int copy_ticket = ct_env ? ct_env : avg_b <= 256 ? 32 : avg_b <= 2048 ? 16 : 8;
+        launch_compute_items(va, vb, ib_.it, pb.W, op, R->d_slab, R->slab_cap, g.d_stats, rules, copy_ticket, g.stream);
         cudaEventRecord(R->ev[2], g.stream);
         launch_finalize_pairs(va, vb, ib_.it, pb.d_off, (uint32_t)np, R->out(), g.d_stats, g.stream);
         ok = ok && cudaMemcpyAsync(R->pstats, g.d_stats, sizeof(OpStats), cudaMemcpyDeviceToHost, g.stream) == cudaSuccess;

@@ -218,7 +218,7 @@ extern "C" __attribute__((visibility("default"))) void rb200_debug_probe(unsigne
 template <int OP, bool LAZY>
 __global__ void __launch_bounds__(128, RB200_CI_MINBLOCKS)
 k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
-                uint64_t slab_cap, OpStats *st, int rules) {
+                uint64_t slab_cap, OpStats *st, int rules, int copy_ticket) {
     __shared__ __align__(16) uint32_t s_acc[4][ACC_WORDS];
     __shared__ __align__(16) uint16_t s_pre[4][512];   // rank-scatter prefix table (rb200_device.cuh)
     const int lane = threadIdx.x & 31;
@@ -232,7 +232,7 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
     //  launched behind this one: 4.78 vs 4.53 ms per step, the copies no longer overlap the cells)
     // Ticket granularity (measured, tools/scale_probe.py): cells take ONE item per ticket — four
     // consecutive heavy cells on one warp were the tail of every launch (weather OR at 1/8 of the
-    // pairs: 363 -> 218 us) — pass-through copies four (fewer atomics on the copy-heavy launches).
+    // pairs: 363 -> 218 us) — pass-through copies 32, one per lane (below).
     unsigned long long n_cells = W, T = W;      // no order list (small batches): tickets of one item
     if (it.order) {
         unsigned long long live = 0;
@@ -240,7 +240,7 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
         for (int c = 0; c < N_CLS; c++) live += st->cls_count[c];
         W = live;
         n_cells = live - st->cls_count[CLS_COPY];
-        T = n_cells + (st->cls_count[CLS_COPY] + 3) / 4;
+        T = n_cells + (st->cls_count[CLS_COPY] + copy_ticket - 1) / copy_ticket;
     }
     unsigned long long tk = 0;
 #ifdef RB200_PROBE
@@ -252,8 +252,74 @@ k_compute_items(SetView A, SetView B, Items it, uint64_t W, uint8_t *slab,
     while (tk < T) {
         unsigned long long next = 0;
         if (lane == 0) next = atomicAdd(&st->work_counter, 1ull);
-        const unsigned long long t0 = tk < n_cells ? tk : n_cells + (tk - n_cells) * 4;
-        const unsigned long long tend = tk < n_cells ? tk + 1 : (t0 + 4 < W ? t0 + 4 : W);
+        if (tk >= n_cells) {
+            // ---- pass-through ticket: copy_ticket (4 .. 32) items, ONE PER LANE through the dependent metadata chain
+            // (order -> item -> container -> payload address: ~3 us per item when a warp walked it
+            // item by item — the whole cost of the copy-heavy launches), then the warp copies the
+            // payloads, the first 512 bytes of four items in flight at a time
+            const unsigned long long slot = n_cells + (tk - n_cells) * copy_ticket + lane;
+            const bool valid = lane < copy_ticket && slot < W;
+            const uint8_t *src = nullptr;
+            uint8_t *dst = nullptr;
+            uint32_t nvec = 0;
+            if (valid) {
+                const unsigned long long item = it.order[slot];
+                const int kind = it.kind[item];
+                const uint64_t off = it.slot_off[item];
+                const uint32_t cap = it.slot_cap[item];
+                const SetView &S = (kind == K_COPY_A) ? A : B;
+                const uint32_t c = (kind == K_COPY_A) ? it.ca[item] : it.cb[item];
+                int otype = S.c_type[c];
+                uint32_t ocard = S.c_card[c], olen = S.c_len[c];
+                // roaring_bitmap_flip on an absent key: container_range_of_ones (containers.h:300-312)
+                // makes a one-value range an ARRAY; {start, 0} and {start} share their first 2 bytes
+                if (LAZY && (rules & RULES_FLIP) && kind == K_COPY_B && (ocard & CARD_MASK) == 1u) {
+                    otype = T_ARRAY;
+                    olen = 1;
+                }
+                if (off + cap > slab_cap) {
+                    atomicExch(&st->error, 2u);
+                    otype = 0;
+                    ocard = olen = 0;
+                } else {
+                    src = S.payload + S.c_off[c];
+                    dst = slab + off;
+                    nvec = (stored_bytes(otype, olen) + 15) >> 4;
+                }
+                it.otype[item] = (uint8_t)otype;
+                it.ocard[item] = ocard;
+                it.olen[item] = olen;
+            }
+            const int cnt = __popc(__ballot_sync(FULLMASK, valid));   // valid lanes are 0 .. cnt-1
+            for (int j0 = 0; j0 < cnt; j0 += 4) {
+                const uint4 *sp[4];
+                uint4 *dp[4];
+                uint32_t nv[4];
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int j = (j0 + k) & 31;
+                    sp[k] = reinterpret_cast<const uint4 *>(__shfl_sync(FULLMASK, (unsigned long long)src, j));
+                    dp[k] = reinterpret_cast<uint4 *>(__shfl_sync(FULLMASK, (unsigned long long)dst, j));
+                    nv[k] = __shfl_sync(FULLMASK, nvec, j);
+                    if (j0 + k >= cnt) nv[k] = 0;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((uint32_t)lane < nv[k]) v[k] = __ldg(sp[k] + lane);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((uint32_t)lane < nv[k]) dp[k][lane] = v[k];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (nv[k] > 32)
+                        warp_copy16(reinterpret_cast<uint8_t *>(dp[k] + 32), reinterpret_cast<const uint8_t *>(sp[k] + 32),
+                                    (nv[k] - 32) * 16, lane);
+            }
+            tk = __shfl_sync(FULLMASK, next, 0);
+            continue;
+        }
+        const unsigned long long t0 = tk, tend = tk + 1;
         // (tried in round 2: fetching the metadata of the whole ticket with its first lanes and passing
         //  the fields by shuffle — 17 more live registers, spills at the 6-CTA register budget and
         //  8-item tickets made every launch 15-60 % SLOWER; the per-item dependent loads stay)
@@ -699,21 +765,21 @@ void launch_order_items(Items it, uint64_t W, OpStats *st, cudaStream_t s) {
 }
 
 void launch_compute_items(const SetView &A, const SetView &B, Items it, uint64_t W, int op,
-                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int rules,
+                          uint8_t *slab, uint64_t slab_cap, OpStats *st, int rules, int copy_ticket,
                           cudaStream_t s) {
     if (!W) return;
     const uint32_t g = blocks_for_warps(W, 4, sm_count() * 6);
     switch (op) {
-        case OP_AND: k_compute_items<OP_AND, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules); break;
+        case OP_AND: k_compute_items<OP_AND, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules, copy_ticket); break;
         case OP_OR:
-            if (rules & RULES_LAZY) k_compute_items<OP_OR, true><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules);
-            else k_compute_items<OP_OR, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules);
+            if (rules & RULES_LAZY) k_compute_items<OP_OR, true><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules, copy_ticket);
+            else k_compute_items<OP_OR, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules, copy_ticket);
             break;
         case OP_XOR:
-            if (rules & RULES_LAZY) k_compute_items<OP_XOR, true><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules);
-            else k_compute_items<OP_XOR, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules);
+            if (rules & RULES_LAZY) k_compute_items<OP_XOR, true><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules, copy_ticket);
+            else k_compute_items<OP_XOR, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules, copy_ticket);
             break;
-        default: k_compute_items<OP_ANDNOT, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules); break;
+        default: k_compute_items<OP_ANDNOT, false><<<g, 128, 0, s>>>(A, B, it, W, slab, slab_cap, st, rules, copy_ticket); break;
     }
     g_launches++;
 }

@@ -8,6 +8,10 @@ for d in 0.01 0.03 0.1 0.3; do
     RB200_LIB=$PWD/croaring_b200/$lib.so timeout 300 python tools/prof_many.py $d 4 2>&1 | tail -n 1 >> gpurun_out/many_variants.log
   done
 done
+echo "== product direct (RB200_OR_MANY_TMA=0) d=0.3" >> gpurun_out/many_variants.log
+RB200_OR_MANY_TMA=0 timeout 300 python tools/prof_many.py 0.3 4 2>&1 | tail -n 1 >> gpurun_out/many_variants.log
+echo "== product TMA (RB200_OR_MANY_TMA=1) d=0.1" >> gpurun_out/many_variants.log
+RB200_OR_MANY_TMA=1 timeout 300 python tools/prof_many.py 0.1 4 2>&1 | tail -n 1 >> gpurun_out/many_variants.log
 cat gpurun_out/many_variants.log
 for lib in libroaring_b200 _sp1k _sp4k; do
   RB200_LIB=$PWD/croaring_b200/$lib.so timeout 300 python tools/time_ops.py --ops and,or,xor --reps 5 --tag $lib > gpurun_out/ops_$lib.json 2> gpurun_out/ops_$lib.err
