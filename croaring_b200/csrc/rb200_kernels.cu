@@ -64,18 +64,23 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
              const uint32_t *__restrict__ ib, const uint64_t *__restrict__ item_off,
              uint32_t npairs, int op, bool card_only, int rules, Items it, OpStats *st) {
     __shared__ unsigned int s_cls[N_CLS];   // live items per class of this block (one global atomic per class at the end)
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    // the four pairs of a block reserve their result slots with ONE atomic per round (the slab cursor
+    // is a single address: a returning atomic per pair serialised 19 900 of them per launch)
+    __shared__ uint32_t s_tot[4];
+    __shared__ unsigned long long s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x < N_CLS) s_cls[threadIdx.x] = 0;
     __syncthreads();
-    for (uint32_t p = warp; p < npairs; p += nwarps) {
-        const uint32_t a = ia[p], b = ib[p];
-        const uint32_t a0 = A.bm_beg[a], na = A.bm_cnt[a];
-        const uint32_t b0 = B.bm_beg[b], nb = B.bm_cnt[b];
-        const uint64_t base_item = item_off[p];
+    for (uint32_t p0 = blockIdx.x * 4; p0 < npairs; p0 += gridDim.x * 4) {
+        const uint32_t p = p0 + wid;
+        const bool vp = p < npairs;
+        const uint32_t a = vp ? ia[p] : 0, b = vp ? ib[p] : 0;
+        const uint32_t a0 = vp ? A.bm_beg[a] : 0, na = vp ? A.bm_cnt[a] : 0;
+        const uint32_t b0 = vp ? B.bm_beg[b] : 0, nb = vp ? B.bm_cnt[b] : 0;
+        const uint64_t base_item = vp ? item_off[p] : 0;
         const uint32_t tot = na + nb;
-        for (uint32_t t0 = 0; t0 < tot; t0 += 32) {
+        for (uint32_t t0 = 0;; t0 += 32) {
+            if (!__syncthreads_or(t0 < tot)) break;   // (also keeps the rounds' shared words apart)
             const uint32_t t = t0 + lane;
             int kind = K_HOLE, cls = CLS_NONE;
             uint32_t ca = 0, cb = 0, cap = 0, pos = 0, key = 0;
@@ -118,9 +123,15 @@ k_plan_pairs(SetView A, SetView B, const uint32_t *__restrict__ ia,
             // warp-aggregated bump allocation of the output slots
             const uint32_t incl = warp_incl_scan(cap, lane);
             const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
-            unsigned long long slab_base = 0;
-            if (lane == 31 && total) slab_base = atomicAdd(&st->slab_cursor, (unsigned long long)total);
-            slab_base = __shfl_sync(FULLMASK, slab_base, 31);
+            if (lane == 31) s_tot[wid] = total;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned long long sum = (unsigned long long)s_tot[0] + s_tot[1] + s_tot[2] + s_tot[3];
+                s_base = sum ? atomicAdd(&st->slab_cursor, sum) : 0ull;
+            }
+            __syncthreads();
+            unsigned long long slab_base = s_base;
+            for (int w = 0; w < wid; w++) slab_base += s_tot[w];
             if (t < tot) {
                 const uint64_t idx = base_item + pos;
                 it.kind[idx] = (uint8_t)kind;
@@ -468,15 +479,22 @@ __device__ __forceinline__ uint32_t portable_header_bytes(uint32_t n, bool hasru
     return 4u + ((n + 7u) >> 3) + (n < 4u ? 4u * n : 8u * n);
 }
 
+#ifndef RB200_FIN_BLOCKS
+#define RB200_FIN_BLOCKS 16
+#endif
 __global__ void __launch_bounds__(128)
 k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ item_off,
                  uint32_t npairs, SetOut out, OpStats *st) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // the four pairs of a block reserve their directory range with ONE atomic (the cursor is a single
+    // address: one returning atomic per pair serialised 19 900 of them per launch)
+    __shared__ uint32_t s_cnt[4];
+    __shared__ unsigned long long s_base;
     unsigned long long acc_bytes = 0, acc_outb = 0;  // per-warp totals: one atomic each at the end
-    for (uint32_t p = warp; p < npairs; p += nwarps) {
-        const uint64_t i0 = item_off[p], i1 = item_off[p + 1];
+    for (uint32_t p0 = blockIdx.x * 4; p0 < npairs; p0 += gridDim.x * 4) {
+        const uint32_t p = p0 + wid;
+        const bool vp = p < npairs;
+        const uint64_t i0 = vp ? item_off[p] : 0, i1 = vp ? item_off[p + 1] : 0;
         // pass 1: count surviving containers, cardinality and algorithmic bytes
         uint32_t cnt = 0, anyrun = 0;
         unsigned long long card = 0, bytes = 0, outb = 0, sbytes = 0, ebytes = 0;
@@ -512,9 +530,17 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
             sbytes += __shfl_xor_sync(FULLMASK, sbytes, d);
             ebytes += __shfl_xor_sync(FULLMASK, ebytes, d);
         }
-        unsigned long long base = 0;
-        if (lane == 0) {
-            base = atomicAdd(&st->dir_cursor, (unsigned long long)cnt);
+        if (lane == 0) s_cnt[wid] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long tot = (unsigned long long)s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+            s_base = tot ? atomicAdd(&st->dir_cursor, tot) : 0ull;
+        }
+        __syncthreads();
+        unsigned long long base = s_base;
+        for (int w = 0; w < wid; w++) base += s_cnt[w];
+        __syncthreads();   // s_cnt / s_base are rewritten by the next round
+        if (lane == 0 && vp) {
             acc_bytes += bytes;
             acc_outb += outb + portable_header_bytes(cnt, anyrun != 0);
             out.bm_beg[p] = (uint32_t)base;
@@ -523,7 +549,6 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
             out.bm_bytes[p] = sbytes;
             out.bm_ebytes[p] = ebytes;
         }
-        base = __shfl_sync(FULLMASK, base, 0);
         // pass 2: ordered compaction into the directory
         uint32_t done = 0;
         for (uint64_t i = i0; i < i1; i += 32) {
@@ -543,9 +568,12 @@ k_finalize_pairs(SetView A, SetView B, Items it, const uint64_t *__restrict__ it
             done += __popc(m);
         }
     }
-    if (lane == 0 && (acc_bytes | acc_outb)) {
-        atomicAdd(&st->algo_bytes, acc_bytes);
-        atomicAdd(&st->out_portable, acc_outb);
+    __shared__ unsigned long long s_tot[4][2];
+    if (lane == 0) { s_tot[wid][0] = acc_bytes; s_tot[wid][1] = acc_outb; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const unsigned long long v = s_tot[0][threadIdx.x] + s_tot[1][threadIdx.x] + s_tot[2][threadIdx.x] + s_tot[3][threadIdx.x];
+        if (v) atomicAdd(threadIdx.x ? &st->out_portable : &st->algo_bytes, v);
     }
 }
 
@@ -795,9 +823,8 @@ void launch_card_items(const SetView &A, const SetView &B, Items it, uint64_t W,
 void launch_finalize_pairs(const SetView &A, const SetView &B, Items it, const uint64_t *item_off,
                            uint32_t npairs, SetOut out, OpStats *st, cudaStream_t s) {
     if (!npairs) return;
-    // ~4 pairs per warp on big batches: the two per-warp counter atomics amortise, the per-pair
-    // directory allocation stays one atomic per pair
-    const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * 8);
+    // a warp per pair, full residency (16 CTAs of 4 warps per SM); counters: one atomic per block
+    const uint32_t g = blocks_for_warps(npairs, 4, sm_count() * RB200_FIN_BLOCKS);
     k_finalize_pairs<<<g, 128, 0, s>>>(A, B, it, item_off, npairs, out, st);
     g_launches++;
 }
