@@ -395,7 +395,9 @@ constexpr uint32_t M2_HALF_ENTRIES = 128;  // participants staged per half at mo
 struct Many2Smem {
     uint32_t acc[ACC_WORDS];    // union of the inputs up to L (or of all of them when L is not needed)
     uint32_t acc2[ACC_WORDS];   // union of the inputs after L
-    uint64_t bar[2];            // mbarriers of the two halves
+    uint64_t bar[2];            // mbarriers of the two halves: "the bytes have landed"
+    uint64_t ebar[2];           // RB200_M2_PIPE: "all eight warps are done with the half"
+    uint32_t h_last[2];         // RB200_M2_PIPE: the half holds the last entries of the round
     uint16_t h_bs[2][M2_HALF_ENTRIES], h_ar[2][M2_HALF_ENTRIES];   // staged bitsets / arrays+runs of a half (entry ids)
     uint32_t h_soff[M2_STAGE];  // byte offset of a staged entry inside its half
     uint32_t h_nbs[2], h_nar[2], h_big[2];
@@ -431,6 +433,9 @@ __device__ __forceinline__ unsigned long long block_min64(Many2Smem &sm, unsigne
 
 // TMA = true: operands staged by bulk copies (bitset-dominated inputs); false: direct global loads
 // (array-dominated inputs, where a bulk copy per small container costs more than it hides)
+#ifndef RB200_M2_PIPE
+#define RB200_M2_PIPE 0   // 1: warp-level full / empty mbarrier pipeline in the TMA path (no block barrier per half)
+#endif
 #ifndef RB200_M2_MINB
 #define RB200_M2_MINB 4   // resident CTAs per SM of the direct path (register budget 64 at 4)
 #endif
@@ -446,9 +451,12 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
     if (TMA && tid == 0) {
         mbar_init(&sm.bar[0], 1);
         mbar_init(&sm.bar[1], 1);
+        mbar_init(&sm.ebar[0], M2_THREADS / 32);
+        mbar_init(&sm.ebar[1], M2_THREADS / 32);
         mbar_fence_init();
     }
     uint32_t ph0 = 0, ph1 = 0;   // phase parity of the two staging halves (every thread tracks both)
+    uint32_t fills0 = 0, fills1 = 0;   // RB200_M2_PIPE: fills issued per half (thread 0)
     __syncthreads();
     if (tid == 0) sm.unit = (uint32_t)atomicAdd(&st->work_counter2, 1ull);
     for (;;) {
@@ -597,6 +605,91 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                 }
                 continue;
             }
+#if RB200_M2_PIPE
+            // ---- two-half pipeline without block-wide barriers: thread 0 is the producer (packs entries
+            // into a half, arms its "full" mbarrier with the byte count, issues the bulk copies); every
+            // warp consumes a half as soon as its bytes have landed and then arrives on the half's
+            // "empty" mbarrier; thread 0 refills the half once all eight warps have arrived.
+            uint32_t next = 0;   // next entry of the round to stage (thread 0 only)
+            auto fill = [&](int h) {   // thread 0 only
+                const uint32_t fills = h ? fills1 : fills0;
+                if (fills) mbar_wait(&sm.ebar[h], (fills - 1) & 1);   // the previous content has been consumed
+                uint32_t bytes = 0, nbs = 0, nar = 0, big = POS_NONE;
+                while (next < R && nbs + nar < M2_HALF_ENTRIES) {
+                    const uint32_t tf = sm.s_tf[next], t = tf & 15;
+                    const uint32_t sz = (tf & TF_FULL_RUN) ? 0u : round16(stored_bytes((int)t, sm.s_len[next]));
+                    if (sz > M2_HALF) {   // an oversized run container (unoptimised input): straight from global
+                        if (nbs + nar == 0 && big == POS_NONE) { big = next; next++; }
+                        break;
+                    }
+                    if (bytes + sz > M2_HALF) break;
+                    sm.h_soff[next] = bytes;
+                    if (sz) {
+                        if (t == T_BITSET) sm.h_bs[h][nbs++] = (uint16_t)next;
+                        else sm.h_ar[h][nar++] = (uint16_t)next;
+                    }
+                    bytes += sz;
+                    next++;
+                }
+                sm.h_nbs[h] = nbs;
+                sm.h_nar[h] = nar;
+                sm.h_big[h] = big;
+                sm.h_last[h] = next >= R ? 1u : 0u;
+                mbar_arrive_expect_tx(&sm.bar[h], bytes);
+                for (uint32_t k = 0; k < nbs; k++) {
+                    const uint32_t q = sm.h_bs[h][k];
+                    bulk_copy_g2s(ring[h] + sm.h_soff[q], S.payload + sm.s_off[q], BITSET_BYTES, &sm.bar[h]);
+                }
+                for (uint32_t k = 0; k < nar; k++) {
+                    const uint32_t q = sm.h_ar[h][k];
+                    bulk_copy_g2s(ring[h] + sm.h_soff[q], S.payload + sm.s_off[q],
+                                  round16(stored_bytes(sm.s_tf[q] & 15, sm.s_len[q])), &sm.bar[h]);
+                }
+                if (h) fills1++; else fills0++;
+            };
+            if (tid == 0) {
+                fill(0);
+                if (next < R) fill(1);
+            }
+            for (int h = 0;; h ^= 1) {
+                mbar_wait(&sm.bar[h], h ? ph1 : ph0);
+                if (h) ph1 ^= 1; else ph0 ^= 1;
+                const uint32_t nbs = sm.h_nbs[h], nar = sm.h_nar[h];
+                for (uint32_t j = 0; j < nbs; j += 2) {
+                    const uint4 *s0 = reinterpret_cast<const uint4 *>(ring[h] + sm.h_soff[sm.h_bs[h][j]]);
+                    const uint4 a0 = s0[tid], b0 = s0[tid + M2_THREADS];
+                    r0.x |= a0.x; r0.y |= a0.y; r0.z |= a0.z; r0.w |= a0.w;
+                    r1.x |= b0.x; r1.y |= b0.y; r1.z |= b0.z; r1.w |= b0.w;
+                    if (j + 1 < nbs) {
+                        const uint4 *s1 = reinterpret_cast<const uint4 *>(ring[h] + sm.h_soff[sm.h_bs[h][j + 1]]);
+                        const uint4 a1 = s1[tid], b1 = s1[tid + M2_THREADS];
+                        r0.x |= a1.x; r0.y |= a1.y; r0.z |= a1.z; r0.w |= a1.w;
+                        r1.x |= b1.x; r1.y |= b1.y; r1.z |= b1.z; r1.w |= b1.w;
+                    }
+                }
+                for (uint32_t j = wid; j < nar; j += M2_THREADS / 32) {
+                    const uint32_t q = sm.h_ar[h][j];
+                    uint32_t *dst = (L != POS_NONE && sm.s_pos[q] > L) ? sm.acc2 : sm.acc;
+                    const uint8_t *p = ring[h] + sm.h_soff[q];
+                    if ((sm.s_tf[q] & 15) == T_ARRAY) acc_apply_array_s<0>(dst, p, sm.s_len[q], lane);
+                    else acc_apply_runs_s<0, true>(dst, p, sm.s_len[q], lane);
+                }
+                const uint32_t big = sm.h_big[h];
+                if (big != POS_NONE) {   // oversized run container: every warp takes a share, from global
+                    uint32_t *dst = (L != POS_NONE && sm.s_pos[big] > L) ? sm.acc2 : sm.acc;
+                    const uint32_t nr = sm.s_len[big], per_w = (nr + M2_THREADS / 32 - 1) / (M2_THREADS / 32);
+                    const uint32_t r_lo = min((uint32_t)wid * per_w, nr), r_hi = min(r_lo + per_w, nr);
+                    if (r_hi > r_lo)
+                        acc_apply_runs<0, true>(dst, S.payload + sm.s_off[big] + 4ull * r_lo, r_hi - r_lo, lane);
+                }
+                const uint32_t last = sm.h_last[h];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.ebar[h]);          // this warp is done with the half
+                if (tid == 0 && !last && next < R) fill(h);       // (waits for all eight warps first)
+                __syncwarp();
+                if (last) break;
+            }
+#else
             // ---- two-half pipeline: thread 0 packs the next entries of the round into a half and
             // issues their bulk copies; everybody consumes the other half meanwhile
             uint32_t next = 0;   // next entry of the round to stage (thread 0's cursor, kept uniform)
@@ -682,6 +775,7 @@ k_or_many2(SetView S, Many2Index ix, uint32_t n, uint32_t *__restrict__ scratch,
                 if (next < R) { issue(h); staged++; }
                 h ^= 1;
             }
+#endif
         }
         __syncthreads();
         anyfull = __syncthreads_or(anyfull);
