@@ -201,7 +201,8 @@ void launch_or_many(const SetView &S, const uint32_t *idx, uint32_t n, const uin
 void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
                      const Many2Index &ix, uint32_t max_units, uint32_t *scratch, uint32_t *tickets,
                      uint32_t scratch_slots, SetOut out, uint32_t *card_per_key, OpStats *st, int sms,
-                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma, bool window_index);
+                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma, bool window_index, uint32_t *cnt_tab);
+constexpr uint32_t M2W_MAX_CHUNKS = 64;   // key-window index build: chunks of 256 input bitmaps per window
 
 void launch_pack_scan(const uint64_t *bytes, const uint32_t *cnts, uint32_t n, uint64_t *off,
                       uint64_t *beg, cudaStream_t s);

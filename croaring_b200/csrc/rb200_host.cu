@@ -1576,7 +1576,10 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
     uint64_t tot_kib = 0;
     for (size_t i = 0; i < n; i++) tot_kib += (S->h_bytes[idx ? idx[i] : i] >> 10) + 1;
     const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>(tot, std::min<uint64_t>(65536, tot) + tot_kib / 32 + 1));
-    const size_t e_bytes = al256(16 * tot) + al256(4 * max_units);
+    // key-window index build: per-(window, chunk of 256 bitmaps) key counts when there are several chunks
+    const uint64_t m2_chunks = (n + 255) / 256;
+    const size_t tab_bytes = m2_chunks > 1 && m2_chunks <= M2W_MAX_CHUNKS ? (size_t)2048 * m2_chunks * 32 * 4 : 0;
+    const size_t e_bytes = al256(16 * tot) + al256(4 * max_units) + al256(tab_bytes);
     uint8_t *d_index = nullptr;
     if (ok && !use_v1) { d_index = (uint8_t *)dev_alloc(e_bytes); ok = d_index != nullptr; }
     if (ok && !use_v1) {
@@ -1606,12 +1609,13 @@ static rb200_set *or_many_impl(const rb200_set_t *S, const uint32_t *idx, size_t
         // costs one directory search per input), one L2 atomic per container otherwise
         // (RB200_OR_MANY_INDEX=window / atomic forces the choice)
         static const int win_env = []() { const char *e = getenv("RB200_OR_MANY_INDEX"); return !e ? -1 : !strcmp(e, "window") ? 1 : 0; }();
-        const bool window_index = win_env >= 0 ? win_env != 0 : (tot >= 64 * (uint64_t)n);
+        const bool window_index = m2_chunks <= M2W_MAX_CHUNKS && n > 0 && (win_env >= 0 ? win_env != 0 : (tot >= 64 * (uint64_t)n));
         cudaMemsetAsync(g.d_m2_tables, 0, 3 * 65536 * sizeof(uint32_t), g.stream);
         if (want_ck) cudaMemsetAsync(g.d_cardkey, 0, 65536 * 4, g.stream);
         launch_or_many2(vs, d_idx, (uint32_t)n, key_lo, key_hi, ix, (uint32_t)std::min<uint64_t>(max_units, 0xffffffffu),
                         g.d_m2_scratch, g.d_m2_tickets, M2_SCRATCH_SLOTS, R->out(), want_ck ? g.d_cardkey : nullptr,
-                        g.d_stats, g.sms, g.stream, g.evk0, use_tma, window_index);
+                        g.d_stats, g.sms, g.stream, g.evk0, use_tma, window_index,
+                        (uint32_t *)(d_index + al256(16 * tot) + al256(4 * max_units)));
     }
     if (ok && use_v1) {
         cudaEventRecord(g.ev0, g.stream);

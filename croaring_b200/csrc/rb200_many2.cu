@@ -133,63 +133,76 @@ __device__ __forceinline__ uint32_t window_lower_bound(const uint16_t *__restric
 template <bool FILL>
 __global__ void __launch_bounds__(M2W_THREADS)
 k_many2_window(SetView S, const uint32_t *__restrict__ idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
-               Many2Index ix) {
+               Many2Index ix, uint32_t nchunks, uint32_t *__restrict__ cnt_tab) {
+    // work unit = (window of 32 keys, chunk of 256 input bitmaps); with several chunks the count pass
+    // leaves the unit's per-key counts in cnt_tab and the fill pass starts a key's entries of chunk c
+    // behind those of the chunks before it — still no atomic per container
     __shared__ uint32_t s_cnt[M2W_KEYS], s_b16[M2W_KEYS], s_start[M2W_KEYS];
     __shared__ uint32_t s_seg[M2W_THREADS], s_c0[M2W_THREADS], s_nc[M2W_THREADS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t span_hi = min(ix.key_fill[0], key_hi), span_lo = max(65535u - ix.key_fill[1], key_lo);
     if (span_lo > span_hi) return;
     const uint32_t w0 = span_lo / M2W_KEYS, w1 = span_hi / M2W_KEYS;
-    for (uint32_t w = w0 + blockIdx.x; w <= w1; w += gridDim.x) {
-        const uint32_t k0 = w * M2W_KEYS;
+    const uint32_t units = (w1 - w0 + 1) * nchunks;
+    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const uint32_t w = w0 + u / nchunks, c = u % nchunks;
+        const uint32_t k0 = w * M2W_KEYS, base = c * M2W_THREADS;
         if (tid < M2W_KEYS) {
             s_cnt[tid] = 0;
             s_b16[tid] = 0;
-            if (FILL) s_start[tid] = ix.key_start[k0 + tid];
-        }
-        for (uint32_t base = 0; base < n; base += M2W_THREADS) {
-            __syncthreads();
-            {   // every thread: where the window starts in one bitmap's directory
-                const uint32_t i = base + tid;
-                uint32_t nc = 0, c0 = 0, seg = 0;
-                if (i < n) {
-                    const uint32_t b = idx ? idx[i] : i;
-                    nc = S.bm_cnt[b];
-                    c0 = S.bm_beg[b];
-                    if (nc) {
-                        if ((uint32_t)S.c_key[c0 + nc - 1] < k0) nc = 0;   // directory ends before the window
-                        else seg = window_lower_bound(S.c_key + c0, nc, k0);
-                    }
-                }
-                s_seg[tid] = seg;
-                s_c0[tid] = c0;
-                s_nc[tid] = nc;
+            if (FILL) {
+                uint32_t st = ix.key_start[k0 + tid];
+                for (uint32_t cc = 0; cc < c; cc++) st += cnt_tab[(size_t)(u - c + cc) * M2W_KEYS + tid];
+                s_start[tid] = st;
             }
-            __syncthreads();
-            const uint32_t m = min((uint32_t)M2W_THREADS, n - base);
-            for (uint32_t q = wid; q < m; q += M2W_THREADS / 32) {
-                const uint32_t nc = s_nc[q], p = s_seg[q] + lane;
-                if (p >= nc) continue;                     // (whole warp when the bitmap has nothing here)
-                const uint32_t c = s_c0[q] + p;
-                const uint32_t k = S.c_key[c];
-                if (k >= k0 + M2W_KEYS || k < key_lo || k > key_hi) continue;
-                const uint32_t t = S.c_type[c], l = S.c_len[c];
-                if (!FILL) {
-                    atomicAdd(&s_cnt[k - k0], 1u);
-                    atomicAdd(&s_b16[k - k0], round16(stored_bytes(t, l)) >> 4);
-                } else {
-                    const uint32_t cd = S.c_card[c] & CARD_MASK;
-                    uint32_t f = t;
-                    if (t == T_RUN && l == 1 && cd == 65536) f |= TF_FULL_RUN;
-                    if (t == T_BITSET && cd == 65536) f |= TF_FULL_BITSET;
-                    const uint32_t slot = s_start[k - k0] + atomicAdd(&s_cnt[k - k0], 1u);
-                    ix.ent[slot] = make_uint4((uint32_t)(S.c_off[c] >> 4), base + q, l, f);
+        }
+        {   // every thread: where the window starts in one bitmap's directory
+            const uint32_t i = base + tid;
+            uint32_t nc = 0, c0 = 0, seg = 0;
+            if (i < n) {
+                const uint32_t b = idx ? idx[i] : i;
+                nc = S.bm_cnt[b];
+                c0 = S.bm_beg[b];
+                if (nc) {
+                    if ((uint32_t)S.c_key[c0 + nc - 1] < k0) nc = 0;   // directory ends before the window
+                    else seg = window_lower_bound(S.c_key + c0, nc, k0);
                 }
+            }
+            s_seg[tid] = seg;
+            s_c0[tid] = c0;
+            s_nc[tid] = nc;
+        }
+        __syncthreads();
+        const uint32_t m = min((uint32_t)M2W_THREADS, n - base);
+        for (uint32_t q = wid; q < m; q += M2W_THREADS / 32) {
+            const uint32_t nc = s_nc[q], p = s_seg[q] + lane;
+            if (p >= nc) continue;                     // (whole warp when the bitmap has nothing here)
+            const uint32_t cix = s_c0[q] + p;
+            const uint32_t k = S.c_key[cix];
+            if (k >= k0 + M2W_KEYS || k < key_lo || k > key_hi) continue;
+            const uint32_t t = S.c_type[cix], l = S.c_len[cix];
+            if (!FILL) {
+                atomicAdd(&s_cnt[k - k0], 1u);
+                atomicAdd(&s_b16[k - k0], round16(stored_bytes(t, l)) >> 4);
+            } else {
+                const uint32_t cd = S.c_card[cix] & CARD_MASK;
+                uint32_t f = t;
+                if (t == T_RUN && l == 1 && cd == 65536) f |= TF_FULL_RUN;
+                if (t == T_BITSET && cd == 65536) f |= TF_FULL_BITSET;
+                const uint32_t slot = s_start[k - k0] + atomicAdd(&s_cnt[k - k0], 1u);
+                ix.ent[slot] = make_uint4((uint32_t)(S.c_off[cix] >> 4), base + q, l, f);
             }
         }
         __syncthreads();
-        if (!FILL && tid < M2W_KEYS && k0 + tid <= 65535u)
-            ix.key_cu[k0 + tid] = ((unsigned long long)s_cnt[tid] << 40) | s_b16[tid];
+        if (!FILL && tid < M2W_KEYS && k0 + tid <= 65535u) {
+            const unsigned long long packed = ((unsigned long long)s_cnt[tid] << 40) | s_b16[tid];
+            if (nchunks == 1) {
+                ix.key_cu[k0 + tid] = packed;
+            } else {
+                if (packed) atomicAdd(ix.key_cu + k0 + tid, packed);   // one atomic per (unit, live key)
+                cnt_tab[(size_t)u * M2W_KEYS + tid] = s_cnt[tid];
+            }
+        }
         __syncthreads();
     }
 }
@@ -913,15 +926,16 @@ __global__ void k_many2_sum_cards(const uint32_t *__restrict__ c_card, const OpS
 void launch_or_many2(const SetView &S, const uint32_t *idx, uint32_t n, uint32_t key_lo, uint32_t key_hi,
                      const Many2Index &ix, uint32_t max_units, uint32_t *scratch, uint32_t *tickets,
                      uint32_t scratch_slots, SetOut out, uint32_t *card_per_key, OpStats *st, int sms,
-                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma, bool window_index) {
+                     cudaStream_t s, cudaEvent_t ev_kernel_start, bool use_tma, bool window_index, uint32_t *cnt_tab) {
     const uint32_t gw = (uint32_t)sms * 8;
     if (window_index) {
         // long directories: key-window index build, shared-memory counting, no global atomics
         const uint32_t gs = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 4));
         k_many2_span<<<gs, 256, 0, s>>>(S, idx, n, ix.key_fill);
-        k_many2_window<false><<<sms * 6, M2W_THREADS, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+        const uint32_t nchunks = (n + M2W_THREADS - 1) / M2W_THREADS;
+        k_many2_window<false><<<sms * 6, M2W_THREADS, 0, s>>>(S, idx, n, key_lo, key_hi, ix, nchunks, cnt_tab);
         k_many2_scan<<<1, 1024, 0, s>>>(ix, scratch_slots, max_units, (uint32_t)sms * 8, out, st, 1);
-        k_many2_window<true><<<sms * 6, M2W_THREADS, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
+        k_many2_window<true><<<sms * 6, M2W_THREADS, 0, s>>>(S, idx, n, key_lo, key_hi, ix, nchunks, cnt_tab);
         g_launches += 1;
     } else {
         k_many2_count<<<gw, 128, 0, s>>>(S, idx, n, key_lo, key_hi, ix);
