@@ -3623,7 +3623,16 @@ int rb200_r64_batch_op(int op, const roaring64_bitmap_t *const *a, const roaring
         if (!out[k]) ok = false;
     });
     rb200_serialized_free(blob, off, len);
-    if (!ok) { t_err = "roaring64: the host library refused a result blob"; return -1; }
+    if (!ok) {
+        // all or nothing: the results that were built go back to the host library
+        auto r64_free = (void (*)(roaring64_bitmap_t *))dlsym(RTLD_DEFAULT, "roaring64_bitmap_free");
+        for (size_t k = 0; k < npairs; k++) {
+            if (out[k] && r64_free) r64_free(out[k]);
+            out[k] = nullptr;
+        }
+        t_err = "roaring64: the host library refused a result blob";
+        return -1;
+    }
     return 0;
 }
 

@@ -359,7 +359,12 @@ RB_API rb200_set_t *rb200_set_upload_serialized_keyrange(const char *const *bufs
     });
     rb200_set_t *S = nullptr;
     bool ok = true;
-    for (size_t b = 0; b < n; b++) ok = ok && rc[b] == 0;
+    for (size_t b = 0; b < n && ok; b++)
+        if (rc[b] != 0) {
+            // the slices ran on worker threads and rb200_last_error() is per thread: report on the caller's
+            rb200::set_error("set_upload_serialized_keyrange: malformed portable bitmap at index " + std::to_string(b));
+            ok = false;
+        }
     if (ok) S = rb200_set_upload_serialized(part.data(), plen.data(), n);
     for (char *p : part) free(p);
     return S;
