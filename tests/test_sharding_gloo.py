@@ -106,3 +106,58 @@ def test_or_many_sharded_world2_gloo(seed):
     assert all(ok for _, ok, _, _ in res), res
     ranges = sorted((lo, hi) for _, _, lo, hi in res)
     assert ranges[0][0] == 0 and ranges[1][1] == 65535 and ranges[0][1] + 1 == ranges[1][0]
+
+
+def _blob(R, values, run_optimize=False):
+    r = R.from_values(np.asarray(values, dtype=np.uint32), run_optimize=run_optimize)
+    b = R.serialize(r)
+    R.free(r)
+    return b
+
+
+def test_blob_algebra_edge_cases(R):
+    """Edges of the host blob algebra: empty bitmaps, run cookies with fewer than four containers
+    (no offset header, roaring_array.c:500-506), slices that keep nothing, more ranks than live
+    keys, malformed inputs."""
+    empty = _blob(R, [])
+    assert len(empty) == 8
+    assert sh.slice_blob_by_keys(empty, 0, 65535) == empty
+    assert sh.concat_blobs([empty, empty, empty]) == empty
+    assert sh.concat_blobs([]) == empty
+    # three run containers: run cookie WITHOUT offsets; slicing to two keeps the short header form,
+    # concatenating two such bitmaps (4 containers) must grow the offset header
+    runs3 = _blob(R, list(range(0, 5000)) + list(range(1 << 16, (1 << 16) + 7000)) + list(range(5 << 16, (5 << 16) + 4500)), True)
+    cookie = int(np.frombuffer(runs3[:4], dtype="<u4")[0])
+    assert (cookie & 0xFFFF) == 12347 and (cookie >> 16) + 1 == 3
+    two = sh.slice_blob_by_keys(runs3, 0, 1)
+    rt = R.deserialize(two)
+    assert R.validate(rt)[0] and R.card(rt) == 12000
+    assert R.serialize(rt) == two                       # canonical bytes (what the reference would write)
+    R.free(rt)
+    other = _blob(R, list(range(9 << 16, (9 << 16) + 6000)) + [(11 << 16) + 5, (11 << 16) + 9], True)
+    cat = sh.concat_blobs([runs3, other])               # 3 + 2 containers, mixed run / array
+    rc = R.deserialize(cat)
+    assert R.validate(rc)[0] and R.card(rc) == 5000 + 7000 + 4500 + 6000 + 2
+    assert R.serialize(rc) == cat
+    R.free(rc)
+    # a slice that keeps nothing is the canonical empty bitmap
+    assert sh.slice_blob_by_keys(runs3, 2, 4) == empty
+    assert sh.slice_blob_by_keys(runs3, 6, 65535) == empty
+    # more ranks than live keys: ranges still cover 0..65535, are disjoint and non-empty as key ranges
+    rs, span = sh.plan_key_ranges([runs3, other], 8)
+    assert span == (0, 11) and rs[0][0] == 0 and rs[-1][1] == 65535
+    for (a, b), (c, d) in zip(rs, rs[1:]):
+        assert a <= b and b + 1 == c and c <= d
+    parts = [sh.concat_blobs([sh.slice_blob_by_keys(x, lo, hi) for x in (runs3, other)]) for lo, hi in rs]
+    assert sh.concat_blobs(parts) == cat
+    # no container at all: an empty span
+    rs, span = sh.plan_key_ranges([empty, empty], 2)
+    assert span[0] > span[1] and rs[0][0] == 0 and rs[-1][1] == 65535
+    # malformed inputs are refused, not read out of bounds
+    for bad in (b"", b"\x00\x01", runs3[:-1], runs3[:10], b"\xff" * 16):
+        with pytest.raises(Exception):
+            sh.slice_blob_by_keys(bad, 0, 65535)
+        with pytest.raises(Exception):
+            sh.plan_key_ranges([runs3, bad], 2)
+        with pytest.raises(Exception):
+            sh.concat_blobs([bad])
