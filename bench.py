@@ -70,6 +70,18 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+def headline_config(pairs_per_dataset, set_ops_per_step):
+    """`config` of the headline workload: ONE definition, printed verbatim by both arms (the reference
+    arm runs on our arm's config).  `l2`, `batching` and `sharding` say how the CUDA arm executes it;
+    the reference arm runs the same pairs with every result created, measured and freed on the host."""
+    return {"workload": "realdata_allpairs", "datasets": DATASETS, "ops": OPS,
+            "pairs_per_dataset": int(pairs_per_dataset), "set_ops_per_step": int(set_ops_per_step),
+            "l2": "flushed between timed steps (256 MB memset)",
+            "batching": "one rb200_batch_op call per (dataset, op); the 9 calls of a step queue back to back",
+            "sharding": "pairs r, r+N, ... of every list on rank r; one NCCL all-reduce of the device "
+                        "checksum closes the step (inside the timed region)"}
+
+
 def all_pairs(n):
     i, j = np.triu_indices(n, 1)
     return i.astype(np.uint32), j.astype(np.uint32)
@@ -214,8 +226,7 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u16/u64 bitwise", "data": "reference realdata fixtures",
-        "config": {"workload": "realdata_allpairs", "datasets": DATASETS, "ops": OPS,
-                   "pairs_per_dataset": 19900, "set_ops_per_step": r["ops_per_step"]},
+        "config": headline_config(19900, r["ops_per_step"]),
         "checksum_sum_card": r["checksum"],
         "parity": (gold is not None and r["checksum"] == gold["bench_checksum_and_or_xor"]),
         "cpu_baseline": {"value": r["value"], "unit": "set-ops/s", "cores": T, "kind": "reference",
@@ -732,12 +743,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u16/u64 bitwise",
         "data": "reference realdata fixtures (portable-serialized, run-optimized)",
-        "config": {"workload": "realdata_allpairs", "datasets": DATASETS, "ops": OPS,
-                   "pairs_per_dataset": int(len(full_pairs[DATASETS[0]][0])),
-                   "set_ops_per_step": ops_per_step, "l2": "flushed between timed steps (256 MB memset)",
-                   "batching": "one rb200_batch_op call per (dataset, op); the 9 calls of a step queue back to back",
-                   "sharding": "pairs r, r+N, ... of every list on rank r; one NCCL all-reduce of the device "
-                               "checksum closes the step (inside the timed region)"},
+        "config": headline_config(len(full_pairs[DATASETS[0]][0]), ops_per_step),
         "checksum_sum_card": stats["checksum"],
         "parity": bool(headline_parity),
         "roofline": roofline,
