@@ -1319,6 +1319,7 @@ struct PairBuf {
     bool build(const rb200_set *A, const rb200_set *B, const uint32_t *ia, const uint32_t *ib,
                size_t np, int op, bool lazy = false) {
         if (!ensure_mirrors(A) || !ensure_mirrors(B)) return false;
+        if (np > 0xffffffffull) { t_err = "too many pairs in one batch (2^32 - 1 at most)"; return false; }
         const size_t o_off = 0, o_ia = al256(8 * (np + 1)), o_ib = o_ia + al256(4 * np);
         bytes = o_ib + al256(4 * np);
         h = (uint8_t *)pin_alloc(bytes);
@@ -1357,6 +1358,8 @@ struct PairBuf {
             }
         }
         off[np] = w;
+        // item ids, directory positions of the result and the order list are 32-bit on the device
+        if (w > 0xffffffffull) { t_err = "batch too large: more than 2^32 - 1 container slots, split the pair list"; return false; }
         W = w;
         slab_bound = sb;
         d_off = (uint64_t *)(d + o_off);
