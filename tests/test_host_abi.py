@@ -117,3 +117,53 @@ def test_compute_fails_loudly_without_gpu():
         _ = a & a
     with pytest.raises(rb.RB200Error):
         rb.DeviceSet.upload([a])
+
+
+def test_mutated_blobs_never_crash_the_host_parsers(R):
+    """Seeded mutation fuzz of the two host-side portable-format readers (rb200_host.cu parse_portable
+    behind rb200_bitmap_portable_deserialize_safe; rb200_shard.cu index_blob behind the blob algebra):
+    byte flips, truncations, garbage tails and splices must be either refused or handled
+    consistently — what one reader accepts the other slices, and accepted bytes re-serialize stably."""
+    import random
+    from croaring_b200 import sharding as sh
+    rng = random.Random(20260923)
+    base = rb.load_realdata("wikileaks-noquotes")[:10] + rb.load_realdata("census1881")[:4] + synth_blobs(R, 11, 24)
+    base = [b for b in base if len(b) < 40000]
+    accepted = sliceable = 0
+    for _ in range(3000):
+        b = bytearray(rng.choice(base))
+        mode = rng.randrange(5)
+        if mode == 0:
+            for _k in range(rng.randrange(1, 4)):
+                b[rng.randrange(min(len(b), 64))] = rng.randrange(256)
+        elif mode == 1:
+            for _k in range(rng.randrange(1, 6)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        elif mode == 2:
+            b = b[:rng.randrange(len(b))]
+        elif mode == 3:
+            b += bytes(rng.randrange(256) for _k in range(rng.randrange(1, 40)))
+        else:
+            c = rng.choice(base)
+            k = rng.randrange(len(b))
+            b = b[:k] + c[rng.randrange(len(c)):]
+        b = bytes(b)
+        try:
+            x = rb.Bitmap.deserialize(b)
+            s = x.serialize()
+            y = rb.Bitmap.deserialize(s)
+            assert y.serialize() == s
+            x.free()
+            y.free()
+            accepted += 1
+        except rb.RB200Error:
+            pass
+        try:
+            parts = [sh.slice_blob_by_keys(b, lo, hi) for lo, hi in ((0, 7), (8, 300), (301, 65535))]
+            full = sh.concat_blobs(parts)
+            assert sh.slice_blob_by_keys(full, 0, 65535) == full
+            sh.plan_key_ranges([b, full], 3)
+            sliceable += 1
+        except rb.RB200Error:
+            pass
+    assert accepted == sliceable and 0 < accepted < 3000
