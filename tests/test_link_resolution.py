@@ -48,3 +48,23 @@ def test_cpp_wrapper_binds_hot_path_to_our_library(tmp_path):
     hdr = open(os.path.join(ROOT, "include", "roaring_b200.h")).read()
     declared = set(re.findall(r"\b(roaring_bitmap_[a-z0-9_]+)\s*\(", hdr))
     assert all(n in declared for n, lib in bound.items() if lib == "libroaring_b200.so")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFDIR, "dropin_caller_ref")), reason="needs oracle/_ref (make -C oracle)")
+def test_ld_preload_rebinds_an_existing_binary():
+    """The other deployment of INTEGRATION.md section 1: a binary linked against the reference ALONE
+    (oracle/_ref/dropin_caller_ref), started under LD_PRELOAD=libroaring_b200.so — every symbol our
+    header declares under a reference name is taken from our library, the rest stays the reference's."""
+    exe = os.path.join(REFDIR, "dropin_caller_ref")
+    env = dict(os.environ, LD_BIND_NOW="1", LD_DEBUG="bindings", LD_PRELOAD=rb.api.LIB_PATH)
+    p = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)   # no arguments: usage, exit 2
+    bound = {}
+    for m in re.finditer(r"binding file (\S+) \[\d+\] to (\S+) \[\d+\]: normal symbol `(roaring\w*_bitmap_\w+)'", p.stderr):
+        if m.group(1) == exe:
+            bound[m.group(3)] = os.path.basename(m.group(2))
+    hdr = open(os.path.join(ROOT, "include", "roaring_b200.h")).read()
+    declared = set(re.findall(r"\b(roaring(?:64)?_bitmap_[a-z0-9_]+)\s*\(", hdr))
+    used_ours = {n for n in bound if n in declared}
+    assert len(used_ours) >= 15, sorted(bound)
+    for n, lib in bound.items():
+        assert lib == ("libroaring_b200.so" if n in declared else "libroaring_ref.so"), (n, lib)
