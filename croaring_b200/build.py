@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3",
     "--expt-relaxed-constexpr",
     "-cudart", "static",
+    "-DRB200_BUILDING_LIBRARY",   # include/roaring_b200.h: never pull an installed copy of the reference's headers
 ]
 
 

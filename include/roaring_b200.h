@@ -23,12 +23,22 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* The reference's own headers, when they are on the include path: its types are then used below,
+ * whatever the order in which the application includes the two headers.  (The library itself is
+ * built with RB200_BUILDING_LIBRARY: it never depends on an installed copy of the reference.) */
+#if !defined(ROARING_H) && !defined(RB200_BUILDING_LIBRARY) && defined(__has_include)
+#if __has_include(<roaring/roaring.h>)
+#include <roaring/roaring.h>
+#endif
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
 
 /* ---------------------------------------------------------------------------------------
- * Layout-compatible types.  If the reference's headers are already included we use theirs.
+ * Layout-compatible types.  If the reference's headers are already included — or can be (they are
+ * found on the include path) — we use theirs.
  * include/roaring/roaring_types.h:61-68 (roaring_array_t), include/roaring/roaring.h:39-41
  * (roaring_bitmap_t), containers/array.h:46-50, containers/bitset.h:45-48,
  * containers/run.h:48-51,69-73, containers/containers.h:48-51 (typecodes).

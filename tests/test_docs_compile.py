@@ -36,3 +36,31 @@ def test_integration_examples_compile():
                                 "-Wno-unused-variable", "-Wno-unused-but-set-variable",
                                 "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
             assert r.returncode == 0, f"INTEGRATION.md example {i} does not compile:\n{r.stderr[-3000:]}"
+
+
+def test_header_coexists_with_the_reference_headers():
+    """include/roaring_b200.h next to the reference's own headers, in either include order, as C and as
+    C++: the drop-in prototypes must be compatible declarations of the reference's (a conflicting
+    signature is a compile error) and the layout types must not be defined twice."""
+    ref_inc = "/root/reference/include"
+    if not os.path.isdir(ref_inc):
+        import pytest
+        pytest.skip("needs the reference headers (build container)")
+    orders = [("#include <roaring/roaring.h>\n#include <roaring/roaring64.h>\n#include <roaring_b200.h>\n"),
+              ("#include <roaring_b200.h>\n#include <roaring/roaring.h>\n#include <roaring/roaring64.h>\n")]
+    with tempfile.TemporaryDirectory() as d:
+        for i, inc in enumerate(orders):
+            for cc, std, ext in (("gcc", "-std=c11", "c"), ("g++", "-std=c++17", "cpp")):
+                src = os.path.join(d, f"order{i}.{ext}")
+                with open(src, "w") as f:
+                    f.write(inc + "int main(void) { roaring_bitmap_t *r = 0; (void)r; return 0; }\n")
+                r = subprocess.run([cc, std, "-fsyntax-only", "-Wall", "-I", ref_inc, "-I", os.path.join(ROOT, "include"), src],
+                                   capture_output=True, text=True)
+                assert r.returncode == 0, f"{cc} include order {i}:\n{r.stderr[-3000:]}"
+        # and alone, without the reference anywhere on the include path
+        src = os.path.join(d, "alone.c")
+        with open(src, "w") as f:
+            f.write("#include <roaring_b200.h>\nint main(void) { roaring_bitmap_t r; (void)r; return 0; }\n")
+        r = subprocess.run(["gcc", "-std=c11", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), src],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]

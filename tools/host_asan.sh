@@ -10,7 +10,7 @@ mkdir -p "$OUT"
 python -m croaring_b200.build > /dev/null            # the product's objects (device code)
 cd "$ROOT/croaring_b200/csrc"
 for f in rb200_host rb200_shard; do
-  nvcc -O1 -g -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr -cudart static \
+  nvcc -O1 -g -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr -cudart static -DRB200_BUILDING_LIBRARY \
        -Xcompiler -fPIC,-fvisibility=hidden,-fsanitize=address,-fsanitize=undefined,-fno-omit-frame-pointer \
        -c $f.cu -o "$OUT/$f.o" 2>&1 | grep -v deprecated || true
 done
