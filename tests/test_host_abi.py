@@ -22,6 +22,8 @@ def test_exports_match_header():
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     missing = declared - exported
     assert not missing, f"declared in roaring_b200.h but not exported: {sorted(missing)}"
+    extra = exported - declared      # nothing else may leak (an undeclared reference name would shadow libroaring's)
+    assert not extra, f"exported but not declared in roaring_b200.h: {sorted(extra)}"
     L = rb.lib()
     for name in declared:
         assert getattr(L, name) is not None
